@@ -1,0 +1,1187 @@
+// fpm_host.cu -- host driver + C ABI (include/fpm_b200.h) of the B200 NCC matcher.
+//
+// Mirrors TemplateMatcher::learnPattern / match (/root/reference/src/TemplateMatcher.cpp:45-437)
+// as a sequence of batched kernel launches; all pixel work happens on the device, the host only
+// computes the angle schedule and the per-angle top-layer geometry (a few dozen doubles) and reads
+// back one counter per pyramid layer.  There is no CPU fallback: without a CUDA device
+// fpm_create() fails.
+#include "../../include/fpm_b200.h"
+#include "fpm_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// getTopLayer, src/TemplateMatcher.cpp:445-455
+int get_top_layer(int w, int h, int min_dst_length)
+{
+    int top = 0;
+    int min_area = min_dst_length * min_dst_length;
+    int area = w * h;
+    while (area > min_area) { area /= 4; top++; }
+    return top;
+}
+
+// getBestRotationSize, src/TemplateMatcher.cpp:901-969
+void best_rotation_size(int sw, int sh, int dw, int dh, double dRAngle, int* ow, int* oh)
+{
+    double rad = dRAngle * FPM_D2R;
+    float cx = (sw - 1) / 2.0f, cy = (sh - 1) / 2.0f;
+    float x[4], y[4];
+    fpm_pt_rotate(0.f, 0.f, cx, cy, rad, &x[0], &y[0]);
+    fpm_pt_rotate(0.f, (float)(sh - 1), cx, cy, rad, &x[1], &y[1]);
+    fpm_pt_rotate((float)(sw - 1), (float)(sh - 1), cx, cy, rad, &x[2], &y[2]);
+    fpm_pt_rotate((float)(sw - 1), 0.f, cx, cy, rad, &x[3], &y[3]);
+    float fTopY = std::max(std::max(y[0], y[1]), std::max(y[2], y[3]));
+    float fBottomY = std::min(std::min(y[0], y[1]), std::min(y[2], y[3]));
+    float fRightX = std::max(std::max(x[0], x[1]), std::max(x[2], x[3]));
+    float fLeftX = std::min(std::min(x[0], x[1]), std::min(x[2], x[3]));
+    if (dRAngle > 360) dRAngle -= 360;
+    else if (dRAngle < 0) dRAngle += 360;
+    if (fabs(fabs(dRAngle) - 90) < FPM_VISION_TOLERANCE || fabs(fabs(dRAngle) - 270) < FPM_VISION_TOLERANCE) {
+        *ow = sh; *oh = sw; return;
+    } else if (fabs(dRAngle) < FPM_VISION_TOLERANCE || fabs(fabs(dRAngle) - 180) < FPM_VISION_TOLERANCE) {
+        *ow = sw; *oh = sh; return;
+    }
+    double dAngle = dRAngle;
+    if (dAngle > 0 && dAngle < 90) {}
+    else if (dAngle > 90 && dAngle < 180) dAngle -= 90;
+    else if (dAngle > 180 && dAngle < 270) dAngle -= 180;
+    else if (dAngle > 270 && dAngle < 360) dAngle -= 270;
+    float fH1 = (float)(dw * sin(dAngle * FPM_D2R) * cos(dAngle * FPM_D2R));
+    float fH2 = (float)(dh * sin(dAngle * FPM_D2R) * cos(dAngle * FPM_D2R));
+    int iHalfHeight = (int)ceilf(fTopY - cy - fH1);
+    int iHalfWidth = (int)ceilf(fRightX - cx - fH2);
+    int rw = iHalfWidth * 2, rh = iHalfHeight * 2;
+    bool wrong = (dw < rw && dh > rh) || (dw > rw && dh < rh) || ((long long)dw * dh > (long long)rw * rh);
+    if (wrong) {
+        rw = (int)((double)(fRightX - fLeftX) + 0.5);
+        rh = (int)((double)(fTopY - fBottomY) + 0.5);
+    }
+    *ow = rw; *oh = rh;
+}
+
+struct TplLevelHost {
+    int w = 0, h = 0, pitch = 0;
+    size_t dev_off = 0;
+    double mean = 0, norm = 0, inv_area = 1;
+    int equal1 = 0;
+    std::vector<uint8_t> pix;    // w*h
+};
+
+struct TopPlan {                  // cached per (source size, parameters)
+    int sw = 0, sh = 0, top = -1, batch = 0, a0 = 0, a1 = 0;
+    double tol = -1;
+    std::vector<double> angles;   // full schedule
+    std::vector<float> ftx, fty;  // for [a0, a1)
+    int maxW = 0, maxH = 0;
+    int n_ang = 0;                // a1 - a0
+    bool valid = false;
+};
+
+}  // namespace
+
+struct fpm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // parameters (src/TemplateMatcher.cpp:28-39)
+    int max_pos = 70;
+    double max_overlap = 0.0, score = 0.7, tol_angle = 0.0;
+    int min_reduce_area = 256;
+    int use_simd = 1, subpixel = 0, trace = 0;
+    double workspace_mb = 4096;
+    // template
+    bool learned = false;
+    int learned_mra = -1;
+    int border = 0;
+    std::vector<uint8_t> tpl0;    // level-0 copy for re-learning when MinReduceArea changes
+    int tpl0_w = 0, tpl0_h = 0;
+    std::vector<TplLevelHost> tpl;
+    DevBuf d_tpl;
+    // user rect (pure storage)
+    int ur[4] = {0, 0, 0, 0};
+    int has_ur = 0;
+    // workspace
+    DevBuf d_src, d_pyr, d_rot, d_score, d_blkv, d_blkl, d_picks, d_pickcnt, d_jobs_top, d_angles, d_ftx, d_fty;
+    DevBuf d_off, d_keys, d_cand[2], d_candcnt, d_toppt, d_counters, d_jobs_ref, d_roi, d_rowsum, d_rowS, d_rowQ;
+    DevBuf d_refined, d_rects, d_del, d_idmap, d_results, d_rescnt, d_trace, d_trace_sc, d_dbg[4];
+    PinnedBuf h_counts, h_results, h_stage;
+    std::vector<FpmLevel> levels; // source pyramid of the current batch
+    TopPlan plan;
+    std::string err;
+    double last_ms = 0;
+    long long launches = 0;
+    // trace
+    std::vector<double> tr_cands;                 // n*4
+    std::vector<std::vector<double>> tr_evals;    // per level, n*5
+};
+
+namespace {
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
+            return FPM_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define CKL()                                                                            \
+    do {                                                                                 \
+        h->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e__);           \
+            return FPM_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+FpmTplLevel tpl_level_dev(const fpm_handle* h, int l)
+{
+    const TplLevelHost& t = h->tpl[l];
+    FpmTplLevel d;
+    d.ptr = h->d_tpl.as<uint8_t>() + t.dev_off;
+    d.w = t.w; d.h = t.h; d.pitch = t.pitch;
+    d.mean = t.mean; d.norm = t.norm; d.inv_area = t.inv_area; d.result_equal1 = t.equal1;
+    return d;
+}
+
+int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& dst, int batch)
+{
+    int vec_ok = ((reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0) && (src.pitch % 4 == 0) && (src.img_stride % 4 == 0);
+    dim3 grid((dst.w + PD_TW - 1) / PD_TW, (dst.h + PD_TH - 1) / PD_TH, batch);
+    fpm_pyrdown_kernel<<<grid, PD_THREADS, 0, h->stream>>>(src, dst, vec_ok);
+    CKL();
+    return FPM_OK;
+}
+
+// ---- learnPattern, src/TemplateMatcher.cpp:45-95 ------------------------------------
+int do_learn(fpm_handle* h)
+{
+    const int w0 = h->tpl0_w, h0 = h->tpl0_h;
+    CK(cudaSetDevice(h->device));
+    int top = get_top_layer(w0, h0, (int)sqrt((double)h->min_reduce_area));
+    if (top + 1 > FPM_MAX_LEVELS) { h->err = "too many pyramid levels"; return FPM_ERR_LIMIT; }
+    h->tpl.assign(top + 1, TplLevelHost());
+    size_t off = 0;
+    int w = w0, hh = h0;
+    for (int l = 0; l <= top; l++) {
+        TplLevelHost& t = h->tpl[l];
+        t.w = w; t.h = hh; t.pitch = (int)align_up(w, 16);
+        t.dev_off = off;
+        off += align_up((size_t)t.pitch * hh, 256);
+        w = (w + 1) / 2; hh = (hh + 1) / 2;
+    }
+    CK(h->d_tpl.ensure(off));
+    CK(cudaMemsetAsync(h->d_tpl.p, 0, off, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_tpl.as<uint8_t>() + h->tpl[0].dev_off, h->tpl[0].pitch, h->tpl0.data(), w0, w0, h0,
+                         cudaMemcpyHostToDevice, h->stream));
+    for (int l = 1; l <= top; l++) {
+        FpmLevel s{h->d_tpl.as<uint8_t>() + h->tpl[l - 1].dev_off, h->tpl[l - 1].w, h->tpl[l - 1].h, h->tpl[l - 1].pitch, 0};
+        FpmLevel d{h->d_tpl.as<uint8_t>() + h->tpl[l].dev_off, h->tpl[l].w, h->tpl[l].h, h->tpl[l].pitch, 0};
+        int rc = launch_pyrdown(h, s, d, 1);
+        if (rc) return rc;
+    }
+    for (int l = 0; l <= top; l++) {
+        TplLevelHost& t = h->tpl[l];
+        t.pix.resize((size_t)t.w * t.h);
+        CK(cudaMemcpy2DAsync(t.pix.data(), t.w, h->d_tpl.as<uint8_t>() + t.dev_off, t.pitch, t.w, t.h,
+                             cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    // iBorderColor = mean(templ) < 128 ? 255 : 0  (:58-59)
+    for (int l = 0; l <= top; l++) {
+        TplLevelHost& t = h->tpl[l];
+        unsigned long long S = 0, Q = 0;
+        for (uint8_t v : t.pix) { S += v; Q += (unsigned long long)v * v; }
+        double N = (double)t.h * t.w;
+        // cv::meanStdDev (u8): scale = 1/N; mean = S*scale; var = max(Q*scale - mean^2, 0); sdv = sqrt(var)
+        double scale = 1.0 / N;
+        double mean = (double)S * scale;
+        double var = std::max((double)Q * scale - mean * mean, 0.0);
+        double sdv = sqrt(var);
+        double invArea = 1.0 / ((double)t.h * t.w);
+        double templNorm = sdv * sdv;                       // :74
+        t.equal1 = templNorm < DBL_EPSILON ? 1 : 0;         // :77
+        templNorm = sqrt(templNorm);                        // :85
+        templNorm /= sqrt(invArea);                         // :86
+        t.mean = mean; t.norm = templNorm; t.inv_area = invArea;
+        if (l == 0) h->border = ((double)S / N) < 128 ? 255 : 0;
+    }
+    h->learned = true;
+    h->learned_mra = h->min_reduce_area;
+    h->plan.valid = false;
+    return FPM_OK;
+}
+
+// ---- source pyramid -----------------------------------------------------------------
+int build_pyramid(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt, int stride, size_t frame_stride, int top)
+{
+    h->levels.assign(top + 1, FpmLevel());
+    h->levels[0] = FpmLevel{const_cast<uint8_t*>(d_src), w, hgt, stride, frame_stride};
+    size_t off = 0;
+    int lw = w, lh = hgt;
+    std::vector<size_t> offs(top + 1, 0);
+    for (int l = 1; l <= top; l++) {
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        int pitch = (int)align_up(lw, 128);
+        size_t img = align_up((size_t)pitch * lh, 256);
+        h->levels[l] = FpmLevel{nullptr, lw, lh, pitch, img};
+        offs[l] = off;
+        off += img * batch;
+    }
+    CK(h->d_pyr.ensure(off + 256));
+    for (int l = 1; l <= top; l++) {
+        h->levels[l].ptr = h->d_pyr.as<uint8_t>() + offs[l];
+        int rc = launch_pyrdown(h, h->levels[l - 1], h->levels[l], batch);
+        if (rc) return rc;
+    }
+    return FPM_OK;
+}
+
+// ---- angle schedule + per-angle top-layer geometry (src/TemplateMatcher.cpp:130-173) -----
+void angle_schedule(const fpm_handle* h, int top, std::vector<double>& angles)
+{
+    const TplLevelHost& t = h->tpl[top];
+    double dAngleStep = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
+    angles.clear();
+    if (h->tol_angle < FPM_VISION_TOLERANCE) {
+        angles.push_back(0.0);
+    } else {
+        for (double a = 0; a < h->tol_angle + dAngleStep; a += dAngleStep) angles.push_back(a);
+        for (double a = -dAngleStep; a > -h->tol_angle - dAngleStep; a -= dAngleStep) angles.push_back(a);
+    }
+}
+
+int make_top_plan(fpm_handle* h, int top, int batch, int a0, int a1)
+{
+    const FpmLevel& L = h->levels[top];
+    TopPlan& p = h->plan;
+    if (p.valid && p.sw == L.w && p.sh == L.h && p.top == top && p.batch == batch && p.tol == h->tol_angle &&
+        p.a0 == a0 && (p.a1 == a1 || a1 < 0))
+        return FPM_OK;
+    angle_schedule(h, top, p.angles);
+    if (a1 < 0) a1 = (int)p.angles.size();
+    a0 = std::max(0, std::min(a0, (int)p.angles.size()));
+    a1 = std::max(a0, std::min(a1, (int)p.angles.size()));
+    p.sw = L.w; p.sh = L.h; p.top = top; p.batch = batch; p.tol = h->tol_angle; p.a0 = a0; p.a1 = a1;
+    p.n_ang = a1 - a0;
+    const TplLevelHost& t = h->tpl[top];
+    float cx = (L.w - 1) / 2.0f, cy = (L.h - 1) / 2.0f;
+    std::vector<FpmWarpJob> jobs((size_t)batch * std::max(p.n_ang, 1));
+    p.ftx.assign(p.n_ang, 0.f); p.fty.assign(p.n_ang, 0.f);
+    p.maxW = p.maxH = 1;
+    for (int a = a0; a < a1; a++) {
+        FpmWarpJob jb;
+        fpm_rotation_matrix(cx, cy, p.angles[a], jb.m);
+        int bw, bh;
+        best_rotation_size(L.w, L.h, t.w, t.h, p.angles[a], &bw, &bh);
+        float fTx = (bw - 1) / 2.0f - cx, fTy = (bh - 1) / 2.0f - cy;
+        jb.m[2] += (double)fTx; jb.m[5] += (double)fTy;
+        fpm_invert_affine(jb.m);
+        jb.dw = bw; jb.dh = bh; jb.valid = (bw > 0 && bh > 0) ? 1 : 0;
+        p.ftx[a - a0] = fTx; p.fty[a - a0] = fTy;
+        p.maxW = std::max(p.maxW, bw); p.maxH = std::max(p.maxH, bh);
+        for (int b = 0; b < batch; b++) { jb.src_img = b; jobs[(size_t)b * p.n_ang + (a - a0)] = jb; }
+    }
+    if (p.n_ang > 0) {
+        CK(h->d_jobs_top.ensure(jobs.size() * sizeof(FpmWarpJob)));
+        CK(cudaMemcpyAsync(h->d_jobs_top.p, jobs.data(), jobs.size() * sizeof(FpmWarpJob), cudaMemcpyHostToDevice, h->stream));
+        CK(h->d_angles.ensure(p.n_ang * sizeof(double)));
+        CK(cudaMemcpyAsync(h->d_angles.p, p.angles.data() + a0, p.n_ang * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(h->d_ftx.ensure(p.n_ang * sizeof(float)));
+        CK(h->d_fty.ensure(p.n_ang * sizeof(float)));
+        CK(cudaMemcpyAsync(h->d_ftx.p, p.ftx.data(), p.n_ang * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_fty.p, p.fty.data(), p.n_ang * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));   // jobs is a local vector
+    }
+    p.valid = true;
+    return FPM_OK;
+}
+
+// ---- top-layer sweep: warp + score + peaks for every (image, angle) ---------------------
+// leaves picks in d_picks [batch*n_ang][max_picks], counts in d_pickcnt
+int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
+{
+    TopPlan& p = h->plan;
+    const int njobs = batch * p.n_ang;
+    const int max_picks = h->max_pos + FPM_MATCH_CANDIDATE_NUM;
+    *max_picks_out = max_picks;
+    if (njobs == 0) return FPM_OK;
+    const TplLevelHost& t = h->tpl[top];
+    const int rpitch = (int)align_up(p.maxW, 16);
+    const size_t rot_stride = (size_t)rpitch * p.maxH;
+    const int maxRW = std::max(p.maxW - t.w + 1, 1), maxRH = std::max(p.maxH - t.h + 1, 1);
+    const int spitch = (int)align_up(maxRW, 4);
+    const size_t score_stride = (size_t)spitch * maxRH;
+    CK(h->d_rot.ensure(rot_stride * njobs));
+    CK(h->d_score.ensure(score_stride * njobs * sizeof(float)));
+    CK(h->d_picks.ensure((size_t)njobs * max_picks * sizeof(FpmPick)));
+    CK(h->d_pickcnt.ensure((size_t)njobs * sizeof(int)));
+    {
+        dim3 grid((p.maxH + WA_ROWS - 1) / WA_ROWS, njobs);
+        fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->levels[top], h->d_rot.as<uint8_t>(),
+                                                            rpitch, rot_stride, h->border);
+        CKL();
+    }
+    {
+        size_t smem = (size_t)t.w * t.h + (size_t)(TS_TILE + t.w - 1) * (TS_TILE + t.h - 1);
+        if (smem > 200 * 1024) { h->err = "top-layer template too large for the score kernel"; return FPM_ERR_LIMIT; }
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((maxRW + TS_TILE - 1) / TS_TILE, (maxRH + TS_TILE - 1) / TS_TILE, njobs);
+        dim3 block(TS_TILE, TS_TILE);
+        fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->d_rot.as<uint8_t>(), rpitch,
+                                                               rot_stride, tpl_level_dev(h, top), h->d_score.as<float>(), spitch,
+                                                               score_stride);
+        CKL();
+    }
+    {
+        // bCalMaxByBlock, src/TemplateMatcher.cpp:158-159
+        const FpmLevel& L = h->levels[top];
+        bool by_block = ((L.w * L.h) / (t.w * t.h) > 500) && h->max_pos > 10;
+        int mode = by_block ? 1 : 0;
+        int tile = 8;
+        while ((long long)((maxRW + tile - 1) / tile) * ((maxRH + tile - 1) / tile) > 1024 && tile < 256) tile *= 2;
+        int blk_stride;
+        if (mode) blk_stride = (maxRW / t.w) * (maxRH / t.h) + 3;
+        else blk_stride = ((maxRW + tile - 1) / tile) * ((maxRH + tile - 1) / tile);
+        blk_stride = std::max(blk_stride, 1);
+        CK(h->d_blkv.ensure((size_t)njobs * blk_stride * sizeof(float)));
+        CK(h->d_blkl.ensure((size_t)njobs * blk_stride * sizeof(int)));
+        double thresh = h->score;
+        for (int l = 0; l < top; l++) thresh *= 0.9;          // vecLayerScore, :153-156
+        fpm_top_peaks_kernel<<<njobs, PK_THREADS, 0, h->stream>>>(
+            h->d_jobs_top.as<FpmWarpJob>(), h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
+            h->d_blkv.as<float>(), h->d_blkl.as<int>(), blk_stride, thresh, h->max_overlap, max_picks,
+            h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>());
+        CKL();
+    }
+    return FPM_OK;
+}
+
+enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_N = 8 };
+
+// ---- refinement of a flat candidate list held in d_cand[0] ------------------------------
+int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
+{
+    int* counters = h->d_counters.as<int>();
+    int* hc = h->h_counts.as<int>();
+    CK(h->d_refined.ensure((size_t)std::max(n_cands, 1) * sizeof(FpmRefined)));
+    CK(cudaMemsetAsync(counters + CNT_REFINED, 0, sizeof(int), h->stream));
+    *n_refined_out = 0;
+    if (n_cands == 0) return FPM_OK;
+    if (top == 0) {
+        fpm_cands_to_refined_kernel<<<(n_cands + 255) / 256, 256, 0, h->stream>>>(h->d_cand[0].as<FpmCand>(), n_cands, top,
+                                                                               h->d_refined.as<FpmRefined>(), counters + CNT_REFINED);
+        CKL();
+        *n_refined_out = n_cands;
+        return FPM_OK;
+    }
+    const int n_ang = (h->tol_angle < FPM_VISION_TOLERANCE) ? 1 : 3;
+    CK(h->d_cand[1].ensure((size_t)n_cands * sizeof(FpmCand)));
+    int cur = 0, n = n_cands;
+    double layer_score[FPM_MAX_LEVELS + 1];
+    layer_score[0] = h->score;
+    for (int l = 1; l <= top; l++) layer_score[l] = layer_score[l - 1] * 0.9;
+    if (h->trace) h->tr_evals.assign(top + 1, std::vector<double>());
+    for (int layer = top - 1; layer >= 0 && n > 0; layer--) {
+        const TplLevelHost& t = h->tpl[layer];
+        const FpmLevel& L = h->levels[layer];
+        const double step = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
+        const int rpitch = (int)align_up(t.w + FPM_ROI_PAD, 16) + 16;
+        const size_t roi_stride = (size_t)rpitch * (t.h + FPM_ROI_PAD);
+        const size_t per_eval = roi_stride + (size_t)t.h * FPM_NCELL * 4 + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 +
+                                sizeof(FpmWarpJob);
+        size_t budget = (size_t)(h->workspace_mb * 1024.0 * 1024.0);
+        int wave_cands = (int)std::max<size_t>(1, budget / (per_eval * n_ang));
+        wave_cands = std::min(wave_cands, n);
+        const int wave_evals = wave_cands * n_ang;
+        CK(h->d_jobs_ref.ensure((size_t)wave_evals * sizeof(FpmWarpJob)));
+        CK(h->d_roi.ensure(roi_stride * wave_evals));
+        CK(h->d_rowsum.ensure((size_t)wave_evals * t.h * FPM_NCELL * 4));
+        CK(h->d_rowS.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
+        CK(h->d_rowQ.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
+        if (h->trace) {
+            CK(h->d_trace.ensure((size_t)n * n_ang * sizeof(FpmEvalTrace)));
+            CK(cudaMemsetAsync(h->d_trace.p, 0, (size_t)n * n_ang * sizeof(FpmEvalTrace), h->stream));
+        }
+        CK(cudaMemsetAsync(counters + CNT_NEXT, 0, sizeof(int), h->stream));
+        // row chunk: enough CTAs to fill the machine, at most 32 template rows per CTA
+        int rc = 32;
+        while (rc > 8 && (long long)wave_evals * ((t.h + rc - 1) / rc) < 2 * 148) rc /= 2;
+        size_t smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * t.pitch;
+        while (smem > 200 * 1024 && rc > 1) { rc /= 2; smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * t.pitch; }
+        if (smem > 200 * 1024) { h->err = "template row too wide for the correlation kernel"; return FPM_ERR_LIMIT; }
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const FpmTplLevel td = tpl_level_dev(h, layer);
+        const FpmCand* cands = h->d_cand[cur].as<FpmCand>();
+        for (int c0 = 0; c0 < n; c0 += wave_cands) {
+            const int nc = std::min(wave_cands, n - c0);
+            const int ne = nc * n_ang;
+            fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
+                                                                          h->d_jobs_ref.as<FpmWarpJob>());
+            CKL();
+            dim3 wgrid((t.h + FPM_ROI_PAD + WA_ROWS - 1) / WA_ROWS, ne);
+            fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), L, h->d_roi.as<uint8_t>(), rpitch,
+                                                                 roi_stride, 0);
+            CKL();
+            dim3 cgrid((t.h + rc - 1) / rc, ne);
+            fpm_corr_rows_kernel<<<cgrid, CR_THREADS, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, rc,
+                                                                         h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(),
+                                                                         h->d_rowQ.as<int32_t>());
+            CKL();
+            fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
+                cands + c0, n_ang, step, h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w, L.h,
+                layer_score[layer], h->use_simd, layer == 0 ? 1 : 0, h->subpixel, h->d_cand[cur ^ 1].as<FpmCand>(),
+                counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
+                h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr);
+            CKL();
+        }
+        CK(cudaMemcpyAsync(hc, counters, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->trace) {
+            std::vector<FpmEvalTrace> tr((size_t)n * n_ang);
+            std::vector<FpmCand> cc(n);
+            CK(cudaMemcpy(tr.data(), h->d_trace.p, tr.size() * sizeof(FpmEvalTrace), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(cc.data(), cands, cc.size() * sizeof(FpmCand), cudaMemcpyDeviceToHost));
+            std::vector<double>& rows = h->tr_evals[layer];
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n_ang; j++) {
+                    const FpmEvalTrace& e = tr[(size_t)i * n_ang + j];
+                    rows.push_back(cc[i].id); rows.push_back(e.angle); rows.push_back(e.score);
+                    rows.push_back(e.locx); rows.push_back(e.locy);
+                }
+        }
+        n = (layer == 0) ? 0 : hc[CNT_NEXT];
+        *n_refined_out = hc[CNT_REFINED];
+        cur ^= 1;
+    }
+    return FPM_OK;
+}
+
+// ---- final stage: filterWithScore + NMS + conversion, results to host ---------------------
+int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_result* out, int cap, int* n_out)
+{
+    int* counters = h->d_counters.as<int>();
+    key_stride = std::max(key_stride, 1);
+    int ks = 1;
+    while (ks < key_stride) ks <<= 1;
+    CK(h->d_keys.ensure((size_t)batch * ks * sizeof(unsigned long long)));
+    CK(h->d_rects.ensure((size_t)batch * ks * sizeof(FpmRRect)));
+    CK(h->d_del.ensure((size_t)batch * ks * sizeof(int)));
+    CK(h->d_idmap.ensure((size_t)batch * ks * sizeof(int)));
+    const int rcap = std::max(cap, 1);
+    CK(h->d_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev)));
+    CK(h->d_rescnt.ensure((size_t)batch * sizeof(int)));
+    CK(h->h_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev) + (size_t)batch * sizeof(int)));
+    (void)n_refined;
+    fpm_final_kernel<<<batch, FN_THREADS, 0, h->stream>>>(h->d_refined.as<FpmRefined>(), counters + CNT_REFINED, h->score,
+                                                          h->max_overlap, h->tpl[0].w, h->tpl[0].h,
+                                                          h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
+                                                          h->d_del.as<int>(), h->d_idmap.as<int>(), h->d_results.as<FpmResultDev>(),
+                                                          rcap, h->d_rescnt.as<int>());
+    CKL();
+    FpmResultDev* hr = h->h_results.as<FpmResultDev>();
+    int* hn = reinterpret_cast<int*>(hr + (size_t)batch * rcap);
+    CK(cudaMemcpyAsync(hn, h->d_rescnt.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hr, h->d_results.p, (size_t)batch * rcap * sizeof(FpmResultDev), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < batch; b++) {
+        n_out[b] = hn[b];
+        int m = std::min(hn[b], cap);
+        for (int i = 0; i < m; i++) {
+            const FpmResultDev& r = hr[(size_t)b * rcap + i];
+            fpm_result& o = out[(size_t)b * cap + i];
+            o.score = r.score; o.angle = r.angle; o.cx = r.cx; o.cy = r.cy;
+            o.ltx = r.ltx; o.lty = r.lty; o.rtx = r.rtx; o.rty = r.rty;
+            o.rbx = r.rbx; o.rby = r.rby; o.lbx = r.lbx; o.lby = r.lby;
+        }
+    }
+    return FPM_OK;
+}
+
+// guards of match(), src/TemplateMatcher.cpp:99-114; returns 1 when the match must return empty
+int match_guards(fpm_handle* h, int w, int hgt)
+{
+    int tw = h->tpl0_w, th = h->tpl0_h;
+    if ((tw < w && th > hgt) || (tw > w && th < hgt)) return 1;
+    if ((long long)tw * th > (long long)w * hgt) return 1;
+    return 0;
+}
+
+int ensure_learned_for_mra(fpm_handle* h)
+{
+    if (!h->learned) return FPM_ERR_NOT_LEARNED;
+    if (h->learned_mra != h->min_reduce_area) return do_learn(h);   // SURVEY 8a hazard: re-learn
+    return FPM_OK;
+}
+
+// whole match() over a device-resident batch
+int match_device(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt, int stride, size_t frame_stride,
+                 fpm_result* out, int cap, int* n_out)
+{
+    for (int b = 0; b < batch; b++) n_out[b] = 0;
+    if (!h->learned) return FPM_OK;                          // :99-101 -> empty
+    int rc = ensure_learned_for_mra(h);
+    if (rc) return rc;
+    if (match_guards(h, w, hgt)) return FPM_OK;
+    const int top = (int)h->tpl.size() - 1;
+    CK(h->d_counters.ensure(CNT_N * sizeof(int)));
+    CK(h->h_counts.ensure((CNT_N + batch) * sizeof(int)));
+    CK(cudaMemsetAsync(h->d_counters.p, 0, CNT_N * sizeof(int), h->stream));
+    rc = build_pyramid(h, d_src, batch, w, hgt, stride, frame_stride, top);
+    if (rc) return rc;
+    rc = make_top_plan(h, top, batch, 0, -1);
+    if (rc) return rc;
+    int max_picks = 0;
+    rc = run_top(h, top, batch, &max_picks);
+    if (rc) return rc;
+    const TopPlan& p = h->plan;
+    const int cand_stride = std::max(p.n_ang * max_picks, 1);
+    int n_pad = 1;
+    while (n_pad < cand_stride) n_pad <<= 1;
+    CK(h->d_cand[0].ensure((size_t)batch * cand_stride * sizeof(FpmCand)));
+    CK(h->d_candcnt.ensure((size_t)batch * sizeof(int)));
+    CK(h->d_off.ensure((size_t)batch * std::max(p.n_ang, 1) * sizeof(int)));
+    const int use_smem = (size_t)n_pad * 8 <= 96 * 1024;
+    if (!use_smem) CK(h->d_keys.ensure((size_t)batch * n_pad * sizeof(unsigned long long)));
+    if (h->trace) CK(h->d_toppt.ensure((size_t)batch * cand_stride * 4 * sizeof(float)));
+    {
+        const FpmLevel& L = h->levels[top];
+        size_t smem = use_smem ? (size_t)n_pad * 8 : 0;
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(fpm_collect_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fpm_collect_sort_kernel<<<batch, CS_THREADS, smem, h->stream>>>(
+            h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), p.n_ang, max_picks, h->d_angles.as<double>(), h->d_ftx.as<float>(),
+            h->d_fty.as<float>(), (L.w - 1) / 2.0f, (L.h - 1) / 2.0f, h->d_keys.as<unsigned long long>(), n_pad, use_smem,
+            h->d_off.as<int>(), h->d_cand[0].as<FpmCand>(), h->d_counters.as<int>() + CNT_FLAT,
+            h->trace ? h->d_toppt.as<float>() : nullptr, cand_stride, h->d_candcnt.as<int>(), 0);
+        CKL();
+    }
+    int* hc = h->h_counts.as<int>();
+    CK(cudaMemcpyAsync(hc, h->d_counters.p, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int n_cands = hc[CNT_FLAT];
+    if (h->trace) {
+        std::vector<float> tp((size_t)cand_stride * 4);
+        int n0 = 0;
+        CK(cudaMemcpy(&n0, h->d_candcnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tp.data(), h->d_toppt.p, (size_t)n0 * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+        h->tr_cands.clear();
+        for (int i = 0; i < n0 * 4; i++) h->tr_cands.push_back(tp[i]);
+    }
+    int n_refined = 0;
+    rc = run_refine(h, top, n_cands, &n_refined);
+    if (rc) return rc;
+    return run_final(h, batch, n_refined, cand_stride, out, cap, n_out);
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+const char* fpm_version(void) { return "fpm-b200 0.1 (sm_100a)"; }
+
+fpm_handle* fpm_create(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return nullptr;                       // no CPU fallback
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    fpm_handle* h = new fpm_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return nullptr;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    }
+    cudaEventCreate(&h->ev_t0);
+    cudaEventCreate(&h->ev_t1);
+    return h;
+}
+
+void fpm_destroy(fpm_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->copy_stream);
+    DevBuf* bufs[] = {&h->d_tpl, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+                      &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
+                      &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
+                      &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
+                      &h->d_dbg[0], &h->d_dbg[1], &h->d_dbg[2], &h->d_dbg[3]};
+    for (DevBuf* b : bufs) b->release();
+    h->h_counts.release(); h->h_results.release(); h->h_stage.release();
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(h->ev_copy[i]); cudaEventDestroy(h->ev_done[i]); }
+    cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
+    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+const char* fpm_last_error(const fpm_handle* h) { return h ? h->err.c_str() : "null handle (no CUDA device?)"; }
+
+int fpm_set_param(fpm_handle* h, int param, double v)
+{
+    if (!h) return FPM_ERR_INVALID;
+    switch (param) {
+    case FPM_PARAM_MAX_POSITIONS: h->max_pos = (int)v; break;
+    case FPM_PARAM_MAX_OVERLAP: h->max_overlap = v; break;
+    case FPM_PARAM_SCORE: h->score = v; break;
+    case FPM_PARAM_TOLERANCE_ANGLE: h->tol_angle = v; break;
+    case FPM_PARAM_MIN_REDUCE_AREA: h->min_reduce_area = (int)v; break;
+    case FPM_PARAM_USE_SIMD: h->use_simd = v != 0; break;
+    case FPM_PARAM_SUBPIXEL: h->subpixel = v != 0; break;
+    case FPM_PARAM_TRACE: h->trace = v != 0; break;
+    case FPM_PARAM_WORKSPACE_MB: h->workspace_mb = v; break;
+    default: h->err = "unknown parameter"; return FPM_ERR_INVALID;
+    }
+    return FPM_OK;
+}
+
+double fpm_get_param(const fpm_handle* h, int param)
+{
+    if (!h) return 0;
+    switch (param) {
+    case FPM_PARAM_MAX_POSITIONS: return h->max_pos;
+    case FPM_PARAM_MAX_OVERLAP: return h->max_overlap;
+    case FPM_PARAM_SCORE: return h->score;
+    case FPM_PARAM_TOLERANCE_ANGLE: return h->tol_angle;
+    case FPM_PARAM_MIN_REDUCE_AREA: return h->min_reduce_area;
+    case FPM_PARAM_USE_SIMD: return h->use_simd;
+    case FPM_PARAM_SUBPIXEL: return h->subpixel;
+    case FPM_PARAM_TRACE: return h->trace;
+    case FPM_PARAM_WORKSPACE_MB: return h->workspace_mb;
+    default: return 0;
+    }
+}
+
+int fpm_learn(fpm_handle* h, const uint8_t* tpl, int width, int height, int stride)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!tpl || width <= 0 || height <= 0 || stride < width) { h->err = "empty template"; return FPM_ERR_INVALID; }   // :47-49
+    h->learned = false;
+    h->tpl0.resize((size_t)width * height);
+    for (int y = 0; y < height; y++) memcpy(h->tpl0.data() + (size_t)y * width, tpl + (size_t)y * stride, width);
+    h->tpl0_w = width; h->tpl0_h = height;
+    return do_learn(h);
+}
+
+int fpm_is_learned(const fpm_handle* h) { return h && h->learned ? 1 : 0; }
+
+void fpm_clear(fpm_handle* h)
+{
+    if (!h) return;
+    h->learned = false; h->tpl.clear(); h->tpl0.clear(); h->has_ur = 0;
+    h->ur[0] = h->ur[1] = h->ur[2] = h->ur[3] = 0;
+}
+
+int fpm_match_batch_device(fpm_handle* h, const uint8_t* d_src, int batch, int width, int height, int stride,
+                           size_t frame_stride, fpm_result* out, int cap, int* n)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!n || batch < 0 || cap < 0 || (cap > 0 && !out)) { h->err = "bad output arguments"; return FPM_ERR_INVALID; }
+    for (int b = 0; b < batch; b++) n[b] = 0;
+    if (!d_src || width <= 0 || height <= 0 || batch == 0) return FPM_OK;       // empty source -> empty result
+    if (stride < width) { h->err = "stride < width"; return FPM_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    auto t0 = std::chrono::high_resolution_clock::now();
+    int rc = match_device(h, d_src, batch, width, height, stride, frame_stride, out, cap, n);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    h->last_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    return rc;
+}
+
+int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int height, int stride, size_t frame_stride,
+                    fpm_result* out, int cap, int* n)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!n || batch < 0 || cap < 0 || (cap > 0 && !out)) { h->err = "bad output arguments"; return FPM_ERR_INVALID; }
+    for (int b = 0; b < batch; b++) n[b] = 0;
+    if (!src || width <= 0 || height <= 0 || batch == 0) return FPM_OK;
+    if (stride < width) { h->err = "stride < width"; return FPM_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    auto t0 = std::chrono::high_resolution_clock::now();
+    // double-buffered chunks: the H2D copy of chunk k+1 overlaps the matching of chunk k
+    const int pitch = (int)align_up(width, 128);
+    const size_t img = align_up((size_t)pitch * height, 256);
+    int chunk = std::max(1, std::min(batch, (int)std::max<size_t>(1, (size_t)(512ull << 20) / img)));
+    if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
+    CK(h->d_src.ensure(img * chunk * 2));
+    const int nchunks = (batch + chunk - 1) / chunk;
+    auto enqueue_copy = [&](int k) -> cudaError_t {
+        int b0 = k * chunk, nb = std::min(chunk, batch - b0);
+        uint8_t* dst = h->d_src.as<uint8_t>() + (size_t)(k & 1) * img * chunk;
+        if (k >= 2) {
+            cudaError_t e = cudaStreamWaitEvent(h->copy_stream, h->ev_done[k & 1], 0);
+            if (e != cudaSuccess) return e;
+        }
+        for (int b = 0; b < nb; b++) {
+            cudaError_t e = cudaMemcpy2DAsync(dst + (size_t)b * img, pitch, src + (size_t)(b0 + b) * frame_stride, stride, width,
+                                              height, cudaMemcpyHostToDevice, h->copy_stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaEventRecord(h->ev_copy[k & 1], h->copy_stream);
+    };
+    CK(enqueue_copy(0));
+    int rc = FPM_OK;
+    for (int k = 0; k < nchunks && rc == FPM_OK; k++) {
+        if (k + 1 < nchunks) CK(enqueue_copy(k + 1));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_copy[k & 1], 0));
+        int b0 = k * chunk, nb = std::min(chunk, batch - b0);
+        rc = match_device(h, h->d_src.as<uint8_t>() + (size_t)(k & 1) * img * chunk, nb, width, height, pitch, img,
+                          out + (size_t)b0 * cap, cap, n + b0);
+        CK(cudaEventRecord(h->ev_done[k & 1], h->stream));
+    }
+    cudaStreamSynchronize(h->copy_stream);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    h->last_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    return rc;
+}
+
+int fpm_match(fpm_handle* h, const uint8_t* src, int width, int height, int stride, fpm_result* out, int cap, int* n)
+{
+    return fpm_match_batch(h, src, 1, width, height, stride, (size_t)stride * (size_t)std::max(height, 0), out, cap, n);
+}
+
+double fpm_last_time_ms(const fpm_handle* h) { return h ? h->last_ms : 0; }
+
+void fpm_set_user_rect(fpm_handle* h, int x, int y, int w, int hgt)
+{
+    if (!h) return;
+    h->ur[0] = x; h->ur[1] = y; h->ur[2] = w; h->ur[3] = hgt; h->has_ur = 1;
+}
+
+int fpm_get_user_rect(const fpm_handle* h, int* x, int* y, int* w, int* hgt)
+{
+    if (!h) return 0;
+    if (x) *x = h->ur[0];
+    if (y) *y = h->ur[1];
+    if (w) *w = h->ur[2];
+    if (hgt) *hgt = h->ur[3];
+    return h->has_ur;
+}
+
+long long fpm_launch_count(const fpm_handle* h) { return h ? h->launches : 0; }
+
+int fpm_tpl_levels(const fpm_handle* h) { return (h && h->learned) ? (int)h->tpl.size() : 0; }
+
+int fpm_tpl_level_info(const fpm_handle* h, int level, int* w, int* hgt, double* mean, double* norm, double* inv_area,
+                       int* result_equal1)
+{
+    if (!h || !h->learned || level < 0 || level >= (int)h->tpl.size()) return FPM_ERR_INVALID;
+    const TplLevelHost& t = h->tpl[level];
+    if (w) *w = t.w;
+    if (hgt) *hgt = t.h;
+    if (mean) *mean = t.mean;
+    if (norm) *norm = t.norm;
+    if (inv_area) *inv_area = t.inv_area;
+    if (result_equal1) *result_equal1 = t.equal1;
+    return FPM_OK;
+}
+
+int fpm_tpl_level_pixels(const fpm_handle* h, int level, uint8_t* out)
+{
+    if (!h || !h->learned || level < 0 || level >= (int)h->tpl.size() || !out) return FPM_ERR_INVALID;
+    memcpy(out, h->tpl[level].pix.data(), h->tpl[level].pix.size());
+    return FPM_OK;
+}
+
+int fpm_tpl_border_color(const fpm_handle* h) { return h ? h->border : 0; }
+
+// ---- stage API (angle-sharded latency mode) -------------------------------------------
+int fpm_stage_num_angles(fpm_handle* h, int width, int height)
+{
+    (void)width; (void)height;
+    if (!h || !h->learned) return 0;
+    if (ensure_learned_for_mra(h)) return 0;
+    std::vector<double> a;
+    angle_schedule(h, (int)h->tpl.size() - 1, a);
+    return (int)a.size();
+}
+
+int fpm_stage_top(fpm_handle* h, const uint8_t* src, int width, int height, int stride, int src_on_device, int a0, int a1,
+                  double* rows, int cap, int* n)
+{
+    if (!h || !n) return FPM_ERR_INVALID;
+    *n = 0;
+    if (!h->learned) return FPM_ERR_NOT_LEARNED;
+    int rc = ensure_learned_for_mra(h);
+    if (rc) return rc;
+    if (!src || width <= 0 || height <= 0) return FPM_OK;
+    CK(cudaSetDevice(h->device));
+    h->levels.clear();
+    if (match_guards(h, width, height)) return FPM_OK;
+    const uint8_t* d_src = src;
+    int pitch = stride;
+    size_t img = (size_t)stride * height;
+    if (!src_on_device) {
+        pitch = (int)align_up(width, 128);
+        img = align_up((size_t)pitch * height, 256);
+        CK(h->d_src.ensure(img));
+        CK(cudaMemcpy2DAsync(h->d_src.p, pitch, src, stride, width, height, cudaMemcpyHostToDevice, h->stream));
+        d_src = h->d_src.as<uint8_t>();
+    }
+    const int top = (int)h->tpl.size() - 1;
+    CK(h->d_counters.ensure(CNT_N * sizeof(int)));
+    CK(h->h_counts.ensure((CNT_N + 1) * sizeof(int)));
+    rc = build_pyramid(h, d_src, 1, width, height, pitch, img, top);
+    if (rc) return rc;
+    rc = make_top_plan(h, top, 1, a0, a1);
+    if (rc) return rc;
+    int max_picks = 0;
+    rc = run_top(h, top, 1, &max_picks);
+    if (rc) return rc;
+    const TopPlan& p = h->plan;
+    if (p.n_ang == 0) return FPM_OK;
+    std::vector<FpmPick> picks((size_t)p.n_ang * max_picks);
+    std::vector<int> cnt(p.n_ang);
+    CK(cudaMemcpyAsync(picks.data(), h->d_picks.p, picks.size() * sizeof(FpmPick), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cnt.data(), h->d_pickcnt.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int k = 0;
+    for (int a = 0; a < p.n_ang; a++)
+        for (int j = 0; j < cnt[a]; j++) {
+            if (k < cap) {
+                const FpmPick& pk = picks[(size_t)a * max_picks + j];
+                double* r = rows + (size_t)k * 5;
+                // translation removed here like :186 (float arithmetic)
+                r[0] = p.a0 + a;
+                r[1] = (double)((float)pk.x - p.ftx[a]);
+                r[2] = (double)((float)pk.y - p.fty[a]);
+                r[3] = pk.v;
+                r[4] = p.angles[p.a0 + a];
+            }
+            k++;
+        }
+    *n = k;
+    return FPM_OK;
+}
+
+// picks rows {angle_index, x, y, score, angle} in global (angle, pick) order -> candidate rows
+// {id, ptLT.x, ptLT.y, score, angle}: stable sort by score descending (:214) and the un-rotation of
+// :265-266.  Host side on purpose: it runs on the allgathered list, a few hundred rows.
+int fpm_stage_sort_candidates(fpm_handle* h, const double* picks, int n, double* cands)
+{
+    if (!h || n < 0) return FPM_ERR_INVALID;
+    if (h->levels.empty()) { h->err = "fpm_stage_top must run first"; return FPM_ERR_INVALID; }
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; i++) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return (float)picks[a * 5 + 3] > (float)picks[b * 5 + 3]; });
+    const FpmLevel& L = h->levels.back();
+    float cx = (L.w - 1) / 2.0f, cy = (L.h - 1) / 2.0f;
+    for (int i = 0; i < n; i++) {
+        const double* p = picks + (size_t)idx[i] * 5;
+        float rx, ry;
+        fpm_pt_rotate((float)p[1], (float)p[2], cx, cy, -p[4] * FPM_D2R, &rx, &ry);
+        double* c = cands + (size_t)i * 5;
+        c[0] = i; c[1] = rx; c[2] = ry; c[3] = p[3]; c[4] = p[4];
+    }
+    return FPM_OK;
+}
+
+int fpm_stage_refine(fpm_handle* h, const double* cands, int n, double* rows, int cap, int* n_out)
+{
+    if (!h || !n_out) return FPM_ERR_INVALID;
+    *n_out = 0;
+    if (h->levels.empty()) { h->err = "fpm_stage_top must run first"; return FPM_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const int top = (int)h->tpl.size() - 1;
+    std::vector<FpmCand> cc(std::max(n, 1));
+    for (int i = 0; i < n; i++) {
+        const double* c = cands + (size_t)i * 5;
+        cc[i].id = (int)c[0]; cc[i].ptx = (float)c[1]; cc[i].pty = (float)c[2]; cc[i].score = c[3]; cc[i].angle = c[4];
+        cc[i].img = 0;
+    }
+    CK(h->d_cand[0].ensure(cc.size() * sizeof(FpmCand)));
+    CK(cudaMemcpyAsync(h->d_cand[0].p, cc.data(), cc.size() * sizeof(FpmCand), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int n_ref = 0;
+    int rc = run_refine(h, top, n, &n_ref);
+    if (rc) return rc;
+    std::vector<FpmRefined> rr(std::max(n_ref, 1));
+    if (n_ref) {
+        CK(cudaMemcpyAsync(rr.data(), h->d_refined.p, (size_t)n_ref * sizeof(FpmRefined), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    std::sort(rr.begin(), rr.begin() + n_ref, [](const FpmRefined& a, const FpmRefined& b) { return a.id < b.id; });
+    for (int i = 0; i < n_ref && i < cap; i++) {
+        double* r = rows + (size_t)i * 5;
+        r[0] = rr[i].id; r[1] = rr[i].ptx; r[2] = rr[i].pty; r[3] = rr[i].score; r[4] = rr[i].angle;
+    }
+    *n_out = n_ref;
+    return FPM_OK;
+}
+
+int fpm_stage_final(fpm_handle* h, const double* refined, int n, fpm_result* out, int cap, int* n_out)
+{
+    if (!h || !n_out) return FPM_ERR_INVALID;
+    *n_out = 0;
+    if (!h->learned) return FPM_ERR_NOT_LEARNED;
+    CK(cudaSetDevice(h->device));
+    std::vector<FpmRefined> rr(std::max(n, 1));
+    int max_id = 0;
+    for (int i = 0; i < n; i++) {
+        const double* r = refined + (size_t)i * 5;
+        rr[i].id = (int)r[0]; rr[i].ptx = r[1]; rr[i].pty = r[2]; rr[i].score = r[3]; rr[i].angle = r[4]; rr[i].img = 0;
+        max_id = std::max(max_id, rr[i].id);
+    }
+    CK(h->d_counters.ensure(CNT_N * sizeof(int)));
+    CK(h->d_refined.ensure(rr.size() * sizeof(FpmRefined)));
+    CK(cudaMemcpyAsync(h->d_refined.p, rr.data(), rr.size() * sizeof(FpmRefined), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_counters.as<int>() + CNT_REFINED, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return run_final(h, 1, n, std::max(max_id + 1, n), out, cap, n_out);
+}
+
+// ---- stage kernels for parity tests ----------------------------------------------------
+int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, uint8_t* dst)
+{
+    if (!h || !src || !dst || w <= 0 || hgt <= 0) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int dw = (w + 1) / 2, dh = (hgt + 1) / 2;
+    int sp = (int)align_up(w, 128), dp = (int)align_up(dw, 128);
+    CK(h->d_dbg[0].ensure((size_t)sp * hgt));
+    CK(h->d_dbg[1].ensure((size_t)dp * dh));
+    CK(cudaMemcpy2DAsync(h->d_dbg[0].p, sp, src, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    FpmLevel s{h->d_dbg[0].as<uint8_t>(), w, hgt, sp, 0}, d{h->d_dbg[1].as<uint8_t>(), dw, dh, dp, 0};
+    int rc = launch_pyrdown(h, s, d, 1);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FPM_OK;
+}
+
+int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, const double m[6], int dw, int dh,
+                        int border, uint8_t* dst)
+{
+    if (!h || !src || !dst || w <= 0 || hgt <= 0 || dw <= 0 || dh <= 0) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    int sp = (int)align_up(w, 128), dp = (int)align_up(dw, 16);
+    CK(h->d_dbg[0].ensure((size_t)sp * hgt));
+    CK(h->d_dbg[1].ensure((size_t)dp * dh));
+    CK(h->d_dbg[2].ensure(sizeof(FpmWarpJob)));
+    FpmWarpJob jb;
+    for (int i = 0; i < 6; i++) jb.m[i] = m[i];
+    fpm_invert_affine(jb.m);
+    jb.src_img = 0; jb.dw = dw; jb.dh = dh; jb.valid = 1;
+    CK(cudaMemcpy2DAsync(h->d_dbg[0].p, sp, src, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_dbg[2].p, &jb, sizeof(jb), cudaMemcpyHostToDevice, h->stream));
+    FpmLevel s{h->d_dbg[0].as<uint8_t>(), w, hgt, sp, 0};
+    dim3 grid((dh + WA_ROWS - 1) / WA_ROWS, 1);
+    fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), s, h->d_dbg[1].as<uint8_t>(), dp, 0, border);
+    CKL();
+    CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FPM_OK;
+}
+
+int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int tw, int th, int32_t* rowsum, int32_t* rowS,
+                      int32_t* rowQ)
+{
+    if (!h || !roi || !tpl || tw <= 0 || th <= 0) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int rpitch = (int)align_up(tw + FPM_ROI_PAD, 16) + 16, tp = (int)align_up(tw, 16);
+    const size_t roi_bytes = (size_t)rpitch * (th + FPM_ROI_PAD), t_bytes = (size_t)tp * th;
+    CK(h->d_dbg[0].ensure(roi_bytes));
+    CK(h->d_dbg[1].ensure(t_bytes));
+    CK(h->d_dbg[2].ensure((size_t)th * FPM_NCELL * 4));
+    CK(h->d_dbg[3].ensure(2 * (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4));
+    CK(cudaMemsetAsync(h->d_dbg[0].p, 0, roi_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_dbg[1].p, 0, t_bytes, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_dbg[0].p, rpitch, roi, tw + FPM_ROI_PAD, tw + FPM_ROI_PAD, th + FPM_ROI_PAD, cudaMemcpyHostToDevice,
+                         h->stream));
+    CK(cudaMemcpy2DAsync(h->d_dbg[1].p, tp, tpl, tw, tw, th, cudaMemcpyHostToDevice, h->stream));
+    FpmTplLevel td;
+    td.ptr = h->d_dbg[1].as<uint8_t>(); td.w = tw; td.h = th; td.pitch = tp;
+    td.mean = 0; td.norm = 1; td.inv_area = 1; td.result_equal1 = 0;
+    int rc = 32;
+    size_t smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * tp;
+    while (smem > 200 * 1024 && rc > 1) { rc /= 2; smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * tp; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int32_t* dS = h->d_dbg[3].as<int32_t>();
+    int32_t* dQ = dS + (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT;
+    dim3 grid((th + rc - 1) / rc, 1);
+    fpm_corr_rows_kernel<<<grid, CR_THREADS, smem, h->stream>>>(h->d_dbg[0].as<uint8_t>(), rpitch, roi_bytes, td, rc,
+                                                                 h->d_dbg[2].as<int32_t>(), dS, dQ);
+    CKL();
+    CK(cudaMemcpyAsync(rowsum, h->d_dbg[2].p, (size_t)th * FPM_NCELL * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rowS, dS, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rowQ, dQ, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FPM_OK;
+}
+
+// dense NCC map of `img` against the learned TOP-layer template
+int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score)
+{
+    if (!h || !img || !score) return FPM_ERR_INVALID;
+    if (!h->learned) return FPM_ERR_NOT_LEARNED;
+    CK(cudaSetDevice(h->device));
+    const int top = (int)h->tpl.size() - 1;
+    const TplLevelHost& t = h->tpl[top];
+    const int RW = w - t.w + 1, RH = hgt - t.h + 1;
+    if (RW <= 0 || RH <= 0) return FPM_ERR_INVALID;
+    const int rp = (int)align_up(w, 16), sp = (int)align_up(RW, 4);
+    CK(h->d_dbg[0].ensure((size_t)rp * hgt));
+    CK(h->d_dbg[1].ensure((size_t)sp * RH * 4));
+    CK(h->d_dbg[2].ensure(sizeof(FpmWarpJob)));
+    FpmWarpJob jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.dw = w; jb.dh = hgt; jb.valid = 1;
+    CK(cudaMemcpy2DAsync(h->d_dbg[0].p, rp, img, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_dbg[2].p, &jb, sizeof(jb), cudaMemcpyHostToDevice, h->stream));
+    size_t smem = (size_t)t.w * t.h + (size_t)(TS_TILE + t.w - 1) * (TS_TILE + t.h - 1);
+    if (smem > 200 * 1024) { h->err = "template too large"; return FPM_ERR_LIMIT; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((RW + TS_TILE - 1) / TS_TILE, (RH + TS_TILE - 1) / TS_TILE, 1), block(TS_TILE, TS_TILE);
+    fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<uint8_t>(), rp, 0,
+                                                           tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0);
+    CKL();
+    CK(cudaMemcpy2DAsync(score, (size_t)RW * 4, h->d_dbg[1].p, (size_t)sp * 4, (size_t)RW * 4, RH, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FPM_OK;
+}
+
+int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw, int th, int block_mode, double thresh,
+                  double max_overlap, int max_picks, double* picks, int* n)
+{
+    if (!h || !score || !picks || !n || cols <= 0 || rows <= 0 || max_picks <= 0) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int sp = (int)align_up(cols, 4);
+    CK(h->d_dbg[0].ensure((size_t)sp * rows * 4));
+    CK(h->d_dbg[2].ensure(sizeof(FpmWarpJob)));
+    FpmWarpJob jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.dw = cols + tw - 1; jb.dh = rows + th - 1; jb.valid = 1;
+    int tile = 8;
+    while ((long long)((cols + tile - 1) / tile) * ((rows + tile - 1) / tile) > 1024 && tile < 256) tile *= 2;
+    int blk_stride = block_mode ? (cols / tw) * (rows / th) + 3 : ((cols + tile - 1) / tile) * ((rows + tile - 1) / tile);
+    CK(h->d_dbg[1].ensure((size_t)blk_stride * 8));
+    CK(h->d_dbg[3].ensure((size_t)max_picks * sizeof(FpmPick) + 16));
+    CK(cudaMemcpy2DAsync(h->d_dbg[0].p, (size_t)sp * 4, score, (size_t)cols * 4, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_dbg[2].p, &jb, sizeof(jb), cudaMemcpyHostToDevice, h->stream));
+    float* bv = h->d_dbg[1].as<float>();
+    int* bl = reinterpret_cast<int*>(bv + blk_stride);
+    FpmPick* dp = h->d_dbg[3].as<FpmPick>();
+    int* dn = reinterpret_cast<int*>(dp + max_picks);
+    fpm_top_peaks_kernel<<<1, PK_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<float>(), sp, 0, tw, th,
+                                                          block_mode, tile, bv, bl, blk_stride, thresh, max_overlap, max_picks, dp, dn);
+    CKL();
+    std::vector<FpmPick> hp(max_picks);
+    int hn = 0;
+    CK(cudaMemcpyAsync(hp.data(), dp, (size_t)max_picks * sizeof(FpmPick), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&hn, dn, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < hn; i++) { picks[i * 3] = hp[i].x; picks[i * 3 + 1] = hp[i].y; picks[i * 3 + 2] = hp[i].v; }
+    *n = hn;
+    return FPM_OK;
+}
+
+int fpm_dbg_rrect_overlap(const float r1[5], const float r2[5], double max_overlap, int* type, double* ratio)
+{
+    FpmRRect a{r1[0], r1[1], r1[2], r1[3], r1[4]}, b{r2[0], r2[1], r2[2], r2[3], r2[4]};
+    return fpm_rrect_overlap_decision(a, b, max_overlap, type, ratio);
+}
+
+int fpm_dbg_rrect_from3(const float pts[6], float out[5])
+{
+    FpmRRect r = fpm_rrect_from3(pts[0], pts[1], pts[2], pts[3], pts[4], pts[5]);
+    out[0] = r.cx; out[1] = r.cy; out[2] = r.w; out[3] = r.h; out[4] = r.angle;
+    return 0;
+}
+
+// ---- trace access -----------------------------------------------------------------------
+int fpm_trace_num_candidates(const fpm_handle* h) { return h ? (int)(h->tr_cands.size() / 4) : 0; }
+
+int fpm_trace_candidates(const fpm_handle* h, double* rows)
+{
+    if (!h || !rows) return FPM_ERR_INVALID;
+    for (size_t i = 0; i < h->tr_cands.size(); i++) rows[i] = h->tr_cands[i];
+    return FPM_OK;
+}
+
+int fpm_trace_num_evals(const fpm_handle* h, int level)
+{
+    if (!h || level < 0 || level >= (int)h->tr_evals.size()) return 0;
+    return (int)(h->tr_evals[level].size() / 5);
+}
+
+int fpm_trace_evals(const fpm_handle* h, int level, double* rows)
+{
+    if (!h || !rows || level < 0 || level >= (int)h->tr_evals.size()) return FPM_ERR_INVALID;
+    for (size_t i = 0; i < h->tr_evals[level].size(); i++) rows[i] = h->tr_evals[level][i];
+    return FPM_OK;
+}
+
+int fpm_trace_level(const fpm_handle* hc, int level, uint8_t* out, int* w, int* hgt)
+{
+    fpm_handle* h = const_cast<fpm_handle*>(hc);
+    if (!h || level < 0 || level >= (int)h->levels.size()) return FPM_ERR_INVALID;
+    const FpmLevel& L = h->levels[level];
+    if (w) *w = L.w;
+    if (hgt) *hgt = L.h;
+    if (out) {
+        CK(cudaMemcpy2D(out, L.w, L.ptr, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    }
+    return FPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,984 @@
+// fpm_kernels.cuh -- hand-written sm_100a kernels for every stage of TemplateMatcher::match
+// (/root/reference/src/TemplateMatcher.cpp:97-437).  One kernel per reference stage:
+//
+//   fpm_pyrdown_kernel        cv::buildPyramid / pyrDown                     (:55, :124)
+//   fpm_warp_kernel           cv::warpAffine INTER_LINEAR, BORDER_CONSTANT    (:175, :1089)
+//   fpm_top_score_kernel      matchTemplate(TM_CCORR) + CCOEFF_Denominator    (:177, :514, :527-598)
+//   fpm_top_peaks_kernel      minMaxLoc / s_BlockMax / getNextMaxLoc          (:179-210, :1196-1221)
+//   fpm_collect_sort_kernel   candidate list + std::sort                      (:186-214, :265-266)
+//   fpm_refine_prep_kernel    getRotatedROI matrix                            (:1074-1088)
+//   fpm_corr_rows_kernel      IM_Conv_SIMD row dot products (dp4a)            (:461-483, :496-510)
+//   fpm_refine_finalize_kernel float row chain + CCOEFF_Denominator + argmax + pose update (:304-367)
+//   fpm_final_kernel          filterWithScore / RotatedRect / NMS / output    (:373-432)
+//
+// All integer work is exact; all double/float epilogues are written op-by-op (the library is
+// compiled with -fmad=false) so they round like the reference's x86-64 (no FMA) build.
+#pragma once
+#include "fpm_common.cuh"
+#include "fpm_geometry.cuh"
+
+// =====================================================================================
+// K1  pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, (s+128)>>8, out ((w+1)/2,(h+1)/2)
+// HBM-bound: reads W*H, writes W*H/4.  Tile = 128x32 outputs per CTA, input tile staged in
+// shared memory with coalesced 32-bit loads, separable passes out of shared memory.
+// =====================================================================================
+#define PD_TW 128
+#define PD_TH 32
+#define PD_IH (2 * PD_TH + 3)
+#define PD_IW (2 * PD_TW + 8)      // input columns [2*ox0-4, 2*ox0+2*TW+4)
+#define PD_THREADS 256
+
+__global__ void __launch_bounds__(PD_THREADS)
+fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec_ok)
+{
+    __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
+    __shared__ __align__(16) uint16_t s_h[PD_IH][PD_TW];
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
+    const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
+    uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
+    const int xs = 2 * ox0 - 4, ys = 2 * oy0 - 2;
+    const int nout_rows = min(PD_TH, dst.h - oy0);
+    const int nout_cols = min(PD_TW, dst.w - ox0);
+    const int nin_rows = 2 * nout_rows + 3;
+    const int nin_words = min(PD_IW / 4, (2 * nout_cols + 8) / 4 + 2);   // columns 0 .. 2*nout_cols+9 touched
+
+    for (int i = tid; i < nin_rows * (PD_IW / 4); i += PD_THREADS) {
+        int r = i / (PD_IW / 4), wc = i - r * (PD_IW / 4);
+        if (wc >= nin_words) continue;
+        int iy = fpm_reflect101(ys + r, src.h);
+        int x = xs + 4 * wc;
+        const uint8_t* row = s + (size_t)iy * src.pitch;
+        uint32_t v;
+        if (vec_ok && x >= 0 && x + 3 < src.w) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+        } else {
+            v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, src.w)) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
+    }
+    __syncthreads();
+
+    // horizontal pass: output column ox has its centre at smem column 2*ox+4; two outputs / thread
+    const int npairs = (nout_cols + 1) / 2;
+    for (int i = tid; i < nin_rows * (PD_TW / 2); i += PD_THREADS) {
+        int r = i / (PD_TW / 2), k = i - r * (PD_TW / 2);
+        if (k >= npairs) continue;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_in[r][4 * k]);
+        uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        // bytes 4k+2 .. 4k+8
+        int b2 = (w0 >> 16) & 255, b3 = w0 >> 24;
+        int b4 = w1 & 255, b5 = (w1 >> 8) & 255, b6 = (w1 >> 16) & 255, b7 = w1 >> 24;
+        int b8 = w2 & 255;
+        int h0 = b2 + b6 + 4 * (b3 + b5) + 6 * b4;
+        int h1 = b4 + b8 + 4 * (b5 + b7) + 6 * b6;
+        *reinterpret_cast<uint32_t*>(&s_h[r][2 * k]) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    }
+    __syncthreads();
+
+    // vertical pass: 4 outputs / thread
+    for (int i = tid; i < nout_rows * (PD_TW / 4); i += PD_THREADS) {
+        int oy = i / (PD_TW / 4), g = i - oy * (PD_TW / 4);
+        int ox = 4 * g;
+        if (ox >= nout_cols) continue;
+        int acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int c = ox + k;
+            acc[k] = s_h[2 * oy][c] + s_h[2 * oy + 4][c] + 4 * (s_h[2 * oy + 1][c] + s_h[2 * oy + 3][c]) +
+                     6 * s_h[2 * oy + 2][c];
+            acc[k] = (acc[k] + 128) >> 8;
+        }
+        uint8_t* o = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + ox;
+        if (ox + 3 < nout_cols) {
+            *reinterpret_cast<uint32_t*>(o) = (uint32_t)acc[0] | ((uint32_t)acc[1] << 8) | ((uint32_t)acc[2] << 16) |
+                                              ((uint32_t)acc[3] << 24);
+        } else {
+            for (int k = 0; k < 4 && ox + k < nout_cols; k++) o[k] = (uint8_t)acc[k];
+        }
+    }
+}
+
+// =====================================================================================
+// K2/K3  warpAffine, u8 C1, INTER_LINEAR, BORDER_CONSTANT -- OpenCV's fixed-point path:
+//   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,
+//   weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15.
+// One job per output image (top-layer angle or refinement ROI).  4 pixels / thread / row,
+// packed 32-bit stores; the padding columns up to dpitch are written as zero.
+// =====================================================================================
+#define WA_ROWS 8
+#define WA_THREADS 256
+
+__global__ void __launch_bounds__(WA_THREADS)
+fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __restrict__ dst,
+                int dpitch, size_t dst_job_stride, int border)
+{
+    const FpmWarpJob& jb = jobs[blockIdx.y];
+    const int row0 = blockIdx.x * WA_ROWS;
+    const int dw = jb.dw, dh = jb.dh;
+    if (!jb.valid || row0 >= dh) return;
+    __shared__ int sX0[WA_ROWS], sY0[WA_ROWS];
+    const double m0 = jb.m[0], m3 = jb.m[3];
+    if (threadIdx.x < WA_ROWS) {
+        double y = (double)(row0 + (int)threadIdx.x);
+        sX0[threadIdx.x] = fpm_cvround((jb.m[1] * y + jb.m[2]) * 1024.0) + 16;
+        sY0[threadIdx.x] = fpm_cvround((jb.m[4] * y + jb.m[5]) * 1024.0) + 16;
+    }
+    __syncthreads();
+    const uint8_t* __restrict__ s = src.ptr + (size_t)jb.src_img * src.img_stride;
+    uint8_t* __restrict__ d = dst + (size_t)blockIdx.y * dst_job_stride;
+    const int sw = src.w, sh = src.h, sp = src.pitch;
+    const int nrows = min(WA_ROWS, dh - row0);
+    const int ngroups = dpitch / 4;
+    for (int g = threadIdx.x; g < ngroups; g += WA_THREADS) {
+        int ad[4], bd[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double x = (double)(4 * g + k);
+            ad[k] = fpm_cvround(m0 * x * 1024.0);
+            bd[k] = fpm_cvround(m3 * x * 1024.0);
+        }
+        for (int r = 0; r < nrows; r++) {
+            uint32_t pack = 0;
+            const int X0 = sX0[r], Y0 = sY0[r];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (4 * g + k < dw) {
+                    int X = (X0 + ad[k]) >> 5, Y = (Y0 + bd[k]) >> 5;
+                    int sx = X >> 5, sy = Y >> 5;
+                    int ax = X & 31, ay = Y & 31;
+                    int p00, p01, p10, p11;
+                    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+                        const uint8_t* p = s + (size_t)sy * sp + sx;
+                        p00 = __ldg(p); p01 = __ldg(p + 1); p10 = __ldg(p + sp); p11 = __ldg(p + sp + 1);
+                    } else {
+                        bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+                        bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+                        const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
+                        p00 = (x0in && y0in) ? __ldg(p) : border;
+                        p01 = (x1in && y0in) ? __ldg(p + 1) : border;
+                        p10 = (x0in && y1in) ? __ldg(p + sp) : border;
+                        p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
+                    }
+                    int v = (32 - ax) * (32 - ay) * 32 * p00 + ax * (32 - ay) * 32 * p01 +
+                            (32 - ax) * ay * 32 * p10 + ax * ay * 32 * p11;
+                    v = (v + 16384) >> 15;
+                    pack |= (uint32_t)v << (8 * k);
+                }
+            }
+            *reinterpret_cast<uint32_t*>(d + (size_t)(row0 + r) * dpitch + 4 * g) = pack;
+        }
+    }
+}
+
+// =====================================================================================
+// shared CCOEFF_NORMED epilogue (CCOEFF_Denominator, src/TemplateMatcher.cpp:567-595)
+// =====================================================================================
+__device__ __forceinline__ float fpm_ccoeff_epilogue(float numerator, double wsum, double wsqsum,
+                                                     double tmean, double tnorm, double inv_area)
+{
+    double num = (double)numerator, t;
+    double wndMean2 = 0, wndSum2 = 0;
+    t = wsum;
+    wndMean2 += t * t;
+    num -= t * tmean;
+    wndMean2 *= inv_area;
+    t = wsqsum;
+    wndSum2 += t;
+    double diff2 = fmax(wndSum2 - wndMean2, 0.0);
+    if (diff2 <= fmin(0.5, (double)(10 * FLT_EPSILON) * wndSum2))
+        t = 0;
+    else
+        t = sqrt(diff2) * tnorm;
+    if (fabs(num) < t)
+        num /= t;
+    else if (fabs(num) < t * 1.125)
+        num = num > 0 ? 1 : -1;
+    else
+        num = 0;
+    return (float)num;
+}
+
+// =====================================================================================
+// K4+K7  top-layer dense score map: exact integer TM_CCORR numerator, exact window sum / sqsum,
+// CCOEFF_NORMED epilogue.  One CTA = 16x16 scores; image patch + template in shared memory.
+// =====================================================================================
+#define TS_TILE 16
+
+__global__ void __launch_bounds__(TS_TILE * TS_TILE)
+fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restrict__ rot, int rpitch,
+                     size_t rot_job_stride, FpmTplLevel tpl, float* __restrict__ score, int spitch,
+                     size_t score_job_stride)
+{
+    extern __shared__ uint8_t smem[];
+    const FpmWarpJob& jb = jobs[blockIdx.z];
+    const int tw = tpl.w, th = tpl.h;
+    const int RW = jb.dw - tw + 1, RH = jb.dh - th + 1;
+    const int x0 = blockIdx.x * TS_TILE, y0 = blockIdx.y * TS_TILE;
+    if (!jb.valid || RW <= 0 || RH <= 0 || x0 >= RW || y0 >= RH) return;
+    const int pw = TS_TILE + tw - 1, ph = TS_TILE + th - 1;
+    uint8_t* s_t = smem;                 // th*tw
+    uint8_t* s_p = smem + th * tw;       // ph*pw
+    const int tid = threadIdx.y * TS_TILE + threadIdx.x;
+    const uint8_t* __restrict__ r = rot + (size_t)blockIdx.z * rot_job_stride;
+    for (int i = tid; i < th * tw; i += TS_TILE * TS_TILE) {
+        int yy = i / tw, xx = i - yy * tw;
+        s_t[i] = tpl.ptr[yy * tpl.pitch + xx];
+    }
+    for (int i = tid; i < ph * pw; i += TS_TILE * TS_TILE) {
+        int yy = i / pw, xx = i - yy * pw;
+        int gx = x0 + xx, gy = y0 + yy;
+        s_p[i] = (gx < jb.dw && gy < jb.dh) ? r[(size_t)gy * rpitch + gx] : 0;
+    }
+    __syncthreads();
+    const int ox = x0 + threadIdx.x, oy = y0 + threadIdx.y;
+    if (ox >= RW || oy >= RH) return;
+    float* out = score + (size_t)blockIdx.z * score_job_stride + (size_t)oy * spitch + ox;
+    if (tpl.result_equal1) { *out = 1.0f; return; }
+    long long num = 0, wsum = 0, wsq = 0;
+    for (int yy = 0; yy < th; yy++) {
+        const uint8_t* prow = s_p + (threadIdx.y + yy) * pw + threadIdx.x;
+        const uint8_t* trow = s_t + yy * tw;
+        int a = 0, b = 0, c = 0;
+        for (int xx = 0; xx < tw; xx++) {
+            int p = prow[xx];
+            a += p * trow[xx];
+            b += p;
+            c += p * p;
+        }
+        num += a; wsum += b; wsq += c;
+    }
+    // TM_CCORR result cell is a float32 (cv::matchTemplate output depth), here the rounded exact sum
+    *out = fpm_ccoeff_epilogue((float)num, (double)wsum, (double)wsq, tpl.mean, tpl.norm, tpl.inv_area);
+}
+
+// =====================================================================================
+// K8  greedy peak extraction per (image, angle): minMaxLoc / s_BlockMax + getNextMaxLoc.
+// One CTA per score map.  A table of (max, location) per block is kept in global scratch;
+// every pick is an argmax over the table, a paint of the suppression rectangle with -1 and a
+// rescan of the blocks the rectangle touches.
+//   mode 0 (plain minMaxLoc path): own square tiles; ties -> first in row-major scan order
+//   mode 1 (Qt s_BlockMax path, DataStructures.h:150-245): template-sized blocks + right strip +
+//          bottom strip + corner; ties -> first block in construction order
+// =====================================================================================
+struct FpmPick { int x, y; float v; };
+
+struct FpmBlockGeom { int mode, bw, bh, ncol, nrow, nblocks, has_right, has_bottom, has_corner; };
+
+__device__ __forceinline__ FpmBlockGeom fpm_block_geom(int mode, int cols, int rows, int bw, int bh)
+{
+    FpmBlockGeom g;
+    g.mode = mode; g.bw = bw; g.bh = bh;
+    if (mode == 0) {
+        g.ncol = (cols + bw - 1) / bw; g.nrow = (rows + bh - 1) / bh;
+        g.has_right = g.has_bottom = g.has_corner = 0;
+        g.nblocks = g.ncol * g.nrow;
+    } else {
+        g.ncol = cols / bw; g.nrow = rows / bh;
+        g.has_right = g.ncol * bw < cols;
+        g.has_bottom = (g.nrow * bh < rows) && (g.ncol * bw > 0);
+        g.has_corner = (g.ncol * bw < cols) && (g.nrow * bh < rows);
+        g.nblocks = g.ncol * g.nrow + g.has_right + g.has_bottom + g.has_corner;
+    }
+    return g;
+}
+
+__device__ __forceinline__ void fpm_block_rect(const FpmBlockGeom& g, int k, int cols, int rows,
+                                               int& x, int& y, int& w, int& h)
+{
+    int regular = g.ncol * g.nrow;
+    if (k < regular) {
+        int by = k / g.ncol, bx = k - by * g.ncol;
+        x = bx * g.bw; y = by * g.bh;
+        w = min(g.bw, cols - x); h = min(g.bh, rows - y);
+        return;
+    }
+    k -= regular;
+    if (g.has_right) { if (k == 0) { x = g.ncol * g.bw; y = 0; w = cols - x; h = rows; return; } k--; }
+    if (g.has_bottom) { if (k == 0) { x = 0; y = g.nrow * g.bh; w = g.ncol * g.bw; h = rows - y; return; } k--; }
+    x = g.ncol * g.bw; y = g.nrow * g.bh; w = cols - x; h = rows - y;
+}
+
+// warp-cooperative scan of one block: max value, first location in row-major order
+__device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, int pitch, int x, int y,
+                                               int w, int h, int lane, float& bv, int& bx, int& by)
+{
+    float best = -INFINITY; int bidx = 0x7fffffff;
+    int n = w * h;
+    for (int i = lane; i < n; i += 32) {
+        int yy = i / w, xx = i - yy * w;
+        float v = map[(size_t)(y + yy) * pitch + x + xx];
+        if (v > best) { best = v; bidx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    bv = best;
+    if (bidx == 0x7fffffff) bidx = 0;
+    by = y + bidx / w; bx = x + (bidx - (bidx / w) * w);
+}
+
+#define PK_THREADS 512
+
+__global__ void __launch_bounds__(PK_THREADS)
+fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ score, int spitch,
+                     size_t score_job_stride, int tw, int th, int mode, int tile,
+                     float* __restrict__ blk_val, int* __restrict__ blk_loc, int blk_stride,
+                     double thresh, double max_overlap, int max_picks,
+                     FpmPick* __restrict__ picks, int* __restrict__ pick_count)
+{
+    const int job = blockIdx.x;
+    const FpmWarpJob& jb = jobs[job];
+    const int cols = jb.dw - tw + 1, rows = jb.dh - th + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PK_THREADS / 32;
+    if (!jb.valid || cols <= 0 || rows <= 0) { if (tid == 0) pick_count[job] = 0; return; }
+    float* __restrict__ map = score + (size_t)job * score_job_stride;
+    float* bval = blk_val + (size_t)job * blk_stride;
+    int* bloc = blk_loc + (size_t)job * blk_stride;
+    const FpmBlockGeom g = fpm_block_geom(mode, cols, rows, mode ? tw : tile, mode ? th : tile);
+    __shared__ float s_v[PK_THREADS / 32];
+    __shared__ int s_k[PK_THREADS / 32], s_loc[PK_THREADS / 32];
+    __shared__ float s_best_v;
+    __shared__ int s_best_loc;
+
+    for (int k = warp; k < g.nblocks; k += nwarps) {
+        int x, y, w, h; float v; int bx, by;
+        fpm_block_rect(g, k, cols, rows, x, y, w, h);
+        fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
+        if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
+    }
+    __syncthreads();
+
+    int npicks = 0;
+    int lastx = 0, lasty = 0;
+    for (int it = 0; it < max_picks; it++) {
+        if (it > 0) {
+            // getNextMaxLoc: paint the suppression rectangle, refresh the touched blocks
+            int sx = (int)((double)lastx - (double)tw * (1 - max_overlap));
+            int sy = (int)((double)lasty - (double)th * (1 - max_overlap));
+            int rw = (int)(2 * (double)tw * (1 - max_overlap));
+            int rh = (int)(2 * (double)th * (1 - max_overlap));
+            if (rw > 0 && rh > 0) {
+                int px0 = max(sx, 0), py0 = max(sy, 0), px1 = min(sx + rw, cols), py1 = min(sy + rh, rows);
+                int pw = px1 - px0, ph = py1 - py0;
+                if (pw > 0 && ph > 0)
+                    for (int i = tid; i < pw * ph; i += PK_THREADS) {
+                        int yy = i / pw, xx = i - yy * pw;
+                        map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
+                    }
+                __syncthreads();
+                for (int k = warp; k < g.nblocks; k += nwarps) {
+                    int x, y, w, h;
+                    fpm_block_rect(g, k, cols, rows, x, y, w, h);
+                    int ix0 = max(x, sx), iy0 = max(y, sy), ix1 = min(x + w, sx + rw), iy1 = min(y + h, sy + rh);
+                    if (ix1 > ix0 && iy1 > iy0) {
+                        float v; int bx, by;
+                        fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
+                        if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // argmax over the block table
+        float best = -INFINITY; int bk = 0x7fffffff, bl = 0x7fffffff;
+        for (int k = tid; k < g.nblocks; k += PK_THREADS) {
+            float v = bval[k]; int l = bloc[k];
+            bool better = (v > best) || (v == best && (mode ? (k < bk) : (l < bl)));
+            if (better) { best = v; bk = k; bl = l; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            bool better = (ov > best) || (ov == best && (mode ? (ok < bk) : (ol < bl)));
+            if (better) { best = ov; bk = ok; bl = ol; }
+        }
+        if (lane == 0) { s_v[warp] = best; s_k[warp] = bk; s_loc[warp] = bl; }
+        __syncthreads();
+        if (tid == 0) {
+            float b = s_v[0]; int k0 = s_k[0], l0 = s_loc[0];
+            for (int w = 1; w < nwarps; w++) {
+                bool better = (s_v[w] > b) || (s_v[w] == b && (mode ? (s_k[w] < k0) : (s_loc[w] < l0)));
+                if (better) { b = s_v[w]; k0 = s_k[w]; l0 = s_loc[w]; }
+            }
+            if (g.nblocks == 0) { b = -1.0f; l0 = -1; }      // s_BlockMax::GetMaxValueLoc on empty
+            s_best_v = b; s_best_loc = l0;
+        }
+        __syncthreads();
+        float v = s_best_v; int loc = s_best_loc;
+        __syncthreads();
+        if ((double)v < thresh) break;
+        lastx = loc >= 0 ? loc % cols : -1; lasty = loc >= 0 ? loc / cols : -1;
+        if (tid == 0) { FpmPick p; p.x = lastx; p.y = lasty; p.v = v; picks[(size_t)job * max_picks + npicks] = p; }
+        npicks++;
+    }
+    if (tid == 0) pick_count[job] = npicks;
+}
+
+// =====================================================================================
+// bitonic sort of 64-bit keys held in shared or global memory by one CTA (n_pad power of two)
+// =====================================================================================
+__device__ __forceinline__ void fpm_bitonic_sort(unsigned long long* keys, int n_pad, int tid, int nthreads)
+{
+    for (int k = 2; k <= n_pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pad; i += nthreads) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// float -> uint32 whose unsigned order is the DESCENDING float order
+__device__ __forceinline__ uint32_t fpm_desc_key(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending-order key
+    return ~u;
+}
+
+// =====================================================================================
+// candidate list of one image: gather the picks of all angles (angle-major, pick order), sort by
+// score descending (ties keep gather order, like the oracle's stable sort), undo the canvas
+// translation (:186) and rotate back into the un-rotated top layer (:265-266).
+// =====================================================================================
+#define CS_THREADS 1024
+
+__global__ void __launch_bounds__(CS_THREADS)
+fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict__ pick_count,
+                        int n_angles, int max_picks, const double* __restrict__ angles,
+                        const float* __restrict__ ftx, const float* __restrict__ fty,
+                        float centre_x, float centre_y,
+                        unsigned long long* __restrict__ key_scratch, int key_stride, int use_smem,
+                        int* __restrict__ off_scratch,
+                        FpmCand* __restrict__ cands_flat, int* __restrict__ flat_counter,
+                        float* __restrict__ top_pt, int cand_stride,
+                        int* __restrict__ cand_count, int angle_idx_base)
+{
+    extern __shared__ unsigned long long s_keys[];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_n, s_base;
+    int* s_off = off_scratch + (size_t)img * n_angles;     // prefix of pick counts
+    if (tid == 0) {
+        int n = 0;
+        for (int a = 0; a < n_angles; a++) { s_off[a] = n; n += pick_count[img * n_angles + a]; }
+        s_n = n;
+        s_base = atomicAdd(flat_counter, n);
+    }
+    __syncthreads();
+    const int n = s_n;
+    const int base = s_base;
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    unsigned long long* keys = use_smem ? s_keys : key_scratch + (size_t)img * key_stride;
+    for (int i = tid; i < n_pad; i += CS_THREADS) keys[i] = ~0ull;
+    __syncthreads();
+    for (int a = 0; a < n_angles; a++) {
+        int c = pick_count[img * n_angles + a];
+        for (int j = tid; j < c; j += CS_THREADS) {
+            const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+            uint32_t order = (uint32_t)(a * max_picks + j);
+            keys[s_off[a] + j] = ((unsigned long long)fpm_desc_key(p.v) << 32) | order;
+        }
+    }
+    __syncthreads();
+    fpm_bitonic_sort(keys, n_pad, tid, CS_THREADS);
+    for (int i = tid; i < n; i += CS_THREADS) {
+        uint32_t order = (uint32_t)(keys[i] & 0xffffffffu);
+        int a = order / max_picks, j = order - a * max_picks;
+        const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+        float ptx = (float)p.x - ftx[a], pty = (float)p.y - fty[a];
+        FpmCand c;
+        c.angle = angles[a];
+        c.score = (double)p.v;
+        c.img = img; c.id = i;
+        double dRAngle = -c.angle * FPM_D2R;
+        fpm_pt_rotate(ptx, pty, centre_x, centre_y, dRAngle, &c.ptx, &c.pty);
+        cands_flat[base + i] = c;
+        if (top_pt) {
+            float* t = top_pt + ((size_t)img * cand_stride + i) * 4;
+            t[0] = ptx; t[1] = pty; t[2] = p.v; t[3] = (float)(a + angle_idx_base);
+        }
+    }
+    if (tid == 0) cand_count[img] = n;
+}
+
+// =====================================================================================
+// refinement, per layer.  Eval e = candidate * n_ang + j.
+// prep: rotation matrix of getRotatedROI (src/TemplateMatcher.cpp:1074-1088), inverted like warpAffine
+// =====================================================================================
+__global__ void fpm_refine_prep_kernel(const FpmCand* __restrict__ cands, int n_cands, int n_ang,
+                                       double angle_step, int lvl_w, int lvl_h, int tpl_w, int tpl_h,
+                                       FpmWarpJob* __restrict__ jobs)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_cands * n_ang) return;
+    int ci = e / n_ang, j = e - ci * n_ang;
+    const FpmCand c = cands[ci];
+    double angle = (n_ang == 1) ? 0.0 : c.angle + angle_step * (double)(j - 1);
+    float ptcx = (float)(lvl_w - 1) / 2.0f, ptcy = (float)(lvl_h - 1) / 2.0f;
+    float ltx = c.ptx * 2, lty = c.pty * 2;
+    float rx, ry;
+    fpm_pt_rotate(ltx, lty, ptcx, ptcy, angle * FPM_D2R, &rx, &ry);
+    FpmWarpJob jb;
+    fpm_rotation_matrix(ptcx, ptcy, angle, jb.m);
+    jb.m[2] -= (double)(rx - 3);
+    jb.m[5] -= (double)(ry - 3);
+    fpm_invert_affine(jb.m);
+    jb.src_img = c.img;
+    jb.dw = tpl_w + FPM_ROI_PAD; jb.dh = tpl_h + FPM_ROI_PAD;
+    jb.valid = 1;
+    jobs[e] = jb;
+}
+
+// =====================================================================================
+// K5  correlation row sums (replaces IM_Conv_SIMD, src/TemplateMatcher.cpp:461-483):
+//   rowsum[e][tr][r*7+c] = sum_x T[tr][x] * S_e[tr + r][x + c]      exact s32, dp4a
+//   rowS[e][y][c] = sum_{x<w} S_e[y][x+c],  rowQ[e][y][c] = sum_{x<w} S_e[y][x+c]^2
+// One CTA = (chunk of RC template rows, eval); ROI rows and template rows staged in shared
+// memory; a warp owns a template row at a time, lanes split the row by 32-bit words.
+// =====================================================================================
+#define CR_THREADS 256
+
+__device__ __forceinline__ uint32_t fpm_shift_bytes(uint32_t lo, uint32_t hi, int c)
+{
+    return __funnelshift_r(lo, hi, 8 * c);
+}
+
+__global__ void __launch_bounds__(CR_THREADS)
+fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, FpmTplLevel tpl,
+                     int rc, int32_t* __restrict__ rowsum, int32_t* __restrict__ rowS,
+                     int32_t* __restrict__ rowQ)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int e = blockIdx.y;
+    const int t0 = blockIdx.x * rc;
+    const int tw = tpl.w, th = tpl.h;
+    const int nT = min(rc, th - t0);
+    const int nS = nT + FPM_ROI_PAD;
+    const int tp = tpl.pitch;
+    uint8_t* s_s = smem;                              // nS rows x rpitch
+    uint8_t* s_t = smem + (size_t)(rc + FPM_ROI_PAD) * rpitch;   // nT rows x tp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = CR_THREADS / 32;
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(roi + (size_t)e * roi_stride + (size_t)t0 * rpitch);
+        uint4* d = reinterpret_cast<uint4*>(s_s);
+        int n16 = nS * rpitch / 16;
+        for (int i = tid; i < n16; i += CR_THREADS) d[i] = g[i];
+        const uint4* gt = reinterpret_cast<const uint4*>(tpl.ptr + (size_t)t0 * tp);
+        uint4* dt = reinterpret_cast<uint4*>(s_t);
+        int t16 = nT * tp / 16;
+        for (int i = tid; i < t16; i += CR_THREADS) dt[i] = __ldg(gt + i);
+    }
+    __syncthreads();
+    const int nw = (tw + 3) / 4;                      // template words per row (zero padded)
+    const int tail = tw & 3;
+    const uint32_t tailmask = tail ? (0x01010101u >> (8 * (4 - tail))) : 0x01010101u;
+
+    // ---- correlation row sums
+    for (int tl = warp; tl < nT; tl += nwarps) {
+        const uint32_t* trow = reinterpret_cast<const uint32_t*>(s_t + (size_t)tl * tp);
+        int32_t* out = rowsum + ((size_t)e * th + (t0 + tl)) * FPM_NCELL;
+        for (int r = 0; r < FPM_NSHIFT; r++) {
+            const uint32_t* srow = reinterpret_cast<const uint32_t*>(s_s + (size_t)(tl + r) * rpitch);
+            uint32_t acc[FPM_NSHIFT];
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) acc[c] = 0;
+            for (int xw = lane; xw < nw; xw += 32) {
+                uint32_t t = trow[xw];
+                uint32_t w0 = srow[xw], w1 = srow[xw + 1], w2 = srow[xw + 2];
+                acc[0] = __dp4a(t, w0, acc[0]);
+                acc[1] = __dp4a(t, fpm_shift_bytes(w0, w1, 1), acc[1]);
+                acc[2] = __dp4a(t, fpm_shift_bytes(w0, w1, 2), acc[2]);
+                acc[3] = __dp4a(t, fpm_shift_bytes(w0, w1, 3), acc[3]);
+                acc[4] = __dp4a(t, w1, acc[4]);
+                acc[5] = __dp4a(t, fpm_shift_bytes(w1, w2, 1), acc[5]);
+                acc[6] = __dp4a(t, fpm_shift_bytes(w1, w2, 2), acc[6]);
+            }
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < FPM_NSHIFT; c++) out[r * FPM_NSHIFT + c] = (int32_t)acc[c];
+            }
+        }
+    }
+    // ---- window row sums over the ROI rows this chunk owns: [t0, t0+nT) plus the 6 tail rows
+    const bool last = (t0 + nT == th);
+    const int nOwn = last ? nS : nT;
+    for (int yl = warp; yl < nOwn; yl += nwarps) {
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(s_s + (size_t)yl * rpitch);
+        uint32_t sS[FPM_NSHIFT], sQ[FPM_NSHIFT];
+#pragma unroll
+        for (int c = 0; c < FPM_NSHIFT; c++) { sS[c] = 0; sQ[c] = 0; }
+        for (int xw = lane; xw < nw; xw += 32) {
+            uint32_t ones = (xw == nw - 1) ? tailmask : 0x01010101u;
+            uint32_t bm = ones * 255u;
+            uint32_t w0 = srow[xw], w1 = srow[xw + 1], w2 = srow[xw + 2];
+            uint32_t v[FPM_NSHIFT];
+            v[0] = w0; v[1] = fpm_shift_bytes(w0, w1, 1); v[2] = fpm_shift_bytes(w0, w1, 2);
+            v[3] = fpm_shift_bytes(w0, w1, 3); v[4] = w1; v[5] = fpm_shift_bytes(w1, w2, 1);
+            v[6] = fpm_shift_bytes(w1, w2, 2);
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) {
+                uint32_t m = v[c] & bm;
+                sS[c] = __dp4a(m, 0x01010101u, sS[c]);
+                sQ[c] = __dp4a(m, m, sQ[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < FPM_NSHIFT; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sS[c] += __shfl_xor_sync(0xffffffffu, sS[c], o);
+                sQ[c] += __shfl_xor_sync(0xffffffffu, sQ[c], o);
+            }
+        }
+        if (lane == 0) {
+            size_t base = ((size_t)e * (th + FPM_ROI_PAD) + (t0 + yl)) * FPM_NSHIFT;
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) { rowS[base + c] = (int32_t)sS[c]; rowQ[base + c] = (int32_t)sQ[c]; }
+        }
+    }
+}
+
+// =====================================================================================
+// sub-pixel / sub-angle fit (subPixEstimation, src/TemplateMatcher.cpp:1002-1072):
+// Z = (A^T A)^-1 A^T s via LU with partial pivoting (cv::Mat::inv DECOMP_LU for n > 3),
+// optimum = K1^-1 K2 with the closed-form 3x3 inverse.
+// =====================================================================================
+__device__ int fpm_lu_inverse10(double* A /*10x10, destroyed*/, double* B /*10x10 out*/)
+{
+    const int m = 10;
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) B[i * m + j] = (i == j) ? 1.0 : 0.0;
+    const double eps = DBL_EPSILON * 100;
+    for (int i = 0; i < m; i++) {
+        int k = i;
+        for (int j = i + 1; j < m; j++)
+            if (fabs(A[j * m + i]) > fabs(A[k * m + i])) k = j;
+        if (fabs(A[k * m + i]) < eps) return 0;
+        if (k != i) {
+            for (int j = i; j < m; j++) { double t = A[i * m + j]; A[i * m + j] = A[k * m + j]; A[k * m + j] = t; }
+            for (int j = 0; j < m; j++) { double t = B[i * m + j]; B[i * m + j] = B[k * m + j]; B[k * m + j] = t; }
+        }
+        double d = -1 / A[i * m + i];
+        for (int j = i + 1; j < m; j++) {
+            double alpha = A[j * m + i] * d;
+            for (int kk = i + 1; kk < m; kk++) A[j * m + kk] += alpha * A[i * m + kk];
+            for (int kk = 0; kk < m; kk++) B[j * m + kk] += alpha * B[i * m + kk];
+        }
+    }
+    for (int i = m - 1; i >= 0; i--)
+        for (int j = 0; j < m; j++) {
+            double s = B[i * m + j];
+            for (int k = i + 1; k < m; k++) s -= A[i * m + k] * B[k * m + j];
+            B[i * m + j] = s / A[i * m + i];
+        }
+    return 1;
+}
+
+__device__ void fpm_subpix(const double* sc27 /* [theta][y][x] */, double xm, double ym, double tm,
+                           double angle_step, double* outx, double* outy, double* outa,
+                           double* scratch /* >= 27*10 + 100 + 100 + 270 doubles */)
+{
+    double* A = scratch;             // 27x10
+    double* AtA = A + 270;           // 10x10
+    double* Inv = AtA + 100;         // 10x10
+    double* P = Inv + 100;           // 10x27
+    int row = 0;
+    for (int theta = 0; theta <= 2; theta++)
+        for (int y = -1; y <= 1; y++)
+            for (int x = -1; x <= 1; x++) {
+                double dX = xm + x, dY = ym + y;
+                double dT = (tm + (theta - 1) * angle_step) * FPM_D2R;
+                double* a = A + row * 10;
+                a[0] = dX * dX; a[1] = dY * dY; a[2] = dT * dT; a[3] = dX * dY; a[4] = dX * dT;
+                a[5] = dY * dT; a[6] = dX; a[7] = dY; a[8] = dT; a[9] = 1.0;
+                row++;
+            }
+    for (int i = 0; i < 10; i++)
+        for (int j = 0; j < 10; j++) {
+            double s = 0;
+            for (int k = 0; k < 27; k++) s += A[k * 10 + i] * A[k * 10 + j];
+            AtA[i * 10 + j] = s;
+        }
+    double Z[10];
+    if (!fpm_lu_inverse10(AtA, Inv)) {
+        for (int i = 0; i < 100; i++) Inv[i] = 0;   // cv::invert returns a zero matrix when singular
+    }
+    for (int i = 0; i < 10; i++)
+        for (int j = 0; j < 27; j++) {
+            double s = 0;
+            for (int k = 0; k < 10; k++) s += Inv[i * 10 + k] * A[j * 10 + k];
+            P[i * 27 + j] = s;
+        }
+    for (int i = 0; i < 10; i++) {
+        double s = 0;
+        for (int k = 0; k < 27; k++) s += P[i * 27 + k] * sc27[k];
+        Z[i] = s;
+    }
+    // K1^-1 * K2, closed-form 3x3 inverse (cv::invert, n == 3)
+    double a00 = 2 * Z[0], a01 = Z[3], a02 = Z[4];
+    double a10 = Z[3], a11 = 2 * Z[1], a12 = Z[5];
+    double a20 = Z[4], a21 = Z[5], a22 = 2 * Z[2];
+    double d = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
+    double b0 = -Z[6], b1 = -Z[7], b2 = -Z[8];
+    if (d != 0.) {
+        d = 1. / d;
+        double t0 = (a11 * a22 - a12 * a21) * d, t1 = (a02 * a21 - a01 * a22) * d, t2 = (a01 * a12 - a02 * a11) * d;
+        double t3 = (a12 * a20 - a10 * a22) * d, t4 = (a00 * a22 - a02 * a20) * d, t5 = (a02 * a10 - a00 * a12) * d;
+        double t6 = (a10 * a21 - a11 * a20) * d, t7 = (a01 * a20 - a00 * a21) * d, t8 = (a00 * a11 - a01 * a10) * d;
+        *outx = t0 * b0 + t1 * b1 + t2 * b2;
+        *outy = t3 * b0 + t4 * b1 + t5 * b2;
+        *outa = (t6 * b0 + t7 * b1 + t8 * b2) * FPM_R2D;
+    } else {
+        *outx = 0; *outy = 0; *outa = 0;
+    }
+}
+
+// =====================================================================================
+// refine_finalize: one CTA per candidate, 64 threads per angle.
+//   numerator  = float32 chain over template rows of the exact s32 row sums (reference order,
+//                src/TemplateMatcher.cpp:505-508) or exact s64 total when use_chain == 0
+//   window sums from rowS/rowQ (exact), CCOEFF_NORMED epilogue, minMaxLoc over the 7x7 patch,
+//   best of the 3 angles, layer threshold, pose update (src/TemplateMatcher.cpp:331-367)
+// =====================================================================================
+#define RF_THREADS 192
+
+__global__ void __launch_bounds__(RF_THREADS)
+fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double angle_step,
+                           const int32_t* __restrict__ rowsum, const int32_t* __restrict__ rowS,
+                           const int32_t* __restrict__ rowQ, FpmTplLevel tpl, int lvl_w, int lvl_h,
+                           double layer_score, int use_chain, int is_last, int subpixel,
+                           FpmCand* __restrict__ next, int* __restrict__ next_count,
+                           FpmRefined* __restrict__ refined, int* __restrict__ refined_count,
+                           FpmEvalTrace* __restrict__ trace, float* __restrict__ trace_scores)
+{
+    const int ci = blockIdx.x;
+    const int tid = threadIdx.x, j = tid >> 6, cell = tid & 63;
+    __shared__ float s_sc[3][FPM_NCELL];
+    __shared__ float s_best[3];
+    __shared__ int s_loc[3];
+    __shared__ double s_scratch[27 + 270 + 100 + 100 + 270];
+    const int th = tpl.h;
+    if (j < n_ang && cell < FPM_NCELL) {
+        const int e = ci * n_ang + j;
+        const int r = cell / FPM_NSHIFT, c = cell - r * FPM_NSHIFT;
+        float sc;
+        if (tpl.result_equal1) {
+            sc = 1.0f;
+        } else {
+            const int32_t* rs = rowsum + (size_t)e * th * FPM_NCELL + cell;
+            float numf;
+            if (use_chain) {
+                float acc = 0.0f;
+                for (int tr = 0; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * FPM_NCELL]));
+                numf = acc;
+            } else {
+                long long acc = 0;
+                for (int tr = 0; tr < th; tr++) acc += rs[(size_t)tr * FPM_NCELL];
+                numf = (float)acc;
+            }
+            const int32_t* ps = rowS + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;
+            const int32_t* pq = rowQ + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;
+            long long ws = 0, wq = 0;
+            for (int y = 0; y < th; y++) { ws += ps[(size_t)y * FPM_NSHIFT]; wq += pq[(size_t)y * FPM_NSHIFT]; }
+            sc = fpm_ccoeff_epilogue(numf, (double)ws, (double)wq, tpl.mean, tpl.norm, tpl.inv_area);
+        }
+        s_sc[j][cell] = sc;
+        if (trace_scores) trace_scores[(size_t)e * FPM_NCELL + cell] = sc;
+    }
+    __syncthreads();
+    if (j < n_ang && cell == 0) {
+        float best = s_sc[j][0]; int loc = 0;
+        for (int i = 1; i < FPM_NCELL; i++) if (s_sc[j][i] > best) { best = s_sc[j][i]; loc = i; }
+        s_best[j] = best; s_loc[j] = loc;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    const FpmCand c = cands[ci];
+    int bi = 0; double big = -1;
+    for (int k = 0; k < n_ang; k++) {
+        double ang = (n_ang == 1) ? 0.0 : c.angle + angle_step * (double)(k - 1);
+        if ((double)s_best[k] > big) { bi = k; big = (double)s_best[k]; }
+        if (trace) {
+            FpmEvalTrace t; t.angle = ang; t.score = s_best[k]; t.locx = s_loc[k] % FPM_NSHIFT; t.locy = s_loc[k] / FPM_NSHIFT;
+            trace[ci * n_ang + k] = t;
+        }
+    }
+    if ((double)s_best[bi] < layer_score) return;                      // :331-332
+    double new_angle = (n_ang == 1) ? 0.0 : c.angle + angle_step * (double)(bi - 1);
+    int lx = s_loc[bi] % FPM_NSHIFT, ly = s_loc[bi] / FPM_NSHIFT;
+    double ptx = (double)lx, pty = (double)ly;
+    bool on_border = (lx == 0 || ly == 0 || lx == FPM_NSHIFT - 1 || ly == FPM_NSHIFT - 1);
+    if (subpixel && is_last && !on_border && bi == 1 && n_ang == 3) {    // :334-344
+        // neighbours of the other two angles are taken around THEIR OWN maxima (vecResult, :323-328);
+        // an angle whose maximum sits on the border leaves vecResult unset in the reference -> 0 here
+        double* sc27 = s_scratch;
+        for (int t = 0; t < 3; t++) {
+            int tx = s_loc[t] % FPM_NSHIFT, ty = s_loc[t] / FPM_NSHIFT;
+            bool tb = (tx == 0 || ty == 0 || tx == FPM_NSHIFT - 1 || ty == FPM_NSHIFT - 1);
+            for (int y = -1; y <= 1; y++)
+                for (int x = -1; x <= 1; x++)
+                    sc27[t * 9 + (y + 1) * 3 + (x + 1)] = tb ? 0.0 : (double)s_sc[t][(ty + y) * FPM_NSHIFT + tx + x];
+        }
+        double nx, ny, na;
+        fpm_subpix(sc27, ptx, pty, new_angle, angle_step, &nx, &ny, &na, s_scratch + 27);
+        ptx = nx; pty = ny; new_angle = na;
+    }
+    float ptcx = (float)(lvl_w - 1) / 2.0f, ptcy = (float)(lvl_h - 1) / 2.0f;
+    float ltx = c.ptx * 2, lty = c.pty * 2;
+    float padx, pady;
+    fpm_pt_rotate(ltx, lty, ptcx, ptcy, new_angle * FPM_D2R, &padx, &pady);      // :350
+    padx = padx - 3.0f; pady = pady - 3.0f;
+    float qx = (float)(ptx + (double)padx), qy = (float)(pty + (double)pady);    // :351
+    float rx, ry;
+    fpm_pt_rotate(qx, qy, ptcx, ptcy, -new_angle * FPM_D2R, &rx, &ry);           // :353
+    if (is_last) {
+        FpmRefined o;
+        o.angle = new_angle; o.score = (double)s_best[bi];
+        o.ptx = (double)rx; o.pty = (double)ry;
+        o.img = c.img; o.id = c.id;
+        refined[atomicAdd(refined_count, 1)] = o;
+    } else {
+        FpmCand o = c;
+        o.angle = new_angle;
+        o.score = (double)s_best[bi];
+        o.ptx = rx; o.pty = ry;
+        next[atomicAdd(next_count, 1)] = o;
+    }
+}
+
+// top == 0: the top-layer picks are final (src/TemplateMatcher.cpp:272-276)
+__global__ void fpm_cands_to_refined_kernel(const FpmCand* __restrict__ cands, int n, int top,
+                                            FpmRefined* __restrict__ refined, int* __restrict__ refined_count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FpmCand c = cands[i];
+    FpmRefined o;
+    float k = (top == 0) ? 1.0f : 2.0f;
+    o.angle = c.angle; o.score = c.score;
+    o.ptx = (double)(c.ptx * k); o.pty = (double)(c.pty * k);
+    o.img = c.img; o.id = c.id;
+    refined[i] = o;
+    if (i == 0) *refined_count = n;
+}
+
+// =====================================================================================
+// K9  final stage per image: filterWithScore (:984-1000), corner construction + RotatedRect
+// (:380-390), filterWithRotatedRect (:1133-1194), result conversion (:407-432).
+// =====================================================================================
+struct FpmResultDev {
+    double score, angle, cx, cy, ltx, lty, rtx, rty, rbx, rby, lbx, lby;
+};
+
+__device__ __forceinline__ void fpm_corners(double ptx, double pty, double angle, int w, int h, float* lt,
+                                            float* rt, float* lb, float* rb)
+{
+    double dRAngle = -angle * FPM_D2R;
+    float c = (float)cos(dRAngle), s = (float)sin(dRAngle);
+    lt[0] = (float)ptx; lt[1] = (float)pty;
+    rt[0] = lt[0] + w * c; rt[1] = lt[1] - w * s;
+    lb[0] = lt[0] + h * s; lb[1] = lt[1] + h * c;
+    rb[0] = rt[0] + h * s; rb[1] = rt[1] + h * c;
+}
+
+#define FN_THREADS 256
+
+__global__ void __launch_bounds__(FN_THREADS)
+fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__ refined_count,
+                 double score_thresh, double max_overlap, int tpl_w, int tpl_h,
+                 unsigned long long* __restrict__ key_scratch, int key_stride,
+                 FpmRRect* __restrict__ rect_scratch, int* __restrict__ del_scratch,
+                 int* __restrict__ idmap_scratch,
+                 FpmResultDev* __restrict__ results, int result_cap, int* __restrict__ result_count)
+{
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int n_total = *refined_count;
+    unsigned long long* keys = key_scratch + (size_t)img * key_stride;
+    FpmRRect* rects = rect_scratch + (size_t)img * key_stride;
+    int* del = del_scratch + (size_t)img * key_stride;
+    int* idmap = idmap_scratch + (size_t)img * key_stride;
+    __shared__ int s_n, s_cut;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int i = tid; i < n_total; i += FN_THREADS)
+        if (refined[i].img == img) {
+            // ties: lower candidate id first (the oracle's stable sort order); id is unique per image
+            int slot = atomicAdd(&s_n, 1);
+            keys[slot] = ((unsigned long long)fpm_desc_key((float)refined[i].score) << 32) |
+                         (unsigned long long)(uint32_t)refined[i].id;
+            idmap[refined[i].id] = i;
+        }
+    __syncthreads();
+    const int n = s_n;
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    for (int i = n + tid; i < n_pad; i += FN_THREADS) keys[i] = ~0ull;
+    if (tid == 0) s_cut = n;
+    __syncthreads();
+    fpm_bitonic_sort(keys, n_pad, tid, FN_THREADS);
+    // replace the id by the record index; filterWithScore: cut at the first score < Score
+    for (int i = tid; i < n; i += FN_THREADS) {
+        int idx = idmap[(uint32_t)(keys[i] & 0xffffffffu)];
+        keys[i] = (keys[i] & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)idx;
+        if (refined[idx].score < score_thresh) atomicMin(&s_cut, i);
+    }
+    __syncthreads();
+    const int m = s_cut;
+    for (int i = tid; i < m; i += FN_THREADS) {
+        const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
+        float lt[2], rt[2], lb[2], rb[2];
+        fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
+        rects[i] = fpm_rrect_from3(lt[0], lt[1], rt[0], rt[1], rb[0], rb[1]);
+        del[i] = 0;
+    }
+    __syncthreads();
+    // filterWithRotatedRect: scores are sorted descending so the later index always loses
+    for (int i = 0; i < m - 1; i++) {
+        if (!del[i]) {
+            const FpmRRect ri = rects[i];
+            for (int k = i + 1 + tid; k < m; k += FN_THREADS)
+                if (!del[k] && fpm_rrect_overlap_decision(ri, rects[k], max_overlap, nullptr, nullptr)) del[k] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int cnt = 0;
+        for (int i = 0; i < m; i++) {
+            if (del[i]) continue;
+            if (cnt < result_cap) {
+                const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
+                float lt[2], rt[2], lb[2], rb[2];
+                fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
+                FpmResultDev o;
+                o.score = r.score; o.angle = r.angle;
+                o.cx = (double)((lt[0] + rt[0] + lb[0] + rb[0]) / 4.0f);
+                o.cy = (double)((lt[1] + rt[1] + lb[1] + rb[1]) / 4.0f);
+                o.ltx = lt[0]; o.lty = lt[1]; o.rtx = rt[0]; o.rty = rt[1];
+                o.rbx = rb[0]; o.rby = rb[1]; o.lbx = lb[0]; o.lby = lb[1];
+                results[(size_t)img * result_cap + cnt] = o;
+            }
+            cnt++;
+        }
+        result_count[img] = cnt;
+    }
+}

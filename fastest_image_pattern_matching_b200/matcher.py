@@ -1,0 +1,292 @@
+"""Host-side mirror of the reference's `TemplateMatcher` class
+(/root/reference/include/TemplateMatcher.h:9-52), bound to the CUDA library through the C ABI.
+
+Same method names, argument meaning and error behaviour as the reference:
+`learnPattern` returns False for an empty template, `match` returns an empty list when nothing
+is learned / the source is empty / the template does not fit / nothing is found.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+class FpmError(RuntimeError):
+    pass
+
+
+@dataclass
+class SingleTargetMatch:
+    """s_SingleTargetMatch (/root/reference/include/DataStructures.h:97-115)."""
+    ptLT: Tuple[float, float]
+    ptRT: Tuple[float, float]
+    ptRB: Tuple[float, float]
+    ptLB: Tuple[float, float]
+    ptCenter: Tuple[float, float]
+    dMatchedAngle: float
+    dMatchScore: float
+
+
+def _as_u8_2d(img) -> np.ndarray:
+    a = np.asarray(img)
+    if a.ndim != 2 or a.dtype != np.uint8:
+        raise FpmError("images must be single-channel 8-bit (IMREAD_GRAYSCALE), got %s %s" % (a.dtype, a.shape))
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def _convert(res, n) -> List[SingleTargetMatch]:
+    out = []
+    for i in range(n):
+        r = res[i]
+        out.append(SingleTargetMatch((r.ltx, r.lty), (r.rtx, r.rty), (r.rbx, r.rby), (r.lbx, r.lby),
+                                     (r.cx, r.cy), r.angle, r.score))
+    return out
+
+
+class TemplateMatcher:
+    def __init__(self, device: int = 0, result_capacity: int = 4096):
+        self._lib = L.load()
+        self._h = self._lib.fpm_create(device)
+        if not self._h:
+            raise FpmError("fpm_create(%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
+        self.device = device
+        self.result_capacity = result_capacity
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.fpm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    close = __del__
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FpmError("fpm error %d: %s" % (rc, self._lib.fpm_last_error(self._h).decode()))
+
+    # ---- parameters (include/TemplateMatcher.h:22-37) ----
+    def _set(self, p, v): self._check(self._lib.fpm_set_param(self._h, p, float(v)))
+    def _get(self, p): return self._lib.fpm_get_param(self._h, p)
+    def setMaxPositions(self, v: int): self._set(L.PARAM_MAX_POSITIONS, v)
+    def setMaxOverlap(self, v: float): self._set(L.PARAM_MAX_OVERLAP, v)
+    def setScore(self, v: float): self._set(L.PARAM_SCORE, v)
+    def setToleranceAngle(self, v: float): self._set(L.PARAM_TOLERANCE_ANGLE, v)
+    def setMinReduceArea(self, v: int): self._set(L.PARAM_MIN_REDUCE_AREA, v)
+    def setUseSIMD(self, v: bool): self._set(L.PARAM_USE_SIMD, 1 if v else 0)
+    def setSubPixelEstimation(self, v: bool): self._set(L.PARAM_SUBPIXEL, 1 if v else 0)
+    def getMaxPositions(self) -> int: return int(self._get(L.PARAM_MAX_POSITIONS))
+    def getMaxOverlap(self) -> float: return self._get(L.PARAM_MAX_OVERLAP)
+    def getScore(self) -> float: return self._get(L.PARAM_SCORE)
+    def getToleranceAngle(self) -> float: return self._get(L.PARAM_TOLERANCE_ANGLE)
+    def getMinReduceArea(self) -> int: return int(self._get(L.PARAM_MIN_REDUCE_AREA))
+    def getUseSIMD(self) -> bool: return bool(self._get(L.PARAM_USE_SIMD))
+    def getSubPixelEstimation(self) -> bool: return bool(self._get(L.PARAM_SUBPIXEL))
+    def setTrace(self, v: bool): self._set(L.PARAM_TRACE, 1 if v else 0)
+    def setWorkspaceMB(self, v: float): self._set(L.PARAM_WORKSPACE_MB, v)
+
+    def getLastExecutionTime(self) -> float:
+        """seconds, like the reference (include/TemplateMatcher.h:40)"""
+        return self._lib.fpm_last_time_ms(self._h) / 1000.0
+
+    def isPatternLearned(self) -> bool: return bool(self._lib.fpm_is_learned(self._h))
+    def clearPattern(self): self._lib.fpm_clear(self._h)
+    def setUserDefinedRect(self, rect: Sequence[int]): self._lib.fpm_set_user_rect(self._h, *[int(v) for v in rect])
+
+    def getUserDefinedRect(self):
+        v = [C.c_int() for _ in range(4)]
+        self._lib.fpm_get_user_rect(self._h, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def hasUserDefinedRect(self) -> bool:
+        return bool(self._lib.fpm_get_user_rect(self._h, None, None, None, None))
+
+    def launchCount(self) -> int: return int(self._lib.fpm_launch_count(self._h))
+
+    # ---- learnPattern (src/TemplateMatcher.cpp:45-95) ----
+    def learnPattern(self, templateImage) -> bool:
+        if templateImage is None or np.asarray(templateImage).size == 0:
+            return False
+        t = _as_u8_2d(templateImage)
+        self._tpl_keepalive = t
+        self._check(self._lib.fpm_learn(self._h, t.ctypes.data, t.shape[1], t.shape[0], t.strides[0]))
+        return True
+
+    # ---- match (src/TemplateMatcher.cpp:97-437) ----
+    def match(self, sourceImage) -> List[SingleTargetMatch]:
+        if sourceImage is None or np.asarray(sourceImage).size == 0:
+            return []
+        s = _as_u8_2d(sourceImage)
+        cap = self.result_capacity
+        res = (L.fpm_result * cap)()
+        n = C.c_int(0)
+        self._check(self._lib.fpm_match(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], res, cap, C.byref(n)))
+        return _convert(res, min(n.value, cap))
+
+    def matchBatch(self, frames: np.ndarray) -> List[List[SingleTargetMatch]]:
+        """frames: [B, H, W] uint8 in host memory (pinned for full PCIe speed)."""
+        f = np.asarray(frames)
+        if f.ndim != 3 or f.dtype != np.uint8 or f.strides[2] != 1:
+            raise FpmError("frames must be a [B,H,W] uint8 array with unit pixel stride")
+        B, H, W = f.shape
+        cap = self.result_capacity
+        res = (L.fpm_result * (cap * B))()
+        n = (C.c_int * B)()
+        self._check(self._lib.fpm_match_batch(self._h, f.ctypes.data, B, W, H, f.strides[1], f.strides[0], res, cap, n))
+        return [_convert(res[b * cap:(b + 1) * cap], min(n[b], cap)) for b in range(B)]
+
+    def matchBatchRaw(self, ptr: int, B: int, W: int, H: int, stride: int, frame_stride: int, on_device: bool,
+                      res=None, counts=None):
+        """Pointer-level entry used by bench.py (torch tensors): returns (results ctypes array, counts)."""
+        cap = self.result_capacity
+        if res is None:
+            res = (L.fpm_result * (cap * B))()
+        if counts is None:
+            counts = (C.c_int * B)()
+        fn = self._lib.fpm_match_batch_device if on_device else self._lib.fpm_match_batch
+        self._check(fn(self._h, ptr, B, W, H, stride, frame_stride, res, cap, counts))
+        return res, counts
+
+    # ---- learned-template introspection ----
+    def templateLevels(self):
+        out = []
+        for l in range(self._lib.fpm_tpl_levels(self._h)):
+            w, h, eq = C.c_int(), C.c_int(), C.c_int()
+            mean, norm, inv = C.c_double(), C.c_double(), C.c_double()
+            self._check(self._lib.fpm_tpl_level_info(self._h, l, C.byref(w), C.byref(h), C.byref(mean), C.byref(norm),
+                                                     C.byref(inv), C.byref(eq)))
+            pix = np.empty((h.value, w.value), np.uint8)
+            self._check(self._lib.fpm_tpl_level_pixels(self._h, l, pix.ctypes.data))
+            out.append(dict(w=w.value, h=h.value, mean=mean.value, norm=norm.value, inv_area=inv.value,
+                            result_equal1=bool(eq.value), pixels=pix))
+        return out
+
+    def borderColor(self) -> int: return self._lib.fpm_tpl_border_color(self._h)
+
+    # ---- traces (FPM_PARAM_TRACE) ----
+    def traceCandidates(self) -> np.ndarray:
+        n = self._lib.fpm_trace_num_candidates(self._h)
+        rows = np.zeros((n, 4), np.float64)
+        if n:
+            self._check(self._lib.fpm_trace_candidates(self._h, rows.ctypes.data))
+        return rows
+
+    def traceEvals(self, level: int) -> np.ndarray:
+        n = self._lib.fpm_trace_num_evals(self._h, level)
+        rows = np.zeros((n, 5), np.float64)
+        if n:
+            self._check(self._lib.fpm_trace_evals(self._h, level, rows.ctypes.data))
+        return rows
+
+    def traceLevel(self, level: int) -> Optional[np.ndarray]:
+        w, h = C.c_int(), C.c_int()
+        if self._lib.fpm_trace_level(self._h, level, None, C.byref(w), C.byref(h)) != 0:
+            return None
+        out = np.empty((h.value, w.value), np.uint8)
+        self._check(self._lib.fpm_trace_level(self._h, level, out.ctypes.data, C.byref(w), C.byref(h)))
+        return out
+
+    # ---- stage kernels (parity tests) ----
+    def dbgPyrDown(self, img) -> np.ndarray:
+        s = _as_u8_2d(img)
+        out = np.empty(((s.shape[0] + 1) // 2, (s.shape[1] + 1) // 2), np.uint8)
+        self._check(self._lib.fpm_dbg_pyrdown(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], out.ctypes.data))
+        return out
+
+    def dbgWarpAffine(self, img, M, dsize, border=0) -> np.ndarray:
+        s = _as_u8_2d(img)
+        m = np.ascontiguousarray(np.asarray(M, np.float64).reshape(6))
+        out = np.empty((dsize[1], dsize[0]), np.uint8)
+        self._check(self._lib.fpm_dbg_warp_affine(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0],
+                                                  m.ctypes.data, dsize[0], dsize[1], int(border), out.ctypes.data))
+        return out
+
+    def dbgCorrRows(self, roi, tpl):
+        r = np.ascontiguousarray(_as_u8_2d(roi))
+        t = np.ascontiguousarray(_as_u8_2d(tpl))
+        th, tw = t.shape
+        assert r.shape == (th + 6, tw + 6)
+        rowsum = np.zeros((th, 7, 7), np.int32)
+        rowS = np.zeros((th + 6, 7), np.int32)
+        rowQ = np.zeros((th + 6, 7), np.int32)
+        self._check(self._lib.fpm_dbg_corr_rows(self._h, r.ctypes.data, t.ctypes.data, tw, th, rowsum.ctypes.data,
+                                                rowS.ctypes.data, rowQ.ctypes.data))
+        return rowsum, rowS, rowQ
+
+    def dbgTopScore(self, img) -> np.ndarray:
+        s = np.ascontiguousarray(_as_u8_2d(img))
+        lv = self.templateLevels()[-1]
+        out = np.zeros((s.shape[0] - lv["h"] + 1, s.shape[1] - lv["w"] + 1), np.float32)
+        self._check(self._lib.fpm_dbg_top_score(self._h, s.ctypes.data, s.shape[1], s.shape[0], out.ctypes.data))
+        return out
+
+    def dbgPeaks(self, score, tw, th, block_mode, thresh, max_overlap, max_picks):
+        sc = np.ascontiguousarray(np.asarray(score, np.float32))
+        picks = np.zeros((max_picks, 3), np.float64)
+        n = C.c_int(0)
+        self._check(self._lib.fpm_dbg_peaks(self._h, sc.ctypes.data, sc.shape[1], sc.shape[0], tw, th, int(block_mode),
+                                            float(thresh), float(max_overlap), max_picks, picks.ctypes.data, C.byref(n)))
+        return picks[:n.value]
+
+    # ---- angle-sharded stage API ----
+    def stageNumAngles(self, W, H) -> int: return self._lib.fpm_stage_num_angles(self._h, W, H)
+
+    def stageTop(self, src, a0, a1, ptr=None, shape=None, stride=None) -> np.ndarray:
+        cap = (self.getMaxPositions() + 5) * max(a1 - a0, 1)
+        rows = np.zeros((cap, 5), np.float64)
+        n = C.c_int(0)
+        if ptr is None:
+            s = _as_u8_2d(src)
+            self._check(self._lib.fpm_stage_top(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], 0, a0, a1,
+                                                rows.ctypes.data, cap, C.byref(n)))
+        else:
+            self._check(self._lib.fpm_stage_top(self._h, ptr, shape[1], shape[0], stride, 1, a0, a1, rows.ctypes.data, cap,
+                                                C.byref(n)))
+        return rows[:n.value]
+
+    def stageSortCandidates(self, picks: np.ndarray) -> np.ndarray:
+        p = np.ascontiguousarray(picks, np.float64).reshape(-1, 5)
+        out = np.zeros_like(p)
+        self._check(self._lib.fpm_stage_sort_candidates(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def stageRefine(self, cands: np.ndarray) -> np.ndarray:
+        c = np.ascontiguousarray(cands, np.float64).reshape(-1, 5)
+        rows = np.zeros((max(c.shape[0], 1), 5), np.float64)
+        n = C.c_int(0)
+        self._check(self._lib.fpm_stage_refine(self._h, c.ctypes.data, c.shape[0], rows.ctypes.data, rows.shape[0], C.byref(n)))
+        return rows[:n.value]
+
+    def stageFinal(self, refined: np.ndarray) -> List[SingleTargetMatch]:
+        r = np.ascontiguousarray(refined, np.float64).reshape(-1, 5)
+        cap = self.result_capacity
+        res = (L.fpm_result * cap)()
+        n = C.c_int(0)
+        self._check(self._lib.fpm_stage_final(self._h, r.ctypes.data, r.shape[0], res, cap, C.byref(n)))
+        return _convert(res, min(n.value, cap))
+
+
+def rrect_overlap_host(r1, r2, max_overlap=0.0):
+    """CPU evaluation of the NMS pair decision (shared host/device geometry code); for tests."""
+    lib = L.load()
+    a = (C.c_float * 5)(*r1)
+    b = (C.c_float * 5)(*r2)
+    typ, ratio = C.c_int(), C.c_double()
+    d = lib.fpm_dbg_rrect_overlap(a, b, float(max_overlap), C.byref(typ), C.byref(ratio))
+    return d, typ.value, ratio.value
+
+
+def rrect_from3_host(p1, p2, p3):
+    lib = L.load()
+    pts = (C.c_float * 6)(p1[0], p1[1], p2[0], p2[1], p3[0], p3[1])
+    out = (C.c_float * 5)()
+    lib.fpm_dbg_rrect_from3(pts, out)
+    return tuple(out)

@@ -1,0 +1,144 @@
+/* fpm_b200.h -- C ABI of the B200-native NCC template matcher (libfpm_b200.so).
+ *
+ * Drop-in boundary for the reference's `TemplateMatcher` class
+ * (/root/reference/include/TemplateMatcher.h:9-52): every public method of that class has
+ * one entry point here (plain pointers and sizes, no C++/torch/OpenCV types), so a binding for
+ * the Qt app (include/fpm_template_matcher.hpp), pybind11 or ctypes is a thin wrapper.
+ *
+ * All functions return 0 on success and a negative FPM_ERR_* code on failure; they never
+ * throw.  "No match" is n == 0, not an error (the reference returns an empty vector,
+ * src/TemplateMatcher.cpp:99-114, :398-399).  A handle owns one CUDA device, one stream and all
+ * device memory; it is not thread-safe, distinct handles are independent.
+ */
+#ifndef FPM_B200_H
+#define FPM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fpm_handle fpm_handle;
+
+/* POD mirror of s_SingleTargetMatch (/root/reference/include/DataStructures.h:97-115). */
+typedef struct fpm_result {
+    double score;            /* dMatchScore   */
+    double angle;            /* dMatchedAngle (degrees, Qt sign convention) */
+    double cx, cy;           /* ptCenter      */
+    double ltx, lty;         /* ptLT          */
+    double rtx, rty;         /* ptRT          */
+    double rbx, rby;         /* ptRB          */
+    double lbx, lby;         /* ptLB          */
+} fpm_result;
+
+/* Parameters = the setters of TemplateMatcher (include/TemplateMatcher.h:22-28). */
+enum fpm_param {
+    FPM_PARAM_MAX_POSITIONS = 0,   /* setMaxPositions  (TargetNum), default 70   */
+    FPM_PARAM_MAX_OVERLAP = 1,     /* setMaxOverlap,               default 0.0  */
+    FPM_PARAM_SCORE = 2,           /* setScore,                    default 0.7  */
+    FPM_PARAM_TOLERANCE_ANGLE = 3, /* setToleranceAngle,           default 0.0  */
+    FPM_PARAM_MIN_REDUCE_AREA = 4, /* setMinReduceArea,            default 256  */
+    FPM_PARAM_USE_SIMD = 5,        /* setUseSIMD,                  default 1    */
+    FPM_PARAM_SUBPIXEL = 6,        /* setSubPixelEstimation,       default 0    */
+    FPM_PARAM_TRACE = 7,           /* keep per-stage records for fpm_trace_*   (tests) */
+    FPM_PARAM_WORKSPACE_MB = 8,    /* refinement workspace budget per wave, default 4096 */
+    FPM_PARAM_COUNT_
+};
+
+enum fpm_error {
+    FPM_OK = 0,
+    FPM_ERR_INVALID = -1,      /* bad argument                                   */
+    FPM_ERR_CUDA = -2,         /* CUDA runtime error, see fpm_last_error         */
+    FPM_ERR_NOT_LEARNED = -3,
+    FPM_ERR_NO_DEVICE = -4,    /* no CUDA device: there is NO CPU fallback       */
+    FPM_ERR_LIMIT = -5         /* a documented capacity limit was exceeded       */
+};
+
+/* TemplateMatcher::TemplateMatcher / ~TemplateMatcher (src/TemplateMatcher.cpp:28-43). */
+fpm_handle* fpm_create(int device);
+void fpm_destroy(fpm_handle* h);
+const char* fpm_last_error(const fpm_handle* h);
+const char* fpm_version(void);
+
+/* setX / getX (include/TemplateMatcher.h:22-37). */
+int fpm_set_param(fpm_handle* h, int param, double value);
+double fpm_get_param(const fpm_handle* h, int param);
+
+/* learnPattern (src/TemplateMatcher.cpp:45-95).  tpl: host pointer, u8, `stride` bytes per row. */
+int fpm_learn(fpm_handle* h, const uint8_t* tpl, int width, int height, int stride);
+/* isPatternLearned / clearPattern (include/TemplateMatcher.h:43-46). */
+int fpm_is_learned(const fpm_handle* h);
+void fpm_clear(fpm_handle* h);
+
+/* match (src/TemplateMatcher.cpp:97-437).  src: HOST pointer, u8.  Writes up to `cap` results sorted
+ * by score descending and the total number found to *n (which may exceed cap). */
+int fpm_match(fpm_handle* h, const uint8_t* src, int width, int height, int stride,
+              fpm_result* out, int cap, int* n);
+
+/* Batch of equally sized frames in HOST memory (frame i at src + i*frame_stride).  out holds
+ * batch*cap records, n holds batch counts.  Host->device copies are pipelined with the matching. */
+int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int height, int stride,
+                    size_t frame_stride, fpm_result* out, int cap, int* n);
+
+/* Same, frames already resident in DEVICE memory of the handle's device. */
+int fpm_match_batch_device(fpm_handle* h, const uint8_t* d_src, int batch, int width, int height,
+                           int stride, size_t frame_stride, fpm_result* out, int cap, int* n);
+
+/* getLastExecutionTime (include/TemplateMatcher.h:40), milliseconds of the last match call. */
+double fpm_last_time_ms(const fpm_handle* h);
+
+/* setUserDefinedRect / getUserDefinedRect / hasUserDefinedRect (src/TemplateMatcher.cpp:1224-1238):
+ * pure storage, kept for API completeness. */
+void fpm_set_user_rect(fpm_handle* h, int x, int y, int w, int hgt);
+int fpm_get_user_rect(const fpm_handle* h, int* x, int* y, int* w, int* hgt); /* returns hasUserRect */
+
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+long long fpm_launch_count(const fpm_handle* h);
+
+/* ---- learned-template introspection (s_TemplData, DataStructures.h:16-55) ---- */
+int fpm_tpl_levels(const fpm_handle* h);                 /* pyramid size (top layer + 1) */
+int fpm_tpl_level_info(const fpm_handle* h, int level, int* w, int* hgt, double* mean, double* norm,
+                       double* inv_area, int* result_equal1);
+int fpm_tpl_level_pixels(const fpm_handle* h, int level, uint8_t* out /* w*h */);
+int fpm_tpl_border_color(const fpm_handle* h);
+
+/* ---- angle-sharded (multi-GPU latency mode) stage API; records are plain doubles ----
+ * top:    run the top-layer sweep for angle indices [a0, a1) of the schedule; returns raw picks
+ *         as rows of 5 doubles {angle_index, x, y, score, angle_deg} in (angle, pick) order.
+ * refine: descend the pyramid for the given globally sorted candidate rows
+ *         {id, ptx, pty, score, angle_deg} (pt already un-rotated, src/TemplateMatcher.cpp:265-266);
+ *         returns rows of 5 doubles {id, ptx, pty, score, angle_deg}.
+ * final:  filterWithScore + NMS + conversion over the union of refined rows. */
+int fpm_stage_num_angles(fpm_handle* h, int width, int height);
+int fpm_stage_top(fpm_handle* h, const uint8_t* src, int width, int height, int stride, int src_on_device,
+                  int a0, int a1, double* rows, int cap, int* n);
+int fpm_stage_sort_candidates(fpm_handle* h, const double* picks, int n, double* cands /* n*5 */);
+int fpm_stage_refine(fpm_handle* h, const double* cands, int n, double* rows, int cap, int* n_out);
+int fpm_stage_final(fpm_handle* h, const double* refined, int n, fpm_result* out, int cap, int* n_out);
+
+/* ---- stage kernels exposed for bit-exact parity tests (host pointers in and out) ---- */
+int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, uint8_t* dst /* ((w+1)/2)*((h+1)/2) */);
+int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, const double m[6] /* forward 2x3 */,
+                        int dw, int dh, int border, uint8_t* dst /* dw*dh */);
+int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi /* (th+6)x(tw+6) */, const uint8_t* tpl, int tw, int th,
+                      int32_t* rowsum /* th*49 */, int32_t* rowS /* (th+6)*7 */, int32_t* rowQ /* (th+6)*7 */);
+int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score /* (h-th+1)*(w-tw+1) */);
+int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw, int th, int block_mode,
+                  double thresh, double max_overlap, int max_picks, double* picks /* max_picks*3: x,y,v */, int* n);
+/* host-side (CPU) evaluation of the NMS pair decision -- geometry code shared with the device */
+int fpm_dbg_rrect_overlap(const float r1[5], const float r2[5], double max_overlap, int* type, double* ratio);
+int fpm_dbg_rrect_from3(const float pts[6], float out[5]);
+
+/* ---- trace access after a match with FPM_PARAM_TRACE = 1 (single image) ---- */
+int fpm_trace_num_candidates(const fpm_handle* h);
+int fpm_trace_candidates(const fpm_handle* h, double* rows /* n*4: x, y, score, angle_index */);
+int fpm_trace_num_evals(const fpm_handle* h, int level);
+int fpm_trace_evals(const fpm_handle* h, int level, double* rows /* n*5: cand id, angle, score, locx, locy */);
+int fpm_trace_level(const fpm_handle* h, int level, uint8_t* out /* w*h of the source pyramid */, int* w, int* hgt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPM_B200_H */

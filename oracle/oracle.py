@@ -421,6 +421,33 @@ class OracleMatcher:
         bm.update_max(sx, sy, rw, rh)
         return bm.get_max()
 
+    # -- greedy peak list of one top-layer score map, src/TemplateMatcher.cpp:179-210 --------
+    def top_picks(self, result, size_pat, thresh, cal_by_block):
+        """Returns [((x, y), value), ...]; `result` is painted in place like the reference does."""
+        picks = []
+        if cal_by_block:
+            bm = BlockMax(result, size_pat)
+            val, loc = bm.get_max()
+            if val < thresh:
+                return picks
+            picks.append((loc, val))
+            for _ in range(self.max_pos + MATCH_CANDIDATE_NUM - 1):
+                val, loc = self._next_max_loc_block(result, loc, size_pat, bm)
+                if val < thresh:
+                    break
+                picks.append((loc, val))
+        else:
+            val, loc = _min_max_loc(result)
+            if val < thresh:
+                return picks
+            picks.append((loc, val))
+            for _ in range(self.max_pos + MATCH_CANDIDATE_NUM - 1):
+                val, loc = self._next_max_loc(result, loc, size_pat)
+                if val < thresh:
+                    break
+                picks.append((loc, val))
+        return picks
+
     def top_angles(self, top):
         """angle schedule, src/TemplateMatcher.cpp:130-144."""
         tp = self.td.pyramid[top]
@@ -487,28 +514,7 @@ class OracleMatcher:
             if tr is not None:
                 tr["top"].append(dict(angle=ang, size=size_best, rot=rot.copy(), score=result.copy(),
                                       M=m.copy(), picks=[]))
-            picks = []
-            if cal_by_block:
-                bm = BlockMax(result, size_pat)
-                val, loc = bm.get_max()
-                if val < layer_score[top]:
-                    continue
-                picks.append((loc, val))
-                for _ in range(self.max_pos + MATCH_CANDIDATE_NUM - 1):
-                    val, loc = self._next_max_loc_block(result, loc, size_pat, bm)
-                    if val < layer_score[top]:
-                        break
-                    picks.append((loc, val))
-            else:
-                val, loc = _min_max_loc(result)
-                if val < layer_score[top]:
-                    continue
-                picks.append((loc, val))
-                for _ in range(self.max_pos + MATCH_CANDIDATE_NUM - 1):
-                    val, loc = self._next_max_loc(result, loc, size_pat)
-                    if val < layer_score[top]:
-                        break
-                    picks.append((loc, val))
+            picks = self.top_picks(result, size_pat, layer_score[top], cal_by_block)
             for loc, val in picks:
                 pt = (f32(f32(loc[0]) - ftx), f32(f32(loc[1]) - fty))
                 cands.append(MatchParameter(pt=(float(pt[0]), float(pt[1])), score=val, angle=ang))

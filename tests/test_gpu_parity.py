@@ -1,0 +1,370 @@
+"""GPU parity tests (run on the B200 box): every CUDA stage and the whole match() against the CPU
+oracle / cv2 on the same inputs, through the C ABI.
+
+Bars (BASELINE.json north_star): bit-exact pyramid, warp, integer correlation sums and window
+sums; scores within 1e-4; positions within 0.05 px; angles within 0.01 deg; identical accepted set.
+"""
+import math
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import assert_results_match, configure, get_image
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------- T0: pyramid, bit-exact ----------------
+@pytest.mark.parametrize("shape", [(7, 9), (1, 1), (1, 5), (2, 2), (3, 300), (480, 640), (101, 333), (64, 47), (259, 517),
+                                   (1519, 2013), (3036, 4024)])
+def test_pyrdown_bit_exact(matcher, shape):
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(matcher.dbgPyrDown(img), cv2.pyrDown(img))
+
+
+def test_pyrdown_unaligned_stride(matcher):
+    rng = np.random.default_rng(9)
+    big = rng.integers(0, 256, (200, 301), dtype=np.uint8)
+    view = big[3:150, 5:222]                       # stride 301, odd offset -> byte path
+    assert np.array_equal(matcher.dbgPyrDown(view), cv2.pyrDown(np.ascontiguousarray(view)))
+
+
+def test_source_pyramid_chain(matcher, golden_cases):
+    c = golden_cases["src8"]
+    src = get_image(c["src"])
+    lv = src
+    for _ in range(4):
+        nxt = matcher.dbgPyrDown(lv)
+        assert np.array_equal(nxt, cv2.pyrDown(lv))
+        lv = nxt
+
+
+# ---------------- T2: warpAffine, bit-exact ----------------
+def test_warp_affine_bit_exact(matcher):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (190, 253), dtype=np.uint8)
+    for ang in [0.0, 9.462, 90.0, -37.3, 180.0, 123.456, 270.0, 359.9]:
+        for border in (0, 255):
+            m = cv2.getRotationMatrix2D((126.0, 94.5), ang, 1)
+            m[0, 2] += 13.5
+            m[1, 2] -= 7.25
+            want = cv2.warpAffine(img, m, (280, 220), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=border)
+            got = matcher.dbgWarpAffine(img, m, (280, 220), border)
+            assert np.array_equal(got, want), (ang, border, int((got != want).sum()))
+
+
+def test_warp_affine_roi_geometry(matcher):
+    """getRotatedROI-style calls (src/TemplateMatcher.cpp:1074-1090) incl. ROIs hanging over the border."""
+    rng = np.random.default_rng(6)
+    src = rng.integers(0, 256, (759, 1006), dtype=np.uint8)
+    for (w, h, ltx, lty, ang) in [(191, 131, 400.3, 300.7, 33.2), (96, 66, -20.0, 10.0, -100.0), (381, 261, 800.5, 600.25, 179.9),
+                                  (48, 33, 990.0, 740.0, 12.0), (24, 17, 3.0, 5.0, 0.0)]:
+        roi = O.OracleMatcher._get_rotated_roi(src, (w, h), (np.float32(ltx), np.float32(lty)), ang)
+        ptc = (np.float32((src.shape[1] - 1) / 2.0), np.float32((src.shape[0] - 1) / 2.0))
+        lt = O.pt_rotate_pt2f((np.float32(ltx), np.float32(lty)), ptc, ang * O.D2R)
+        m = cv2.getRotationMatrix2D((float(ptc[0]), float(ptc[1])), ang, 1)
+        m[0, 2] -= float(np.float32(lt[0] - np.float32(3)))
+        m[1, 2] -= float(np.float32(lt[1] - np.float32(3)))
+        got = matcher.dbgWarpAffine(src, m, (w + 6, h + 6), 0)
+        assert np.array_equal(got, roi), (w, h, ang)
+
+
+def test_warp_affine_large(matcher):
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (1500, 2048), dtype=np.uint8)
+    m = cv2.getRotationMatrix2D((1023.5, 749.5), -119.979, 1)
+    m[0, 2] += 120.5
+    m[1, 2] += 300.0
+    want = cv2.warpAffine(img, m, (2300, 2100), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=255)
+    got = matcher.dbgWarpAffine(img, m, (2300, 2100), 255)
+    assert np.array_equal(got, want)
+
+
+# ---------------- T3: integer correlation row sums + window sums, bit-exact ----------------
+@pytest.mark.parametrize("tw,th", [(12, 9), (24, 17), (48, 33), (54, 54), (27, 27), (14, 14), (96, 66), (191, 131), (1, 1), (5, 3),
+                                   (381, 261), (130, 7)])
+def test_corr_rows_bit_exact(matcher, tw, th):
+    rng = np.random.default_rng(tw * 1000 + th)
+    tpl = rng.integers(0, 256, (th, tw), dtype=np.uint8)
+    roi = rng.integers(0, 256, (th + 6, tw + 6), dtype=np.uint8)
+    rowsum, rowS, rowQ = matcher.dbgCorrRows(roi, tpl)
+    want = O.ccorr_exact_rows(roi, tpl)                      # [7, 7, th]
+    assert np.array_equal(rowsum.astype(np.int64), np.transpose(want, (2, 0, 1)))
+    r64 = roi.astype(np.int64)
+    for c in range(7):
+        assert np.array_equal(rowS[:, c], r64[:, c:c + tw].sum(axis=1))
+        assert np.array_equal(rowQ[:, c], (r64[:, c:c + tw] ** 2).sum(axis=1))
+
+
+def test_corr_rows_saturated_large(matcher):
+    """all-255 rows of the cfg1 template size: the s32 row sums must not overflow (762*255*255 < 2^31)."""
+    tw, th = 762, 64
+    tpl = np.full((th, tw), 255, np.uint8)
+    roi = np.full((th + 6, tw + 6), 255, np.uint8)
+    rowsum, rowS, rowQ = matcher.dbgCorrRows(roi, tpl)
+    assert (rowsum == 762 * 255 * 255).all() and (rowS == 762 * 255).all() and (rowQ == 762 * 255 * 255).all()
+
+
+# ---------------- T1: template learning ----------------
+@pytest.mark.parametrize("case", ["cfg3_src6", "src8", "cfg1_synth", "cfg2_synth", "src4"])
+def test_learn_pattern_matches_golden(matcher, golden_cases, case):
+    c = golden_cases[case]
+    configure(matcher, c["params"])
+    assert matcher.learnPattern(get_image(c["tpl"]))
+    lv = matcher.templateLevels()
+    assert len(lv) == len(c["tpl_levels"])
+    assert matcher.borderColor() == c["border_color"]
+    import hashlib
+    for got, want in zip(lv, c["tpl_levels"]):
+        assert (got["w"], got["h"]) == (want["w"], want["h"])
+        assert hashlib.sha256(got["pixels"].tobytes()).hexdigest()[:16] == want["sha"]       # bit-exact pyramid
+        assert got["mean"] == want["mean"] and got["norm"] == want["norm"] and got["inv_area"] == want["inv_area"]
+        assert got["result_equal1"] == want["equal1"]
+
+
+# ---------------- T4: top-layer score map ----------------
+@pytest.mark.parametrize("case", ["src8", "cfg3_src6"])
+def test_top_score_map_bit_exact_vs_exact_oracle(matcher, golden_cases, case):
+    c = golden_cases[case]
+    configure(matcher, c["params"])
+    tpl = get_image(c["tpl"])
+    matcher.learnPattern(tpl)
+    om = configure(O.OracleMatcher(), c["params"])
+    om.learn_pattern(tpl)
+    top = len(om.td.pyramid) - 1
+    src = get_image(c["src"])
+    pyr = O.build_pyramid(src, top)
+    img = pyr[top]
+    got = matcher.dbgTopScore(img)
+    want = O.ccoeff_denominator(img, om.td, O.ccorr_exact_dense(img, om.td.pyramid[top]), top)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), float(np.abs(got - want).max())
+    # reported delta against the cv::matchTemplate-fed map (DFT float numerator), tolerance only
+    cvmap = O.ccoeff_denominator(img, om.td, cv2.matchTemplate(img, om.td.pyramid[top], cv2.TM_CCORR), top)
+    assert float(np.abs(got - cvmap).max()) < 1e-3
+
+
+# ---------------- T5: peak extraction ----------------
+@pytest.mark.parametrize("block", [False, True])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_peaks_match_oracle(matcher, block, seed):
+    rng = np.random.default_rng(seed)
+    rows, cols = (211, 300) if block else (57, 66)
+    score = rng.uniform(-0.2, 0.9, (rows, cols)).astype(np.float32)
+    score = cv2.GaussianBlur(score, (0, 0), 1.5)
+    # exact ties, including clamped +-1 plateaus
+    for _ in range(12):
+        y, x = int(rng.integers(0, rows)), int(rng.integers(0, cols))
+        score[y, x] = 1.0
+    tw, th = 9, 7
+    om = O.OracleMatcher()
+    om.max_pos, om.max_overlap = 20, 0.25 if seed == 2 else 0.0
+    want = om.top_picks(score.copy(), (tw, th), 0.3, block)
+    got = matcher.dbgPeaks(score, tw, th, block, 0.3, om.max_overlap, om.max_pos + 5)
+    assert len(got) == len(want)
+    for g, (loc, val) in zip(got, want):
+        assert (int(g[0]), int(g[1])) == loc and np.float32(g[2]) == np.float32(val)
+
+
+def test_peaks_nothing_above_threshold(matcher):
+    score = np.full((20, 30), 0.1, np.float32)
+    assert len(matcher.dbgPeaks(score, 5, 5, False, 0.5, 0.0, 10)) == 0
+    assert len(matcher.dbgPeaks(score, 5, 5, True, 0.5, 0.0, 10)) == 0
+
+
+# ---------------- T5..T7: the whole match() ----------------
+ALL_CASES = ["src8", "src9", "test4_src3", "cfg3_src6", "cfg1_synth", "src4", "cfg2_synth", "src9_subpix"]
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_match_against_golden(matcher, golden_cases, case):
+    c = golden_cases[case]
+    configure(matcher, c["params"])
+    matcher.setTrace(True)
+    assert matcher.learnPattern(get_image(c["tpl"]))
+    src = get_image(c["src"])
+    res = matcher.match(src)
+    matcher.setTrace(False)
+    # T0: source pyramid bit-exact
+    import hashlib
+    for l, sha in enumerate(c["src_pyr_sha"]):
+        lv = matcher.traceLevel(l)
+        assert lv is not None and hashlib.sha256(lv.tobytes()).hexdigest()[:16] == sha, "pyramid level %d" % l
+    # T5: ordered top-layer candidate list (exact ties may permute: compare per score class)
+    cand = matcher.traceCandidates()
+    assert len(cand) == c["n_candidates"]
+    want = np.array(c["candidates"])[:, :3] if c["n_candidates"] else np.zeros((0, 3))
+    if c["n_candidates"]:
+        assert np.array_equal(cand[:, 2].astype(np.float32), want[:, 2].astype(np.float32))
+        ties = len(set(want[:, 2].tolist())) != len(want)
+        if not ties:
+            assert np.array_equal(cand[:, :2].astype(np.float32), want[:, :2].astype(np.float32))
+    # T7: accepted set, order, score / angle / pose
+    ties = len({r["score"] for r in c["results"]}) != len(c["results"])
+    if case == "src9_subpix":
+        assert_results_match(res, c["results"], 1e-4, 0.5, 0.1)     # ill-conditioned LSQ fit, see DESIGN.md
+    else:
+        assert_results_match(res, c["results"], ordered=not ties)
+
+
+def test_match_equals_live_oracle_on_jittered_cfg1(matcher, golden_cases):
+    """a pose set that is not in the golden file: oracle and GPU run on the same seeded input here."""
+    from fastest_image_pattern_matching_b200 import synth
+    c = golden_cases["cfg1_synth"]
+    tpl = get_image("Dst7")
+    src = synth.cfg1_source(seed=21, tpl=tpl, jitter=True)
+    configure(matcher, c["params"])
+    matcher.learnPattern(tpl)
+    got = matcher.match(src)
+    om = configure(O.OracleMatcher(), c["params"])
+    om.learn_pattern(tpl)
+    want = om.match(src)
+    assert len(want) == 3
+    assert_results_match(got, want)
+
+
+def test_batch_equals_single(matcher, golden_cases):
+    c = golden_cases["src8"]
+    configure(matcher, c["params"])
+    matcher.learnPattern(get_image(c["tpl"]))
+    a = get_image("Src8")
+    b = get_image("Src9")
+    frames = np.stack([a, b, a, np.zeros_like(a), b])
+    single = [matcher.match(f) for f in frames]
+    batch = matcher.matchBatch(frames)
+    assert [len(x) for x in batch] == [len(x) for x in single]
+    for x, y in zip(batch, single):
+        assert_results_match(x, y, 0, 0, 0)
+    assert len(single[0]) == 3 and len(single[3]) == 0
+
+
+def test_small_workspace_waves_give_same_result(matcher, golden_cases):
+    c = golden_cases["src8"]
+    configure(matcher, c["params"])
+    matcher.learnPattern(get_image(c["tpl"]))
+    src = get_image(c["src"])
+    ref = matcher.match(src)
+    matcher.setWorkspaceMB(0.5)
+    try:
+        res = matcher.match(src)
+    finally:
+        matcher.setWorkspaceMB(4096)
+    assert_results_match(res, ref, 0, 0, 0)
+
+
+def test_use_simd_off(matcher, golden_cases):
+    """SIMD unchecked: the reference falls back to cv::matchTemplate in refinement; here the exact sum."""
+    c = golden_cases["src8"]
+    p = dict(c["params"], use_simd=False)
+    configure(matcher, p)
+    matcher.learnPattern(get_image(c["tpl"]))
+    res = matcher.match(get_image(c["src"]))
+    matcher.setUseSIMD(True)
+    assert_results_match(res, c["results"], 1e-4, 0.05, 0.01)
+
+
+# ---------------- guards / edge cases (src/TemplateMatcher.cpp:99-114 and SURVEY 8a) ----------------
+def test_guards(matcher):
+    matcher.clearPattern()
+    assert not matcher.isPatternLearned()
+    assert matcher.match(np.zeros((50, 50), np.uint8)) == []
+    assert not matcher.learnPattern(np.zeros((0, 0), np.uint8))
+    tpl = np.full((40, 40), 7, np.uint8)
+    tpl[10:30, 10:30] = 200
+    assert matcher.learnPattern(tpl) and matcher.isPatternLearned()
+    assert matcher.match(np.zeros((20, 100), np.uint8)) == []
+    assert matcher.match(np.zeros((30, 30), np.uint8)) == []
+    assert matcher.match(np.zeros((0, 0), np.uint8)) == []
+    matcher.setUserDefinedRect((1, 2, 3, 4))
+    assert matcher.hasUserDefinedRect() and matcher.getUserDefinedRect() == (1, 2, 3, 4)
+
+
+def _edge_case(matcher, tpl, src, params):
+    configure(matcher, params)
+    assert matcher.learnPattern(tpl)
+    got = matcher.match(src)
+    om = configure(O.OracleMatcher(), params)
+    om.learn_pattern(tpl)
+    want = om.match(src)
+    return got, want
+
+
+def test_flat_template_forces_score_one(matcher):
+    tpl = np.full((20, 24), 90, np.uint8)
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, 256, (90, 120), dtype=np.uint8)
+    got, want = _edge_case(matcher, tpl, src, dict(max_pos=3, score=0.9, tolerance_angle=0, min_reduce_area=64))
+    assert len(want) > 0
+    assert_results_match(got, want, ordered=False)
+
+
+def test_top_layer_zero_no_refinement(matcher):
+    """template area <= MinReduceArea: iTopLayer == 0, top-layer picks are final (:272-276)."""
+    rng = np.random.default_rng(3)
+    src = cv2.GaussianBlur(rng.integers(0, 256, (120, 160), dtype=np.uint8), (0, 0), 2)
+    tpl = src[40:55, 60:76].copy()
+    got, want = _edge_case(matcher, tpl, src, dict(max_pos=2, score=0.8, tolerance_angle=20, min_reduce_area=256))
+    assert len(want) >= 1
+    assert_results_match(got, want)
+
+
+def test_zero_tolerance_single_angle(matcher):
+    rng = np.random.default_rng(4)
+    src = cv2.GaussianBlur(rng.integers(0, 256, (300, 400), dtype=np.uint8), (0, 0), 2)
+    tpl = src[100:164, 200:280].copy()
+    got, want = _edge_case(matcher, tpl, src, dict(max_pos=2, score=0.8, tolerance_angle=0, min_reduce_area=256))
+    assert len(want) == 1 and abs(want[0].ptLT[0] - 200) < 0.01
+    assert_results_match(got, want)
+
+
+def test_candidate_near_border(matcher):
+    rng = np.random.default_rng(5)
+    src = cv2.GaussianBlur(rng.integers(0, 256, (300, 400), dtype=np.uint8), (0, 0), 2)
+    tpl = src[0:60, 0:90].copy()                      # ROI taps fall outside -> border 0 (:1089)
+    got, want = _edge_case(matcher, tpl, src, dict(max_pos=2, score=0.6, tolerance_angle=30, min_reduce_area=256))
+    assert len(want) >= 1
+    assert_results_match(got, want)
+
+
+def test_min_reduce_area_change_relearns(matcher, golden_cases):
+    c = golden_cases["src8"]
+    configure(matcher, c["params"])
+    tpl, src = get_image(c["tpl"]), get_image(c["src"])
+    matcher.learnPattern(tpl)
+    matcher.setMinReduceArea(1024)                    # reference would index out of range (SURVEY 8a hazard)
+    got = matcher.match(src)
+    om = configure(O.OracleMatcher(), dict(c["params"], min_reduce_area=1024))
+    om.learn_pattern(tpl)
+    assert_results_match(got, om.match(src))
+
+
+def test_tolerance_360_duplicate_orientations(matcher, golden_cases):
+    c = golden_cases["src9"]
+    p = dict(c["params"], tolerance_angle=360)
+    got, want = _edge_case(matcher, get_image(c["tpl"]), get_image(c["src"]), p)
+    assert_results_match(got, want)
+
+
+# ---------------- angle-sharded stage API == whole match ----------------
+@pytest.mark.parametrize("case", ["src8", "cfg3_src6"])
+def test_stage_api_equals_match(matcher, golden_cases, case):
+    c = golden_cases[case]
+    configure(matcher, c["params"])
+    matcher.learnPattern(get_image(c["tpl"]))
+    src = get_image(c["src"])
+    whole = matcher.match(src)
+    n_ang = matcher.stageNumAngles(src.shape[1], src.shape[0])
+    assert n_ang == c["n_angles"]
+    world = 3
+    per = (n_ang + world - 1) // world
+    picks = [matcher.stageTop(src, r * per, min(n_ang, (r + 1) * per)) for r in range(world)]
+    allp = np.concatenate(picks)
+    cands = matcher.stageSortCandidates(allp)
+    assert len(cands) == c["n_candidates"]
+    matcher.stageTop(src, 0, 0)                                   # pyramid resident, no angles
+    refined = [matcher.stageRefine(cands[r::world]) for r in range(world)]
+    res = matcher.stageFinal(np.concatenate(refined))
+    assert_results_match(res, whole, 0, 0, 0)

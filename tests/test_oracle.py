@@ -1,0 +1,159 @@
+"""CPU tests: the oracle against its pins (known answers, golden vectors, the reference's own
+IM_Conv_SIMD build, cv2 for every OpenCV model the CUDA kernels restate)."""
+import ctypes
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import models as M
+from tests.helpers import assert_results_match, configure, get_image
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+# ---- known answers of the reference (README / Result Images) ----
+@pytest.mark.parametrize("case,count", [("test4_src3", 36), ("cfg3_src6", 15), ("src8", 3), ("src9", 1)])
+def test_known_answer_counts(golden_cases, oracle_lib, case, count):
+    c = golden_cases[case]
+    assert len(c["results"]) == count
+    m = configure(O.OracleMatcher(), c["params"])
+    assert m.learn_pattern(get_image(c["tpl"]))
+    res = m.match(get_image(c["src"]))
+    assert len(res) == count
+    assert_results_match(res, c["results"], 0, 0, 0)      # oracle is deterministic: identical to golden
+
+
+def test_cfg1_recovers_readme_poses(golden_cases):
+    # README.md:47-49 poses (synthetic Src7: Dst7 pasted there); MFC angle sign = -Qt sign
+    from fastest_image_pattern_matching_b200.synth import CFG1_POSES
+    res = golden_cases["cfg1_synth"]["results"]
+    assert len(res) == 3
+    for (cx, cy, a) in CFG1_POSES:
+        best = min(res, key=lambda r: abs(r["cx"] - cx) + abs(r["cy"] - cy))
+        assert abs(best["cx"] - cx) < 1.0 and abs(best["cy"] - cy) < 1.0
+        d = (best["angle"] + a + 180) % 360 - 180
+        assert abs(d) < 0.2
+
+
+def test_numpy_and_sse2_numerators_agree(oracle_lib):
+    rng = np.random.default_rng(0)
+    for (tw, th) in [(12, 9), (54, 54), (191, 131), (33, 17)]:
+        tpl = rng.integers(0, 256, (th, tw), dtype=np.uint8)
+        src = rng.integers(0, 256, (th + 6, tw + 6), dtype=np.uint8)
+        a = O.match_template_simd_numpy(src, tpl)
+        assert O._load_rowdot()
+        b = O.match_template_simd(src, tpl)
+        assert np.array_equal(a, b)
+
+
+def test_restated_simd_matches_reference_build():
+    """oracle/_ref/libimconv_ref.so is the reference's own IM_Conv_SIMD compiled from its source."""
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libimconv_ref.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref not built (reference absent)")
+    ref = ctypes.CDLL(ref_path)
+    ref.ref_IM_Conv_SIMD.restype = ctypes.c_int
+    ref.ref_cell.restype = ctypes.c_float
+    lib = O._load_rowdot()
+    if not lib:
+        pytest.skip("oracle C helper not built")
+    lib.oracle_row_dot.restype = ctypes.c_int
+    rng = np.random.default_rng(1)
+    for n in [1, 7, 15, 16, 17, 54, 762, 1024, 4000]:
+        k = rng.integers(0, 256, n, dtype=np.uint8)
+        c = rng.integers(0, 256, n, dtype=np.uint8)
+        want = int((k.astype(np.int64) * c).sum())
+        assert ref.ref_IM_Conv_SIMD(k.ctypes.data, c.ctypes.data, n) == want
+        assert lib.oracle_row_dot(k.ctypes.data, c.ctypes.data, n) == want
+    # bright rows: float accumulation rounds -- restatement must round identically
+    for (tw, th) in [(762, 521), (1024, 300), (54, 54)]:
+        tpl = rng.integers(200, 256, (th, tw), dtype=np.uint8)
+        src = rng.integers(200, 256, (th, tw), dtype=np.uint8)
+        want = ref.ref_cell(tpl.ctypes.data, tw, th, src.ctypes.data, tw)
+        got = O.match_template_simd(src, tpl)[0, 0]
+        assert np.float32(want) == got
+        assert O.match_template_simd_numpy(src, tpl)[0, 0] == got
+
+
+# ---- OpenCV models the CUDA kernels restate, pinned against cv2 itself ----
+@pytest.mark.parametrize("shape", [(7, 9), (1, 1), (2, 5), (480, 640), (101, 333), (64, 47), (1519, 2013)])
+def test_pyrdown_model(shape):
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(M.pyrdown(img), cv2.pyrDown(img))
+
+
+def test_warp_affine_model():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (190, 253), dtype=np.uint8)
+    for ang in [0.0, 9.462, 90.0, -37.3, 180.0, 123.456]:
+        for border in (0, 255):
+            m = cv2.getRotationMatrix2D((126.0, 94.5), ang, 1)
+            m[0, 2] += 13.5
+            m[1, 2] -= 7.25
+            want = cv2.warpAffine(img, m, (280, 220), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=border)
+            got = M.warp_affine(img, m, (280, 220), border)
+            assert np.array_equal(got, want), (ang, border)
+
+
+def test_rotation_matrix_model():
+    for ang in [0, 33.3, -120.15, 270]:
+        a = cv2.getRotationMatrix2D((100.5, 50.25), ang, 1)
+        assert np.array_equal(M.rotation_matrix(100.5, 50.25, ang), a)
+
+
+def test_mean_stddev_model():
+    rng = np.random.default_rng(3)
+    for shape in [(521, 762), (9, 12), (54, 54), (131, 191)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        mean, sdv = cv2.meanStdDev(img)
+        m2, s2 = M.mean_stddev(img)
+        assert mean[0, 0] == m2 and sdv[0, 0] == s2
+
+
+def test_rectangle_paint_model():
+    for rect in [(3, 4, 5, 6), (-3, -2, 6, 5), (18, 17, 10, 10), (5, 5, 0, 3), (5, 5, -2, 3), (0, 0, 1, 1)]:
+        a = np.zeros((20, 22), np.float32)
+        cv2.rectangle(a, rect, -1.0, cv2.FILLED)
+        b = np.zeros((20, 22), np.float32)
+        M.paint(b, *rect)
+        assert np.array_equal(a, b), rect
+
+
+def test_minmaxloc_first_in_scan_order():
+    a = np.zeros((5, 7), np.float32)
+    a[3, 2] = a[1, 6] = a[1, 4] = 2.0
+    _, mx, _, loc = cv2.minMaxLoc(a)
+    assert mx == 2.0 and loc == (4, 1)
+    assert O._min_max_loc(a) == (2.0, (4, 1))
+
+
+def test_top_numerator_exact_vs_cv(golden_cases):
+    """cv::matchTemplate (DFT float) vs the exact integer numerator: identical candidate list."""
+    c = golden_cases["src8"]
+    src, tpl = get_image(c["src"]), get_image(c["tpl"])
+    outs = []
+    for mode in ("exact", "cv"):
+        m = configure(O.OracleMatcher(), c["params"])
+        m.top_numerator = mode
+        m.trace = {}
+        m.learn_pattern(tpl)
+        res = m.match(src)
+        outs.append((res, m.trace["cands"]))
+    assert len(outs[0][0]) == len(outs[1][0])
+    assert [(c0[0], c0[2]) for c0 in outs[0][1]] == [(c1[0], c1[2]) for c1 in outs[1][1]]
+    assert_results_match(outs[0][0], outs[1][0])
+
+
+def test_guards_and_edge_cases():
+    m = O.OracleMatcher()
+    assert m.match(np.zeros((10, 10), np.uint8)) == []          # not learned
+    assert not m.learn_pattern(np.zeros((0, 0), np.uint8))
+    tpl = np.full((40, 40), 7, np.uint8)
+    tpl[10:30, 10:30] = 200
+    assert m.learn_pattern(tpl)
+    assert m.match(np.zeros((20, 100), np.uint8)) == []         # template taller than source
+    assert m.match(np.zeros((30, 30), np.uint8)) == []          # template area larger
