@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200 NCC matcher on BASELINE.json's headline configuration.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload = "cfg1"): 4024x3036 u8 source (seeded synthetic stand-in for the missing
+Src7.bmp: blurred noise + Dst7 at three jittered README poses), the real 762x521 Dst7 template,
+TargetNum 3, Score 0.8, ToleranceAngle 180, MinReducedArea 256.  One "step" = one pass of
+TemplateMatcher::match over a batch of `--batch` frames per GPU.
+
+value  : images/sec, whole job, frames resident in HBM when the timed region starts.
+e2e    : same metric through the C ABI with HOST (pinned) frames, H2D + D2H inside the timed region.
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (4024x3036 src, 762x521 tpl, +-180deg)"
+UNIT = "images/s"
+WORKLOADS = {
+    # name: (src_w, src_h, template, params)
+    "cfg1": dict(w=4024, h=3036, tpl="Dst7", max_pos=3, score=0.8, tol=180.0, mra=256, overlap=0.0),
+}
+
+
+# ------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------
+def make_frames(n_distinct: int, seed0: int):
+    import numpy as np
+    from fastest_image_pattern_matching_b200 import synth
+    tpl = synth.load_fixture("Dst7")
+    frames = [synth.cfg1_source(seed=seed0 + i, tpl=tpl, jitter=True) for i in range(n_distinct)]
+    return tpl, np.stack(frames)
+
+
+def configure(m, wl):
+    m.setMaxPositions(wl["max_pos"]); m.setScore(wl["score"]); m.setToleranceAngle(wl["tol"])
+    m.setMinReduceArea(wl["mra"]); m.setMaxOverlap(wl["overlap"])
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (Python/cv2 restatement + SSE2 numerator = the reference's CPU path)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n_images, wl = args
+    import cv2
+    import numpy as np  # noqa: F401
+    cv2.setNumThreads(1)
+    from oracle.oracle import OracleMatcher
+    from fastest_image_pattern_matching_b200 import synth
+    tpl = synth.load_fixture("Dst7")
+    m = OracleMatcher()
+    m.max_pos, m.score, m.tolerance_angle, m.min_reduce_area, m.max_overlap = wl["max_pos"], wl["score"], wl["tol"], wl["mra"], wl["overlap"]
+    m.learn_pattern(tpl)
+    frames = [synth.cfg1_source(seed=seed + i, tpl=tpl, jitter=True) for i in range(min(n_images, 2))]
+    m.match(frames[0])                                  # warm-up (page-in, cv2 init)
+    t0 = time.perf_counter()
+    found = 0
+    for i in range(n_images):
+        found += len(m.match(frames[i % len(frames)]))
+    return time.perf_counter() - t0, found
+
+
+def cpu_throughput(wl, workers: int, images_per_worker: int):
+    """images/sec of the CPU oracle with `workers` processes (one single-threaded matcher each)."""
+    import multiprocessing as mp
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "libncc_rowdot.so"], check=True, capture_output=True)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(100 + 10 * r, images_per_worker, wl) for r in range(workers)])
+        wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    total = workers * images_per_worker
+    return total / busy, busy, wall, sum(r[1] for r in res)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images per worker for the CPU baseline (0 = auto)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ---------------- reference arm: the CPU implementation on all host cores -----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = host_cores()
+        per_worker = max(1, args.cpu_images or 2)
+        vals, times = [], []
+        for _ in range(max(args.warmup, 0)):
+            pass                                       # each worker warms itself up (one untimed match)
+        for _ in range(max(args.steps, 1)):
+            v, busy, wall, found = cpu_throughput(wl, cores, per_worker)
+            vals.append(v); times.append(busy)
+            if sum(times) > 150:                       # bounded: the whole run must end within minutes
+                break
+        value = (cores * per_worker * len(vals)) / sum(times)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "src": "%dx%d" % (wl["w"], wl["h"]), "tpl": "762x521 (Dst7.bmp)",
+                       "target_num": wl["max_pos"], "score": wl["score"], "tolerance_angle": wl["tol"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d processes x %d frames; Python/cv2 4.13 oracle + SSE2 IM_Conv_SIMD restatement, "
+                                       "one single-threaded matcher per core (the reference full match() needs OpenCV C++/Qt, unbuildable here)"
+                                       % (len(vals), cores, per_worker)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- CPU baseline first (before CUDA is initialised in this process) ----------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        workers = cores
+        per_worker = args.cpu_images or 4
+        v, busy, wall, found = cpu_throughput(wl, workers, per_worker)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+                        "sample": "%d processes x %d cfg1 frames (%.1f s); Python/cv2 4.13 oracle + SSE2 IM_Conv_SIMD restatement, "
+                                  "single-threaded per process like the reference's own loops" % (workers, per_worker, busy),
+                        "single_core_ms_per_match": 1000.0 * busy / per_worker}
+
+    import numpy as np
+    import torch
+    import ctypes as C
+    from fastest_image_pattern_matching_b200 import TemplateMatcher, build
+    from fastest_image_pattern_matching_b200 import _lib as L
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+    torch.cuda.set_device(local_rank)
+    if rank == 0:
+        build()
+    if dist:
+        dist.barrier()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    # distinct frames: B frames per step; 12.2 MB each -> one step reads 195 MB (> 126 MB L2), and the
+    # steps alternate between two such sets so nothing survives in L2 from one step to the next
+    tpl, frames_np = make_frames(min(B, 8), seed0=1000 * (rank + 1))
+    reps = (B + frames_np.shape[0] - 1) // frames_np.shape[0]
+    H, Wd = frames_np.shape[1:]
+    pitch = (Wd + 127) // 128 * 128
+    dev_sets = []
+    for s in range(2):
+        d = torch.empty((B, H, pitch), dtype=torch.uint8, device="cuda")
+        src = torch.from_numpy(np.roll(frames_np, s, axis=0))
+        for b in range(B):
+            d[b, :, :Wd].copy_(src[b % src.shape[0]])
+        dev_sets.append(d)
+    host_sets = []
+    for s in range(2):
+        hbuf = torch.empty((B, H, Wd), dtype=torch.uint8).pin_memory()
+        src = torch.from_numpy(np.roll(frames_np, s, axis=0))
+        for b in range(B):
+            hbuf[b].copy_(src[b % src.shape[0]])
+        host_sets.append(hbuf)
+    del reps
+
+    m = TemplateMatcher(local_rank, result_capacity=16)
+    configure(m, wl)
+    assert m.learnPattern(tpl)
+    cap = m.result_capacity
+    res = (L.fpm_result * (cap * B))()
+    counts = (C.c_int * B)()
+
+    def step_device(i):
+        d = dev_sets[i & 1]
+        m.matchBatchRaw(d.data_ptr(), B, Wd, H, pitch, H * pitch, True, res, counts)
+
+    def step_host(i):
+        hb = host_sets[i & 1]
+        m.matchBatchRaw(hb.data_ptr(), B, Wd, H, Wd, H * Wd, False, res, counts)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn):
+        for i in range(W):
+            step_fn(i)
+        barrier()
+        l0 = m.launchCount()
+        m.timerRecord(0)
+        t0 = time.perf_counter()
+        for i in range(K):
+            step_fn(i)
+        m.timerRecord(1)
+        ms = m.timerElapsedMs()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        launches = m.launchCount() - l0
+        barrier()
+        ms = max(ms, 0.0)
+        if dist:
+            t = torch.tensor([ms, wall_ms, float(launches)], device="cuda", dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return float(tmax[0]), float(tmax[1]), int(tsum[2])
+        return ms, wall_ms, launches
+
+    # sanity: every frame must yield the 3 pasted targets
+    step_device(0)
+    found = [counts[b] for b in range(B)]
+    ok_found = all(f == 3 for f in found)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, dev_wall_ms, launches = timed(step_device)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, e2e_wall_ms, _ = timed(step_host)
+
+    # per-kernel device time over the same K steps, CUDA events around every launch on the launch stream
+    m.setProfile(True)
+    m.profileReset()
+    for i in range(K):
+        step_device(i)
+    prof = m.profile()
+    m.setProfile(False)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    total_images = world * B * K
+    value = total_images / (dev_ms / 1000.0)
+    e2e_value = total_images / (e2e_ms / 1000.0)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    bf16_sust = peaks.get("bf16_tflops_sustained", 1400.0)
+
+    kern = {}
+    step_ms = sum(v[0] for v in prof.values()) / max(K, 1)
+    for name, (ms, n, work) in prof.items():
+        if n == 0:
+            continue
+        kern[name] = {"ms_per_step": ms / K, "launches_per_step": n / K, "avg_launch_us": 1000.0 * ms / n,
+                      "share": (ms / K) / step_ms if step_ms > 0 else None, "work_per_launch": work / n}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roofline = None
+    if dom:
+        kd = kern[dom]
+        per_launch_s = kd["avg_launch_us"] * 1e-6
+        if "corr" in dom or "top_score" in dom:
+            # integer MACs on the CUDA-core dp4a pipe; reported against the int8 tensor peak the
+            # north_star names (not measured on this pool: 2 x measured sustained bf16 dense)
+            peak = 2.0 * bf16_sust
+            ach = 2.0 * kd["work_per_launch"] / per_launch_s / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": "2 x bf16_tflops_sustained (int8 dense not in MEASURED_PEAKS.json)",
+                        "note": "u8xu8->s32 MACs via dp4a; algorithmic ops = 2*49*w*h per eval"}
+        else:
+            ach = kd["work_per_launch"] / per_launch_s / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": None, "peak_source": hbm_src}
+    # the HBM-bound stage the north_star names first (pyramid): always reported beside the dominant kernel
+    hbm_kernels = {}
+    for name in ("fpm_pyrdown_kernel", "fpm_warp_kernel(roi)"):
+        if name in kern:
+            kd = kern[name]
+            ach = kd["work_per_launch"] / (kd["avg_launch_us"] * 1e-6) / 1e9
+            hbm_kernels[name] = {"achieved_GBps": ach, "frac_of_hbm_peak": ach / hbm_peak}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "p50_ms_per_match_batch1": None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "src": "%dx%d" % (Wd, H), "tpl": "762x521 (Dst7.bmp)", "target_num": wl["max_pos"],
+                   "score": wl["score"], "tolerance_angle": wl["tol"], "min_reduce_area": wl["mra"], "batch_per_gpu": B,
+                   "global_batch": world * B, "sharding": "frames over ranks, no data-path collective",
+                   "l2": "step input %.0f MB > 126 MB L2; two alternating frame sets" % (B * H * Wd / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * Wd, "d2h_bytes_per_step": B * cap * 96 + B * 4,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kern,
+        "hbm_kernels": hbm_kernels,
+        "cpu_baseline": cpu_baseline,
+        "targets_found_per_frame_ok": ok_found,
+        "wall_ms_per_step": dev_wall_ms / K,
+    }
+    # p50 latency of a single-frame match (batch 1, device resident)
+    lat = []
+    d1 = dev_sets[0]
+    for i in range(3 + 20):
+        t0 = time.perf_counter()
+        m.matchBatchRaw(d1[i % B].data_ptr(), 1, Wd, H, pitch, H * pitch, True, res, counts)
+        lat.append((time.perf_counter() - t0) * 1000.0)
+    line["p50_ms_per_match_batch1"] = statistics.median(lat[3:])
+    print(json.dumps(line))
+    m.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

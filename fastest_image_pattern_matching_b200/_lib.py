@@ -19,7 +19,7 @@ class fpm_result(C.Structure):
 
 
 PARAM_MAX_POSITIONS, PARAM_MAX_OVERLAP, PARAM_SCORE, PARAM_TOLERANCE_ANGLE, PARAM_MIN_REDUCE_AREA, \
-    PARAM_USE_SIMD, PARAM_SUBPIXEL, PARAM_TRACE, PARAM_WORKSPACE_MB = range(9)
+    PARAM_USE_SIMD, PARAM_SUBPIXEL, PARAM_TRACE, PARAM_WORKSPACE_MB, PARAM_PROFILE = range(10)
 
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 _pi, _pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -42,6 +42,12 @@ SIGNATURES = {
     "fpm_set_user_rect": (None, [_vp, _i, _i, _i, _i]),
     "fpm_get_user_rect": (_i, [_vp, _pi, _pi, _pi, _pi]),
     "fpm_launch_count": (C.c_longlong, [_vp]),
+    "fpm_timer_record": (_i, [_vp, _i]),
+    "fpm_timer_elapsed_ms": (_d, [_vp]),
+    "fpm_profile_num_kernels": (_i, []),
+    "fpm_profile_name": (C.c_char_p, [_i]),
+    "fpm_profile_get": (_i, [_vp, _i, _pd, C.POINTER(C.c_longlong), _pd]),
+    "fpm_profile_reset": (None, [_vp]),
     "fpm_tpl_levels": (_i, [_vp]),
     "fpm_tpl_level_info": (_i, [_vp, _i, _pi, _pi, _pd, _pd, _pd, _pi]),
     "fpm_tpl_level_pixels": (_i, [_vp, _i, _vp]),

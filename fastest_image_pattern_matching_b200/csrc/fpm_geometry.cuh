@@ -94,14 +94,14 @@ FPM_HD int fpm_rrect_intersection_shifted(const FpmRRect& rect1, const FpmRRect&
             float vx1 = vec1x[i], vy1 = vec1y[i];
             float vx2 = vec2x[j], vy2 = vec2y[j];
             float normalizationScale = fminf(vx1 * vx1 + vy1 * vy1, vx2 * vx2 + vy2 * vy2);
-            if (normalizationScale < 1e-12f) continue;
-            vx1 /= normalizationScale; vy1 /= normalizationScale;
-            vx2 /= normalizationScale; vy2 /= normalizationScale;
-            float det = vx2 * vy1 - vx1 * vy2;
+            normalizationScale = (normalizationScale < 1e-12f) ? 1.f : 1.f / normalizationScale;
+            vx1 *= normalizationScale; vy1 *= normalizationScale;
+            vx2 *= normalizationScale; vy2 *= normalizationScale;
+            const float det = vx2 * vy1 - vx1 * vy2;
             if (fabsf(det) < 1e-12f) continue;
-            float detInvScaled = 1.f / det;
-            float t1 = ((vx2 * y21 - vy2 * x21) * detInvScaled) / normalizationScale;
-            float t2 = ((vx1 * y21 - vy1 * x21) * detInvScaled) / normalizationScale;
+            const float detInvScaled = normalizationScale / det;
+            const float t1 = (vx2 * y21 - vy2 * x21) * detInvScaled;
+            const float t2 = (vx1 * y21 - vy1 * x21) * detInvScaled;
             if (isinf(t1) || isinf(t2) || isnan(t1) || isnan(t2)) continue;
             if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
                 ix[n] = p1x[i] + vec1x[i] * t1;
@@ -117,8 +117,9 @@ FPM_HD int fpm_rrect_intersection_shifted(const FpmRRect& rect1, const FpmRRect&
         float x = p1x[i], y = p1y[i];
         for (int j = 0; j < 4; j++) {
             float normalizationScale = vec2x[j] * vec2x[j] + vec2y[j] * vec2y[j];
-            float A = -vec2y[j] / normalizationScale;
-            float B = vec2x[j] / normalizationScale;
+            normalizationScale = (normalizationScale < 1e-12f) ? 1.f : 1.f / normalizationScale;
+            float A = -vec2y[j] * normalizationScale;
+            float B = vec2x[j] * normalizationScale;
             float C = -(A * p2x[j] + B * p2y[j]);
             float s = A * x + B * y + C;
             if (s >= 0) posSign++; else negSign++;
@@ -131,8 +132,9 @@ FPM_HD int fpm_rrect_intersection_shifted(const FpmRRect& rect1, const FpmRRect&
         float x = p2x[i], y = p2y[i];
         for (int j = 0; j < 4; j++) {
             float normalizationScale = vec1x[j] * vec1x[j] + vec1y[j] * vec1y[j];
-            float A = -vec1y[j] / normalizationScale;
-            float B = vec1x[j] / normalizationScale;
+            normalizationScale = (normalizationScale < 1e-12f) ? 1.f : 1.f / normalizationScale;
+            float A = -vec1y[j] * normalizationScale;
+            float B = vec1x[j] * normalizationScale;
             float C = -(A * p1x[j] + B * p1y[j]);
             float s = A * x + B * y + C;
             if (s >= 0) posSign++; else negSign++;

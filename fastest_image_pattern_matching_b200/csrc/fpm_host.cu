@@ -155,6 +155,14 @@ struct fpm_handle {
     std::string err;
     double last_ms = 0;
     long long launches = 0;
+    // per-kernel profiling (CUDA events on the launch stream)
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    struct ProfRec { int kid; cudaEvent_t a, b; double work; };
+    std::vector<ProfRec> prof_pending;
+    double prof_ms[16] = {0}, prof_work[16] = {0};
+    long long prof_launches[16] = {0};
+    cudaEvent_t prof_cur = nullptr;
     // trace
     std::vector<double> tr_cands;                 // n*4
     std::vector<std::vector<double>> tr_evals;    // per level, n*5
@@ -181,6 +189,56 @@ namespace {
         }                                                                                \
     } while (0)
 
+enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"fpm_pyrdown_kernel", "fpm_warp_kernel(top)", "fpm_top_score_kernel", "fpm_top_peaks_kernel",
+                                           "fpm_collect_sort_kernel", "fpm_refine_prep_kernel", "fpm_warp_kernel(roi)",
+                                           "fpm_corr_rows_kernel", "fpm_refine_finalize_kernel", "fpm_final_kernel"};
+
+cudaEvent_t prof_event(fpm_handle* h)
+{
+    if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+inline void prof_begin(fpm_handle* h)
+{
+    if (!h->profile) return;
+    h->prof_cur = prof_event(h);
+    cudaEventRecord(h->prof_cur, h->stream);
+}
+
+inline void prof_end(fpm_handle* h, int kid, double work)
+{
+    if (!h->profile) return;
+    cudaEvent_t b = prof_event(h);
+    cudaEventRecord(b, h->stream);
+    h->prof_pending.push_back({kid, h->prof_cur, b, work});
+}
+
+void prof_collect(fpm_handle* h)
+{
+    if (h->prof_pending.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto& r : h->prof_pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        h->prof_ms[r.kid] += ms; h->prof_work[r.kid] += r.work; h->prof_launches[r.kid]++;
+        h->ev_pool.push_back(r.a); h->ev_pool.push_back(r.b);
+    }
+    h->prof_pending.clear();
+}
+
+// launch wrapper: KL(kernel id, algorithmic work of this launch, <<<launch>>> statement)
+#define KL(kid, work, ...)                 \
+    do {                                   \
+        prof_begin(h);                     \
+        __VA_ARGS__;                       \
+        prof_end(h, kid, (double)(work));  \
+        CKL();                             \
+    } while (0)
+
 FpmTplLevel tpl_level_dev(const fpm_handle* h, int l)
 {
     const TplLevelHost& t = h->tpl[l];
@@ -195,8 +253,9 @@ int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& dst, int 
 {
     int vec_ok = ((reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0) && (src.pitch % 4 == 0) && (src.img_stride % 4 == 0);
     dim3 grid((dst.w + PD_TW - 1) / PD_TW, (dst.h + PD_TH - 1) / PD_TH, batch);
-    fpm_pyrdown_kernel<<<grid, PD_THREADS, 0, h->stream>>>(src, dst, vec_ok);
-    CKL();
+    // algorithmic bytes: every source pixel read once, every destination pixel written once
+    KL(K_PYRDOWN, (double)batch * ((double)src.w * src.h + (double)dst.w * dst.h),
+       fpm_pyrdown_kernel<<<grid, PD_THREADS, 0, h->stream>>>(src, dst, vec_ok));
     return FPM_OK;
 }
 
@@ -365,9 +424,9 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
     CK(h->d_pickcnt.ensure((size_t)njobs * sizeof(int)));
     {
         dim3 grid((p.maxH + WA_ROWS - 1) / WA_ROWS, njobs);
-        fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->levels[top], h->d_rot.as<uint8_t>(),
-                                                            rpitch, rot_stride, h->border);
-        CKL();
+        KL(K_WARP_TOP, 2.0 * njobs * (double)p.maxW * p.maxH,
+           fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->levels[top],
+                                                               h->d_rot.as<uint8_t>(), rpitch, rot_stride, h->border));
     }
     {
         size_t smem = (size_t)t.w * t.h + (size_t)(TS_TILE + t.w - 1) * (TS_TILE + t.h - 1);
@@ -376,10 +435,10 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
             CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((maxRW + TS_TILE - 1) / TS_TILE, (maxRH + TS_TILE - 1) / TS_TILE, njobs);
         dim3 block(TS_TILE, TS_TILE);
-        fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->d_rot.as<uint8_t>(), rpitch,
-                                                               rot_stride, tpl_level_dev(h, top), h->d_score.as<float>(), spitch,
-                                                               score_stride);
-        CKL();
+        KL(K_TOP_SCORE, (double)njobs * maxRW * maxRH * t.w * t.h,      // MACs
+           fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->d_rot.as<uint8_t>(), rpitch,
+                                                                  rot_stride, tpl_level_dev(h, top), h->d_score.as<float>(),
+                                                                  spitch, score_stride));
     }
     {
         // bCalMaxByBlock, src/TemplateMatcher.cpp:158-159
@@ -396,11 +455,11 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         CK(h->d_blkl.ensure((size_t)njobs * blk_stride * sizeof(int)));
         double thresh = h->score;
         for (int l = 0; l < top; l++) thresh *= 0.9;          // vecLayerScore, :153-156
-        fpm_top_peaks_kernel<<<njobs, PK_THREADS, 0, h->stream>>>(
-            h->d_jobs_top.as<FpmWarpJob>(), h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
-            h->d_blkv.as<float>(), h->d_blkl.as<int>(), blk_stride, thresh, h->max_overlap, max_picks,
-            h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>());
-        CKL();
+        KL(K_TOP_PEAKS, 4.0 * njobs * maxRW * maxRH,
+           fpm_top_peaks_kernel<<<njobs, PK_THREADS, 0, h->stream>>>(
+               h->d_jobs_top.as<FpmWarpJob>(), h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
+               h->d_blkv.as<float>(), h->d_blkl.as<int>(), blk_stride, thresh, h->max_overlap, max_picks,
+               h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>()));
     }
     return FPM_OK;
 }
@@ -465,24 +524,26 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         for (int c0 = 0; c0 < n; c0 += wave_cands) {
             const int nc = std::min(wave_cands, n - c0);
             const int ne = nc * n_ang;
-            fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
-                                                                          h->d_jobs_ref.as<FpmWarpJob>());
-            CKL();
+            KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
+               fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
+                                                                             h->d_jobs_ref.as<FpmWarpJob>()));
             dim3 wgrid((t.h + FPM_ROI_PAD + WA_ROWS - 1) / WA_ROWS, ne);
-            fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), L, h->d_roi.as<uint8_t>(), rpitch,
-                                                                 roi_stride, 0);
-            CKL();
+            // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
+            KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
+               fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), L, h->d_roi.as<uint8_t>(),
+                                                                    rpitch, roi_stride, 0));
             dim3 cgrid((t.h + rc - 1) / rc, ne);
-            fpm_corr_rows_kernel<<<cgrid, CR_THREADS, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, rc,
-                                                                         h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(),
-                                                                         h->d_rowQ.as<int32_t>());
-            CKL();
-            fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
-                cands + c0, n_ang, step, h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w, L.h,
-                layer_score[layer], h->use_simd, layer == 0 ? 1 : 0, h->subpixel, h->d_cand[cur ^ 1].as<FpmCand>(),
-                counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
-                h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr);
-            CKL();
+            // algorithmic MACs: 49 * w * h per eval
+            KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
+               fpm_corr_rows_kernel<<<cgrid, CR_THREADS, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, rc,
+                                                                            h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(),
+                                                                            h->d_rowQ.as<int32_t>()));
+            KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
+               fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
+                   cands + c0, n_ang, step, h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
+                   L.h, layer_score[layer], h->use_simd, layer == 0 ? 1 : 0, h->subpixel, h->d_cand[cur ^ 1].as<FpmCand>(),
+                   counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
+                   h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr));
         }
         CK(cudaMemcpyAsync(hc, counters, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -522,12 +583,12 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
     CK(h->d_rescnt.ensure((size_t)batch * sizeof(int)));
     CK(h->h_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev) + (size_t)batch * sizeof(int)));
     (void)n_refined;
-    fpm_final_kernel<<<batch, FN_THREADS, 0, h->stream>>>(h->d_refined.as<FpmRefined>(), counters + CNT_REFINED, h->score,
-                                                          h->max_overlap, h->tpl[0].w, h->tpl[0].h,
-                                                          h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
-                                                          h->d_del.as<int>(), h->d_idmap.as<int>(), h->d_results.as<FpmResultDev>(),
-                                                          rcap, h->d_rescnt.as<int>());
-    CKL();
+    KL(K_FINAL, 0,
+       fpm_final_kernel<<<batch, FN_THREADS, 0, h->stream>>>(h->d_refined.as<FpmRefined>(), counters + CNT_REFINED, h->score,
+                                                             h->max_overlap, h->tpl[0].w, h->tpl[0].h,
+                                                             h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
+                                                             h->d_del.as<int>(), h->d_idmap.as<int>(),
+                                                             h->d_results.as<FpmResultDev>(), rcap, h->d_rescnt.as<int>()));
     FpmResultDev* hr = h->h_results.as<FpmResultDev>();
     int* hn = reinterpret_cast<int*>(hr + (size_t)batch * rcap);
     CK(cudaMemcpyAsync(hn, h->d_rescnt.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -598,12 +659,13 @@ int match_device(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt,
         size_t smem = use_smem ? (size_t)n_pad * 8 : 0;
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(fpm_collect_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fpm_collect_sort_kernel<<<batch, CS_THREADS, smem, h->stream>>>(
-            h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), p.n_ang, max_picks, h->d_angles.as<double>(), h->d_ftx.as<float>(),
-            h->d_fty.as<float>(), (L.w - 1) / 2.0f, (L.h - 1) / 2.0f, h->d_keys.as<unsigned long long>(), n_pad, use_smem,
-            h->d_off.as<int>(), h->d_cand[0].as<FpmCand>(), h->d_counters.as<int>() + CNT_FLAT,
-            h->trace ? h->d_toppt.as<float>() : nullptr, cand_stride, h->d_candcnt.as<int>(), 0);
-        CKL();
+        KL(K_COLLECT, 0,
+           fpm_collect_sort_kernel<<<batch, CS_THREADS, smem, h->stream>>>(
+               h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), p.n_ang, max_picks, h->d_angles.as<double>(),
+               h->d_ftx.as<float>(), h->d_fty.as<float>(), (L.w - 1) / 2.0f, (L.h - 1) / 2.0f,
+               h->d_keys.as<unsigned long long>(), n_pad, use_smem, h->d_off.as<int>(), h->d_cand[0].as<FpmCand>(),
+               h->d_counters.as<int>() + CNT_FLAT, h->trace ? h->d_toppt.as<float>() : nullptr, cand_stride,
+               h->d_candcnt.as<int>(), 0));
     }
     int* hc = h->h_counts.as<int>();
     CK(cudaMemcpyAsync(hc, h->d_counters.p, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -671,6 +733,8 @@ void fpm_destroy(fpm_handle* h)
     h->h_counts.release(); h->h_results.release(); h->h_stage.release();
     for (int i = 0; i < 2; i++) { cudaEventDestroy(h->ev_copy[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
+    prof_collect(h);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -691,6 +755,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_SUBPIXEL: h->subpixel = v != 0; break;
     case FPM_PARAM_TRACE: h->trace = v != 0; break;
     case FPM_PARAM_WORKSPACE_MB: h->workspace_mb = v; break;
+    case FPM_PARAM_PROFILE: prof_collect(h); h->profile = v != 0; break;
     default: h->err = "unknown parameter"; return FPM_ERR_INVALID;
     }
     return FPM_OK;
@@ -709,6 +774,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_SUBPIXEL: return h->subpixel;
     case FPM_PARAM_TRACE: return h->trace;
     case FPM_PARAM_WORKSPACE_MB: return h->workspace_mb;
+    case FPM_PARAM_PROFILE: return h->profile;
     default: return 0;
     }
 }
@@ -744,6 +810,7 @@ int fpm_match_batch_device(fpm_handle* h, const uint8_t* d_src, int batch, int w
     CK(cudaSetDevice(h->device));
     auto t0 = std::chrono::high_resolution_clock::now();
     int rc = match_device(h, d_src, batch, width, height, stride, frame_stride, out, cap, n);
+    prof_collect(h);
     auto t1 = std::chrono::high_resolution_clock::now();
     h->last_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     return rc;
@@ -789,6 +856,7 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
         rc = match_device(h, h->d_src.as<uint8_t>() + (size_t)(k & 1) * img * chunk, nb, width, height, pitch, img,
                           out + (size_t)b0 * cap, cap, n + b0);
         CK(cudaEventRecord(h->ev_done[k & 1], h->stream));
+        prof_collect(h);
     }
     cudaStreamSynchronize(h->copy_stream);
     auto t1 = std::chrono::high_resolution_clock::now();
@@ -1146,6 +1214,44 @@ int fpm_dbg_rrect_from3(const float pts[6], float out[5])
     FpmRRect r = fpm_rrect_from3(pts[0], pts[1], pts[2], pts[3], pts[4], pts[5]);
     out[0] = r.cx; out[1] = r.cy; out[2] = r.w; out[3] = r.h; out[4] = r.angle;
     return 0;
+}
+
+// ---- timing / profiling -----------------------------------------------------------------
+int fpm_timer_record(fpm_handle* h, int which)
+{
+    if (!h || which < 0 || which > 1) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(which ? h->ev_t1 : h->ev_t0, h->stream));
+    return FPM_OK;
+}
+
+double fpm_timer_elapsed_ms(fpm_handle* h)
+{
+    if (!h) return -1;
+    float ms = -1;
+    if (cudaEventSynchronize(h->ev_t1) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) != cudaSuccess) return -1;
+    return ms;
+}
+
+int fpm_profile_num_kernels(void) { return K_COUNT; }
+const char* fpm_profile_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : ""; }
+
+int fpm_profile_get(fpm_handle* h, int kid, double* ms, long long* launches, double* work)
+{
+    if (!h || kid < 0 || kid >= K_COUNT) return FPM_ERR_INVALID;
+    prof_collect(h);
+    if (ms) *ms = h->prof_ms[kid];
+    if (launches) *launches = h->prof_launches[kid];
+    if (work) *work = h->prof_work[kid];
+    return FPM_OK;
+}
+
+void fpm_profile_reset(fpm_handle* h)
+{
+    if (!h) return;
+    prof_collect(h);
+    for (int i = 0; i < 16; i++) { h->prof_ms[i] = 0; h->prof_work[i] = 0; h->prof_launches[i] = 0; }
 }
 
 // ---- trace access -----------------------------------------------------------------------

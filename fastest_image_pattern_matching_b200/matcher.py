@@ -155,6 +155,21 @@ class TemplateMatcher:
         self._check(fn(self._h, ptr, B, W, H, stride, frame_stride, res, cap, counts))
         return res, counts
 
+    # ---- timing / profiling (bench.py) ----
+    def setProfile(self, v: bool): self._set(L.PARAM_PROFILE, 1 if v else 0)
+    def timerRecord(self, which: int): self._check(self._lib.fpm_timer_record(self._h, which))
+    def timerElapsedMs(self) -> float: return self._lib.fpm_timer_elapsed_ms(self._h)
+    def profileReset(self): self._lib.fpm_profile_reset(self._h)
+
+    def profile(self):
+        """{kernel name: (device ms, launches, algorithmic work)} accumulated since profileReset()."""
+        out = {}
+        for k in range(self._lib.fpm_profile_num_kernels()):
+            ms, n, w = C.c_double(), C.c_longlong(), C.c_double()
+            self._check(self._lib.fpm_profile_get(self._h, k, C.byref(ms), C.byref(n), C.byref(w)))
+            out[self._lib.fpm_profile_name(k).decode()] = (ms.value, n.value, w.value)
+        return out
+
     # ---- learned-template introspection ----
     def templateLevels(self):
         out = []

@@ -44,6 +44,7 @@ enum fpm_param {
     FPM_PARAM_SUBPIXEL = 6,        /* setSubPixelEstimation,       default 0    */
     FPM_PARAM_TRACE = 7,           /* keep per-stage records for fpm_trace_*   (tests) */
     FPM_PARAM_WORKSPACE_MB = 8,    /* refinement workspace budget per wave, default 4096 */
+    FPM_PARAM_PROFILE = 9,         /* bracket every kernel launch with CUDA events (bench.py roofline) */
     FPM_PARAM_COUNT_
 };
 
@@ -96,6 +97,17 @@ int fpm_get_user_rect(const fpm_handle* h, int* x, int* y, int* w, int* hgt); /*
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 long long fpm_launch_count(const fpm_handle* h);
+
+/* CUDA events on the handle's stream: record(0) before / record(1) after a region, then elapsed. */
+int fpm_timer_record(fpm_handle* h, int which);
+double fpm_timer_elapsed_ms(fpm_handle* h);
+
+/* Per-kernel device time (CUDA events around every launch while FPM_PARAM_PROFILE = 1), launch
+ * count and algorithmic work (bytes, or MACs for the correlation kernels) accumulated since reset. */
+int fpm_profile_num_kernels(void);
+const char* fpm_profile_name(int kernel);
+int fpm_profile_get(fpm_handle* h, int kernel, double* ms, long long* launches, double* work);
+void fpm_profile_reset(fpm_handle* h);
 
 /* ---- learned-template introspection (s_TemplData, DataStructures.h:16-55) ---- */
 int fpm_tpl_levels(const fpm_handle* h);                 /* pyramid size (top layer + 1) */

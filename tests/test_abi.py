@@ -102,6 +102,55 @@ def test_rotated_rect_geometry_matches_cv2(fpm_built):
     assert bad_type == 0 and bad_dec == 0
 
 
+def test_rotated_rect_geometry_degenerate_contacts(fpm_built):
+    """axis-aligned / corner- and edge-touching / identical / contained rectangles (all-ties score maps
+    produce exactly these): the delete decision must agree with cv2 for every pair."""
+    import cv2
+    from fastest_image_pattern_matching_b200.matcher import rrect_from3_host, rrect_overlap_host
+    from oracle.oracle import MatchParameter, OracleMatcher
+    f32 = np.float32
+
+    def rect_of(pt, angle, w, h):
+        lt, rt, lb, rb = OracleMatcher._corners(MatchParameter(pt=pt, angle=angle), w, h)
+        return rrect_from3_host(lt, rt, rb)
+
+    def decisions(r1, r2):
+        t1 = ((r1[0], r1[1]), (r1[2], r1[3]), r1[4])
+        t2 = ((r2[0], r2[1]), (r2[2], r2[3]), r2[4])
+        typ, inter = cv2.rotatedRectangleIntersection(t1, t2)
+        out = []
+        for mo in (0.0, 0.3, 0.8):
+            dec, mt, _ = rrect_overlap_host(r1, r2, mo)
+            if typ == 0:
+                od = 0
+            elif typ == 2:
+                od = 1
+            elif inter is None or len(inter) < 3:
+                od = 0
+            else:
+                pts = OracleMatcher._sort_pt_with_center([(f32(p[0][0]), f32(p[0][1])) for p in inter])
+                area = cv2.contourArea(np.array(pts, f32).reshape(-1, 1, 2))
+                od = 1 if area / float(f32(r1[2]) * f32(r1[3])) > mo else 0
+            out.append(od == dec)
+        return all(out)
+
+    w, h = 24, 20
+    angles = [0.0, 90.0, 180.0, -90.0, 270.0, 45.0, 0.5, -180.0, 30.0]
+    bad = 0
+    for a1 in angles:
+        for a2 in angles:
+            for dx in [-48, -24, -12, 0, 12, 24, 48, 23, 25, 1, 0.5]:
+                for dy in [-40, -20, -10, 0, 10, 20, 40, 19, 21, 1]:
+                    bad += not decisions(rect_of((50.0, 60.0), a1, w, h), rect_of((50.0 + dx, 60.0 + dy), a2, w, h))
+    for s in [0.5, 0.9, 1.0, 1.1, 2.0]:
+        for a in angles:
+            r1 = rect_of((100.0, 100.0), a, 100, 80)
+            r2 = (r1[0], r1[1], r1[2] * s, r1[3] * s, r1[4])
+            bad += not decisions(r1, r2)
+            bad += not decisions(r2, r1)
+    assert bad == 0
+
+
 def test_synthetic_generators_are_deterministic(golden_cases):
     import hashlib
     from fastest_image_pattern_matching_b200 import synth
