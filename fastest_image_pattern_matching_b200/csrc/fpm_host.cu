@@ -259,6 +259,36 @@ int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& dst, int 
     return FPM_OK;
 }
 
+// launch geometry of fpm_corr_rows_kernel for a template level
+struct CorrCfg { int rb, evals_per_cta, threads; size_t smem; int blocks_y_rows; };
+
+CorrCfg corr_config(int tpl_h)
+{
+    CorrCfg c;
+    const int rh = tpl_h + FPM_ROI_PAD;
+    if (rh > 128) {
+        int nblk = (rh + CR_MAX_THREADS - 1) / CR_MAX_THREADS;
+        c.rb = (int)align_up((size_t)(rh + nblk - 1) / nblk, 32);
+        c.evals_per_cta = 1;
+        c.blocks_y_rows = (rh + c.rb - 1) / c.rb;
+    } else {
+        c.rb = rh;
+        c.evals_per_cta = CR_MAX_THREADS / rh;
+        c.blocks_y_rows = 1;
+    }
+    c.threads = (int)align_up((size_t)c.rb * c.evals_per_cta, 32);
+    const size_t n_srow = (size_t)c.evals_per_cta * c.rb, n_trow = (size_t)c.rb + FPM_ROI_PAD;
+    size_t stage = (n_srow * CR_SP + n_trow * CR_TP) * 4;
+    size_t outb = (size_t)c.evals_per_cta * n_trow * FPM_NCELL * 4;
+    c.smem = std::max(stage, outb);
+    return c;
+}
+
+inline int level_vec_ok(const FpmLevel& L)
+{
+    return ((reinterpret_cast<uintptr_t>(L.ptr) & 3) == 0) && (L.pitch % 4 == 0) && (L.img_stride % 4 == 0);
+}
+
 // ---- learnPattern, src/TemplateMatcher.cpp:45-95 ------------------------------------
 int do_learn(fpm_handle* h)
 {
@@ -423,10 +453,12 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
     CK(h->d_picks.ensure((size_t)njobs * max_picks * sizeof(FpmPick)));
     CK(h->d_pickcnt.ensure((size_t)njobs * sizeof(int)));
     {
-        dim3 grid((p.maxH + WA_ROWS - 1) / WA_ROWS, njobs);
+        const int tiles_x = (rpitch + WA_TW - 1) / WA_TW;
+        dim3 grid(tiles_x * ((p.maxH + WA_TH - 1) / WA_TH), njobs);
         KL(K_WARP_TOP, 2.0 * njobs * (double)p.maxW * p.maxH,
            fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->levels[top],
-                                                               h->d_rot.as<uint8_t>(), rpitch, rot_stride, h->border));
+                                                               h->d_rot.as<uint8_t>(), rpitch, rot_stride, h->border, tiles_x,
+                                                               level_vec_ok(h->levels[top])));
     }
     {
         size_t smem = (size_t)t.w * t.h + (size_t)(TS_TILE + t.w - 1) * (TS_TILE + t.h - 1);
@@ -511,12 +543,9 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             CK(cudaMemsetAsync(h->d_trace.p, 0, (size_t)n * n_ang * sizeof(FpmEvalTrace), h->stream));
         }
         CK(cudaMemsetAsync(counters + CNT_NEXT, 0, sizeof(int), h->stream));
-        // row chunk: enough CTAs to fill the machine, at most 32 template rows per CTA
-        int rc = 32;
-        while (rc > 8 && (long long)wave_evals * ((t.h + rc - 1) / rc) < 2 * 148) rc /= 2;
-        size_t smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * t.pitch;
-        while (smem > 200 * 1024 && rc > 1) { rc /= 2; smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * t.pitch; }
-        if (smem > 200 * 1024) { h->err = "template row too wide for the correlation kernel"; return FPM_ERR_LIMIT; }
+        const CorrCfg cc = corr_config(t.h);
+        const size_t smem = cc.smem;
+        if (smem > 200 * 1024) { h->err = "correlation kernel shared memory limit"; return FPM_ERR_LIMIT; }
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const FpmTplLevel td = tpl_level_dev(h, layer);
@@ -527,17 +556,18 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
                fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
                                                                              h->d_jobs_ref.as<FpmWarpJob>()));
-            dim3 wgrid((t.h + FPM_ROI_PAD + WA_ROWS - 1) / WA_ROWS, ne);
+            const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
+            dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), ne);
             // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
             KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
                fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), L, h->d_roi.as<uint8_t>(),
-                                                                    rpitch, roi_stride, 0));
-            dim3 cgrid((t.h + rc - 1) / rc, ne);
+                                                                    rpitch, roi_stride, 0, wtiles_x, level_vec_ok(L)));
+            dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
             // algorithmic MACs: 49 * w * h per eval
             KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
-               fpm_corr_rows_kernel<<<cgrid, CR_THREADS, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, rc,
-                                                                            h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(),
-                                                                            h->d_rowQ.as<int32_t>()));
+               fpm_corr_rows_kernel<<<cgrid, cc.threads, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, ne,
+                                                                            cc.rb, cc.evals_per_cta, h->d_rowsum.as<int32_t>(),
+                                                                            h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>()));
             KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
                fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
                    cands + c0, n_ang, step, h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
@@ -826,24 +856,36 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
     if (stride < width) { h->err = "stride < width"; return FPM_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
     auto t0 = std::chrono::high_resolution_clock::now();
-    // double-buffered chunks: the H2D copy of chunk k+1 overlaps the matching of chunk k
-    const int pitch = (int)align_up(width, 128);
-    const size_t img = align_up((size_t)pitch * height, 256);
+    // double-buffered chunks: the H2D copy of chunk k+1 overlaps the matching of chunk k.
+    // Contiguous frames whose width is a multiple of 4 keep their host layout on the device so that a
+    // chunk is ONE linear copy (2D pitched copies from pinned memory run well below PCIe speed).
+    const bool linear = (stride == width) && (width % 4 == 0) && (frame_stride == (size_t)stride * height) &&
+                        (frame_stride % 4 == 0);
+    const int pitch = linear ? width : (int)align_up(width, 128);
+    const size_t img = linear ? frame_stride : align_up((size_t)pitch * height, 256);
     int chunk = std::max(1, std::min(batch, (int)std::max<size_t>(1, (size_t)(512ull << 20) / img)));
-    if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
-    CK(h->d_src.ensure(img * chunk * 2));
+    if (batch >= 8) chunk = std::min(chunk, (batch + 3) / 4);
+    else if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
+    const size_t buf_bytes = align_up(img * chunk, 256);
+    CK(h->d_src.ensure(buf_bytes * 2));
     const int nchunks = (batch + chunk - 1) / chunk;
     auto enqueue_copy = [&](int k) -> cudaError_t {
         int b0 = k * chunk, nb = std::min(chunk, batch - b0);
-        uint8_t* dst = h->d_src.as<uint8_t>() + (size_t)(k & 1) * img * chunk;
+        uint8_t* dst = h->d_src.as<uint8_t>() + (size_t)(k & 1) * buf_bytes;
         if (k >= 2) {
             cudaError_t e = cudaStreamWaitEvent(h->copy_stream, h->ev_done[k & 1], 0);
             if (e != cudaSuccess) return e;
         }
-        for (int b = 0; b < nb; b++) {
-            cudaError_t e = cudaMemcpy2DAsync(dst + (size_t)b * img, pitch, src + (size_t)(b0 + b) * frame_stride, stride, width,
-                                              height, cudaMemcpyHostToDevice, h->copy_stream);
+        if (linear) {
+            cudaError_t e = cudaMemcpyAsync(dst, src + (size_t)b0 * frame_stride, (size_t)nb * frame_stride, cudaMemcpyHostToDevice,
+                                            h->copy_stream);
             if (e != cudaSuccess) return e;
+        } else {
+            for (int b = 0; b < nb; b++) {
+                cudaError_t e = cudaMemcpy2DAsync(dst + (size_t)b * img, pitch, src + (size_t)(b0 + b) * frame_stride, stride, width,
+                                                  height, cudaMemcpyHostToDevice, h->copy_stream);
+                if (e != cudaSuccess) return e;
+            }
         }
         return cudaEventRecord(h->ev_copy[k & 1], h->copy_stream);
     };
@@ -853,7 +895,7 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
         if (k + 1 < nchunks) CK(enqueue_copy(k + 1));
         CK(cudaStreamWaitEvent(h->stream, h->ev_copy[k & 1], 0));
         int b0 = k * chunk, nb = std::min(chunk, batch - b0);
-        rc = match_device(h, h->d_src.as<uint8_t>() + (size_t)(k & 1) * img * chunk, nb, width, height, pitch, img,
+        rc = match_device(h, h->d_src.as<uint8_t>() + (size_t)(k & 1) * buf_bytes, nb, width, height, pitch, img,
                           out + (size_t)b0 * cap, cap, n + b0);
         CK(cudaEventRecord(h->ev_done[k & 1], h->stream));
         prof_collect(h);
@@ -1093,8 +1135,10 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     CK(cudaMemcpy2DAsync(h->d_dbg[0].p, sp, src, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_dbg[2].p, &jb, sizeof(jb), cudaMemcpyHostToDevice, h->stream));
     FpmLevel s{h->d_dbg[0].as<uint8_t>(), w, hgt, sp, 0};
-    dim3 grid((dh + WA_ROWS - 1) / WA_ROWS, 1);
-    fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), s, h->d_dbg[1].as<uint8_t>(), dp, 0, border);
+    const int tiles_x = (dp + WA_TW - 1) / WA_TW;
+    dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
+    fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
+                                                        tiles_x, level_vec_ok(s));
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1120,15 +1164,15 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int
     FpmTplLevel td;
     td.ptr = h->d_dbg[1].as<uint8_t>(); td.w = tw; td.h = th; td.pitch = tp;
     td.mean = 0; td.norm = 1; td.inv_area = 1; td.result_equal1 = 0;
-    int rc = 32;
-    size_t smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * tp;
-    while (smem > 200 * 1024 && rc > 1) { rc /= 2; smem = (size_t)(rc + FPM_ROI_PAD) * rpitch + (size_t)rc * tp; }
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const CorrCfg cc = corr_config(th);
+    if (cc.smem > 200 * 1024) { h->err = "correlation kernel shared memory limit"; return FPM_ERR_LIMIT; }
+    if (cc.smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem));
     int32_t* dS = h->d_dbg[3].as<int32_t>();
     int32_t* dQ = dS + (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT;
-    dim3 grid((th + rc - 1) / rc, 1);
-    fpm_corr_rows_kernel<<<grid, CR_THREADS, smem, h->stream>>>(h->d_dbg[0].as<uint8_t>(), rpitch, roi_bytes, td, rc,
-                                                                 h->d_dbg[2].as<int32_t>(), dS, dQ);
+    dim3 grid(cc.blocks_y_rows, 1);
+    fpm_corr_rows_kernel<<<grid, cc.threads, cc.smem, h->stream>>>(h->d_dbg[0].as<uint8_t>(), rpitch, roi_bytes, td, 1, cc.rb,
+                                                                    cc.evals_per_cta, h->d_dbg[2].as<int32_t>(), dS, dQ);
     CKL();
     CK(cudaMemcpyAsync(rowsum, h->d_dbg[2].p, (size_t)th * FPM_NCELL * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(rowS, dS, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));

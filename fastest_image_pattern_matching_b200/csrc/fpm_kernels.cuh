@@ -105,73 +105,123 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec_ok)
 // =====================================================================================
 // K2/K3  warpAffine, u8 C1, INTER_LINEAR, BORDER_CONSTANT -- OpenCV's fixed-point path:
 //   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,
-//   weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15.
-// One job per output image (top-layer angle or refinement ROI).  4 pixels / thread / row,
-// packed 32-bit stores; the padding columns up to dpitch are written as zero.
+//   X = (X0+adelta)>>5, sx = X>>5, ax = X&31, weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15
+//   (== (sum/32 + 512) >> 10).
+// One job per output image (top-layer angle or refinement ROI).  One CTA = 64x16 output pixels:
+// the fixed-point map is separable and monotone in x and y, so the exact source bounding box of
+// the tile follows from its 4 corners; the box (<= 68x68 px for a rotation) is staged in shared
+// memory with coalesced 32-bit loads and the 4 bilinear taps are gathered from shared memory --
+// a diagonal walk through global memory would cost one L1 wavefront per lane.
+// 4 pixels / thread, packed 32-bit stores; padding columns up to dpitch are written as zero.
 // =====================================================================================
-#define WA_ROWS 8
+#define WA_TW 64
+#define WA_TH 16
 #define WA_THREADS 256
+#define WA_SW 80      // staged box: bytes per row (multiple of 4)
+#define WA_SH 72      // staged box: rows
 
 __global__ void __launch_bounds__(WA_THREADS)
 fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __restrict__ dst,
-                int dpitch, size_t dst_job_stride, int border)
+                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok)
 {
     const FpmWarpJob& jb = jobs[blockIdx.y];
-    const int row0 = blockIdx.x * WA_ROWS;
     const int dw = jb.dw, dh = jb.dh;
-    if (!jb.valid || row0 >= dh) return;
-    __shared__ int sX0[WA_ROWS], sY0[WA_ROWS];
-    const double m0 = jb.m[0], m3 = jb.m[3];
-    if (threadIdx.x < WA_ROWS) {
-        double y = (double)(row0 + (int)threadIdx.x);
-        sX0[threadIdx.x] = fpm_cvround((jb.m[1] * y + jb.m[2]) * 1024.0) + 16;
-        sY0[threadIdx.x] = fpm_cvround((jb.m[4] * y + jb.m[5]) * 1024.0) + 16;
+    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const int tx0 = tile_x * WA_TW, ty0 = tile_y * WA_TH;
+    if (!jb.valid || ty0 >= dh || tx0 >= dpitch) return;
+    __shared__ int s_ad[WA_TW], s_bd[WA_TW], s_X0[WA_TH], s_Y0[WA_TH];
+    __shared__ __align__(16) uint8_t s_src[WA_SH * WA_SW];
+    const int tid = threadIdx.x;
+    if (tid < WA_TW) {
+        double x = (double)(tx0 + tid);
+        s_ad[tid] = fpm_cvround(jb.m[0] * x * 1024.0);
+        s_bd[tid] = fpm_cvround(jb.m[3] * x * 1024.0);
+    } else if (tid < WA_TW + WA_TH) {
+        int r = tid - WA_TW;
+        double y = (double)(ty0 + r);
+        s_X0[r] = fpm_cvround((jb.m[1] * y + jb.m[2]) * 1024.0) + 16;
+        s_Y0[r] = fpm_cvround((jb.m[4] * y + jb.m[5]) * 1024.0) + 16;
     }
     __syncthreads();
+    const int ncols = min(WA_TW, dw - tx0);            // real pixels in this tile (may be <= 0 for pad tiles)
+    const int nrows = min(WA_TH, dh - ty0);
     const uint8_t* __restrict__ s = src.ptr + (size_t)jb.src_img * src.img_stride;
     uint8_t* __restrict__ d = dst + (size_t)blockIdx.y * dst_job_stride;
     const int sw = src.w, sh = src.h, sp = src.pitch;
-    const int nrows = min(WA_ROWS, dh - row0);
-    const int ngroups = dpitch / 4;
-    for (int g = threadIdx.x; g < ngroups; g += WA_THREADS) {
-        int ad[4], bd[4];
+    const int row = tid >> 4, xg = tid & 15;
+
+    // exact source box of the tile from its corners (X and Y are sums of monotone functions of x and y)
+    int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+    bool staged = false, inside = false;
+    if (ncols > 0) {
+        int xa = s_ad[0], xb = s_ad[ncols - 1], ya = s_bd[0], yb = s_bd[ncols - 1];
+        int X0a = s_X0[0], X0b = s_X0[nrows - 1], Y0a = s_Y0[0], Y0b = s_Y0[nrows - 1];
+        int Xmin = min(min(X0a + xa, X0a + xb), min(X0b + xa, X0b + xb));
+        int Xmax = max(max(X0a + xa, X0a + xb), max(X0b + xa, X0b + xb));
+        int Ymin = min(min(Y0a + ya, Y0a + yb), min(Y0b + ya, Y0b + yb));
+        int Ymax = max(max(Y0a + ya, Y0a + yb), max(Y0b + ya, Y0b + yb));
+        int sx0 = Xmin >> 10, sx1 = (Xmax >> 10) + 1, sy0 = Ymin >> 10, sy1 = (Ymax >> 10) + 1;
+        inside = sx0 >= 0 && sy0 >= 0 && sx1 < sw && sy1 < sh;
+        bx0 = max(sx0, 0) & ~3; bx1 = min(sx1, sw - 1);
+        by0 = max(sy0, 0); by1 = min(sy1, sh - 1);
+        staged = (bx1 - bx0 + 1 <= WA_SW) && (by1 - by0 + 1 <= WA_SH);
+        if (staged && bx1 >= bx0 && by1 >= by0) {
+            const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;
+            for (int i = tid; i < nr * nwr; i += WA_THREADS) {
+                int r = i / nwr, wc = i - r * nwr;
+                int x = bx0 + 4 * wc;
+                const uint8_t* rowp = s + (size_t)(by0 + r) * sp;
+                uint32_t v;
+                if (vec_ok && x + 3 < sw) {
+                    v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
+                } else {
+                    v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            double x = (double)(4 * g + k);
-            ad[k] = fpm_cvround(m0 * x * 1024.0);
-            bd[k] = fpm_cvround(m3 * x * 1024.0);
-        }
-        for (int r = 0; r < nrows; r++) {
-            uint32_t pack = 0;
-            const int X0 = sX0[r], Y0 = sY0[r];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (4 * g + k < dw) {
-                    int X = (X0 + ad[k]) >> 5, Y = (Y0 + bd[k]) >> 5;
-                    int sx = X >> 5, sy = Y >> 5;
-                    int ax = X & 31, ay = Y & 31;
-                    int p00, p01, p10, p11;
-                    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-                        const uint8_t* p = s + (size_t)sy * sp + sx;
-                        p00 = __ldg(p); p01 = __ldg(p + 1); p10 = __ldg(p + sp); p11 = __ldg(p + sp + 1);
-                    } else {
-                        bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-                        bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-                        const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
-                        p00 = (x0in && y0in) ? __ldg(p) : border;
-                        p01 = (x1in && y0in) ? __ldg(p + 1) : border;
-                        p10 = (x0in && y1in) ? __ldg(p + sp) : border;
-                        p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
-                    }
-                    int v = (32 - ax) * (32 - ay) * 32 * p00 + ax * (32 - ay) * 32 * p01 +
-                            (32 - ax) * ay * 32 * p10 + ax * ay * 32 * p11;
-                    v = (v + 16384) >> 15;
-                    pack |= (uint32_t)v << (8 * k);
+                    for (int k = 0; k < 4; k++)
+                        if (x + k < sw) v |= (uint32_t)__ldg(rowp + x + k) << (8 * k);
                 }
+                *reinterpret_cast<uint32_t*>(&s_src[r * WA_SW + 4 * wc]) = v;
             }
-            *reinterpret_cast<uint32_t*>(d + (size_t)(row0 + r) * dpitch + 4 * g) = pack;
         }
     }
+    __syncthreads();
+    if (row >= nrows || tx0 + 4 * xg >= dpitch) return;
+    uint32_t pack = 0;
+    const int X0 = s_X0[row], Y0 = s_Y0[row];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int lx = 4 * xg + k;
+        if (lx < ncols) {
+            int X = (X0 + s_ad[lx]) >> 5, Y = (Y0 + s_bd[lx]) >> 5;
+            int sx = X >> 5, sy = Y >> 5;
+            int ax = X & 31, ay = Y & 31;
+            int p00, p01, p10, p11;
+            if (staged && inside) {
+                const uint8_t* p = s_src + (sy - by0) * WA_SW + (sx - bx0);
+                p00 = p[0]; p01 = p[1]; p10 = p[WA_SW]; p11 = p[WA_SW + 1];
+            } else {
+                bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+                bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+                if (staged) {
+                    const uint8_t* p = s_src + (sy - by0) * WA_SW + (sx - bx0);
+                    p00 = (x0in && y0in) ? p[0] : border;
+                    p01 = (x1in && y0in) ? p[1] : border;
+                    p10 = (x0in && y1in) ? p[WA_SW] : border;
+                    p11 = (x1in && y1in) ? p[WA_SW + 1] : border;
+                } else {
+                    const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
+                    p00 = (x0in && y0in) ? __ldg(p) : border;
+                    p01 = (x1in && y0in) ? __ldg(p + 1) : border;
+                    p10 = (x0in && y1in) ? __ldg(p + sp) : border;
+                    p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
+                }
+            }
+            int v = (32 - ax) * (32 - ay) * p00 + ax * (32 - ay) * p01 + (32 - ax) * ay * p10 + ax * ay * p11;
+            v = (v + 512) >> 10;
+            pack |= (uint32_t)v << (8 * k);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
 }
 
 // =====================================================================================
@@ -548,113 +598,153 @@ __global__ void fpm_refine_prep_kernel(const FpmCand* __restrict__ cands, int n_
 // K5  correlation row sums (replaces IM_Conv_SIMD, src/TemplateMatcher.cpp:461-483):
 //   rowsum[e][tr][r*7+c] = sum_x T[tr][x] * S_e[tr + r][x + c]      exact s32, dp4a
 //   rowS[e][y][c] = sum_{x<w} S_e[y][x+c],  rowQ[e][y][c] = sum_{x<w} S_e[y][x+c]^2
-// One CTA = (chunk of RC template rows, eval); ROI rows and template rows staged in shared
-// memory; a warp owns a template row at a time, lanes split the row by 32-bit words.
+//
+// One THREAD owns one ROI row y of one eval and keeps all 49 sums (7 template rows y-6..y x 7
+// column shifts) in registers, so no cross-lane reduction is needed at any template width.
+// The CTA walks the row in slabs of 32 words (128 px): the slab of its ROI rows and of the
+// template rows y0-6 .. y0+RB-1 is staged in shared memory with coalesced loads (odd word pitch:
+// lanes read different rows conflict-free).  Per word: 1 new ROI word + 7 template words from
+// shared memory, 5 funnel shifts, 49 dp4a.  Window sums are kept for shift 0 only and the other
+// six follow exactly from the 6 head / 6 tail bytes of the row.  Results leave through a shared
+// memory transpose so the global stores are coalesced.
+//   CTA layout: evals_per_cta x rb threads; thread (el, yl) -> eval blockIdx.y*evals_per_cta+el,
+//   row y = blockIdx.x*rb + yl.
 // =====================================================================================
-#define CR_THREADS 256
+#define CR_SLAB 32
+#define CR_SP (CR_SLAB + 3)       // ROI slab pitch in words (odd; slab + 2 look-ahead words)
+#define CR_TP (CR_SLAB + 1)       // template slab pitch in words (odd)
+#define CR_MAX_THREADS 256
 
 __device__ __forceinline__ uint32_t fpm_shift_bytes(uint32_t lo, uint32_t hi, int c)
 {
     return __funnelshift_r(lo, hi, 8 * c);
 }
 
-__global__ void __launch_bounds__(CR_THREADS)
+__global__ void __launch_bounds__(CR_MAX_THREADS)
 fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, FpmTplLevel tpl,
-                     int rc, int32_t* __restrict__ rowsum, int32_t* __restrict__ rowS,
-                     int32_t* __restrict__ rowQ)
+                     int n_evals, int rb, int evals_per_cta, int32_t* __restrict__ rowsum,
+                     int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int e = blockIdx.y;
-    const int t0 = blockIdx.x * rc;
+    extern __shared__ __align__(16) uint32_t smem_w[];
     const int tw = tpl.w, th = tpl.h;
-    const int nT = min(rc, th - t0);
-    const int nS = nT + FPM_ROI_PAD;
-    const int tp = tpl.pitch;
-    uint8_t* s_s = smem;                              // nS rows x rpitch
-    uint8_t* s_t = smem + (size_t)(rc + FPM_ROI_PAD) * rpitch;   // nT rows x tp
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = CR_THREADS / 32;
-    {
-        const uint4* g = reinterpret_cast<const uint4*>(roi + (size_t)e * roi_stride + (size_t)t0 * rpitch);
-        uint4* d = reinterpret_cast<uint4*>(s_s);
-        int n16 = nS * rpitch / 16;
-        for (int i = tid; i < n16; i += CR_THREADS) d[i] = g[i];
-        const uint4* gt = reinterpret_cast<const uint4*>(tpl.ptr + (size_t)t0 * tp);
-        uint4* dt = reinterpret_cast<uint4*>(s_t);
-        int t16 = nT * tp / 16;
-        for (int i = tid; i < t16; i += CR_THREADS) dt[i] = __ldg(gt + i);
+    const int rh = th + FPM_ROI_PAD;                       // ROI rows per eval
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int el = tid / rb, yl = tid - el * rb;
+    const int e0 = blockIdx.y * evals_per_cta;
+    const int e = e0 + el;
+    const int y0 = blockIdx.x * rb;
+    const int y = y0 + yl;
+    const bool active = (el < evals_per_cta) && (e < n_evals) && (y < rh);
+    const int n_srow = evals_per_cta * rb;                 // staged ROI rows
+    const int n_trow = rb + FPM_ROI_PAD;                   // staged template rows: tr = y0-6 .. y0+rb-1
+    uint32_t* s_s = smem_w;                                // [n_srow][CR_SP]
+    uint32_t* s_t = smem_w + (size_t)n_srow * CR_SP;       // [n_trow][CR_TP]
+    const int nw = (tw + 3) / 4;                           // template words per row
+    const int rwords = rpitch / 4, twords = tpl.pitch / 4;
+    const int tail = tw & 3;
+    const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
+
+    uint32_t acc[FPM_NSHIFT][FPM_NSHIFT];
+#pragma unroll
+    for (int j = 0; j < FPM_NSHIFT; j++)
+#pragma unroll
+        for (int c = 0; c < FPM_NSHIFT; c++) acc[j][c] = 0;
+    uint32_t sS = 0, sQ = 0, head0 = 0, head1 = 0;
+    uint32_t tailb[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) tailb[k] = 0;
+
+    for (int xs = 0; xs < nw; xs += CR_SLAB) {
+        __syncthreads();
+        // ---- stage the slab: ROI words xs .. xs+33 of every row, template words xs .. xs+31
+        for (int i = tid; i < n_srow * (CR_SLAB + 2); i += nthreads) {
+            int r = i / (CR_SLAB + 2), wc = i - r * (CR_SLAB + 2);
+            int rel = r / rb, ry = y0 + (r - rel * rb), re = e0 + rel;
+            uint32_t v = 0;
+            if (re < n_evals && ry < rh && xs + wc < rwords)
+                v = *reinterpret_cast<const uint32_t*>(roi + (size_t)re * roi_stride + (size_t)ry * rpitch + 4 * (xs + wc));
+            s_s[r * CR_SP + wc] = v;
+        }
+        for (int i = tid; i < n_trow * CR_SLAB; i += nthreads) {
+            int r = i / CR_SLAB, wc = i - r * CR_SLAB;
+            int tr = y0 - FPM_ROI_PAD + r;
+            uint32_t v = 0;
+            if (tr >= 0 && tr < th && xs + wc < twords)
+                v = __ldg(reinterpret_cast<const uint32_t*>(tpl.ptr + (size_t)tr * tpl.pitch + 4 * (xs + wc)));
+            s_t[r * CR_TP + wc] = v;
+        }
+        __syncthreads();
+        if (active) {
+            const uint32_t* srow = s_s + (size_t)tid * CR_SP;
+            const uint32_t* trow = s_t + (size_t)(yl + FPM_ROI_PAD) * CR_TP;     // template row tr = y
+            const int nx = min(CR_SLAB, nw - xs);
+            uint32_t w0 = srow[0], w1 = srow[1];
+            if (xs == 0) { head0 = w0; head1 = w1; }
+            for (int xw = 0; xw < nx; xw++) {
+                const uint32_t w2 = srow[xw + 2];
+                uint32_t sh[FPM_NSHIFT];
+                sh[0] = w0;
+                sh[1] = fpm_shift_bytes(w0, w1, 1);
+                sh[2] = fpm_shift_bytes(w0, w1, 2);
+                sh[3] = fpm_shift_bytes(w0, w1, 3);
+                sh[4] = w1;
+                sh[5] = fpm_shift_bytes(w1, w2, 1);
+                sh[6] = fpm_shift_bytes(w1, w2, 2);
+#pragma unroll
+                for (int j = 0; j < FPM_NSHIFT; j++) {
+                    const uint32_t t = trow[xw - j * CR_TP];                     // template row y - j
+#pragma unroll
+                    for (int c = 0; c < FPM_NSHIFT; c++) acc[j][c] = __dp4a(t, sh[c], acc[j][c]);
+                }
+                const uint32_t m0 = (xs + xw == nw - 1) ? (w0 & tailbm) : w0;
+                sS = __dp4a(m0, 0x01010101u, sS);
+                sQ = __dp4a(m0, m0, sQ);
+                w0 = w1; w1 = w2;
+            }
+            if (xs + CR_SLAB >= nw) {
+                // the 6 bytes that follow the template width: S[y][tw .. tw+5]
+                const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
+#pragma unroll
+                for (int k = 0; k < 6; k++) tailb[k] = sb[tw + k - 4 * xs];
+            }
+        }
+    }
+    // ---- window sums of the 7 shifts from shift 0 + head/tail bytes (exact)
+    if (active) {
+        uint32_t hb[6];
+        hb[0] = head0 & 255; hb[1] = (head0 >> 8) & 255; hb[2] = (head0 >> 16) & 255; hb[3] = head0 >> 24;
+        hb[4] = head1 & 255; hb[5] = (head1 >> 8) & 255;
+        size_t base = ((size_t)e * rh + y) * FPM_NSHIFT;
+        uint32_t cs = sS, cq = sQ;
+        rowS[base] = (int32_t)cs; rowQ[base] = (int32_t)cq;
+#pragma unroll
+        for (int c = 1; c < FPM_NSHIFT; c++) {
+            cs = cs - hb[c - 1] + tailb[c - 1];
+            cq = cq - hb[c - 1] * hb[c - 1] + tailb[c - 1] * tailb[c - 1];
+            rowS[base + c] = (int32_t)cs; rowQ[base + c] = (int32_t)cq;
+        }
+    }
+    // ---- transpose through shared memory: out[el][tr_local][cell], then coalesced global stores
+    __syncthreads();
+    uint32_t* s_o = smem_w;                                // [evals_per_cta][n_trow][49]
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < FPM_NSHIFT; j++) {
+            uint32_t* o = s_o + ((size_t)el * n_trow + (yl + FPM_ROI_PAD - j)) * FPM_NCELL + j * FPM_NSHIFT;
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) o[c] = acc[j][c];
+        }
     }
     __syncthreads();
-    const int nw = (tw + 3) / 4;                      // template words per row (zero padded)
-    const int tail = tw & 3;
-    const uint32_t tailmask = tail ? (0x01010101u >> (8 * (4 - tail))) : 0x01010101u;
-
-    // ---- correlation row sums
-    for (int tl = warp; tl < nT; tl += nwarps) {
-        const uint32_t* trow = reinterpret_cast<const uint32_t*>(s_t + (size_t)tl * tp);
-        int32_t* out = rowsum + ((size_t)e * th + (t0 + tl)) * FPM_NCELL;
-        for (int r = 0; r < FPM_NSHIFT; r++) {
-            const uint32_t* srow = reinterpret_cast<const uint32_t*>(s_s + (size_t)(tl + r) * rpitch);
-            uint32_t acc[FPM_NSHIFT];
-#pragma unroll
-            for (int c = 0; c < FPM_NSHIFT; c++) acc[c] = 0;
-            for (int xw = lane; xw < nw; xw += 32) {
-                uint32_t t = trow[xw];
-                uint32_t w0 = srow[xw], w1 = srow[xw + 1], w2 = srow[xw + 2];
-                acc[0] = __dp4a(t, w0, acc[0]);
-                acc[1] = __dp4a(t, fpm_shift_bytes(w0, w1, 1), acc[1]);
-                acc[2] = __dp4a(t, fpm_shift_bytes(w0, w1, 2), acc[2]);
-                acc[3] = __dp4a(t, fpm_shift_bytes(w0, w1, 3), acc[3]);
-                acc[4] = __dp4a(t, w1, acc[4]);
-                acc[5] = __dp4a(t, fpm_shift_bytes(w1, w2, 1), acc[5]);
-                acc[6] = __dp4a(t, fpm_shift_bytes(w1, w2, 2), acc[6]);
-            }
-#pragma unroll
-            for (int c = 0; c < FPM_NSHIFT; c++) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int c = 0; c < FPM_NSHIFT; c++) out[r * FPM_NSHIFT + c] = (int32_t)acc[c];
-            }
-        }
-    }
-    // ---- window row sums over the ROI rows this chunk owns: [t0, t0+nT) plus the 6 tail rows
-    const bool last = (t0 + nT == th);
-    const int nOwn = last ? nS : nT;
-    for (int yl = warp; yl < nOwn; yl += nwarps) {
-        const uint32_t* srow = reinterpret_cast<const uint32_t*>(s_s + (size_t)yl * rpitch);
-        uint32_t sS[FPM_NSHIFT], sQ[FPM_NSHIFT];
-#pragma unroll
-        for (int c = 0; c < FPM_NSHIFT; c++) { sS[c] = 0; sQ[c] = 0; }
-        for (int xw = lane; xw < nw; xw += 32) {
-            uint32_t ones = (xw == nw - 1) ? tailmask : 0x01010101u;
-            uint32_t bm = ones * 255u;
-            uint32_t w0 = srow[xw], w1 = srow[xw + 1], w2 = srow[xw + 2];
-            uint32_t v[FPM_NSHIFT];
-            v[0] = w0; v[1] = fpm_shift_bytes(w0, w1, 1); v[2] = fpm_shift_bytes(w0, w1, 2);
-            v[3] = fpm_shift_bytes(w0, w1, 3); v[4] = w1; v[5] = fpm_shift_bytes(w1, w2, 1);
-            v[6] = fpm_shift_bytes(w1, w2, 2);
-#pragma unroll
-            for (int c = 0; c < FPM_NSHIFT; c++) {
-                uint32_t m = v[c] & bm;
-                sS[c] = __dp4a(m, 0x01010101u, sS[c]);
-                sQ[c] = __dp4a(m, m, sQ[c]);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < FPM_NSHIFT; c++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                sS[c] += __shfl_xor_sync(0xffffffffu, sS[c], o);
-                sQ[c] += __shfl_xor_sync(0xffffffffu, sQ[c], o);
-            }
-        }
-        if (lane == 0) {
-            size_t base = ((size_t)e * (th + FPM_ROI_PAD) + (t0 + yl)) * FPM_NSHIFT;
-#pragma unroll
-            for (int c = 0; c < FPM_NSHIFT; c++) { rowS[base + c] = (int32_t)sS[c]; rowQ[base + c] = (int32_t)sQ[c]; }
-        }
+    const int per_eval = n_trow * FPM_NCELL;
+    for (int i = tid; i < evals_per_cta * per_eval; i += nthreads) {
+        int oel = i / per_eval, rem = i - oel * per_eval;
+        int trl = rem / FPM_NCELL, cell = rem - trl * FPM_NCELL;
+        int tr = y0 - FPM_ROI_PAD + trl, oe = e0 + oel;
+        int j = cell / FPM_NSHIFT;
+        int oy = tr + j;                                     // the ROI row (thread) that produced this cell
+        if (oe < n_evals && tr >= 0 && tr < th && oy >= y0 && oy < y0 + rb && oy < rh)
+            rowsum[((size_t)oe * th + tr) * FPM_NCELL + cell] = (int32_t)s_o[i];
     }
 }
 
