@@ -19,85 +19,114 @@
 
 // =====================================================================================
 // K1  pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, (s+128)>>8, out ((w+1)/2,(h+1)/2)
-// HBM-bound: reads W*H, writes W*H/4.  Tile = 128x32 outputs per CTA, input tile staged in
-// shared memory with coalesced 32-bit loads, separable passes out of shared memory.
+// HBM-bound: reads W*H, writes W*H/4.  One CTA = 128x32 outputs.  The 67 input rows x 288 B of the
+// tile are staged in shared memory with 128-bit (or 32-bit) coalesced loads; the horizontal taps are
+// one dp4a (weights 1,4,6,4) + one byte per output, the vertical taps run on two 16-bit lanes packed
+// in a 32-bit register (sums < 65536, so no carry crosses lanes).
 // =====================================================================================
 #define PD_TW 128
 #define PD_TH 32
 #define PD_IH (2 * PD_TH + 3)
-#define PD_IW (2 * PD_TW + 8)      // input columns [2*ox0-4, 2*ox0+2*TW+4)
+#define PD_IW (2 * PD_TW + 32)     // staged input columns [2*ox0-16, 2*ox0+2*TW+16), 16-byte chunks
 #define PD_THREADS 256
 
 __global__ void __launch_bounds__(PD_THREADS)
-fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec_ok)
+fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 {
     __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
-    __shared__ __align__(16) uint16_t s_h[PD_IH][PD_TW];
+    __shared__ __align__(16) uint32_t s_h[PD_IH][PD_TW / 2];     // two u16 horizontal sums per word
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
     const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
     uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
-    const int xs = 2 * ox0 - 4, ys = 2 * oy0 - 2;
+    const int xs = 2 * ox0 - 16, ys = 2 * oy0 - 2;
     const int nout_rows = min(PD_TH, dst.h - oy0);
     const int nout_cols = min(PD_TW, dst.w - ox0);
     const int nin_rows = 2 * nout_rows + 3;
-    const int nin_words = min(PD_IW / 4, (2 * nout_cols + 8) / 4 + 2);   // columns 0 .. 2*nout_cols+9 touched
+    const int sw = src.w, sh = src.h;
+    // smem columns actually read by the horizontal pass: words 3 .. (nout_cols+1)/2 + 4
+    const int need_lo = 12, need_hi = 4 * ((nout_cols + 1) / 2 + 4) + 3;
 
-    for (int i = tid; i < nin_rows * (PD_IW / 4); i += PD_THREADS) {
-        int r = i / (PD_IW / 4), wc = i - r * (PD_IW / 4);
-        if (wc >= nin_words) continue;
-        int iy = fpm_reflect101(ys + r, src.h);
-        int x = xs + 4 * wc;
-        const uint8_t* row = s + (size_t)iy * src.pitch;
-        uint32_t v;
-        if (vec_ok && x >= 0 && x + 3 < src.w) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
-        } else {
-            v = 0;
+    if (vec == 16) {
+        const int nch = (need_hi + 16) / 16;                     // 16-byte chunks per row (<= 18)
+        for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
+            const int c = tid & 31;
+            if (c >= nch) continue;
+            const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
+            const int x = xs + 16 * c;
+            uint4 v;
+            if (x >= 0 && x + 15 < sw) {
+                v = __ldg(reinterpret_cast<const uint4*>(row + x));
+            } else {
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (16 * c + 15 >= need_lo) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, src.w)) << (8 * k);
+                    for (int k = 0; k < 16; k++)
+                        w[k >> 2] |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * (k & 3));
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(&s_in[r][16 * c]) = v;
         }
-        *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
+    } else {
+        const int w_lo = need_lo / 4, nwd = need_hi / 4 - w_lo + 1;   // words 3 .. need_hi/4 (<= 66)
+        for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
+            const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
+            for (int c = tid & 63; c < nwd; c += 64) {
+                const int wc = w_lo + c;
+                const int x = xs + 4 * wc;
+                uint32_t v;
+                if (vec == 4 && x >= 0 && x + 3 < sw) {
+                    v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+                } else {
+                    v = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
+            }
+        }
     }
     __syncthreads();
 
-    // horizontal pass: output column ox has its centre at smem column 2*ox+4; two outputs / thread
-    const int npairs = (nout_cols + 1) / 2;
-    for (int i = tid; i < nin_rows * (PD_TW / 2); i += PD_THREADS) {
-        int r = i / (PD_TW / 2), k = i - r * (PD_TW / 2);
-        if (k >= npairs) continue;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_in[r][4 * k]);
-        uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-        // bytes 4k+2 .. 4k+8
-        int b2 = (w0 >> 16) & 255, b3 = w0 >> 24;
-        int b4 = w1 & 255, b5 = (w1 >> 8) & 255, b6 = (w1 >> 16) & 255, b7 = w1 >> 24;
-        int b8 = w2 & 255;
-        int h0 = b2 + b6 + 4 * (b3 + b5) + 6 * b4;
-        int h1 = b4 + b8 + 4 * (b5 + b7) + 6 * b6;
-        *reinterpret_cast<uint32_t*>(&s_h[r][2 * k]) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    // horizontal pass: outputs 2k, 2k+1 have their centres at smem bytes 4k+16, 4k+18
+    {
+        const int k = tid & 63;
+        if (2 * k < nout_cols) {
+            for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_in[r][4 * k + 12]);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 16), 0x04060401u, (w1 >> 16) & 255u);
+                const uint32_t h1 = __dp4a(w1, 0x04060401u, w2 & 255u);
+                s_h[r][k] = h0 | (h1 << 16);
+            }
+        }
     }
     __syncthreads();
 
-    // vertical pass: 4 outputs / thread
-    for (int i = tid; i < nout_rows * (PD_TW / 4); i += PD_THREADS) {
-        int oy = i / (PD_TW / 4), g = i - oy * (PD_TW / 4);
-        int ox = 4 * g;
-        if (ox >= nout_cols) continue;
-        int acc[4];
+    // vertical pass: 4 outputs (two packed pairs) per thread
+    {
+        const int g = tid & 31;
+        if (4 * g < nout_cols) {
+            for (int oy = tid >> 5; oy < nout_rows; oy += PD_THREADS / 32) {
+                uint32_t o[2];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int c = ox + k;
-            acc[k] = s_h[2 * oy][c] + s_h[2 * oy + 4][c] + 4 * (s_h[2 * oy + 1][c] + s_h[2 * oy + 3][c]) +
-                     6 * s_h[2 * oy + 2][c];
-            acc[k] = (acc[k] + 128) >> 8;
-        }
-        uint8_t* o = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + ox;
-        if (ox + 3 < nout_cols) {
-            *reinterpret_cast<uint32_t*>(o) = (uint32_t)acc[0] | ((uint32_t)acc[1] << 8) | ((uint32_t)acc[2] << 16) |
-                                              ((uint32_t)acc[3] << 24);
-        } else {
-            for (int k = 0; k < 4 && ox + k < nout_cols; k++) o[k] = (uint8_t)acc[k];
+                for (int q = 0; q < 2; q++) {
+                    const int c = 2 * g + q;
+                    const uint32_t a = s_h[2 * oy][c] + s_h[2 * oy + 4][c];
+                    const uint32_t b = s_h[2 * oy + 1][c] + s_h[2 * oy + 3][c];
+                    const uint32_t v = a + 4u * b + 6u * s_h[2 * oy + 2][c] + 0x00800080u;
+                    o[q] = (v >> 8) & 0x00ff00ffu;
+                }
+                const uint32_t pack = (o[0] & 255u) | ((o[0] >> 8) & 0xff00u) | ((o[1] & 255u) << 16) | ((o[1] & 0x00ff0000u) << 8);
+                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 4 * g;
+                if (4 * g + 3 < nout_cols) {
+                    *reinterpret_cast<uint32_t*>(op) = pack;
+                } else {
+                    for (int k = 0; k < 4 && 4 * g + k < nout_cols; k++) op[k] = (uint8_t)(pack >> (8 * k));
+                }
+            }
         }
     }
 }
@@ -106,19 +135,19 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec_ok)
 // K2/K3  warpAffine, u8 C1, INTER_LINEAR, BORDER_CONSTANT -- OpenCV's fixed-point path:
 //   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,
 //   X = (X0+adelta)>>5, sx = X>>5, ax = X&31, weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15
-//   (== (sum/32 + 512) >> 10).
-// One job per output image (top-layer angle or refinement ROI).  One CTA = 64x16 output pixels:
-// the fixed-point map is separable and monotone in x and y, so the exact source bounding box of
-// the tile follows from its 4 corners; the box (<= 68x68 px for a rotation) is staged in shared
-// memory with coalesced 32-bit loads and the 4 bilinear taps are gathered from shared memory --
-// a diagonal walk through global memory would cost one L1 wavefront per lane.
-// 4 pixels / thread, packed 32-bit stores; padding columns up to dpitch are written as zero.
+//   == ((top<<5) + ay*(bot-top) + 512) >> 10 with top = (p00<<5) + ax*(p01-p00)   (same integers).
+// One job per output image (top-layer angle or refinement ROI).  One CTA = 64x64 output pixels,
+// 16 pixels per thread.  The fixed-point map is separable and monotone in x and y, so the exact
+// source bounding box of the tile follows from its 4 corners; the box (<= 92x92 px for a rotation)
+// is staged in shared memory with coalesced 32-bit loads and the 4 bilinear taps are gathered from
+// shared memory -- a diagonal walk through global memory costs one L1 wavefront per lane.
+// Packed 32-bit stores; padding columns up to dpitch are written as zero.
 // =====================================================================================
 #define WA_TW 64
-#define WA_TH 16
+#define WA_TH 64
 #define WA_THREADS 256
-#define WA_SW 80      // staged box: bytes per row (multiple of 4)
-#define WA_SH 72      // staged box: rows
+#define WA_SW 96      // staged box: bytes per row (multiple of 4)
+#define WA_SH 96      // staged box: rows
 
 __global__ void __launch_bounds__(WA_THREADS)
 fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __restrict__ dst,
@@ -143,15 +172,14 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
         s_Y0[r] = fpm_cvround((jb.m[4] * y + jb.m[5]) * 1024.0) + 16;
     }
     __syncthreads();
-    const int ncols = min(WA_TW, dw - tx0);            // real pixels in this tile (may be <= 0 for pad tiles)
+    const int ncols = min(WA_TW, dw - tx0);            // real pixels in this tile (<= 0 for pad-only tiles)
     const int nrows = min(WA_TH, dh - ty0);
     const uint8_t* __restrict__ s = src.ptr + (size_t)jb.src_img * src.img_stride;
     uint8_t* __restrict__ d = dst + (size_t)blockIdx.y * dst_job_stride;
     const int sw = src.w, sh = src.h, sp = src.pitch;
-    const int row = tid >> 4, xg = tid & 15;
 
     // exact source box of the tile from its corners (X and Y are sums of monotone functions of x and y)
-    int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+    int bx0 = 0, by0 = 0;
     bool staged = false, inside = false;
     if (ncols > 0) {
         int xa = s_ad[0], xb = s_ad[ncols - 1], ya = s_bd[0], yb = s_bd[ncols - 1];
@@ -162,66 +190,94 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
         int Ymax = max(max(Y0a + ya, Y0a + yb), max(Y0b + ya, Y0b + yb));
         int sx0 = Xmin >> 10, sx1 = (Xmax >> 10) + 1, sy0 = Ymin >> 10, sy1 = (Ymax >> 10) + 1;
         inside = sx0 >= 0 && sy0 >= 0 && sx1 < sw && sy1 < sh;
-        bx0 = max(sx0, 0) & ~3; bx1 = min(sx1, sw - 1);
-        by0 = max(sy0, 0); by1 = min(sy1, sh - 1);
+        bx0 = max(sx0, 0) & ~3;
+        by0 = max(sy0, 0);
+        const int bx1 = min(sx1, sw - 1), by1 = min(sy1, sh - 1);
         staged = (bx1 - bx0 + 1 <= WA_SW) && (by1 - by0 + 1 <= WA_SH);
         if (staged && bx1 >= bx0 && by1 >= by0) {
-            const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;
-            for (int i = tid; i < nr * nwr; i += WA_THREADS) {
-                int r = i / nwr, wc = i - r * nwr;
-                int x = bx0 + 4 * wc;
-                const uint8_t* rowp = s + (size_t)(by0 + r) * sp;
-                uint32_t v;
+            const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;      // nwr <= 24
+            const int wc = tid & 31;
+            if (wc < nwr) {
+                const int x = bx0 + 4 * wc;
+                const uint8_t* rowp = s + (size_t)(by0 + (tid >> 5)) * sp + x;
+                uint8_t* sp_out = s_src + (tid >> 5) * WA_SW + 4 * wc;
                 if (vec_ok && x + 3 < sw) {
-                    v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
+                    for (int r = tid >> 5; r < nr; r += WA_THREADS / 32, rowp += (size_t)(WA_THREADS / 32) * sp,
+                             sp_out += (WA_THREADS / 32) * WA_SW)
+                        *reinterpret_cast<uint32_t*>(sp_out) = __ldg(reinterpret_cast<const uint32_t*>(rowp));
                 } else {
-                    v = 0;
+                    for (int r = tid >> 5; r < nr; r += WA_THREADS / 32, rowp += (size_t)(WA_THREADS / 32) * sp,
+                             sp_out += (WA_THREADS / 32) * WA_SW) {
+                        uint32_t v = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (x + k < sw) v |= (uint32_t)__ldg(rowp + x + k) << (8 * k);
+                        for (int k = 0; k < 4; k++)
+                            if (x + k < sw) v |= (uint32_t)__ldg(rowp + k) << (8 * k);
+                        *reinterpret_cast<uint32_t*>(sp_out) = v;
+                    }
                 }
-                *reinterpret_cast<uint32_t*>(&s_src[r * WA_SW + 4 * wc]) = v;
             }
         }
     }
     __syncthreads();
-    if (row >= nrows || tx0 + 4 * xg >= dpitch) return;
-    uint32_t pack = 0;
-    const int X0 = s_X0[row], Y0 = s_Y0[row];
+    const int xg = tid & 15;
+    if (tx0 + 4 * xg >= dpitch) return;
+    int adj[4], bdj[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int lx = 4 * xg + k;
-        if (lx < ncols) {
-            int X = (X0 + s_ad[lx]) >> 5, Y = (Y0 + s_bd[lx]) >> 5;
-            int sx = X >> 5, sy = Y >> 5;
-            int ax = X & 31, ay = Y & 31;
-            int p00, p01, p10, p11;
-            if (staged && inside) {
-                const uint8_t* p = s_src + (sy - by0) * WA_SW + (sx - bx0);
-                p00 = p[0]; p01 = p[1]; p10 = p[WA_SW]; p11 = p[WA_SW + 1];
-            } else {
-                bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-                bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-                if (staged) {
-                    const uint8_t* p = s_src + (sy - by0) * WA_SW + (sx - bx0);
-                    p00 = (x0in && y0in) ? p[0] : border;
-                    p01 = (x1in && y0in) ? p[1] : border;
-                    p10 = (x0in && y1in) ? p[WA_SW] : border;
-                    p11 = (x1in && y1in) ? p[WA_SW + 1] : border;
-                } else {
-                    const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
-                    p00 = (x0in && y0in) ? __ldg(p) : border;
-                    p01 = (x1in && y0in) ? __ldg(p + 1) : border;
-                    p10 = (x0in && y1in) ? __ldg(p + sp) : border;
-                    p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
+        adj[k] = s_ad[4 * xg + k] - (bx0 << 10);
+        bdj[k] = s_bd[4 * xg + k] - (by0 << 10);
+    }
+    const bool fast = staged && inside;
+    for (int row = tid >> 4; row < nrows; row += WA_THREADS / 16) {
+        uint32_t pack = 0;
+        const int X0 = s_X0[row], Y0 = s_Y0[row];
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (4 * xg + k < ncols) {
+                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                    const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
+                    const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
+                    const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
+                    const int top = (p00 << 5) + ax * (p01 - p00);
+                    const int bot = (p10 << 5) + ax * (p11 - p10);
+                    const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
+                    pack |= (uint32_t)v << (8 * k);
                 }
             }
-            int v = (32 - ax) * (32 - ay) * p00 + ax * (32 - ay) * p01 + (32 - ax) * ay * p10 + ax * ay * p11;
-            v = (v + 512) >> 10;
-            pack |= (uint32_t)v << (8 * k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (4 * xg + k < ncols) {
+                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                    const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
+                    const int lx = XX >> 10, ly = YY >> 10;              // relative to (bx0, by0)
+                    const int sx = lx + bx0, sy = ly + by0;
+                    const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+                    const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+                    int p00, p01, p10, p11;
+                    if (staged) {
+                        const uint8_t* p = s_src + ly * WA_SW + lx;
+                        p00 = (x0in && y0in) ? p[0] : border;
+                        p01 = (x1in && y0in) ? p[1] : border;
+                        p10 = (x0in && y1in) ? p[WA_SW] : border;
+                        p11 = (x1in && y1in) ? p[WA_SW + 1] : border;
+                    } else {
+                        const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
+                        p00 = (x0in && y0in) ? __ldg(p) : border;
+                        p01 = (x1in && y0in) ? __ldg(p + 1) : border;
+                        p10 = (x0in && y1in) ? __ldg(p + sp) : border;
+                        p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
+                    }
+                    const int top = (p00 << 5) + ax * (p01 - p00);
+                    const int bot = (p10 << 5) + ax * (p11 - p10);
+                    const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
+                    pack |= (uint32_t)v << (8 * k);
+                }
+            }
         }
+        *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
     }
-    *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
 }
 
 // =====================================================================================
@@ -657,17 +713,24 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
     for (int xs = 0; xs < nw; xs += CR_SLAB) {
         __syncthreads();
         // ---- stage the slab: ROI words xs .. xs+33 of every row, template words xs .. xs+31
-        for (int i = tid; i < n_srow * (CR_SLAB + 2); i += nthreads) {
-            int r = i / (CR_SLAB + 2), wc = i - r * (CR_SLAB + 2);
-            int rel = r / rb, ry = y0 + (r - rel * rb), re = e0 + rel;
-            uint32_t v = 0;
-            if (re < n_evals && ry < rh && xs + wc < rwords)
-                v = *reinterpret_cast<const uint32_t*>(roi + (size_t)re * roi_stride + (size_t)ry * rpitch + 4 * (xs + wc));
-            s_s[r * CR_SP + wc] = v;
+        // (incremental (row, word) bookkeeping instead of a division per element)
+        {
+            int r = tid / (CR_SLAB + 2), wc = tid - r * (CR_SLAB + 2);
+            const int dr = nthreads / (CR_SLAB + 2), dwc = nthreads - dr * (CR_SLAB + 2);
+            while (r < n_srow) {
+                const int rel = (evals_per_cta == 1) ? 0 : r / rb;
+                const int ry = y0 + (r - rel * rb), re = e0 + rel;
+                uint32_t v = 0;
+                if (re < n_evals && ry < rh && xs + wc < rwords)
+                    v = *reinterpret_cast<const uint32_t*>(roi + (size_t)re * roi_stride + (size_t)ry * rpitch + 4 * (xs + wc));
+                s_s[r * CR_SP + wc] = v;
+                r += dr; wc += dwc;
+                if (wc >= CR_SLAB + 2) { wc -= CR_SLAB + 2; r++; }
+            }
         }
-        for (int i = tid; i < n_trow * CR_SLAB; i += nthreads) {
-            int r = i / CR_SLAB, wc = i - r * CR_SLAB;
-            int tr = y0 - FPM_ROI_PAD + r;
+        for (int r = tid >> 5; r < n_trow; r += nthreads >> 5) {
+            const int wc = tid & 31;
+            const int tr = y0 - FPM_ROI_PAD + r;
             uint32_t v = 0;
             if (tr >= 0 && tr < th && xs + wc < twords)
                 v = __ldg(reinterpret_cast<const uint32_t*>(tpl.ptr + (size_t)tr * tpl.pitch + 4 * (xs + wc)));
