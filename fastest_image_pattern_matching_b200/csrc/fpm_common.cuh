@@ -65,6 +65,22 @@ struct FpmEvalTrace {
     int locx, locy;
 };
 
+// ---- cp.async (LDGSTS) helpers: global -> shared copies that bypass registers, so a thread can
+// keep many copies in flight (deep memory-level parallelism for the staging loops) ----
+__device__ __forceinline__ void fpm_cp_async4(void* smem, const void* gmem, bool valid)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = valid ? 4 : 0;                                   // src-size 0 -> zero fill, no global read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void fpm_cp_async16(void* smem, const void* gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fpm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void fpm_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Round-half-to-even of a double, like cvRound / saturate_cast<int>(double) (lrint).
 __device__ __forceinline__ int fpm_cvround(double v) { return __double2int_rn(v); }
 

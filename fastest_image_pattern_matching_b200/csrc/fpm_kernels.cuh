@@ -47,36 +47,30 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
     // smem columns actually read by the horizontal pass: words 3 .. (nout_cols+1)/2 + 4
     const int need_lo = 12, need_hi = 4 * ((nout_cols + 1) / 2 + 4) + 3;
 
-    if (vec == 16) {
-        const int nch = (need_hi + 16) / 16;                     // 16-byte chunks per row (<= 18)
-        for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
-            const int c = tid & 31;
-            if (c >= nch) continue;
-            const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
-            const int x = xs + 16 * c;
-            uint4 v;
-            if (x >= 0 && x + 15 < sw) {
-                v = __ldg(reinterpret_cast<const uint4*>(row + x));
-            } else {
-                uint32_t w[4] = {0, 0, 0, 0};
-                if (16 * c + 15 >= need_lo) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                        w[k >> 2] |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * (k & 3));
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            *reinterpret_cast<uint4*>(&s_in[r][16 * c]) = v;
+    const int nch = (need_hi + 16) / 16;                         // 16-byte chunks per row (<= 18)
+    const bool interior = ys >= 0 && ys + nin_rows <= sh && xs >= 0 && xs + 16 * nch <= sw;
+    if (interior && vec == 16) {
+        const int c = tid & 31;
+        if (c < nch) {
+            const uint8_t* g = s + (size_t)(ys + (tid >> 5)) * src.pitch + xs + 16 * c;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
+                fpm_cp_async16(&s_in[r][16 * c], g);
+        }
+    } else if (interior && vec == 4) {
+        const int w_lo = need_lo / 4, nwd = need_hi / 4 - w_lo + 1;   // words 3 .. need_hi/4 (<= 66)
+        for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
+            const uint8_t* row = s + (size_t)(ys + r) * src.pitch + xs;
+            for (int c = (tid & 63) + w_lo; c < w_lo + nwd; c += 64) fpm_cp_async4(&s_in[r][4 * c], row + 4 * c, true);
         }
     } else {
-        const int w_lo = need_lo / 4, nwd = need_hi / 4 - w_lo + 1;   // words 3 .. need_hi/4 (<= 66)
+        const int w_lo = need_lo / 4, nwd = need_hi / 4 - w_lo + 1;
         for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
             const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
             for (int c = tid & 63; c < nwd; c += 64) {
                 const int wc = w_lo + c;
                 const int x = xs + 4 * wc;
                 uint32_t v;
-                if (vec == 4 && x >= 0 && x + 3 < sw) {
+                if (vec >= 4 && x >= 0 && x + 3 < sw) {
                     v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
                 } else {
                     v = 0;
@@ -88,6 +82,8 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
             }
         }
     }
+    fpm_cp_async_commit();
+    fpm_cp_async_wait<0>();
     __syncthreads();
 
     // horizontal pass: outputs 2k, 2k+1 have their centres at smem bytes 4k+16, 4k+18
@@ -204,7 +200,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
                 if (vec_ok && x + 3 < sw) {
                     for (int r = tid >> 5; r < nr; r += WA_THREADS / 32, rowp += (size_t)(WA_THREADS / 32) * sp,
                              sp_out += (WA_THREADS / 32) * WA_SW)
-                        *reinterpret_cast<uint32_t*>(sp_out) = __ldg(reinterpret_cast<const uint32_t*>(rowp));
+                        fpm_cp_async4(sp_out, rowp, true);
                 } else {
                     for (int r = tid >> 5; r < nr; r += WA_THREADS / 32, rowp += (size_t)(WA_THREADS / 32) * sp,
                              sp_out += (WA_THREADS / 32) * WA_SW) {
@@ -218,6 +214,8 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
             }
         }
     }
+    fpm_cp_async_commit();
+    fpm_cp_async_wait<0>();
     __syncthreads();
     const int xg = tid & 15;
     if (tx0 + 4 * xg >= dpitch) return;
@@ -693,12 +691,38 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
     const bool active = (el < evals_per_cta) && (e < n_evals) && (y < rh);
     const int n_srow = evals_per_cta * rb;                 // staged ROI rows
     const int n_trow = rb + FPM_ROI_PAD;                   // staged template rows: tr = y0-6 .. y0+rb-1
-    uint32_t* s_s = smem_w;                                // [n_srow][CR_SP]
-    uint32_t* s_t = smem_w + (size_t)n_srow * CR_SP;       // [n_trow][CR_TP]
-    const int nw = (tw + 3) / 4;                           // template words per row
+    const int stage_words = n_srow * CR_SP + n_trow * CR_TP;   // one slab buffer: ROI rows then template rows
+    const int nw = (tw + 3) / 4;                               // template words per row
     const int rwords = rpitch / 4, twords = tpl.pitch / 4;
     const int tail = tw & 3;
     const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
+    const int nslabs = (nw + CR_SLAB - 1) / CR_SLAB;
+
+    // stage slab `si` (ROI words xs .. xs+33 of every row, template words xs .. xs+31) into buffer si&1
+    auto stage = [&](int si) {
+        const int xs = si * CR_SLAB;
+        uint32_t* b_s = smem_w + (size_t)(si & 1) * stage_words;
+        uint32_t* b_t = b_s + (size_t)n_srow * CR_SP;
+        int r = tid / (CR_SLAB + 2), wc = tid - r * (CR_SLAB + 2);
+        const int dr = nthreads / (CR_SLAB + 2), dwc = nthreads - dr * (CR_SLAB + 2);
+        while (r < n_srow) {
+            const int rel = (evals_per_cta == 1) ? 0 : r / rb;
+            const int ry = y0 + (r - rel * rb), re = e0 + rel;
+            const bool ok = re < n_evals && ry < rh && xs + wc < rwords;
+            const uint8_t* g = ok ? roi + (size_t)re * roi_stride + (size_t)ry * rpitch + 4 * (xs + wc) : roi;
+            fpm_cp_async4(b_s + r * CR_SP + wc, g, ok);
+            r += dr; wc += dwc;
+            if (wc >= CR_SLAB + 2) { wc -= CR_SLAB + 2; r++; }
+        }
+        for (int tr_l = tid >> 5; tr_l < n_trow; tr_l += nthreads >> 5) {
+            const int wct = tid & 31;
+            const int tr = y0 - FPM_ROI_PAD + tr_l;
+            const bool ok = tr >= 0 && tr < th && xs + wct < twords;
+            const uint8_t* g = ok ? tpl.ptr + (size_t)tr * tpl.pitch + 4 * (xs + wct) : tpl.ptr;
+            fpm_cp_async4(b_t + tr_l * CR_TP + wct, g, ok);
+        }
+        fpm_cp_async_commit();
+    };
 
     uint32_t acc[FPM_NSHIFT][FPM_NSHIFT];
 #pragma unroll
@@ -710,34 +734,19 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
 #pragma unroll
     for (int k = 0; k < 6; k++) tailb[k] = 0;
 
-    for (int xs = 0; xs < nw; xs += CR_SLAB) {
-        __syncthreads();
-        // ---- stage the slab: ROI words xs .. xs+33 of every row, template words xs .. xs+31
-        // (incremental (row, word) bookkeeping instead of a division per element)
-        {
-            int r = tid / (CR_SLAB + 2), wc = tid - r * (CR_SLAB + 2);
-            const int dr = nthreads / (CR_SLAB + 2), dwc = nthreads - dr * (CR_SLAB + 2);
-            while (r < n_srow) {
-                const int rel = (evals_per_cta == 1) ? 0 : r / rb;
-                const int ry = y0 + (r - rel * rb), re = e0 + rel;
-                uint32_t v = 0;
-                if (re < n_evals && ry < rh && xs + wc < rwords)
-                    v = *reinterpret_cast<const uint32_t*>(roi + (size_t)re * roi_stride + (size_t)ry * rpitch + 4 * (xs + wc));
-                s_s[r * CR_SP + wc] = v;
-                r += dr; wc += dwc;
-                if (wc >= CR_SLAB + 2) { wc -= CR_SLAB + 2; r++; }
-            }
-        }
-        for (int r = tid >> 5; r < n_trow; r += nthreads >> 5) {
-            const int wc = tid & 31;
-            const int tr = y0 - FPM_ROI_PAD + r;
-            uint32_t v = 0;
-            if (tr >= 0 && tr < th && xs + wc < twords)
-                v = __ldg(reinterpret_cast<const uint32_t*>(tpl.ptr + (size_t)tr * tpl.pitch + 4 * (xs + wc)));
-            s_t[r * CR_TP + wc] = v;
+    stage(0);
+    for (int si = 0; si < nslabs; si++) {
+        const int xs = si * CR_SLAB;
+        if (si + 1 < nslabs) {
+            stage(si + 1);                 // buffer (si+1)&1 was last read in iteration si-1: all threads are past it
+            fpm_cp_async_wait<1>();        // slab si has landed (for this thread's copies)
+        } else {
+            fpm_cp_async_wait<0>();
         }
         __syncthreads();
         if (active) {
+            const uint32_t* s_s = smem_w + (size_t)(si & 1) * stage_words;
+            const uint32_t* s_t = s_s + (size_t)n_srow * CR_SP;
             const uint32_t* srow = s_s + (size_t)tid * CR_SP;
             const uint32_t* trow = s_t + (size_t)(yl + FPM_ROI_PAD) * CR_TP;     // template row tr = y
             const int nx = min(CR_SLAB, nw - xs);
@@ -764,13 +773,14 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
                 sQ = __dp4a(m0, m0, sQ);
                 w0 = w1; w1 = w2;
             }
-            if (xs + CR_SLAB >= nw) {
+            if (si == nslabs - 1) {
                 // the 6 bytes that follow the template width: S[y][tw .. tw+5]
                 const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
 #pragma unroll
                 for (int k = 0; k < 6; k++) tailb[k] = sb[tw + k - 4 * xs];
             }
         }
+        __syncthreads();                   // everyone is done with buffer si&1 before it is refilled
     }
     // ---- window sums of the 7 shifts from shift 0 + head/tail bytes (exact)
     if (active) {
