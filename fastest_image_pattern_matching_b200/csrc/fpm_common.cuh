@@ -78,6 +78,12 @@ __device__ __forceinline__ void fpm_cp_async16(void* smem, const void* gmem)
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void fpm_cp_async16z(void* smem, const void* gmem, bool valid)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = valid ? 16 : 0;                                  // src-size 0 -> 16 zero bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void fpm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void fpm_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 

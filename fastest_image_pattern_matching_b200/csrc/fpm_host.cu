@@ -279,7 +279,7 @@ CorrCfg corr_config(int tpl_h)
     }
     c.threads = (int)align_up((size_t)c.rb * c.evals_per_cta, 32);
     const size_t n_srow = (size_t)c.evals_per_cta * c.rb, n_trow = (size_t)c.rb + FPM_ROI_PAD;
-    size_t stage = (n_srow * CR_SP + n_trow * CR_TP) * 4;
+    size_t stage = (n_srow + n_trow) * CR_PW * 4;
     size_t outb = (size_t)c.evals_per_cta * n_trow * FPM_NCELL * 4;
     c.smem = std::max(2 * stage, outb);      // two slab buffers (cp.async double buffering)
     return c;

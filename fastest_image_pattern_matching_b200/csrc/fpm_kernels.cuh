@@ -56,29 +56,39 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
             for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
                 fpm_cp_async16(&s_in[r][16 * c], g);
         }
-    } else if (interior && vec == 4) {
-        const int w_lo = need_lo / 4, nwd = need_hi / 4 - w_lo + 1;   // words 3 .. need_hi/4 (<= 66)
-        for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
-            const uint8_t* row = s + (size_t)(ys + r) * src.pitch + xs;
-            for (int c = (tid & 63) + w_lo; c < w_lo + nwd; c += 64) fpm_cp_async4(&s_in[r][4 * c], row + 4 * c, true);
+    } else if (vec == 16) {
+        const int c = tid & 31;
+        if (c < nch) {
+            const int x = xs + 16 * c;
+            const bool xin = x >= 0 && x + 15 < sw;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
+                const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
+                if (xin) {
+                    fpm_cp_async16(&s_in[r][16 * c], row + x);
+                } else if (16 * c + 15 >= need_lo) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        w[k >> 2] |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * (k & 3));
+                    *reinterpret_cast<uint4*>(&s_in[r][16 * c]) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
         }
     } else {
-        const int w_lo = need_lo / 4, nwd = need_hi / 4 - w_lo + 1;
+        const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
         for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
             const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
-            for (int c = tid & 63; c < nwd; c += 64) {
-                const int wc = w_lo + c;
+            for (int wc = w_lo + (tid & 63); wc <= w_hi; wc += 64) {
                 const int x = xs + 4 * wc;
-                uint32_t v;
-                if (vec >= 4 && x >= 0 && x + 3 < sw) {
-                    v = __ldg(reinterpret_cast<const uint32_t*>(row + x));
+                if (vec == 4 && x >= 0 && x + 3 < sw) {
+                    fpm_cp_async4(&s_in[r][4 * wc], row + x, true);
                 } else {
-                    v = 0;
+                    uint32_t v = 0;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * k);
+                    *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
                 }
-                *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
             }
         }
     }
@@ -142,7 +152,8 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 #define WA_TW 64
 #define WA_TH 64
 #define WA_THREADS 256
-#define WA_SW 96      // staged box: bytes per row (multiple of 4)
+#define WA_SW 100     // staged box pitch in bytes: 25 words (odd) -> rows fall in different banks
+#define WA_BW 96      // staged box: max bytes per row actually used
 #define WA_SH 96      // staged box: rows
 
 __global__ void __launch_bounds__(WA_THREADS)
@@ -189,7 +200,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
         bx0 = max(sx0, 0) & ~3;
         by0 = max(sy0, 0);
         const int bx1 = min(sx1, sw - 1), by1 = min(sy1, sh - 1);
-        staged = (bx1 - bx0 + 1 <= WA_SW) && (by1 - by0 + 1 <= WA_SH);
+        staged = (bx1 - bx0 + 1 <= WA_BW) && (by1 - by0 + 1 <= WA_SH);
         if (staged && bx1 >= bx0 && by1 >= by0) {
             const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;      // nwr <= 24
             const int wc = tid & 31;
@@ -229,19 +240,17 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
     for (int row = tid >> 4; row < nrows; row += WA_THREADS / 16) {
         uint32_t pack = 0;
         const int X0 = s_X0[row], Y0 = s_Y0[row];
-        if (fast) {
+        if (fast && 4 * xg + 3 < ncols) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (4 * xg + k < ncols) {
-                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
-                    const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
-                    const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
-                    const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
-                    const int top = (p00 << 5) + ax * (p01 - p00);
-                    const int bot = (p10 << 5) + ax * (p11 - p10);
-                    const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
-                    pack |= (uint32_t)v << (8 * k);
-                }
+                const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
+                const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
+                const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
+                const int top = (p00 << 5) + ax * (p01 - p00);
+                const int bot = (p10 << 5) + ax * (p11 - p10);
+                const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
+                pack |= (uint32_t)v << (8 * k);
             }
         } else {
 #pragma unroll
@@ -664,15 +673,17 @@ __global__ void fpm_refine_prep_kernel(const FpmCand* __restrict__ cands, int n_
 //   CTA layout: evals_per_cta x rb threads; thread (el, yl) -> eval blockIdx.y*evals_per_cta+el,
 //   row y = blockIdx.x*rb + yl.
 // =====================================================================================
-#define CR_SLAB 32
-#define CR_SP (CR_SLAB + 3)       // ROI slab pitch in words (odd; slab + 2 look-ahead words)
-#define CR_TP (CR_SLAB + 1)       // template slab pitch in words (odd)
+#define CR_SLAB 32                // template words per slab (128 px)
+#define CR_PW 36                  // slab row pitch in words: 32 + 4 look-ahead; 36 = 4 (mod 32), so a
+                                  // warp of lanes reading 16 B each from consecutive rows is conflict-free
 #define CR_MAX_THREADS 256
 
 __device__ __forceinline__ uint32_t fpm_shift_bytes(uint32_t lo, uint32_t hi, int c)
 {
     return __funnelshift_r(lo, hi, 8 * c);
 }
+
+__device__ __forceinline__ uint32_t fpm_u4(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 __global__ void __launch_bounds__(CR_MAX_THREADS)
 fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, FpmTplLevel tpl,
@@ -691,35 +702,34 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
     const bool active = (el < evals_per_cta) && (e < n_evals) && (y < rh);
     const int n_srow = evals_per_cta * rb;                 // staged ROI rows
     const int n_trow = rb + FPM_ROI_PAD;                   // staged template rows: tr = y0-6 .. y0+rb-1
-    const int stage_words = n_srow * CR_SP + n_trow * CR_TP;   // one slab buffer: ROI rows then template rows
-    const int nw = (tw + 3) / 4;                               // template words per row
-    const int rwords = rpitch / 4, twords = tpl.pitch / 4;
+    const int stage_words = (n_srow + n_trow) * CR_PW;     // one slab buffer: ROI rows then template rows
+    const int nw = (tw + 3) / 4;                           // template words per row
     const int tail = tw & 3;
     const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
     const int nslabs = (nw + CR_SLAB - 1) / CR_SLAB;
 
-    // stage slab `si` (ROI words xs .. xs+33 of every row, template words xs .. xs+31) into buffer si&1
+    // stage slab `si` into buffer si&1 with 16-byte cp.async:
+    //   ROI words xs .. xs+35 of every row (9 chunks), template words xs .. xs+31 (8 chunks)
     auto stage = [&](int si) {
-        const int xs = si * CR_SLAB;
+        const int xb = si * CR_SLAB * 4;                     // byte offset of the slab in a row
         uint32_t* b_s = smem_w + (size_t)(si & 1) * stage_words;
-        uint32_t* b_t = b_s + (size_t)n_srow * CR_SP;
-        int r = tid / (CR_SLAB + 2), wc = tid - r * (CR_SLAB + 2);
-        const int dr = nthreads / (CR_SLAB + 2), dwc = nthreads - dr * (CR_SLAB + 2);
-        while (r < n_srow) {
-            const int rel = (evals_per_cta == 1) ? 0 : r / rb;
-            const int ry = y0 + (r - rel * rb), re = e0 + rel;
-            const bool ok = re < n_evals && ry < rh && xs + wc < rwords;
-            const uint8_t* g = ok ? roi + (size_t)re * roi_stride + (size_t)ry * rpitch + 4 * (xs + wc) : roi;
-            fpm_cp_async4(b_s + r * CR_SP + wc, g, ok);
-            r += dr; wc += dwc;
-            if (wc >= CR_SLAB + 2) { wc -= CR_SLAB + 2; r++; }
+        uint32_t* b_t = b_s + (size_t)n_srow * CR_PW;
+        for (int i = tid; i < n_srow * 9; i += nthreads) {
+            const int r = i / 9, c = i - r * 9;
+            int rel = 0, ry = r;
+            if (evals_per_cta > 1) { rel = r / rb; ry = r - rel * rb; }
+            ry += y0;
+            const int re = e0 + rel;
+            const bool ok = re < n_evals && ry < rh && xb + 16 * c < rpitch;
+            const uint8_t* g = ok ? roi + (size_t)re * roi_stride + (size_t)ry * rpitch + xb + 16 * c : roi;
+            fpm_cp_async16z(b_s + r * CR_PW + 4 * c, g, ok);
         }
-        for (int tr_l = tid >> 5; tr_l < n_trow; tr_l += nthreads >> 5) {
-            const int wct = tid & 31;
-            const int tr = y0 - FPM_ROI_PAD + tr_l;
-            const bool ok = tr >= 0 && tr < th && xs + wct < twords;
-            const uint8_t* g = ok ? tpl.ptr + (size_t)tr * tpl.pitch + 4 * (xs + wct) : tpl.ptr;
-            fpm_cp_async4(b_t + tr_l * CR_TP + wct, g, ok);
+        for (int i = tid; i < n_trow * 8; i += nthreads) {
+            const int r = i >> 3, c = i & 7;
+            const int tr = y0 - FPM_ROI_PAD + r;
+            const bool ok = tr >= 0 && tr < th && xb + 16 * c < tpl.pitch;
+            const uint8_t* g = ok ? tpl.ptr + (size_t)tr * tpl.pitch + xb + 16 * c : tpl.ptr;
+            fpm_cp_async16z(b_t + r * CR_PW + 4 * c, g, ok);
         }
         fpm_cp_async_commit();
     };
@@ -739,43 +749,53 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
         const int xs = si * CR_SLAB;
         if (si + 1 < nslabs) {
             stage(si + 1);                 // buffer (si+1)&1 was last read in iteration si-1: all threads are past it
-            fpm_cp_async_wait<1>();        // slab si has landed (for this thread's copies)
+            fpm_cp_async_wait<1>();        // slab si has landed (this thread's copies)
         } else {
             fpm_cp_async_wait<0>();
         }
         __syncthreads();
         if (active) {
             const uint32_t* s_s = smem_w + (size_t)(si & 1) * stage_words;
-            const uint32_t* s_t = s_s + (size_t)n_srow * CR_SP;
-            const uint32_t* srow = s_s + (size_t)tid * CR_SP;
-            const uint32_t* trow = s_t + (size_t)(yl + FPM_ROI_PAD) * CR_TP;     // template row tr = y
+            const uint32_t* s_t = s_s + (size_t)n_srow * CR_PW;
+            const uint4* srow4 = reinterpret_cast<const uint4*>(s_s + (size_t)tid * CR_PW);
+            const uint4* trow4 = reinterpret_cast<const uint4*>(s_t + (size_t)(yl + FPM_ROI_PAD) * CR_PW);   // row tr = y
             const int nx = min(CR_SLAB, nw - xs);
-            uint32_t w0 = srow[0], w1 = srow[1];
-            if (xs == 0) { head0 = w0; head1 = w1; }
-            for (int xw = 0; xw < nx; xw++) {
-                const uint32_t w2 = srow[xw + 2];
-                uint32_t sh[FPM_NSHIFT];
-                sh[0] = w0;
-                sh[1] = fpm_shift_bytes(w0, w1, 1);
-                sh[2] = fpm_shift_bytes(w0, w1, 2);
-                sh[3] = fpm_shift_bytes(w0, w1, 3);
-                sh[4] = w1;
-                sh[5] = fpm_shift_bytes(w1, w2, 1);
-                sh[6] = fpm_shift_bytes(w1, w2, 2);
+            const int ngroups = (nx + 3) >> 2;
+            uint4 cur = srow4[0];
+            if (xs == 0) { head0 = cur.x; head1 = cur.y; }
+            for (int g = 0; g < ngroups; g++) {
+                const uint4 nxt = srow4[g + 1];
+                uint4 t4[FPM_NSHIFT];
 #pragma unroll
-                for (int j = 0; j < FPM_NSHIFT; j++) {
-                    const uint32_t t = trow[xw - j * CR_TP];                     // template row y - j
+                for (int j = 0; j < FPM_NSHIFT; j++) t4[j] = trow4[g - j * (CR_PW / 4)];        // template row y - j
+                const uint32_t w[6] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y};
 #pragma unroll
-                    for (int c = 0; c < FPM_NSHIFT; c++) acc[j][c] = __dp4a(t, sh[c], acc[j][c]);
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t w0 = w[u], w1 = w[u + 1], w2 = w[u + 2];
+                    uint32_t sh[FPM_NSHIFT];
+                    sh[0] = w0;
+                    sh[1] = fpm_shift_bytes(w0, w1, 1);
+                    sh[2] = fpm_shift_bytes(w0, w1, 2);
+                    sh[3] = fpm_shift_bytes(w0, w1, 3);
+                    sh[4] = w1;
+                    sh[5] = fpm_shift_bytes(w1, w2, 1);
+                    sh[6] = fpm_shift_bytes(w1, w2, 2);
+#pragma unroll
+                    for (int j = 0; j < FPM_NSHIFT; j++) {
+                        const uint32_t t = fpm_u4(t4[j], u);             // zero beyond the template width
+#pragma unroll
+                        for (int c = 0; c < FPM_NSHIFT; c++) acc[j][c] = __dp4a(t, sh[c], acc[j][c]);
+                    }
+                    const int idx = xs + 4 * g + u;
+                    const uint32_t m0 = idx < nw - 1 ? w0 : (idx == nw - 1 ? (w0 & tailbm) : 0u);
+                    sS = __dp4a(m0, 0x01010101u, sS);
+                    sQ = __dp4a(m0, m0, sQ);
                 }
-                const uint32_t m0 = (xs + xw == nw - 1) ? (w0 & tailbm) : w0;
-                sS = __dp4a(m0, 0x01010101u, sS);
-                sQ = __dp4a(m0, m0, sQ);
-                w0 = w1; w1 = w2;
+                cur = nxt;
             }
             if (si == nslabs - 1) {
                 // the 6 bytes that follow the template width: S[y][tw .. tw+5]
-                const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow);
+                const uint8_t* sb = reinterpret_cast<const uint8_t*>(srow4);
 #pragma unroll
                 for (int k = 0; k < 6; k++) tailb[k] = sb[tw + k - 4 * xs];
             }
@@ -798,7 +818,6 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
         }
     }
     // ---- transpose through shared memory: out[el][tr_local][cell], then coalesced global stores
-    __syncthreads();
     uint32_t* s_o = smem_w;                                // [evals_per_cta][n_trow][49]
     if (active) {
 #pragma unroll
