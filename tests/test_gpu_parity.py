@@ -368,3 +368,15 @@ def test_stage_api_equals_match(matcher, golden_cases, case):
     refined = [matcher.stageRefine(cands[r::world]) for r in range(world)]
     res = matcher.stageFinal(np.concatenate(refined))
     assert_results_match(res, whole, 0, 0, 0)
+
+
+def test_angle_sharded_driver_single_rank(matcher, golden_cases):
+    """dist.match_angle_sharded with the real engine (world 1) == match()."""
+    from fastest_image_pattern_matching_b200 import dist as D
+    c = golden_cases["src8"]
+    configure(matcher, c["params"])
+    matcher.learnPattern(get_image(c["tpl"]))
+    src = get_image(c["src"])
+    assert_results_match(D.match_angle_sharded(matcher, src, None), matcher.match(src), 0, 0, 0)
+    rows = D.match_frames_sharded(matcher, [src, get_image("Src9")], None)
+    assert rows[0].shape == (3, 12) and abs(rows[0][0, 0] - c["results"][0]["score"]) <= 1e-4
