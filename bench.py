@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=0, help="images per worker for the CPU baseline (0 = auto)")
+    ap.add_argument("--h2d-chunk", type=int, default=0, help="frames per H2D chunk of the e2e path (0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +242,8 @@ def main():
     m = TemplateMatcher(local_rank, result_capacity=16)
     configure(m, wl)
     assert m.learnPattern(tpl)
+    if args.h2d_chunk:
+        m.setH2DChunk(args.h2d_chunk)
     cap = m.result_capacity
     res = (L.fpm_result * (cap * B))()
     counts = (C.c_int * B)()
@@ -294,6 +297,19 @@ def main():
     dev_ms, dev_wall_ms, launches = timed(step_device)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, e2e_wall_ms, _ = timed(step_host)
+
+    # raw pinned-host -> device copy rate of one step's frames (context for e2e: the PCIe bound)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = torch.empty_like(host_sets[0], device="cuda")
+    scratch.copy_(host_sets[0], non_blocking=True)
+    ev0.record()
+    for _ in range(3):
+        scratch.copy_(host_sets[0], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * B * H * Wd / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del scratch
 
     # per-kernel device time over the same K steps, CUDA events around every launch on the launch stream
     m.setProfile(True)
@@ -362,7 +378,8 @@ def main():
                    "global_batch": world * B, "sharding": "frames over ranks, no data-path collective",
                    "l2": "step input %.0f MB > 126 MB L2; two alternating frame sets" % (B * H * Wd / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * Wd, "d2h_bytes_per_step": B * cap * 96 + B * 4,
-                "ms_per_step": e2e_ms / K},
+                "ms_per_step": e2e_ms / K, "h2d_copy_only_GBps": h2d_gbps,
+                "pcie_bound_images_per_s": world * h2d_gbps * 1e9 / (H * Wd)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -134,6 +134,7 @@ struct fpm_handle {
     int min_reduce_area = 256;
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
+    int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
     // template
     bool learned = false;
     int learned_mra = -1;
@@ -148,7 +149,7 @@ struct fpm_handle {
     // workspace
     DevBuf d_src, d_pyr, d_rot, d_score, d_blkv, d_blkl, d_picks, d_pickcnt, d_jobs_top, d_angles, d_ftx, d_fty;
     DevBuf d_off, d_keys, d_cand[2], d_candcnt, d_toppt, d_counters, d_jobs_ref, d_roi, d_rowsum, d_rowS, d_rowQ;
-    DevBuf d_refined, d_rects, d_del, d_idmap, d_results, d_rescnt, d_trace, d_trace_sc, d_dbg[4];
+    DevBuf d_pairs, d_refined, d_rects, d_del, d_idmap, d_results, d_rescnt, d_trace, d_trace_sc, d_dbg[4];
     PinnedBuf h_counts, h_results, h_stage;
     std::vector<FpmLevel> levels; // source pyramid of the current batch
     TopPlan plan;
@@ -283,6 +284,12 @@ CorrCfg corr_config(int tpl_h)
     size_t outb = (size_t)c.evals_per_cta * n_trow * FPM_NCELL * 4;
     c.smem = std::max(2 * stage, outb);      // two slab buffers (cp.async double buffering)
     return c;
+}
+
+inline size_t top_score_smem(int tw, int th)
+{
+    size_t nwt = (tw + 3) / 4, pww = (TS_TILE + tw - 1 + 3) / 4 + 2;
+    return 4 * ((size_t)th * nwt + (size_t)(TS_TILE + th - 1) * pww);
 }
 
 inline int level_vec_ok(const FpmLevel& L)
@@ -462,7 +469,7 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
                                                                level_vec_ok(h->levels[top])));
     }
     {
-        size_t smem = (size_t)t.w * t.h + (size_t)(TS_TILE + t.w - 1) * (TS_TILE + t.h - 1);
+        size_t smem = top_score_smem(t.w, t.h);
         if (smem > 200 * 1024) { h->err = "top-layer template too large for the score kernel"; return FPM_ERR_LIMIT; }
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -609,6 +616,8 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
     CK(h->d_rects.ensure((size_t)batch * ks * sizeof(FpmRRect)));
     CK(h->d_del.ensure((size_t)batch * ks * sizeof(int)));
     CK(h->d_idmap.ensure((size_t)batch * ks * sizeof(int)));
+    const int pair_cap = std::min(ks, 512);                 // all-pairs NMS matrix for up to 512 survivors per frame
+    CK(h->d_pairs.ensure((size_t)batch * pair_cap * pair_cap));
     const int rcap = std::max(cap, 1);
     CK(h->d_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev)));
     CK(h->d_rescnt.ensure((size_t)batch * sizeof(int)));
@@ -619,6 +628,7 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
                                                              h->max_overlap, h->tpl[0].w, h->tpl[0].h,
                                                              h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
                                                              h->d_del.as<int>(), h->d_idmap.as<int>(),
+                                                             h->d_pairs.as<unsigned char>(), pair_cap,
                                                              h->d_results.as<FpmResultDev>(), rcap, h->d_rescnt.as<int>()));
     FpmResultDev* hr = h->h_results.as<FpmResultDev>();
     int* hn = reinterpret_cast<int*>(hr + (size_t)batch * rcap);
@@ -758,7 +768,7 @@ void fpm_destroy(fpm_handle* h)
     DevBuf* bufs[] = {&h->d_tpl, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
-                      &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
+                      &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
                       &h->d_dbg[0], &h->d_dbg[1], &h->d_dbg[2], &h->d_dbg[3]};
     for (DevBuf* b : bufs) b->release();
     h->h_counts.release(); h->h_results.release(); h->h_stage.release();
@@ -787,6 +797,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_TRACE: h->trace = v != 0; break;
     case FPM_PARAM_WORKSPACE_MB: h->workspace_mb = v; break;
     case FPM_PARAM_PROFILE: prof_collect(h); h->profile = v != 0; break;
+    case FPM_PARAM_H2D_CHUNK: h->h2d_chunk = (int)v; break;
     default: h->err = "unknown parameter"; return FPM_ERR_INVALID;
     }
     return FPM_OK;
@@ -806,6 +817,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_TRACE: return h->trace;
     case FPM_PARAM_WORKSPACE_MB: return h->workspace_mb;
     case FPM_PARAM_PROFILE: return h->profile;
+    case FPM_PARAM_H2D_CHUNK: return h->h2d_chunk;
     default: return 0;
     }
 }
@@ -867,6 +879,7 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
     int chunk = std::max(1, std::min(batch, (int)std::max<size_t>(1, (size_t)(512ull << 20) / img)));
     if (batch >= 8) chunk = std::min(chunk, (batch + 3) / 4);
     else if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
+    if (h->h2d_chunk > 0) chunk = std::min(batch, h->h2d_chunk);
     const size_t buf_bytes = align_up(img * chunk, 256);
     CK(h->d_src.ensure(buf_bytes * 2));
     const int nchunks = (batch + chunk - 1) / chunk;
@@ -1201,7 +1214,7 @@ int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* 
     jb.dw = w; jb.dh = hgt; jb.valid = 1;
     CK(cudaMemcpy2DAsync(h->d_dbg[0].p, rp, img, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_dbg[2].p, &jb, sizeof(jb), cudaMemcpyHostToDevice, h->stream));
-    size_t smem = (size_t)t.w * t.h + (size_t)(TS_TILE + t.w - 1) * (TS_TILE + t.h - 1);
+    size_t smem = top_score_smem(t.w, t.h);
     if (smem > 200 * 1024) { h->err = "template too large"; return FPM_ERR_LIMIT; }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((RW + TS_TILE - 1) / TS_TILE, (RH + TS_TILE - 1) / TS_TILE, 1), block(TS_TILE, TS_TILE);

@@ -317,7 +317,9 @@ __device__ __forceinline__ float fpm_ccoeff_epilogue(float numerator, double wsu
 
 // =====================================================================================
 // K4+K7  top-layer dense score map: exact integer TM_CCORR numerator, exact window sum / sqsum,
-// CCOEFF_NORMED epilogue.  One CTA = 16x16 scores; image patch + template in shared memory.
+// CCOEFF_NORMED epilogue.  One CTA = 16x16 scores; image patch + template in shared memory as
+// 32-bit words (rows zero padded); every thread walks its window 4 pixels at a time: the patch
+// words are re-aligned with a funnel shift and fed to dp4a (numerator, sum, sum of squares).
 // =====================================================================================
 #define TS_TILE 16
 
@@ -326,43 +328,64 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
                      size_t rot_job_stride, FpmTplLevel tpl, float* __restrict__ score, int spitch,
                      size_t score_job_stride)
 {
-    extern __shared__ uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     const FpmWarpJob& jb = jobs[blockIdx.z];
     const int tw = tpl.w, th = tpl.h;
     const int RW = jb.dw - tw + 1, RH = jb.dh - th + 1;
     const int x0 = blockIdx.x * TS_TILE, y0 = blockIdx.y * TS_TILE;
     if (!jb.valid || RW <= 0 || RH <= 0 || x0 >= RW || y0 >= RH) return;
-    const int pw = TS_TILE + tw - 1, ph = TS_TILE + th - 1;
-    uint8_t* s_t = smem;                 // th*tw
-    uint8_t* s_p = smem + th * tw;       // ph*pw
+    const int nwt = (tw + 3) / 4;                          // template words per row
+    const int ph = TS_TILE + th - 1;
+    const int pww = (TS_TILE + tw - 1 + 3) / 4 + 2;        // patch words per row (+1 for the shifted read)
+    uint32_t* s_t = reinterpret_cast<uint32_t*>(smem);     // th * nwt
+    uint32_t* s_p = s_t + th * nwt;                        // ph * pww
     const int tid = threadIdx.y * TS_TILE + threadIdx.x;
     const uint8_t* __restrict__ r = rot + (size_t)blockIdx.z * rot_job_stride;
-    for (int i = tid; i < th * tw; i += TS_TILE * TS_TILE) {
-        int yy = i / tw, xx = i - yy * tw;
-        s_t[i] = tpl.ptr[yy * tpl.pitch + xx];
+    for (int i = tid; i < th * nwt; i += TS_TILE * TS_TILE) {
+        int yy = i / nwt, xw = i - yy * nwt;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (4 * xw + k < tw) v |= (uint32_t)tpl.ptr[yy * tpl.pitch + 4 * xw + k] << (8 * k);
+        s_t[i] = v;
     }
-    for (int i = tid; i < ph * pw; i += TS_TILE * TS_TILE) {
-        int yy = i / pw, xx = i - yy * pw;
-        int gx = x0 + xx, gy = y0 + yy;
-        s_p[i] = (gx < jb.dw && gy < jb.dh) ? r[(size_t)gy * rpitch + gx] : 0;
+    for (int i = tid; i < ph * pww; i += TS_TILE * TS_TILE) {
+        int yy = i / pww, xw = i - yy * pww;
+        int gy = y0 + yy;
+        uint32_t v = 0;
+        if (gy < jb.dh) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int gx = x0 + 4 * xw + k;
+                if (gx < jb.dw) v |= (uint32_t)r[(size_t)gy * rpitch + gx] << (8 * k);
+            }
+        }
+        s_p[i] = v;
     }
     __syncthreads();
     const int ox = x0 + threadIdx.x, oy = y0 + threadIdx.y;
     if (ox >= RW || oy >= RH) return;
     float* out = score + (size_t)blockIdx.z * score_job_stride + (size_t)oy * spitch + ox;
     if (tpl.result_equal1) { *out = 1.0f; return; }
+    const int wo = threadIdx.x >> 2, sh = 8 * (threadIdx.x & 3);
+    const int tail = tw & 3;
+    const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
     long long num = 0, wsum = 0, wsq = 0;
     for (int yy = 0; yy < th; yy++) {
-        const uint8_t* prow = s_p + (threadIdx.y + yy) * pw + threadIdx.x;
-        const uint8_t* trow = s_t + yy * tw;
-        int a = 0, b = 0, c = 0;
-        for (int xx = 0; xx < tw; xx++) {
-            int p = prow[xx];
-            a += p * trow[xx];
-            b += p;
-            c += p * p;
+        const uint32_t* prow = s_p + (threadIdx.y + yy) * pww + wo;
+        const uint32_t* trow = s_t + yy * nwt;
+        uint32_t a = 0, b = 0, c = 0;
+        uint32_t lo = prow[0];
+        for (int xw = 0; xw < nwt; xw++) {
+            const uint32_t hi = prow[xw + 1];
+            uint32_t p = __funnelshift_r(lo, hi, sh);
+            if (xw == nwt - 1) p &= tailbm;
+            a = __dp4a(p, trow[xw], a);
+            b = __dp4a(p, 0x01010101u, b);
+            c = __dp4a(p, p, c);
+            lo = hi;
         }
-        num += a; wsum += b; wsq += c;
+        num += a; wsum += b; wsq += c;                     // per-row s32 sums, s64 across rows
     }
     // TM_CCORR result cell is a float32 (cv::matchTemplate output depth), here the rounded exact sum
     *out = fpm_ccoeff_epilogue((float)num, (double)wsum, (double)wsq, tpl.mean, tpl.norm, tpl.inv_area);
@@ -969,19 +992,39 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
         } else {
             const int32_t* rs = rowsum + (size_t)e * th * FPM_NCELL + cell;
             float numf;
+            // loads are issued 8 at a time (independent), the additions stay in template-row order
             if (use_chain) {
                 float acc = 0.0f;
-                for (int tr = 0; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * FPM_NCELL]));
+                int tr = 0;
+                for (; tr + 8 <= th; tr += 8) {
+                    int v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = rs[(size_t)(tr + k) * FPM_NCELL];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
+                }
+                for (; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * FPM_NCELL]));
                 numf = acc;
             } else {
                 long long acc = 0;
+#pragma unroll 8
                 for (int tr = 0; tr < th; tr++) acc += rs[(size_t)tr * FPM_NCELL];
                 numf = (float)acc;
             }
             const int32_t* ps = rowS + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;
             const int32_t* pq = rowQ + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;
             long long ws = 0, wq = 0;
-            for (int y = 0; y < th; y++) { ws += ps[(size_t)y * FPM_NSHIFT]; wq += pq[(size_t)y * FPM_NSHIFT]; }
+            {
+                int y = 0;
+                for (; y + 8 <= th; y += 8) {
+                    int a[8], b[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { a[k] = ps[(size_t)(y + k) * FPM_NSHIFT]; b[k] = pq[(size_t)(y + k) * FPM_NSHIFT]; }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { ws += a[k]; wq += b[k]; }
+                }
+                for (; y < th; y++) { ws += ps[(size_t)y * FPM_NSHIFT]; wq += pq[(size_t)y * FPM_NSHIFT]; }
+            }
             sc = fpm_ccoeff_epilogue(numf, (double)ws, (double)wq, tpl.mean, tpl.norm, tpl.inv_area);
         }
         s_sc[j][cell] = sc;
@@ -1090,7 +1133,7 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
                  double score_thresh, double max_overlap, int tpl_w, int tpl_h,
                  unsigned long long* __restrict__ key_scratch, int key_stride,
                  FpmRRect* __restrict__ rect_scratch, int* __restrict__ del_scratch,
-                 int* __restrict__ idmap_scratch,
+                 int* __restrict__ idmap_scratch, unsigned char* __restrict__ pair_scratch, int pair_cap,
                  FpmResultDev* __restrict__ results, int result_cap, int* __restrict__ result_count)
 {
     const int img = blockIdx.x, tid = threadIdx.x;
@@ -1134,14 +1177,31 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
         del[i] = 0;
     }
     __syncthreads();
-    // filterWithRotatedRect: scores are sorted descending so the later index always loses
-    for (int i = 0; i < m - 1; i++) {
-        if (!del[i]) {
-            const FpmRRect ri = rects[i];
-            for (int k = i + 1 + tid; k < m; k += FN_THREADS)
-                if (!del[k] && fpm_rrect_overlap_decision(ri, rects[k], max_overlap, nullptr, nullptr)) del[k] = 1;
+    // filterWithRotatedRect: scores are sorted descending so the later index always loses.
+    // Small sets: all pair decisions are evaluated in parallel first (the geometry is the expensive,
+    // latency-bound part), then the greedy pass only reads the byte matrix.
+    if (m <= pair_cap) {
+        unsigned char* ov = pair_scratch + (size_t)img * pair_cap * pair_cap;
+        for (int p = tid; p < m * m; p += FN_THREADS) {
+            int i = p / m, k = p - i * m;
+            if (k > i) ov[p] = (unsigned char)fpm_rrect_overlap_decision(rects[i], rects[k], max_overlap, nullptr, nullptr);
         }
         __syncthreads();
+        for (int i = 0; i < m - 1; i++) {
+            if (!del[i])
+                for (int k = i + 1 + tid; k < m; k += FN_THREADS)
+                    if (ov[i * m + k]) del[k] = 1;
+            __syncthreads();
+        }
+    } else {
+        for (int i = 0; i < m - 1; i++) {
+            if (!del[i]) {
+                const FpmRRect ri = rects[i];
+                for (int k = i + 1 + tid; k < m; k += FN_THREADS)
+                    if (!del[k] && fpm_rrect_overlap_decision(ri, rects[k], max_overlap, nullptr, nullptr)) del[k] = 1;
+            }
+            __syncthreads();
+        }
     }
     if (tid == 0) {
         int cnt = 0;

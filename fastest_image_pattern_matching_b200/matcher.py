@@ -92,6 +92,7 @@ class TemplateMatcher:
     def getSubPixelEstimation(self) -> bool: return bool(self._get(L.PARAM_SUBPIXEL))
     def setTrace(self, v: bool): self._set(L.PARAM_TRACE, 1 if v else 0)
     def setWorkspaceMB(self, v: float): self._set(L.PARAM_WORKSPACE_MB, v)
+    def setH2DChunk(self, v: int): self._set(L.PARAM_H2D_CHUNK, v)
 
     def getLastExecutionTime(self) -> float:
         """seconds, like the reference (include/TemplateMatcher.h:40)"""

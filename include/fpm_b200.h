@@ -45,6 +45,7 @@ enum fpm_param {
     FPM_PARAM_TRACE = 7,           /* keep per-stage records for fpm_trace_*   (tests) */
     FPM_PARAM_WORKSPACE_MB = 8,    /* refinement workspace budget per wave, default 4096 */
     FPM_PARAM_PROFILE = 9,         /* bracket every kernel launch with CUDA events (bench.py roofline) */
+    FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
     FPM_PARAM_COUNT_
 };
 
