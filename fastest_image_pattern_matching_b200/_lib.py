@@ -19,7 +19,7 @@ class fpm_result(C.Structure):
 
 
 PARAM_MAX_POSITIONS, PARAM_MAX_OVERLAP, PARAM_SCORE, PARAM_TOLERANCE_ANGLE, PARAM_MIN_REDUCE_AREA, \
-    PARAM_USE_SIMD, PARAM_SUBPIXEL, PARAM_TRACE, PARAM_WORKSPACE_MB, PARAM_PROFILE, PARAM_H2D_CHUNK = range(11)
+    PARAM_USE_SIMD, PARAM_SUBPIXEL, PARAM_TRACE, PARAM_WORKSPACE_MB, PARAM_PROFILE, PARAM_H2D_CHUNK, PARAM_TENSOR_CORES = range(12)
 
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 _pi, _pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -60,6 +60,7 @@ SIGNATURES = {
     "fpm_dbg_pyrdown": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "fpm_dbg_warp_affine": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "fpm_dbg_corr_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "fpm_dbg_corr_rows_mma": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "fpm_dbg_top_score": (_i, [_vp, _vp, _i, _i, _vp]),
     "fpm_dbg_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _pi]),
     "fpm_dbg_rrect_overlap": (_i, [_vp, _vp, _d, _pi, _pd]),

@@ -7,6 +7,7 @@
 // fpm_create() fails.
 #include "../../include/fpm_b200.h"
 #include "fpm_kernels.cuh"
+#include "fpm_mma.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -106,6 +107,8 @@ void best_rotation_size(int sw, int sh, int dw, int dh, double dRAngle, int* ow,
 struct TplLevelHost {
     int w = 0, h = 0, pitch = 0;
     size_t dev_off = 0;
+    size_t tsh_off = 0;          // 8 pre-shifted copies for the tensor-core path
+    int bpitch = 0;
     double mean = 0, norm = 0, inv_area = 1;
     int equal1 = 0;
     std::vector<uint8_t> pix;    // w*h
@@ -135,6 +138,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
+    int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
     // template
     bool learned = false;
     int learned_mra = -1;
@@ -142,7 +146,7 @@ struct fpm_handle {
     std::vector<uint8_t> tpl0;    // level-0 copy for re-learning when MinReduceArea changes
     int tpl0_w = 0, tpl0_h = 0;
     std::vector<TplLevelHost> tpl;
-    DevBuf d_tpl;
+    DevBuf d_tpl, d_tsh, d_raw;
     // user rect (pure storage)
     int ur[4] = {0, 0, 0, 0};
     int has_ur = 0;
@@ -190,10 +194,11 @@ namespace {
         }                                                                                \
     } while (0)
 
-enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_COUNT };
+enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_ROWSUMS, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"fpm_pyrdown_kernel", "fpm_warp_kernel(top)", "fpm_top_score_kernel", "fpm_top_peaks_kernel",
                                            "fpm_collect_sort_kernel", "fpm_refine_prep_kernel", "fpm_warp_kernel(roi)",
-                                           "fpm_corr_rows_kernel", "fpm_refine_finalize_kernel", "fpm_final_kernel"};
+                                           "fpm_corr_rows_kernel", "fpm_refine_finalize_kernel", "fpm_final_kernel",
+                                           "fpm_corr_mma_kernel", "fpm_row_sums_kernel"};
 
 cudaEvent_t prof_event(fpm_handle* h)
 {
@@ -297,6 +302,83 @@ inline int level_vec_ok(const FpmLevel& L)
     return ((reinterpret_cast<uintptr_t>(L.ptr) & 3) == 0) && (L.pitch % 4 == 0) && (L.img_stride % 4 == 0);
 }
 
+// ---- tensor-core correlation (fpm_mma.cuh): TMA descriptors + launch -----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D u8 tensor [d2][d1][d0 bytes] with byte strides s1, s2; box (b0, b1, b2); 128-byte swizzle, zero OOB fill
+int make_map_3d(fpm_handle* h, CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                uint32_t b0, uint32_t b1, uint32_t b2)
+{
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) { h->err = "cuTensorMapEncodeTiled not available"; return FPM_ERR_CUDA; }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1, s2};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return FPM_ERR_CUDA; }
+    return FPM_OK;
+}
+
+bool mma_usable(const fpm_handle* h, int tw)
+{
+    if (h->use_tc == 0) return false;
+    if (!get_encode_tiled()) return false;
+    return h->use_tc >= 2 ? true : tw >= 64;
+}
+
+// raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
+int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
+                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ)
+{
+    const int rh = th + FPM_ROI_PAD;
+    const int m_tiles = (ne + MM_M - 1) / MM_M;
+    const int e_pad = m_tiles * MM_M;
+    *e_pad_out = e_pad;
+    CK(h->d_raw.ensure((size_t)rh * e_pad * MM_N * sizeof(int32_t)));
+    CUtensorMap map_a, map_b;
+    int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)rpitch, (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
+    if (rc) return rc;
+    rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
+    if (rc) return rc;
+    // enough CTAs for ~2 waves of 148 SMs, at least 2 ROI rows per CTA
+    int chunks = std::max(1, (2 * 148 + m_tiles - 1) / m_tiles);
+    int rows_per_cta = std::max(2, (rh + chunks - 1) / chunks);
+    chunks = (rh + rows_per_cta - 1) / rows_per_cta;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(fpm_corr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid(chunks, m_tiles);
+    KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
+       fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw + FPM_ROI_PAD, rows_per_cta,
+                                                                           h->d_raw.as<int32_t>()));
+    const int n_rows = ne * rh;
+    KL(K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD),
+       fpm_row_sums_kernel<<<(n_rows * 32 + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh, n_rows, rowS, rowQ));
+    return FPM_OK;
+}
+
 // ---- learnPattern, src/TemplateMatcher.cpp:45-95 ------------------------------------
 int do_learn(fpm_handle* h)
 {
@@ -323,6 +405,23 @@ int do_learn(fpm_handle* h)
         FpmLevel d{h->d_tpl.as<uint8_t>() + h->tpl[l].dev_off, h->tpl[l].w, h->tpl[l].h, h->tpl[l].pitch, 0};
         int rc = launch_pyrdown(h, s, d, 1);
         if (rc) return rc;
+    }
+    {
+        size_t toff = 0;
+        for (int l = 0; l <= top; l++) {
+            TplLevelHost& t = h->tpl[l];
+            t.bpitch = (int)align_up(t.w + 8, 16);
+            t.tsh_off = toff;
+            toff += align_up((size_t)8 * t.h * t.bpitch, 256);
+        }
+        CK(h->d_tsh.ensure(toff));
+        for (int l = 0; l <= top; l++) {
+            TplLevelHost& t = h->tpl[l];
+            dim3 g((t.bpitch + 127) / 128, t.h, 8);
+            fpm_shift_template_kernel<<<g, 128, 0, h->stream>>>(h->d_tpl.as<uint8_t>() + t.dev_off, t.w, t.h, t.pitch,
+                                                                h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch);
+            CKL();
+        }
     }
     for (int l = 0; l <= top; l++) {
         TplLevelHost& t = h->tpl[l];
@@ -570,15 +669,23 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
                fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), L, h->d_roi.as<uint8_t>(),
                                                                     rpitch, roi_stride, 0, wtiles_x, level_vec_ok(L)));
-            dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
-            // algorithmic MACs: 49 * w * h per eval
-            KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
-               fpm_corr_rows_kernel<<<cgrid, cc.threads, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, ne,
-                                                                            cc.rb, cc.evals_per_cta, h->d_rowsum.as<int32_t>(),
-                                                                            h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>()));
+            int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
+            if (mma_usable(h, t.w)) {
+                int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                          t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
+                if (rcm) return rcm;
+            } else {
+                dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
+                // algorithmic MACs: 49 * w * h per eval
+                KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
+                   fpm_corr_rows_kernel<<<cgrid, cc.threads, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, ne,
+                                                                                cc.rb, cc.evals_per_cta, h->d_rowsum.as<int32_t>(),
+                                                                                h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>()));
+            }
             KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
                fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
-                   cands + c0, n_ang, step, h->d_rowsum.as<int32_t>(), h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
+                   cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,
+                   h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
                    L.h, layer_score[layer], h->use_simd, layer == 0 ? 1 : 0, h->subpixel, h->d_cand[cur ^ 1].as<FpmCand>(),
                    counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
                    h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr));
@@ -765,7 +872,7 @@ void fpm_destroy(fpm_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
-    DevBuf* bufs[] = {&h->d_tpl, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
                       &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
@@ -798,6 +905,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_WORKSPACE_MB: h->workspace_mb = v; break;
     case FPM_PARAM_PROFILE: prof_collect(h); h->profile = v != 0; break;
     case FPM_PARAM_H2D_CHUNK: h->h2d_chunk = (int)v; break;
+    case FPM_PARAM_TENSOR_CORES: h->use_tc = (int)v; break;
     default: h->err = "unknown parameter"; return FPM_ERR_INVALID;
     }
     return FPM_OK;
@@ -818,6 +926,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_WORKSPACE_MB: return h->workspace_mb;
     case FPM_PARAM_PROFILE: return h->profile;
     case FPM_PARAM_H2D_CHUNK: return h->h2d_chunk;
+    case FPM_PARAM_TENSOR_CORES: return h->use_tc;
     default: return 0;
     }
 }
@@ -877,7 +986,9 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
     const int pitch = linear ? width : (int)align_up(width, 128);
     const size_t img = linear ? frame_stride : align_up((size_t)pitch * height, 256);
     int chunk = std::max(1, std::min(batch, (int)std::max<size_t>(1, (size_t)(512ull << 20) / img)));
-    if (batch >= 8) chunk = std::min(chunk, (batch + 3) / 4);
+    // measured on B200 (cfg1): H2D of c frames takes 0.22c ms, matching c frames 0.63 + 0.073c ms, so the
+    // pipeline is copy-bound from c = 8 on while the fill/drain cost stays small
+    if (batch >= 16) chunk = std::min(chunk, 8);
     else if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
     if (h->h2d_chunk > 0) chunk = std::min(batch, h->h2d_chunk);
     const size_t buf_bytes = align_up(img * chunk, 256);
@@ -1192,6 +1303,48 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int
     CK(cudaMemcpyAsync(rowS, dS, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(rowQ, dQ, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return FPM_OK;
+}
+
+// tensor-core path on `ne` ROI patches (each (th+6)x(tw+6), contiguous); results converted to the [e][tr][49] layout
+int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t* tpl, int tw, int th, int32_t* rowsum,
+                          int32_t* rowS, int32_t* rowQ)
+{
+    if (!h || !rois || !tpl || tw <= 0 || th <= 0 || ne <= 0) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!get_encode_tiled()) { h->err = "cuTensorMapEncodeTiled not available"; return FPM_ERR_CUDA; }
+    const int rh = th + FPM_ROI_PAD, rw = tw + FPM_ROI_PAD;
+    const int rpitch = (int)align_up(rw, 16) + 16, tp = (int)align_up(tw, 16), bpitch = (int)align_up(tw + 8, 16);
+    const size_t roi_stride = (size_t)rpitch * rh;
+    CK(h->d_dbg[0].ensure(roi_stride * ne));
+    CK(h->d_dbg[1].ensure((size_t)tp * th + (size_t)8 * th * bpitch + 256));
+    CK(h->d_dbg[3].ensure(2 * (size_t)ne * rh * FPM_NSHIFT * 4));
+    CK(cudaMemsetAsync(h->d_dbg[0].p, 0, roi_stride * ne, h->stream));
+    CK(cudaMemsetAsync(h->d_dbg[1].p, 0, (size_t)tp * th, h->stream));
+    for (int e = 0; e < ne; e++)
+        CK(cudaMemcpy2DAsync(h->d_dbg[0].as<uint8_t>() + e * roi_stride, rpitch, rois + (size_t)e * rh * rw, rw, rw, rh,
+                             cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_dbg[1].p, tp, tpl, tw, tw, th, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* tsh = h->d_dbg[1].as<uint8_t>() + align_up((size_t)tp * th, 256);
+    dim3 g((bpitch + 127) / 128, th, 8);
+    fpm_shift_template_kernel<<<g, 128, 0, h->stream>>>(h->d_dbg[1].as<uint8_t>(), tw, th, tp, tsh, bpitch);
+    CKL();
+    int32_t* dS = h->d_dbg[3].as<int32_t>();
+    int32_t* dQ = dS + (size_t)ne * rh * FPM_NSHIFT;
+    int e_pad = 0;
+    int rc = launch_corr_mma(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, &e_pad, dS, dQ);
+    if (rc) return rc;
+    std::vector<int32_t> raw((size_t)rh * e_pad * MM_N);
+    CK(cudaMemcpyAsync(raw.data(), h->d_raw.p, raw.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rowS, dS, (size_t)ne * rh * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rowQ, dQ, (size_t)ne * rh * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int e = 0; e < ne; e++)
+        for (int tr = 0; tr < th; tr++)
+            for (int r = 0; r < FPM_NSHIFT; r++)
+                for (int c = 0; c < FPM_NSHIFT; c++)
+                    rowsum[((size_t)e * th + tr) * FPM_NCELL + r * FPM_NSHIFT + c] =
+                        raw[((size_t)(tr + r) * e_pad + e) * MM_N + c * 8 + (7 - r)];
     return FPM_OK;
 }
 

@@ -969,7 +969,7 @@ __device__ void fpm_subpix(const double* sc27 /* [theta][y][x] */, double xm, do
 
 __global__ void __launch_bounds__(RF_THREADS)
 fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double angle_step,
-                           const int32_t* __restrict__ rowsum, const int32_t* __restrict__ rowS,
+                           const int32_t* __restrict__ rowsum, int raw_epad, const int32_t* __restrict__ rowS,
                            const int32_t* __restrict__ rowQ, FpmTplLevel tpl, int lvl_w, int lvl_h,
                            double layer_score, int use_chain, int is_last, int subpixel,
                            FpmCand* __restrict__ next, int* __restrict__ next_count,
@@ -990,7 +990,17 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
         if (tpl.result_equal1) {
             sc = 1.0f;
         } else {
-            const int32_t* rs = rowsum + (size_t)e * th * FPM_NCELL + cell;
+            // row sums either as [e][tr][49] (dp4a kernel) or as raw[y][e_pad][64] with y = tr + r and
+            // column 8c + 7 - r (tensor-core kernel); both walked in template-row order
+            const int32_t* rs;
+            size_t rstride;
+            if (raw_epad) {
+                rs = rowsum + ((size_t)r * raw_epad + e) * 64 + c * 8 + (7 - r);
+                rstride = (size_t)raw_epad * 64;
+            } else {
+                rs = rowsum + (size_t)e * th * FPM_NCELL + cell;
+                rstride = FPM_NCELL;
+            }
             float numf;
             // loads are issued 8 at a time (independent), the additions stay in template-row order
             if (use_chain) {
@@ -999,16 +1009,16 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                 for (; tr + 8 <= th; tr += 8) {
                     int v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = rs[(size_t)(tr + k) * FPM_NCELL];
+                    for (int k = 0; k < 8; k++) v[k] = rs[(size_t)(tr + k) * rstride];
 #pragma unroll
                     for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
                 }
-                for (; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * FPM_NCELL]));
+                for (; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * rstride]));
                 numf = acc;
             } else {
                 long long acc = 0;
 #pragma unroll 8
-                for (int tr = 0; tr < th; tr++) acc += rs[(size_t)tr * FPM_NCELL];
+                for (int tr = 0; tr < th; tr++) acc += rs[(size_t)tr * rstride];
                 numf = (float)acc;
             }
             const int32_t* ps = rowS + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;

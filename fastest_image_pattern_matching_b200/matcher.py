@@ -93,6 +93,7 @@ class TemplateMatcher:
     def setTrace(self, v: bool): self._set(L.PARAM_TRACE, 1 if v else 0)
     def setWorkspaceMB(self, v: float): self._set(L.PARAM_WORKSPACE_MB, v)
     def setH2DChunk(self, v: int): self._set(L.PARAM_H2D_CHUNK, v)
+    def setTensorCores(self, v: int): self._set(L.PARAM_TENSOR_CORES, v)
 
     def getLastExecutionTime(self) -> float:
         """seconds, like the reference (include/TemplateMatcher.h:40)"""
@@ -235,6 +236,20 @@ class TemplateMatcher:
         rowQ = np.zeros((th + 6, 7), np.int32)
         self._check(self._lib.fpm_dbg_corr_rows(self._h, r.ctypes.data, t.ctypes.data, tw, th, rowsum.ctypes.data,
                                                 rowS.ctypes.data, rowQ.ctypes.data))
+        return rowsum, rowS, rowQ
+
+    def dbgCorrRowsMMA(self, rois, tpl):
+        """tensor-core path: rois [ne, th+6, tw+6] u8 -> (rowsum [ne, th, 7, 7], rowS [ne, th+6, 7], rowQ)"""
+        r = np.ascontiguousarray(np.asarray(rois, np.uint8))
+        t = np.ascontiguousarray(_as_u8_2d(tpl))
+        th, tw = t.shape
+        ne = r.shape[0]
+        assert r.shape == (ne, th + 6, tw + 6)
+        rowsum = np.zeros((ne, th, 7, 7), np.int32)
+        rowS = np.zeros((ne, th + 6, 7), np.int32)
+        rowQ = np.zeros((ne, th + 6, 7), np.int32)
+        self._check(self._lib.fpm_dbg_corr_rows_mma(self._h, r.ctypes.data, ne, t.ctypes.data, tw, th, rowsum.ctypes.data,
+                                                    rowS.ctypes.data, rowQ.ctypes.data))
         return rowsum, rowS, rowQ
 
     def dbgTopScore(self, img) -> np.ndarray:

@@ -46,6 +46,7 @@ enum fpm_param {
     FPM_PARAM_WORKSPACE_MB = 8,    /* refinement workspace budget per wave, default 4096 */
     FPM_PARAM_PROFILE = 9,         /* bracket every kernel launch with CUDA events (bench.py roofline) */
     FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
+    FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always */
     FPM_PARAM_COUNT_
 };
 
@@ -137,6 +138,8 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
                         int dw, int dh, int border, uint8_t* dst /* dw*dh */);
 int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi /* (th+6)x(tw+6) */, const uint8_t* tpl, int tw, int th,
                       int32_t* rowsum /* th*49 */, int32_t* rowS /* (th+6)*7 */, int32_t* rowQ /* (th+6)*7 */);
+int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois /* ne x (th+6)x(tw+6) */, int ne, const uint8_t* tpl, int tw, int th,
+                          int32_t* rowsum /* ne*th*49 */, int32_t* rowS /* ne*(th+6)*7 */, int32_t* rowQ);
 int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score /* (h-th+1)*(w-tw+1) */);
 int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw, int th, int block_mode,
                   double thresh, double max_overlap, int max_picks, double* picks /* max_picks*3: x,y,v */, int* n);
