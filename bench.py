@@ -244,6 +244,8 @@ def main():
     assert m.learnPattern(tpl)
     if args.h2d_chunk:
         m.setH2DChunk(args.h2d_chunk)
+    if os.environ.get("FPM_TC"):
+        m.setTensorCores(int(os.environ["FPM_TC"]))
     cap = m.result_capacity
     res = (L.fpm_result * (cap * B))()
     counts = (C.c_int * B)()
