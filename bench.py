@@ -246,6 +246,8 @@ def main():
         m.setH2DChunk(args.h2d_chunk)
     if os.environ.get("FPM_TC"):
         m.setTensorCores(int(os.environ["FPM_TC"]))
+    if os.environ.get("FPM_WS_MB"):
+        m.setWorkspaceMB(float(os.environ["FPM_WS_MB"]))
     cap = m.result_capacity
     res = (L.fpm_result * (cap * B))()
     counts = (C.c_int * B)()
