@@ -109,7 +109,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -192,7 +192,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         workers = cores
-        per_worker = args.cpu_images or 4
+        per_worker = args.cpu_images or 8
         v, busy, wall, found = cpu_throughput(wl, workers, per_worker)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
                         "sample": "%d processes x %d cfg1 frames (%.1f s); Python/cv2 4.13 oracle + SSE2 IM_Conv_SIMD restatement, "

@@ -257,7 +257,9 @@ fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, MM_TMEM_COLS);
 }
 
-// window row sums for the MMA path: rowS/rowQ[e][y][c] = sum_{x<w} S_e[y][x+c] (^2); one warp per ROI row
+// window row sums for the MMA path: rowS/rowQ[e][y][c] = sum_{x<w} S_e[y][x+c] (^2); one warp per ROI row,
+// 128-bit loads, warp-shuffle reduction; the 6 shifted windows follow from 6 head / 6 tail bytes through a
+// 3-step shuffle scan so that lanes 0..6 store the 7 values of the row with one coalesced store each.
 __global__ void __launch_bounds__(256)
 fpm_row_sums_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, int tw, int rh, int n_rows_total,
                     int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
@@ -265,29 +267,38 @@ fpm_row_sums_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stri
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (gw >= n_rows_total) return;
     const int e = gw / rh, y = gw - e * rh;
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(roi + (size_t)e * roi_stride + (size_t)y * rpitch);
-    const int nw = (tw + 3) / 4, tail = tw & 3;
-    const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
+    const uint8_t* rb = roi + (size_t)e * roi_stride + (size_t)y * rpitch;
+    const uint4* row4 = reinterpret_cast<const uint4*>(rb);
+    const int n16 = (tw + 15) / 16;                       // 16-byte chunks covering the template width
     uint32_t s = 0, q = 0;
-    for (int xw = lane; xw < nw; xw += 32) {
-        uint32_t w = row[xw];
-        if (xw == nw - 1) w &= tailbm;
-        s = __dp4a(w, 0x01010101u, s);
-        q = __dp4a(w, w, q);
+    for (int i = lane; i < n16; i += 32) {
+        uint4 v = row4[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int rem = tw - 16 * i;                       // valid bytes in this chunk (>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int nb = rem - 4 * k;                    // valid bytes in this word
+            uint32_t m = nb >= 4 ? w[k] : (nb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - nb)))));
+            s = __dp4a(m, 0x01010101u, s);
+            q = __dp4a(m, m, q);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0) {
-        const uint8_t* rb = reinterpret_cast<const uint8_t*>(row);
-        size_t base = (size_t)gw * FPM_NSHIFT;
-        rowS[base] = (int32_t)s; rowQ[base] = (int32_t)q;
+    // lane k in 1..6 contributes d_k = tail[k-1] - head[k-1]; inclusive scan over lanes 1..6
+    int ds = 0, dq = 0;
+    if (lane >= 1 && lane <= 6) {
+        const int hb = rb[lane - 1], tb = rb[tw + lane - 1];
+        ds = tb - hb; dq = tb * tb - hb * hb;
+    }
 #pragma unroll
-        for (int c = 1; c < FPM_NSHIFT; c++) {
-            uint32_t hb = rb[c - 1], tb = rb[tw + c - 1];
-            s = s - hb + tb;
-            q = q - hb * hb + tb * tb;
-            rowS[base + c] = (int32_t)s; rowQ[base + c] = (int32_t)q;
-        }
+    for (int o = 1; o < 8; o <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, ds, o), b = __shfl_up_sync(0xffffffffu, dq, o);
+        if (lane >= o) { ds += a; dq += b; }
+    }
+    if (lane < FPM_NSHIFT) {
+        rowS[(size_t)gw * FPM_NSHIFT + lane] = (int32_t)s + ds;
+        rowQ[(size_t)gw * FPM_NSHIFT + lane] = (int32_t)q + dq;
     }
 }
 
