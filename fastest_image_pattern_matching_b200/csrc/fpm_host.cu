@@ -375,7 +375,7 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
                                                                            h->d_raw.as<int32_t>()));
     const int n_rows = ne * rh;
     KL(K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD),
-       fpm_row_sums_kernel<<<(n_rows * 32 + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh, n_rows, rowS, rowQ));
+       fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh, n_rows, rowS, rowQ));
     return FPM_OK;
 }
 

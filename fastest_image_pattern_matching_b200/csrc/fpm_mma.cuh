@@ -260,45 +260,60 @@ fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // window row sums for the MMA path: rowS/rowQ[e][y][c] = sum_{x<w} S_e[y][x+c] (^2); one warp per ROI row,
 // 128-bit loads, warp-shuffle reduction; the 6 shifted windows follow from 6 head / 6 tail bytes through a
 // 3-step shuffle scan so that lanes 0..6 store the 7 values of the row with one coalesced store each.
+#define RS_ROWS 4        // ROI rows per warp: all their loads are issued before the first reduction
+
 __global__ void __launch_bounds__(256)
 fpm_row_sums_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, int tw, int rh, int n_rows_total,
                     int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
 {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (gw >= n_rows_total) return;
-    const int e = gw / rh, y = gw - e * rh;
-    const uint8_t* rb = roi + (size_t)e * roi_stride + (size_t)y * rpitch;
-    const uint4* row4 = reinterpret_cast<const uint4*>(rb);
+    const int row0 = gw * RS_ROWS;
+    if (row0 >= n_rows_total) return;
     const int n16 = (tw + 15) / 16;                       // 16-byte chunks covering the template width
-    uint32_t s = 0, q = 0;
+    const uint8_t* rb[RS_ROWS];
+    uint32_t s[RS_ROWS], q[RS_ROWS];
+    int hb[RS_ROWS], tb[RS_ROWS];
+#pragma unroll
+    for (int k = 0; k < RS_ROWS; k++) {
+        const int g = min(row0 + k, n_rows_total - 1);
+        const int e = g / rh, y = g - e * rh;
+        rb[k] = roi + (size_t)e * roi_stride + (size_t)y * rpitch;
+        s[k] = 0; q[k] = 0;
+        hb[k] = 0; tb[k] = 0;
+        if (lane >= 1 && lane <= 6) { hb[k] = rb[k][lane - 1]; tb[k] = rb[k][tw + lane - 1]; }
+    }
     for (int i = lane; i < n16; i += 32) {
-        uint4 v = row4[i];
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint4 v[RS_ROWS];
+#pragma unroll
+        for (int k = 0; k < RS_ROWS; k++) v[k] = reinterpret_cast<const uint4*>(rb[k])[i];
         const int rem = tw - 16 * i;                       // valid bytes in this chunk (>= 1)
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int nb = rem - 4 * k;                    // valid bytes in this word
-            uint32_t m = nb >= 4 ? w[k] : (nb <= 0 ? 0u : (w[k] & (0xffffffffu >> (8 * (4 - nb)))));
-            s = __dp4a(m, 0x01010101u, s);
-            q = __dp4a(m, m, q);
+        for (int k = 0; k < RS_ROWS; k++) {
+            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int nb = rem - 4 * j;                // valid bytes in this word
+                const uint32_t m = nb >= 4 ? w[j] : (nb <= 0 ? 0u : (w[j] & (0xffffffffu >> (8 * (4 - nb)))));
+                s[k] = __dp4a(m, 0x01010101u, s[k]);
+                q[k] = __dp4a(m, m, q[k]);
+            }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    // lane k in 1..6 contributes d_k = tail[k-1] - head[k-1]; inclusive scan over lanes 1..6
-    int ds = 0, dq = 0;
-    if (lane >= 1 && lane <= 6) {
-        const int hb = rb[lane - 1], tb = rb[tw + lane - 1];
-        ds = tb - hb; dq = tb * tb - hb * hb;
-    }
+    for (int k = 0; k < RS_ROWS; k++) {
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        int a = __shfl_up_sync(0xffffffffu, ds, o), b = __shfl_up_sync(0xffffffffu, dq, o);
-        if (lane >= o) { ds += a; dq += b; }
-    }
-    if (lane < FPM_NSHIFT) {
-        rowS[(size_t)gw * FPM_NSHIFT + lane] = (int32_t)s + ds;
-        rowQ[(size_t)gw * FPM_NSHIFT + lane] = (int32_t)q + dq;
+        for (int o = 16; o > 0; o >>= 1) { s[k] += __shfl_xor_sync(0xffffffffu, s[k], o); q[k] += __shfl_xor_sync(0xffffffffu, q[k], o); }
+        // lane c in 1..6 contributes tail[c-1] - head[c-1]; inclusive scan over the lanes gives the shift-c correction
+        int ds = tb[k] - hb[k], dq = tb[k] * tb[k] - hb[k] * hb[k];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int a = __shfl_up_sync(0xffffffffu, ds, o), b = __shfl_up_sync(0xffffffffu, dq, o);
+            if (lane >= o) { ds += a; dq += b; }
+        }
+        if (lane < FPM_NSHIFT && row0 + k < n_rows_total) {
+            rowS[(size_t)(row0 + k) * FPM_NSHIFT + lane] = (int32_t)s[k] + ds;
+            rowQ[(size_t)(row0 + k) * FPM_NSHIFT + lane] = (int32_t)q[k] + dq;
+        }
     }
 }
 
