@@ -35,44 +35,49 @@
 #define PD_TW (128 * PD_WX)
 #define PD_TH (PD_R * PD_WY)
 
-__global__ void __launch_bounds__(PD_THREADS)
-fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec8_ok)
+template <bool INTERIOR>
+__device__ __forceinline__ void fpm_pyrdown_strip(const uint8_t* __restrict__ s, int sw, int sh, int spitch,
+                                                  uint8_t* __restrict__ d, int dw, int dpitch, int ox, int oy0,
+                                                  int nrows_out, int lane, bool need, bool fast)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wx = warp % PD_WX, wy = warp / PD_WX;
-    const int ox = blockIdx.x * PD_TW + wx * 128 + lane * 4;          // first of this lane's 4 outputs
-    const int oy0 = blockIdx.y * PD_TH + wy * PD_R;
-    if (oy0 >= dst.h || blockIdx.x * PD_TW + wx * 128 >= dst.w) return;   // warp-uniform
-    const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
-    uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
-    const int sw = src.w, sh = src.h;
     const int xin = 2 * ox;                                           // multiple of 8
-    const bool need = ox < dst.w + 4;                                 // this lane's word is used by someone
-    const bool fast = vec8_ok && (xin + 7 < sw);
-    const int nrows_out = min(PD_R, dst.h - oy0);
     uint32_t hA[5], hB[5];                                            // packed horizontal sums of the last 5 rows
+    const uint8_t* p = s + (ptrdiff_t)(2 * oy0 - 2) * spitch + xin;   // INTERIOR: plain row walk
 #pragma unroll
     for (int t = 0; t < 2 * PD_R + 3; t++) {
         if (t <= 2 * nrows_out + 2) {
-            const uint8_t* row = s + (size_t)fpm_reflect101(2 * oy0 - 2 + t, sh) * src.pitch;
-            uint32_t lo = 0, hi = 0;
-            if (need) {
-                if (fast) {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + xin));
-                    lo = v.x; hi = v.y;
-                } else {
+            uint32_t lo = 0, hi = 0, prev, next;
+            if (INTERIOR) {
+                // every lane is inside the image: vector load + two tiny halo loads that only lane 0 / lane 31 use
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+                const uint32_t pv = __ldg(reinterpret_cast<const unsigned short*>(lane == 0 ? p - 2 : p));
+                const uint32_t nx = __ldg(lane == 31 ? p + 8 : p);
+                lo = v.x; hi = v.y;
+                prev = __shfl_up_sync(0xffffffffu, hi, 1) >> 16;
+                next = __shfl_down_sync(0xffffffffu, lo, 1) & 255u;
+                if (lane == 0) prev = pv;
+                if (lane == 31) next = nx;
+                p += spitch;
+            } else {
+                const uint8_t* row = s + (size_t)fpm_reflect101(2 * oy0 - 2 + t, sh) * spitch;
+                if (need) {
+                    if (fast) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + xin));
+                        lo = v.x; hi = v.y;
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        lo |= (uint32_t)__ldg(row + fpm_reflect101(xin + k, sw)) << (8 * k);
-                        hi |= (uint32_t)__ldg(row + fpm_reflect101(xin + 4 + k, sw)) << (8 * k);
+                        for (int k = 0; k < 4; k++) {
+                            lo |= (uint32_t)__ldg(row + fpm_reflect101(xin + k, sw)) << (8 * k);
+                            hi |= (uint32_t)__ldg(row + fpm_reflect101(xin + 4 + k, sw)) << (8 * k);
+                        }
                     }
                 }
+                prev = __shfl_up_sync(0xffffffffu, hi, 1) >> 16;                      // bytes xin-2, xin-1
+                next = __shfl_down_sync(0xffffffffu, lo, 1) & 255u;                   // byte xin+8
+                if (lane == 0)
+                    prev = (uint32_t)__ldg(row + fpm_reflect101(xin - 2, sw)) | ((uint32_t)__ldg(row + fpm_reflect101(xin - 1, sw)) << 8);
+                if (lane == 31) next = __ldg(row + fpm_reflect101(xin + 8, sw));
             }
-            uint32_t prev = __shfl_up_sync(0xffffffffu, hi, 1) >> 16;             // bytes xin-2, xin-1
-            uint32_t next = __shfl_down_sync(0xffffffffu, lo, 1) & 255u;          // byte xin+8
-            if (lane == 0)
-                prev = (uint32_t)__ldg(row + fpm_reflect101(xin - 2, sw)) | ((uint32_t)__ldg(row + fpm_reflect101(xin - 1, sw)) << 8);
-            if (lane == 31) next = __ldg(row + fpm_reflect101(xin + 8, sw));
             const uint32_t W = 0x04060401u;
             const uint32_t h0 = __dp4a((lo << 16) | prev, W, (lo >> 16) & 255u);
             const uint32_t h1 = __dp4a(lo, W, hi & 255u);
@@ -88,15 +93,38 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec8_ok)
                 const uint32_t va = ((a0 + 4u * a1 + 6u * hA[(t + 3) % 5] + 0x00800080u) >> 8) & 0x00ff00ffu;
                 const uint32_t vb = ((b0 + 4u * b1 + 6u * hB[(t + 3) % 5] + 0x00800080u) >> 8) & 0x00ff00ffu;
                 const uint32_t pack = (va & 255u) | ((va >> 8) & 0xff00u) | ((vb & 255u) << 16) | ((vb & 0x00ff0000u) << 8);
-                uint8_t* op = d + (size_t)oy * dst.pitch + ox;
-                if (ox + 3 < dst.w) {
+                uint8_t* op = d + (size_t)oy * dpitch + ox;
+                if (INTERIOR || ox + 3 < dw) {
                     *reinterpret_cast<uint32_t*>(op) = pack;
                 } else {
-                    for (int k = 0; k < 4 && ox + k < dst.w; k++) op[k] = (uint8_t)(pack >> (8 * k));
+                    for (int k = 0; k < 4 && ox + k < dw; k++) op[k] = (uint8_t)(pack >> (8 * k));
                 }
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(PD_THREADS)
+fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec8_ok)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wx = warp % PD_WX, wy = warp / PD_WX;
+    const int oxw = blockIdx.x * PD_TW + wx * 128;                    // first output column of the warp
+    const int ox = oxw + lane * 4;                                    // first of this lane's 4 outputs
+    const int oy0 = blockIdx.y * PD_TH + wy * PD_R;
+    if (oy0 >= dst.h || oxw >= dst.w) return;                         // warp-uniform
+    const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
+    uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
+    const int sw = src.w, sh = src.h;
+    const int nrows_out = min(PD_R, dst.h - oy0);
+    // interior warp: all 128 outputs exist, every tap of every lane is inside the image
+    const bool interior = vec8_ok && oxw + 128 <= dst.w && 2 * oxw - 2 >= 0 && 2 * oxw + 256 < sw &&
+                          2 * oy0 - 2 >= 0 && 2 * (oy0 + nrows_out - 1) + 2 < sh;
+    if (interior)
+        fpm_pyrdown_strip<true>(s, sw, sh, src.pitch, d, dst.w, dst.pitch, ox, oy0, nrows_out, lane, true, true);
+    else
+        fpm_pyrdown_strip<false>(s, sw, sh, src.pitch, d, dst.w, dst.pitch, ox, oy0, nrows_out, lane, ox < dst.w + 4,
+                                 vec8_ok && (2 * ox + 7 < sw));
 }
 
 // =====================================================================================
