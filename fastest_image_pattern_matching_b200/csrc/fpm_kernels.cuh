@@ -29,6 +29,7 @@
 // of many rows are in flight at once.
 // =====================================================================================
 #define PD_R 16                 // output rows per warp
+#define PD_PF 8                 // input rows of loads in flight per lane (interior strips)
 #define PD_WX 2                 // warps per CTA in x  (CTA = 256 x 64 outputs)
 #define PD_WY 4                 // warps per CTA in y
 #define PD_THREADS (32 * PD_WX * PD_WY)
@@ -43,21 +44,39 @@ __device__ __forceinline__ void fpm_pyrdown_strip(const uint8_t* __restrict__ s,
     const int xin = 2 * ox;                                           // multiple of 8
     uint32_t hA[5], hB[5];                                            // packed horizontal sums of the last 5 rows
     const uint8_t* p = s + (ptrdiff_t)(2 * oy0 - 2) * spitch + xin;   // INTERIOR: plain row walk
+    // INTERIOR: software pipeline, PD_PF rows of loads in flight per lane
+    uint2 qv[PD_PF];
+    uint32_t qp[PD_PF], qn[PD_PF];
+    const int tmax = 2 * nrows_out + 2;
+    if (INTERIOR) {
+#pragma unroll
+        for (int k = 0; k < PD_PF; k++) {
+            if (k <= tmax) {
+                const uint8_t* r = p + (size_t)k * spitch;
+                qv[k] = __ldg(reinterpret_cast<const uint2*>(r));
+                qp[k] = __ldg(reinterpret_cast<const unsigned short*>(lane == 0 ? r - 2 : r));
+                qn[k] = __ldg(lane == 31 ? r + 8 : r);
+            }
+        }
+    }
 #pragma unroll
     for (int t = 0; t < 2 * PD_R + 3; t++) {
-        if (t <= 2 * nrows_out + 2) {
+        if (t <= tmax) {
             uint32_t lo = 0, hi = 0, prev, next;
             if (INTERIOR) {
                 // every lane is inside the image: vector load + two tiny halo loads that only lane 0 / lane 31 use
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-                const uint32_t pv = __ldg(reinterpret_cast<const unsigned short*>(lane == 0 ? p - 2 : p));
-                const uint32_t nx = __ldg(lane == 31 ? p + 8 : p);
-                lo = v.x; hi = v.y;
+                lo = qv[t % PD_PF].x; hi = qv[t % PD_PF].y;
+                const uint32_t pv = qp[t % PD_PF], nx = qn[t % PD_PF];
+                if (t + PD_PF <= tmax) {
+                    const uint8_t* r = p + (size_t)(t + PD_PF) * spitch;
+                    qv[t % PD_PF] = __ldg(reinterpret_cast<const uint2*>(r));
+                    qp[t % PD_PF] = __ldg(reinterpret_cast<const unsigned short*>(lane == 0 ? r - 2 : r));
+                    qn[t % PD_PF] = __ldg(lane == 31 ? r + 8 : r);
+                }
                 prev = __shfl_up_sync(0xffffffffu, hi, 1) >> 16;
                 next = __shfl_down_sync(0xffffffffu, lo, 1) & 255u;
                 if (lane == 0) prev = pv;
                 if (lane == 31) next = nx;
-                p += spitch;
             } else {
                 const uint8_t* row = s + (size_t)fpm_reflect101(2 * oy0 - 2 + t, sh) * spitch;
                 if (need) {
