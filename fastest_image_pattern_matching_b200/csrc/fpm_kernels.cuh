@@ -29,7 +29,7 @@
 // of many rows are in flight at once.
 // =====================================================================================
 #define PD_R 16                 // output rows per warp
-#define PD_PF 8                 // input rows of loads in flight per lane (interior strips)
+#define PD_PF 4                 // input rows of loads in flight per lane (interior strips)
 #define PD_WX 2                 // warps per CTA in x  (CTA = 256 x 64 outputs)
 #define PD_WY 4                 // warps per CTA in y
 #define PD_THREADS (32 * PD_WX * PD_WY)
@@ -43,19 +43,21 @@ __device__ __forceinline__ void fpm_pyrdown_strip(const uint8_t* __restrict__ s,
 {
     const int xin = 2 * ox;                                           // multiple of 8
     uint32_t hA[5], hB[5];                                            // packed horizontal sums of the last 5 rows
-    const uint8_t* p = s + (ptrdiff_t)(2 * oy0 - 2) * spitch + xin;   // INTERIOR: plain row walk
-    // INTERIOR: software pipeline, PD_PF rows of loads in flight per lane
+    // INTERIOR: one pointer walks the rows; the word itself, the next word (byte xin+8) and -- lane 0 only -- the
+    // previous word (bytes xin-2, xin-1) are fetched with immediate offsets; PD_PF rows of loads stay in flight
+    const uint8_t* p = s + (ptrdiff_t)(2 * oy0 - 2) * spitch + xin;
     uint2 qv[PD_PF];
-    uint32_t qp[PD_PF], qn[PD_PF];
+    uint32_t qn[PD_PF], qp[PD_PF];
     const int tmax = 2 * nrows_out + 2;
     if (INTERIOR) {
 #pragma unroll
         for (int k = 0; k < PD_PF; k++) {
+            qp[k] = 0;
             if (k <= tmax) {
-                const uint8_t* r = p + (size_t)k * spitch;
-                qv[k] = __ldg(reinterpret_cast<const uint2*>(r));
-                qp[k] = __ldg(reinterpret_cast<const unsigned short*>(lane == 0 ? r - 2 : r));
-                qn[k] = __ldg(lane == 31 ? r + 8 : r);
+                qv[k] = __ldg(reinterpret_cast<const uint2*>(p));
+                qn[k] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+                if (lane == 0) qp[k] = __ldg(reinterpret_cast<const uint32_t*>(p - 4));
+                p += spitch;
             }
         }
     }
@@ -64,19 +66,18 @@ __device__ __forceinline__ void fpm_pyrdown_strip(const uint8_t* __restrict__ s,
         if (t <= tmax) {
             uint32_t lo = 0, hi = 0, prev, next;
             if (INTERIOR) {
-                // every lane is inside the image: vector load + two tiny halo loads that only lane 0 / lane 31 use
                 lo = qv[t % PD_PF].x; hi = qv[t % PD_PF].y;
-                const uint32_t pv = qp[t % PD_PF], nx = qn[t % PD_PF];
+                next = qn[t % PD_PF] & 255u;
+                const uint32_t pw = qp[t % PD_PF];
                 if (t + PD_PF <= tmax) {
-                    const uint8_t* r = p + (size_t)(t + PD_PF) * spitch;
-                    qv[t % PD_PF] = __ldg(reinterpret_cast<const uint2*>(r));
-                    qp[t % PD_PF] = __ldg(reinterpret_cast<const unsigned short*>(lane == 0 ? r - 2 : r));
-                    qn[t % PD_PF] = __ldg(lane == 31 ? r + 8 : r);
+                    qv[t % PD_PF] = __ldg(reinterpret_cast<const uint2*>(p));
+                    qn[t % PD_PF] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+                    if (lane == 0) qp[t % PD_PF] = __ldg(reinterpret_cast<const uint32_t*>(p - 4));
+                    p += spitch;
                 }
-                prev = __shfl_up_sync(0xffffffffu, hi, 1) >> 16;
-                next = __shfl_down_sync(0xffffffffu, lo, 1) & 255u;
-                if (lane == 0) prev = pv;
-                if (lane == 31) next = nx;
+                prev = __shfl_up_sync(0xffffffffu, hi, 1);
+                if (lane == 0) prev = pw;
+                prev >>= 16;
             } else {
                 const uint8_t* row = s + (size_t)fpm_reflect101(2 * oy0 - 2 + t, sh) * spitch;
                 if (need) {
@@ -137,7 +138,7 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec8_ok)
     const int sw = src.w, sh = src.h;
     const int nrows_out = min(PD_R, dst.h - oy0);
     // interior warp: all 128 outputs exist, every tap of every lane is inside the image
-    const bool interior = vec8_ok && oxw + 128 <= dst.w && 2 * oxw - 2 >= 0 && 2 * oxw + 256 < sw &&
+    const bool interior = vec8_ok && oxw + 128 <= dst.w && 2 * oxw - 4 >= 0 && 2 * oxw + 260 <= sw &&
                           2 * oy0 - 2 >= 0 && 2 * (oy0 + nrows_out - 1) + 2 < sh;
     if (interior)
         fpm_pyrdown_strip<true>(s, sw, sh, src.pitch, d, dst.w, dst.pitch, ox, oy0, nrows_out, lane, true, true);
