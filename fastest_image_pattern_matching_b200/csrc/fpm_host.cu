@@ -257,7 +257,8 @@ FpmTplLevel tpl_level_dev(const fpm_handle* h, int l)
 
 int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& dst, int batch)
 {
-    const int vec_ok = ((reinterpret_cast<uintptr_t>(src.ptr) % 8) == 0) && (src.pitch % 8 == 0) && (src.img_stride % 8 == 0);
+    auto aligned = [&](int a) { return ((reinterpret_cast<uintptr_t>(src.ptr) % a) == 0) && (src.pitch % a == 0) && (src.img_stride % a == 0); };
+    const int vec_ok = aligned(16) ? 16 : (aligned(4) ? 4 : 1);
     dim3 grid((dst.w + PD_TW - 1) / PD_TW, (dst.h + PD_TH - 1) / PD_TH, batch);
     // algorithmic bytes: every source pixel read once, every destination pixel written once
     KL(K_PYRDOWN, (double)batch * ((double)src.w * src.h + (double)dst.w * dst.h),

@@ -19,132 +19,122 @@
 
 // =====================================================================================
 // K1  pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, (s+128)>>8, out ((w+1)/2,(h+1)/2)
-// HBM-bound: reads W*H, writes W*H/4.  Register-tiled, no shared memory: a warp owns a strip of
-// 128 output columns x PD_R output rows; every lane owns 4 output columns, i.e. ONE aligned 8-byte
-// word of each input row (coalesced 256 B per warp and row).  The 2 bytes left and 1 byte right of
-// the word come from the neighbouring lanes by warp shuffle.  Horizontal taps: one dp4a (weights
-// 1,4,6,4) plus one byte per output; the 5 most recent horizontal rows live in registers as two
-// packed 16-bit lanes per word (sums < 65536, no carry crosses lanes) and every second input row
-// one output row is emitted as a packed 32-bit store.  The row loop is fully unrolled, so the loads
-// of many rows are in flight at once.
+// HBM-bound: reads W*H, writes W*H/4.  One CTA = 128x32 outputs.  The 67 input rows x 288 B of the
+// tile are staged in shared memory with 128-bit (or 32-bit) coalesced loads; the horizontal taps are
+// one dp4a (weights 1,4,6,4) + one byte per output, the vertical taps run on two 16-bit lanes packed
+// in a 32-bit register (sums < 65536, so no carry crosses lanes).
 // =====================================================================================
-#define PD_R 16                 // output rows per warp
-#define PD_PF 4                 // input rows of loads in flight per lane (interior strips)
-#define PD_WX 2                 // warps per CTA in x  (CTA = 256 x 64 outputs)
-#define PD_WY 4                 // warps per CTA in y
-#define PD_THREADS (32 * PD_WX * PD_WY)
-#define PD_TW (128 * PD_WX)
-#define PD_TH (PD_R * PD_WY)
-
-template <bool INTERIOR>
-__device__ __forceinline__ void fpm_pyrdown_strip(const uint8_t* __restrict__ s, int sw, int sh, int spitch,
-                                                  uint8_t* __restrict__ d, int dw, int dpitch, int ox, int oy0,
-                                                  int nrows_out, int lane, bool need, bool fast)
-{
-    const int xin = 2 * ox;                                           // multiple of 8
-    uint32_t hA[5], hB[5];                                            // packed horizontal sums of the last 5 rows
-    // INTERIOR: one pointer walks the rows; the word itself, the next word (byte xin+8) and -- lane 0 only -- the
-    // previous word (bytes xin-2, xin-1) are fetched with immediate offsets; PD_PF rows of loads stay in flight
-    const uint8_t* p = s + (ptrdiff_t)(2 * oy0 - 2) * spitch + xin;
-    uint2 qv[PD_PF];
-    uint32_t qn[PD_PF], qp[PD_PF];
-    const int tmax = 2 * nrows_out + 2;
-    if (INTERIOR) {
-#pragma unroll
-        for (int k = 0; k < PD_PF; k++) {
-            qp[k] = 0;
-            if (k <= tmax) {
-                qv[k] = __ldg(reinterpret_cast<const uint2*>(p));
-                qn[k] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
-                if (lane == 0) qp[k] = __ldg(reinterpret_cast<const uint32_t*>(p - 4));
-                p += spitch;
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 2 * PD_R + 3; t++) {
-        if (t <= tmax) {
-            uint32_t lo = 0, hi = 0, prev, next;
-            if (INTERIOR) {
-                lo = qv[t % PD_PF].x; hi = qv[t % PD_PF].y;
-                next = qn[t % PD_PF] & 255u;
-                const uint32_t pw = qp[t % PD_PF];
-                if (t + PD_PF <= tmax) {
-                    qv[t % PD_PF] = __ldg(reinterpret_cast<const uint2*>(p));
-                    qn[t % PD_PF] = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
-                    if (lane == 0) qp[t % PD_PF] = __ldg(reinterpret_cast<const uint32_t*>(p - 4));
-                    p += spitch;
-                }
-                prev = __shfl_up_sync(0xffffffffu, hi, 1);
-                if (lane == 0) prev = pw;
-                prev >>= 16;
-            } else {
-                const uint8_t* row = s + (size_t)fpm_reflect101(2 * oy0 - 2 + t, sh) * spitch;
-                if (need) {
-                    if (fast) {
-                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + xin));
-                        lo = v.x; hi = v.y;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            lo |= (uint32_t)__ldg(row + fpm_reflect101(xin + k, sw)) << (8 * k);
-                            hi |= (uint32_t)__ldg(row + fpm_reflect101(xin + 4 + k, sw)) << (8 * k);
-                        }
-                    }
-                }
-                prev = __shfl_up_sync(0xffffffffu, hi, 1) >> 16;                      // bytes xin-2, xin-1
-                next = __shfl_down_sync(0xffffffffu, lo, 1) & 255u;                   // byte xin+8
-                if (lane == 0)
-                    prev = (uint32_t)__ldg(row + fpm_reflect101(xin - 2, sw)) | ((uint32_t)__ldg(row + fpm_reflect101(xin - 1, sw)) << 8);
-                if (lane == 31) next = __ldg(row + fpm_reflect101(xin + 8, sw));
-            }
-            const uint32_t W = 0x04060401u;
-            const uint32_t h0 = __dp4a((lo << 16) | prev, W, (lo >> 16) & 255u);
-            const uint32_t h1 = __dp4a(lo, W, hi & 255u);
-            const uint32_t h2 = __dp4a(__funnelshift_r(lo, hi, 16), W, (hi >> 16) & 255u);
-            const uint32_t h3 = __dp4a(hi, W, next);
-            hA[t % 5] = h0 | (h1 << 16);
-            hB[t % 5] = h2 | (h3 << 16);
-            if (t >= 4 && (t & 1) == 0) {
-                const int oy = oy0 + (t - 4) / 2;
-                // window rows t-4 .. t  (weights 1 4 6 4 1)
-                const uint32_t a0 = hA[(t + 1) % 5] + hA[t % 5], a1 = hA[(t + 2) % 5] + hA[(t + 4) % 5];
-                const uint32_t b0 = hB[(t + 1) % 5] + hB[t % 5], b1 = hB[(t + 2) % 5] + hB[(t + 4) % 5];
-                const uint32_t va = ((a0 + 4u * a1 + 6u * hA[(t + 3) % 5] + 0x00800080u) >> 8) & 0x00ff00ffu;
-                const uint32_t vb = ((b0 + 4u * b1 + 6u * hB[(t + 3) % 5] + 0x00800080u) >> 8) & 0x00ff00ffu;
-                const uint32_t pack = (va & 255u) | ((va >> 8) & 0xff00u) | ((vb & 255u) << 16) | ((vb & 0x00ff0000u) << 8);
-                uint8_t* op = d + (size_t)oy * dpitch + ox;
-                if (INTERIOR || ox + 3 < dw) {
-                    *reinterpret_cast<uint32_t*>(op) = pack;
-                } else {
-                    for (int k = 0; k < 4 && ox + k < dw; k++) op[k] = (uint8_t)(pack >> (8 * k));
-                }
-            }
-        }
-    }
-}
+#define PD_TW 128
+#define PD_TH 32
+#define PD_IH (2 * PD_TH + 3)
+#define PD_IW (2 * PD_TW + 32)     // staged input columns [2*ox0-16, 2*ox0+2*TW+16), 16-byte chunks
+#define PD_THREADS 256
 
 __global__ void __launch_bounds__(PD_THREADS)
-fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec8_ok)
+fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wx = warp % PD_WX, wy = warp / PD_WX;
-    const int oxw = blockIdx.x * PD_TW + wx * 128;                    // first output column of the warp
-    const int ox = oxw + lane * 4;                                    // first of this lane's 4 outputs
-    const int oy0 = blockIdx.y * PD_TH + wy * PD_R;
-    if (oy0 >= dst.h || oxw >= dst.w) return;                         // warp-uniform
+    __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
+    __shared__ __align__(16) uint32_t s_h[PD_IH][PD_TW / 2];     // two u16 horizontal sums per word
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
     const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
     uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
+    const int xs = 2 * ox0 - 16, ys = 2 * oy0 - 2;
+    const int nout_rows = min(PD_TH, dst.h - oy0);
+    const int nout_cols = min(PD_TW, dst.w - ox0);
+    const int nin_rows = 2 * nout_rows + 3;
     const int sw = src.w, sh = src.h;
-    const int nrows_out = min(PD_R, dst.h - oy0);
-    // interior warp: all 128 outputs exist, every tap of every lane is inside the image
-    const bool interior = vec8_ok && oxw + 128 <= dst.w && 2 * oxw - 4 >= 0 && 2 * oxw + 260 <= sw &&
-                          2 * oy0 - 2 >= 0 && 2 * (oy0 + nrows_out - 1) + 2 < sh;
-    if (interior)
-        fpm_pyrdown_strip<true>(s, sw, sh, src.pitch, d, dst.w, dst.pitch, ox, oy0, nrows_out, lane, true, true);
-    else
-        fpm_pyrdown_strip<false>(s, sw, sh, src.pitch, d, dst.w, dst.pitch, ox, oy0, nrows_out, lane, ox < dst.w + 4,
-                                 vec8_ok && (2 * ox + 7 < sw));
+    // smem columns actually read by the horizontal pass: words 3 .. (nout_cols+1)/2 + 4
+    const int need_lo = 12, need_hi = 4 * ((nout_cols + 1) / 2 + 4) + 3;
+
+    const int nch = (need_hi + 16) / 16;                         // 16-byte chunks per row (<= 18)
+    const bool interior = ys >= 0 && ys + nin_rows <= sh && xs >= 0 && xs + 16 * nch <= sw;
+    if (interior && vec == 16) {
+        const int c = tid & 31;
+        if (c < nch) {
+            const uint8_t* g = s + (size_t)(ys + (tid >> 5)) * src.pitch + xs + 16 * c;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
+                fpm_cp_async16(&s_in[r][16 * c], g);
+        }
+    } else if (vec == 16) {
+        const int c = tid & 31;
+        if (c < nch) {
+            const int x = xs + 16 * c;
+            const bool xin = x >= 0 && x + 15 < sw;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
+                const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
+                if (xin) {
+                    fpm_cp_async16(&s_in[r][16 * c], row + x);
+                } else if (16 * c + 15 >= need_lo) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        w[k >> 2] |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * (k & 3));
+                    *reinterpret_cast<uint4*>(&s_in[r][16 * c]) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    } else {
+        const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
+        for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
+            const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
+            for (int wc = w_lo + (tid & 63); wc <= w_hi; wc += 64) {
+                const int x = xs + 4 * wc;
+                if (vec == 4 && x >= 0 && x + 3 < sw) {
+                    fpm_cp_async4(&s_in[r][4 * wc], row + x, true);
+                } else {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * k);
+                    *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
+                }
+            }
+        }
+    }
+    fpm_cp_async_commit();
+    fpm_cp_async_wait<0>();
+    __syncthreads();
+
+    // horizontal pass: outputs 2k, 2k+1 have their centres at smem bytes 4k+16, 4k+18
+    {
+        const int k = tid & 63;
+        if (2 * k < nout_cols) {
+            for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_in[r][4 * k + 12]);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 16), 0x04060401u, (w1 >> 16) & 255u);
+                const uint32_t h1 = __dp4a(w1, 0x04060401u, w2 & 255u);
+                s_h[r][k] = h0 | (h1 << 16);
+            }
+        }
+    }
+    __syncthreads();
+
+    // vertical pass: 4 outputs (two packed pairs) per thread
+    {
+        const int g = tid & 31;
+        if (4 * g < nout_cols) {
+            for (int oy = tid >> 5; oy < nout_rows; oy += PD_THREADS / 32) {
+                uint32_t o[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int c = 2 * g + q;
+                    const uint32_t a = s_h[2 * oy][c] + s_h[2 * oy + 4][c];
+                    const uint32_t b = s_h[2 * oy + 1][c] + s_h[2 * oy + 3][c];
+                    const uint32_t v = a + 4u * b + 6u * s_h[2 * oy + 2][c] + 0x00800080u;
+                    o[q] = (v >> 8) & 0x00ff00ffu;
+                }
+                const uint32_t pack = (o[0] & 255u) | ((o[0] >> 8) & 0xff00u) | ((o[1] & 255u) << 16) | ((o[1] & 0x00ff0000u) << 8);
+                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 4 * g;
+                if (4 * g + 3 < nout_cols) {
+                    *reinterpret_cast<uint32_t*>(op) = pack;
+                } else {
+                    for (int k = 0; k < 4 && 4 * g + k < nout_cols; k++) op[k] = (uint8_t)(pack >> (8 * k));
+                }
+            }
+        }
+    }
 }
 
 // =====================================================================================
