@@ -341,6 +341,13 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     bf16_sust = peaks.get("bf16_tflops_sustained", 1400.0)
 
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("config", {}).get("batch_per_gpu") == B and tj.get("config", {}).get("workload") == args.workload:
+            traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}
+    except Exception:
+        pass
     kern = {}
     step_ms = sum(v[0] for v in prof.values()) / max(K, 1)
     for name, (ms, n, work) in prof.items():
@@ -359,19 +366,27 @@ def main():
             peak = 2.0 * bf16_sust
             ach = 2.0 * kd["work_per_launch"] / per_launch_s / 1e12
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None, "peak_source": "2 x bf16_tflops_sustained (int8 dense not in MEASURED_PEAKS.json)",
+                        "traffic": traffic.get(dom), "peak_source": "2 x bf16_tflops_sustained (int8 dense not in MEASURED_PEAKS.json)",
                         "note": "u8xu8->s32 MACs via dp4a; algorithmic ops = 2*49*w*h per eval"}
         else:
             ach = kd["work_per_launch"] / per_launch_s / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None, "peak_source": hbm_src}
+                        "traffic": traffic.get(dom), "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_traffic.json",
+                        "peak_source": hbm_src}
     # the HBM-bound stage the north_star names first (pyramid): always reported beside the dominant kernel
     hbm_kernels = {}
-    for name in ("fpm_pyrdown_kernel", "fpm_warp_kernel(roi)"):
+    for name in ("fpm_pyrdown_kernel", "fpm_warp_kernel(roi)", "fpm_row_sums_kernel"):
         if name in kern:
             kd = kern[name]
             ach = kd["work_per_launch"] / (kd["avg_launch_us"] * 1e-6) / 1e9
-            hbm_kernels[name] = {"achieved_GBps": ach, "frac_of_hbm_peak": ach / hbm_peak}
+            hbm_kernels[name] = {"achieved_GBps": ach, "frac_of_hbm_peak": ach / hbm_peak, "traffic": traffic.get(name)}
+    # the tensor-core correlation: algorithmic int8 ops against the (unmeasured) int8 dense peak, and its DRAM side
+    if "fpm_corr_mma_kernel" in kern:
+        kd = kern["fpm_corr_mma_kernel"]
+        tops = 2.0 * kd["work_per_launch"] / (kd["avg_launch_us"] * 1e-6) / 1e12
+        hbm_kernels["fpm_corr_mma_kernel"] = {"achieved_TOPS": tops, "frac_of_int8_peak": tops / (2.0 * bf16_sust),
+                                             "int8_peak_assumed_TOPS": 2.0 * bf16_sust, "traffic": traffic.get("fpm_corr_mma_kernel"),
+                                             "note": "HBM-bound at this batch size: the ROI patches (~0.96 GB per step) exceed L2"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
