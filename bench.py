@@ -95,6 +95,31 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa(local_rank: int):
+    """Best effort: run this rank (and first-touch its pinned frame buffers) on the NUMA node of its GPU, so that the
+    H2D DMA does not cross the socket interconnect.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "numa node %d (%d cpus)" % (node, len(allowed))
+        return "numa node %d (no allowed cpus)" % node
+    except Exception as e:  # pragma: no cover
+        return "not bound (%s)" % type(e).__name__
+
+
 # ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
@@ -206,11 +231,15 @@ def main():
     from fastest_image_pattern_matching_b200 import _lib as L
 
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry ONE JSON line
+        if not os.environ.get("FPM_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         dist = None
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single process, not bound"
     if rank == 0:
         build()
     if dist:
@@ -397,7 +426,7 @@ def main():
                    "global_batch": world * B, "sharding": "frames over ranks, no data-path collective",
                    "l2": "step input %.0f MB > 126 MB L2; two alternating frame sets" % (B * H * Wd / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * Wd, "d2h_bytes_per_step": B * cap * 96 + B * 4,
-                "ms_per_step": e2e_ms / K, "h2d_copy_only_GBps": h2d_gbps,
+                "ms_per_step": e2e_ms / K, "h2d_copy_only_GBps": h2d_gbps, "host_numa": numa,
                 "pcie_bound_images_per_s": world * h2d_gbps * 1e9 / (H * Wd)},
         "gpu_launches": launches,
         "clocks": clocks,
