@@ -165,7 +165,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
+def emit(line: dict):
+    """the ONE JSON line on the real stdout (fd 1 is pointed at stderr while the bench runs, so that banners
+    printed by NCCL / torchrun children / libraries cannot pollute it)"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -209,7 +222,7 @@ def main():
                                        % (len(vals), cores, per_worker)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------- CPU baseline first (before CUDA is initialised in this process) ----------
@@ -233,7 +246,7 @@ def main():
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry ONE JSON line
         if not os.environ.get("FPM_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ.pop("NCCL_DEBUG", None)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
@@ -445,7 +458,7 @@ def main():
         m.matchBatchRaw(d1[i % B].data_ptr(), 1, Wd, H, pitch, H * pitch, True, res, counts)
         lat.append((time.perf_counter() - t0) * 1000.0)
     line["p50_ms_per_match_batch1"] = statistics.median(lat[3:])
-    print(json.dumps(line))
+    emit(line)
     m.close()
     if dist:
         dist.destroy_process_group()
