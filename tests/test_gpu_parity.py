@@ -380,3 +380,46 @@ def test_angle_sharded_driver_single_rank(matcher, golden_cases):
     assert_results_match(D.match_angle_sharded(matcher, src, None), matcher.match(src), 0, 0, 0)
     rows = D.match_frames_sharded(matcher, [src, get_image("Src9")], None)
     assert rows[0].shape == (3, 12) and abs(rows[0][0, 0] - c["results"][0]["score"]) <= 1e-4
+
+
+# ---------------- BASELINE.json configs 4 and 5 at full size, against the live oracle ----------------
+def _cfg45(matcher, W, H, T, seeds):
+    from fastest_image_pattern_matching_b200 import synth
+    tpl = synth.synth_template(T, 4)
+    frames = [synth.synth_frame(W, H, tpl, s, 4) for s in seeds]
+    params = dict(max_pos=4, score=0.8, tolerance_angle=180, min_reduce_area=256, max_overlap=0.0)
+    configure(matcher, params)
+    assert matcher.learnPattern(tpl)
+    om = configure(O.OracleMatcher(), params)
+    om.learn_pattern(tpl)
+    return tpl, frames, om
+
+
+def test_cfg4_full_size_batch(matcher):
+    """cfg4: 4096x3072 frames x 512x512 template, +-180 deg, 4 instances per frame (batch of 3 here)."""
+    tpl, frames, om = _cfg45(matcher, 4096, 3072, 512, [11, 12, 13])
+    got = matcher.matchBatch(np.stack(frames))
+    for f, g in zip(frames, got):
+        want = om.match(f)
+        assert len(want) == 4
+        assert_results_match(g, want)
+
+
+def test_cfg5_full_size_and_angle_sharded(matcher):
+    """cfg5: one 8192x8192 frame x 1024x1024 template (L0 angular step 0.112 deg); whole match and the
+    angle-sharded stage pipeline (4 virtual ranks) must both equal the oracle."""
+    from fastest_image_pattern_matching_b200 import dist as D
+    tpl, frames, om = _cfg45(matcher, 8192, 8192, 1024, [11])
+    src = frames[0]
+    want = om.match(src)
+    assert len(want) == 4
+    got = matcher.match(src)
+    assert_results_match(got, want)
+    n_ang = matcher.stageNumAngles(src.shape[1], src.shape[0])
+    world = 4
+    picks = np.concatenate([matcher.stageTop(src, *D.angle_range(n_ang, r, world)) for r in range(world)])
+    cands = matcher.stageSortCandidates(picks)
+    matcher.stageTop(src, 0, 0)
+    refined = np.concatenate([matcher.stageRefine(cands[r::world]) for r in range(world)])
+    refined = refined[np.argsort(refined[:, 0], kind="stable")]
+    assert_results_match(matcher.stageFinal(refined), got, 0, 0, 0)
