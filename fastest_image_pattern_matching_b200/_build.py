@@ -43,5 +43,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_pybind(force: bool = False) -> str:
+    """Compile the pybind11 module fpm_b200_pybind (g++, links libfpm_b200.so by rpath $ORIGIN)."""
+    import sysconfig
+    import pybind11
+    build()
+    out = os.path.join(HERE, "fpm_b200_pybind" + sysconfig.get_config_var("EXT_SUFFIX"))
+    src = os.path.join(CSRC, "fpm_pybind.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "fpm_template_matcher.hpp"), os.path.join(HERE, "..", "include", "fpm_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+           src, "-o", out, "-L", HERE, "-l:libfpm_b200.so", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ (pybind) failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

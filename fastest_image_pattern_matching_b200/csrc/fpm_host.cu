@@ -138,6 +138,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
+    int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
     int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
     // template
     bool learned = false;
@@ -735,7 +736,7 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
                                                              h->max_overlap, h->tpl[0].w, h->tpl[0].h,
                                                              h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
                                                              h->d_del.as<int>(), h->d_idmap.as<int>(),
-                                                             h->d_pairs.as<unsigned char>(), pair_cap,
+                                                             h->d_pairs.as<unsigned char>(), pair_cap, h->mfc_compat, h->max_pos,
                                                              h->d_results.as<FpmResultDev>(), rcap, h->d_rescnt.as<int>()));
     FpmResultDev* hr = h->h_results.as<FpmResultDev>();
     int* hn = reinterpret_cast<int*>(hr + (size_t)batch * rcap);
@@ -906,6 +907,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_PROFILE: prof_collect(h); h->profile = v != 0; break;
     case FPM_PARAM_H2D_CHUNK: h->h2d_chunk = (int)v; break;
     case FPM_PARAM_TENSOR_CORES: h->use_tc = (int)v; break;
+    case FPM_PARAM_MFC_COMPAT: h->mfc_compat = v != 0; break;
     default: h->err = "unknown parameter"; return FPM_ERR_INVALID;
     }
     return FPM_OK;
@@ -927,6 +929,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_PROFILE: return h->profile;
     case FPM_PARAM_H2D_CHUNK: return h->h2d_chunk;
     case FPM_PARAM_TENSOR_CORES: return h->use_tc;
+    case FPM_PARAM_MFC_COMPAT: return h->mfc_compat;
     default: return 0;
     }
 }

@@ -1144,7 +1144,7 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
                  unsigned long long* __restrict__ key_scratch, int key_stride,
                  FpmRRect* __restrict__ rect_scratch, int* __restrict__ del_scratch,
                  int* __restrict__ idmap_scratch, unsigned char* __restrict__ pair_scratch, int pair_cap,
-                 FpmResultDev* __restrict__ results, int result_cap, int* __restrict__ result_count)
+                 int mfc_compat, int max_pos, FpmResultDev* __restrict__ results, int result_cap, int* __restrict__ result_count)
 {
     const int img = blockIdx.x, tid = threadIdx.x;
     const int n_total = *refined_count;
@@ -1219,17 +1219,36 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
             if (del[i]) continue;
             if (cnt < result_cap) {
                 const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
-                float lt[2], rt[2], lb[2], rb[2];
-                fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
                 FpmResultDev o;
-                o.score = r.score; o.angle = r.angle;
-                o.cx = (double)((lt[0] + rt[0] + lb[0] + rb[0]) / 4.0f);
-                o.cy = (double)((lt[1] + rt[1] + lb[1] + rb[1]) / 4.0f);
-                o.ltx = lt[0]; o.lty = lt[1]; o.rtx = rt[0]; o.rty = rt[1];
-                o.rbx = rb[0]; o.rby = rb[1]; o.lbx = lb[0]; o.lby = lb[1];
+                o.score = r.score;
+                if (!mfc_compat) {
+                    // Qt TemplateMatcher conversion (src/TemplateMatcher.cpp:407-432): float corner math
+                    float lt[2], rt[2], lb[2], rb[2];
+                    fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
+                    o.angle = r.angle;
+                    o.cx = (double)((lt[0] + rt[0] + lb[0] + rb[0]) / 4.0f);
+                    o.cy = (double)((lt[1] + rt[1] + lb[1] + rb[1]) / 4.0f);
+                    o.ltx = lt[0]; o.lty = lt[1]; o.rtx = rt[0]; o.rty = rt[1];
+                    o.rbx = rb[0]; o.rby = rb[1]; o.lbx = lb[0]; o.lby = lb[1];
+                } else {
+                    // MFC CMatchToolDlg conversion (MatchTool/MatchToolDlg.cpp:1085-1099): double corner math,
+                    // angle negated and wrapped to [-180, 180]
+                    const double a = -r.angle * FPM_D2R, c = cos(a), sn = sin(a);
+                    o.ltx = r.ptx; o.lty = r.pty;
+                    o.rtx = o.ltx + tpl_w * c; o.rty = o.lty - tpl_w * sn;
+                    o.lbx = o.ltx + tpl_h * sn; o.lby = o.lty + tpl_h * c;
+                    o.rbx = o.rtx + tpl_h * sn; o.rby = o.rty + tpl_h * c;
+                    o.cx = (o.ltx + o.rtx + o.rbx + o.lbx) / 4;
+                    o.cy = (o.lty + o.rty + o.rby + o.lby) / 4;
+                    double ang = -r.angle;
+                    if (ang < -180) ang += 360;
+                    if (ang > 180) ang -= 360;
+                    o.angle = ang;
+                }
                 results[(size_t)img * result_cap + cnt] = o;
             }
             cnt++;
+            if (mfc_compat && cnt == max_pos) break;          // MatchToolDlg.cpp:1115-1116
         }
         result_count[img] = cnt;
     }

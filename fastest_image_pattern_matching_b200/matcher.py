@@ -94,6 +94,7 @@ class TemplateMatcher:
     def setWorkspaceMB(self, v: float): self._set(L.PARAM_WORKSPACE_MB, v)
     def setH2DChunk(self, v: int): self._set(L.PARAM_H2D_CHUNK, v)
     def setTensorCores(self, v: int): self._set(L.PARAM_TENSOR_CORES, v)
+    def setMfcCompat(self, v: bool): self._set(L.PARAM_MFC_COMPAT, 1 if v else 0)
 
     def getLastExecutionTime(self) -> float:
         """seconds, like the reference (include/TemplateMatcher.h:40)"""

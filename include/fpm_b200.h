@@ -47,6 +47,8 @@ enum fpm_param {
     FPM_PARAM_PROFILE = 9,         /* bracket every kernel launch with CUDA events (bench.py roofline) */
     FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
     FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always */
+    FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC result convention (MatchTool/MatchToolDlg.cpp:1085-1116): angle = -theta wrapped
+                                      to [-180,180], results truncated to TargetNum, corners in double; default 0 = Qt port */
     FPM_PARAM_COUNT_
 };
 

@@ -423,3 +423,31 @@ def test_cfg5_full_size_and_angle_sharded(matcher):
     refined = np.concatenate([matcher.stageRefine(cands[r::world]) for r in range(world)])
     refined = refined[np.argsort(refined[:, 0], kind="stable")]
     assert_results_match(matcher.stageFinal(refined), got, 0, 0, 0)
+
+
+def test_mfc_compat_result_convention(matcher, golden_cases):
+    """upstream MFC convention (MatchTool/MatchToolDlg.cpp:1085-1116): angle = -theta wrapped, TargetNum truncation,
+    corners in double -- derived here from the Qt-convention golden results; reproduces the README sign (README.md:47-49)."""
+    import math
+    c = golden_cases["cfg3_src6"]
+    configure(matcher, dict(c["params"], max_pos=7))
+    matcher.learnPattern(get_image(c["tpl"]))
+    src = get_image(c["src"])
+    qt = matcher.match(src)
+    matcher.setMfcCompat(True)
+    try:
+        mfc = matcher.match(src)
+    finally:
+        matcher.setMfcCompat(False)
+    assert len(qt) == 15 and len(mfc) == 7                      # truncated to TargetNum
+    w, h = 848, 446
+    for q, m in zip(qt, mfc):
+        ang = -q.dMatchedAngle
+        ang = ang + 360 if ang < -180 else (ang - 360 if ang > 180 else ang)
+        assert m.dMatchedAngle == ang and m.dMatchScore == q.dMatchScore and m.ptLT == q.ptLT
+        a = -q.dMatchedAngle * math.pi / 180
+        rt = (q.ptLT[0] + w * math.cos(a), q.ptLT[1] - w * math.sin(a))
+        rb = (rt[0] + h * math.sin(a), rt[1] + h * math.cos(a))
+        assert abs(m.ptRT[0] - rt[0]) < 1e-9 and abs(m.ptRT[1] - rt[1]) < 1e-9
+        assert abs(m.ptRB[0] - rb[0]) < 1e-9 and abs(m.ptRB[1] - rb[1]) < 1e-9
+        assert abs(m.ptCenter[0] - q.ptCenter[0]) < 1e-3
