@@ -138,6 +138,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
+    bool mma_attr_set = false;
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
     int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
     // template
@@ -365,10 +366,9 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     int chunks = std::max(1, (2 * 148 + m_tiles - 1) / m_tiles);
     int rows_per_cta = std::max(2, (rh + chunks - 1) / chunks);
     chunks = (rh + rows_per_cta - 1) / rows_per_cta;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!h->mma_attr_set) {                                  // per handle: the attribute is per device
         CK(cudaFuncSetAttribute(fpm_corr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
-        attr_set = true;
+        h->mma_attr_set = true;
     }
     dim3 grid(chunks, m_tiles);
     KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
@@ -564,7 +564,7 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         const int tiles_x = (rpitch + WA_TW - 1) / WA_TW;
         dim3 grid(tiles_x * ((p.maxH + WA_TH - 1) / WA_TH), njobs);
         KL(K_WARP_TOP, 2.0 * njobs * (double)p.maxW * p.maxH,
-           fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->levels[top],
+           fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), 1, h->levels[top],
                                                                h->d_rot.as<uint8_t>(), rpitch, rot_stride, h->border, tiles_x,
                                                                level_vec_ok(h->levels[top])));
     }
@@ -665,11 +665,12 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
                                                                              h->d_jobs_ref.as<FpmWarpJob>()));
             const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
-            dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), ne);
+            dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
             // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
             KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
-               fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), L, h->d_roi.as<uint8_t>(),
-                                                                    rpitch, roi_stride, 0, wtiles_x, level_vec_ok(L)));
+               fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
+                                                                    h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
+                                                                    level_vec_ok(L)));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
             if (mma_usable(h, t.w)) {
                 int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
@@ -1265,7 +1266,7 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     FpmLevel s{h->d_dbg[0].as<uint8_t>(), w, hgt, sp, 0};
     const int tiles_x = (dp + WA_TW - 1) / WA_TW;
     dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
-    fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
+    fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), 1, s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
                                                         tiles_x, level_vec_ok(s));
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));

@@ -142,79 +142,90 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 //   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,
 //   X = (X0+adelta)>>5, sx = X>>5, ax = X&31, weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15
 //   == ((top<<5) + ay*(bot-top) + 512) >> 10 with top = (p00<<5) + ax*(p01-p00)   (same integers).
-// One job per output image (top-layer angle or refinement ROI).  One CTA = 64x64 output pixels,
-// 16 pixels per thread.  The fixed-point map is separable and monotone in x and y, so the exact
-// source bounding box of the tile follows from its 4 corners; the box (<= 92x92 px for a rotation)
-// is staged in shared memory with coalesced 32-bit loads and the 4 bilinear taps are gathered from
-// shared memory -- a diagonal walk through global memory costs one L1 wavefront per lane.
-// Packed 32-bit stores; padding columns up to dpitch are written as zero.
+// One job per output image (top-layer angle or refinement ROI).  One CTA = one 64x128 output tile of a
+// GROUP of jobs: the 3 angles of a refinement candidate are anchored at the same source point and differ by
+// less than ~4 px over the tile, so they share one staged source box.  The fixed-point map is separable and
+// monotone in x and y, so the exact source bounding box of a tile follows from its 4 corners; the union box
+// (<= 160x160 px) is staged in shared memory with cp.async (odd word pitch: conflict-free gathers) and the
+// 4 bilinear taps of every pixel are gathered from shared memory -- a diagonal walk through global memory
+// would cost one L1 wavefront per lane.  32 pixels per thread and angle, packed 32-bit stores; padding
+// columns up to dpitch are written as zero.
 // =====================================================================================
 #define WA_TW 64
-#define WA_TH 64
+#define WA_TH 128
 #define WA_THREADS 256
-#define WA_SW 100     // staged box pitch in bytes: 25 words (odd) -> rows fall in different banks
-#define WA_BW 96      // staged box: max bytes per row actually used
-#define WA_SH 96      // staged box: rows
+#define WA_BW 160     // staged box: max bytes per row actually used (40 words)
+#define WA_SW 164     // staged box pitch in bytes: 41 words (odd) -> rows fall in different banks
+#define WA_SH 160     // staged box: rows
+#define WA_MAXG 3     // jobs per group
 
 __global__ void __launch_bounds__(WA_THREADS)
-fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __restrict__ dst,
+fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, uint8_t* __restrict__ dst,
                 int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok)
 {
-    const FpmWarpJob& jb = jobs[blockIdx.y];
-    const int dw = jb.dw, dh = jb.dh;
+    const int g0 = blockIdx.y * group;
+    const FpmWarpJob& jb0 = jobs[g0];
+    const int dw = jb0.dw, dh = jb0.dh;
     const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
     const int tx0 = tile_x * WA_TW, ty0 = tile_y * WA_TH;
-    if (!jb.valid || ty0 >= dh || tx0 >= dpitch) return;
-    __shared__ int s_ad[WA_TW], s_bd[WA_TW], s_X0[WA_TH], s_Y0[WA_TH];
+    if (!jb0.valid || ty0 >= dh || tx0 >= dpitch) return;
+    __shared__ int s_ad[WA_MAXG][WA_TW], s_bd[WA_MAXG][WA_TW], s_X0[WA_MAXG][WA_TH], s_Y0[WA_MAXG][WA_TH];
     __shared__ __align__(16) uint8_t s_src[WA_SH * WA_SW];
     const int tid = threadIdx.x;
-    if (tid < WA_TW) {
-        double x = (double)(tx0 + tid);
-        s_ad[tid] = fpm_cvround(jb.m[0] * x * 1024.0);
-        s_bd[tid] = fpm_cvround(jb.m[3] * x * 1024.0);
-    } else if (tid < WA_TW + WA_TH) {
-        int r = tid - WA_TW;
-        double y = (double)(ty0 + r);
-        s_X0[r] = fpm_cvround((jb.m[1] * y + jb.m[2]) * 1024.0) + 16;
-        s_Y0[r] = fpm_cvround((jb.m[4] * y + jb.m[5]) * 1024.0) + 16;
+    for (int i = tid; i < group * (WA_TW + WA_TH); i += WA_THREADS) {
+        const int j = i / (WA_TW + WA_TH), k = i - j * (WA_TW + WA_TH);
+        const FpmWarpJob& jb = jobs[g0 + j];
+        if (k < WA_TW) {
+            double x = (double)(tx0 + k);
+            s_ad[j][k] = fpm_cvround(jb.m[0] * x * 1024.0);
+            s_bd[j][k] = fpm_cvround(jb.m[3] * x * 1024.0);
+        } else {
+            const int r = k - WA_TW;
+            double y = (double)(ty0 + r);
+            s_X0[j][r] = fpm_cvround((jb.m[1] * y + jb.m[2]) * 1024.0) + 16;
+            s_Y0[j][r] = fpm_cvround((jb.m[4] * y + jb.m[5]) * 1024.0) + 16;
+        }
     }
     __syncthreads();
     const int ncols = min(WA_TW, dw - tx0);            // real pixels in this tile (<= 0 for pad-only tiles)
     const int nrows = min(WA_TH, dh - ty0);
-    const uint8_t* __restrict__ s = src.ptr + (size_t)jb.src_img * src.img_stride;
-    uint8_t* __restrict__ d = dst + (size_t)blockIdx.y * dst_job_stride;
+    const uint8_t* __restrict__ s = src.ptr + (size_t)jb0.src_img * src.img_stride;
     const int sw = src.w, sh = src.h, sp = src.pitch;
 
-    // exact source box of the tile from its corners (X and Y are sums of monotone functions of x and y)
+    // exact source box of the tile for every job of the group from the tile corners (X and Y are sums of
+    // monotone functions of x and y), then the union
     int bx0 = 0, by0 = 0;
     bool staged = false, inside = false;
     if (ncols > 0) {
-        int xa = s_ad[0], xb = s_ad[ncols - 1], ya = s_bd[0], yb = s_bd[ncols - 1];
-        int X0a = s_X0[0], X0b = s_X0[nrows - 1], Y0a = s_Y0[0], Y0b = s_Y0[nrows - 1];
-        int Xmin = min(min(X0a + xa, X0a + xb), min(X0b + xa, X0b + xb));
-        int Xmax = max(max(X0a + xa, X0a + xb), max(X0b + xa, X0b + xb));
-        int Ymin = min(min(Y0a + ya, Y0a + yb), min(Y0b + ya, Y0b + yb));
-        int Ymax = max(max(Y0a + ya, Y0a + yb), max(Y0b + ya, Y0b + yb));
-        int sx0 = Xmin >> 10, sx1 = (Xmax >> 10) + 1, sy0 = Ymin >> 10, sy1 = (Ymax >> 10) + 1;
+        int Xmin = 0x7fffffff, Xmax = -0x7fffffff, Ymin = 0x7fffffff, Ymax = -0x7fffffff;
+        for (int j = 0; j < group; j++) {
+            const int xa = s_ad[j][0], xb = s_ad[j][ncols - 1], ya = s_bd[j][0], yb = s_bd[j][ncols - 1];
+            const int X0a = s_X0[j][0], X0b = s_X0[j][nrows - 1], Y0a = s_Y0[j][0], Y0b = s_Y0[j][nrows - 1];
+            Xmin = min(Xmin, min(min(X0a + xa, X0a + xb), min(X0b + xa, X0b + xb)));
+            Xmax = max(Xmax, max(max(X0a + xa, X0a + xb), max(X0b + xa, X0b + xb)));
+            Ymin = min(Ymin, min(min(Y0a + ya, Y0a + yb), min(Y0b + ya, Y0b + yb)));
+            Ymax = max(Ymax, max(max(Y0a + ya, Y0a + yb), max(Y0b + ya, Y0b + yb)));
+        }
+        const int sx0 = Xmin >> 10, sx1 = (Xmax >> 10) + 1, sy0 = Ymin >> 10, sy1 = (Ymax >> 10) + 1;
         inside = sx0 >= 0 && sy0 >= 0 && sx1 < sw && sy1 < sh;
         bx0 = max(sx0, 0) & ~3;
         by0 = max(sy0, 0);
         const int bx1 = min(sx1, sw - 1), by1 = min(sy1, sh - 1);
         staged = (bx1 - bx0 + 1 <= WA_BW) && (by1 - by0 + 1 <= WA_SH);
         if (staged && bx1 >= bx0 && by1 >= by0) {
-            const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;      // nwr <= 24
-            const int wc = tid & 31;
+            const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;      // nwr <= 40
+            const int wc = tid & 63;
             if (wc < nwr) {
                 const int x = bx0 + 4 * wc;
-                const uint8_t* rowp = s + (size_t)(by0 + (tid >> 5)) * sp + x;
-                uint8_t* sp_out = s_src + (tid >> 5) * WA_SW + 4 * wc;
+                const uint8_t* rowp = s + (size_t)(by0 + (tid >> 6)) * sp + x;
+                uint8_t* sp_out = s_src + (tid >> 6) * WA_SW + 4 * wc;
                 if (vec_ok && x + 3 < sw) {
-                    for (int r = tid >> 5; r < nr; r += WA_THREADS / 32, rowp += (size_t)(WA_THREADS / 32) * sp,
-                             sp_out += (WA_THREADS / 32) * WA_SW)
+                    for (int r = tid >> 6; r < nr; r += WA_THREADS / 64, rowp += (size_t)(WA_THREADS / 64) * sp,
+                             sp_out += (WA_THREADS / 64) * WA_SW)
                         fpm_cp_async4(sp_out, rowp, true);
                 } else {
-                    for (int r = tid >> 5; r < nr; r += WA_THREADS / 32, rowp += (size_t)(WA_THREADS / 32) * sp,
-                             sp_out += (WA_THREADS / 32) * WA_SW) {
+                    for (int r = tid >> 6; r < nr; r += WA_THREADS / 64, rowp += (size_t)(WA_THREADS / 64) * sp,
+                             sp_out += (WA_THREADS / 64) * WA_SW) {
                         uint32_t v = 0;
 #pragma unroll
                         for (int k = 0; k < 4; k++)
@@ -230,60 +241,64 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, FpmLevel src, uint8_t* __re
     __syncthreads();
     const int xg = tid & 15;
     if (tx0 + 4 * xg >= dpitch) return;
-    int adj[4], bdj[4];
+    const bool fast = staged && inside && (4 * xg + 3 < ncols);
+    for (int j = 0; j < group; j++) {
+        if (!jobs[g0 + j].valid) continue;
+        uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride;
+        int adj[4], bdj[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        adj[k] = s_ad[4 * xg + k] - (bx0 << 10);
-        bdj[k] = s_bd[4 * xg + k] - (by0 << 10);
-    }
-    const bool fast = staged && inside;
-    for (int row = tid >> 4; row < nrows; row += WA_THREADS / 16) {
-        uint32_t pack = 0;
-        const int X0 = s_X0[row], Y0 = s_Y0[row];
-        if (fast && 4 * xg + 3 < ncols) {
+        for (int k = 0; k < 4; k++) {
+            adj[k] = s_ad[j][4 * xg + k] - (bx0 << 10);
+            bdj[k] = s_bd[j][4 * xg + k] - (by0 << 10);
+        }
+        for (int row = tid >> 4; row < nrows; row += WA_THREADS / 16) {
+            uint32_t pack = 0;
+            const int X0 = s_X0[j][row], Y0 = s_Y0[j][row];
+            if (fast) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int XX = X0 + adj[k], YY = Y0 + bdj[k];
-                const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
-                const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
-                const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
-                const int top = (p00 << 5) + ax * (p01 - p00);
-                const int bot = (p10 << 5) + ax * (p11 - p10);
-                const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
-                pack |= (uint32_t)v << (8 * k);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (4 * xg + k < ncols) {
+                for (int k = 0; k < 4; k++) {
                     const int XX = X0 + adj[k], YY = Y0 + bdj[k];
                     const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
-                    const int lx = XX >> 10, ly = YY >> 10;              // relative to (bx0, by0)
-                    const int sx = lx + bx0, sy = ly + by0;
-                    const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-                    const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-                    int p00, p01, p10, p11;
-                    if (staged) {
-                        const uint8_t* p = s_src + ly * WA_SW + lx;
-                        p00 = (x0in && y0in) ? p[0] : border;
-                        p01 = (x1in && y0in) ? p[1] : border;
-                        p10 = (x0in && y1in) ? p[WA_SW] : border;
-                        p11 = (x1in && y1in) ? p[WA_SW + 1] : border;
-                    } else {
-                        const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
-                        p00 = (x0in && y0in) ? __ldg(p) : border;
-                        p01 = (x1in && y0in) ? __ldg(p + 1) : border;
-                        p10 = (x0in && y1in) ? __ldg(p + sp) : border;
-                        p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
-                    }
+                    const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
+                    const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
                     const int top = (p00 << 5) + ax * (p01 - p00);
                     const int bot = (p10 << 5) + ax * (p11 - p10);
                     const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
                     pack |= (uint32_t)v << (8 * k);
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (4 * xg + k < ncols) {
+                        const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                        const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
+                        const int lx = XX >> 10, ly = YY >> 10;              // relative to (bx0, by0)
+                        const int sx = lx + bx0, sy = ly + by0;
+                        const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+                        const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+                        int p00, p01, p10, p11;
+                        if (staged) {
+                            const uint8_t* p = s_src + ly * WA_SW + lx;
+                            p00 = (x0in && y0in) ? p[0] : border;
+                            p01 = (x1in && y0in) ? p[1] : border;
+                            p10 = (x0in && y1in) ? p[WA_SW] : border;
+                            p11 = (x1in && y1in) ? p[WA_SW + 1] : border;
+                        } else {
+                            const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
+                            p00 = (x0in && y0in) ? __ldg(p) : border;
+                            p01 = (x1in && y0in) ? __ldg(p + 1) : border;
+                            p10 = (x0in && y1in) ? __ldg(p + sp) : border;
+                            p11 = (x1in && y1in) ? __ldg(p + sp + 1) : border;
+                        }
+                        const int top = (p00 << 5) + ax * (p01 - p00);
+                        const int bot = (p10 << 5) + ax * (p11 - p10);
+                        const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
+                        pack |= (uint32_t)v << (8 * k);
+                    }
+                }
             }
+            *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
         }
-        *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
     }
 }
 

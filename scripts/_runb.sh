@@ -1,4 +1,8 @@
-python -m pytest tests -q -m gpu 2>&1 | tail -2
-python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,launch__grid_size,launch__block_size,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum --clock-control none -s 234 -c 40 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-tail -1 gpurun_out/ncu.log | cut -c1-300
+python -m pytest tests -q -m gpu 2>&1 | tail -3
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/b.json 2> gpurun_out/b.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/b.json"))
+print("value",round(d["value"]),"ms/step",round(d["ms_per_step"],3),"| e2e",round(d["e2e"]["value"]),"p50",round(d["p50_ms_per_match_batch1"],3),"ok",d["targets_found_per_frame_ok"])
+print("   "+"  ".join("%s %.3f"%(k.replace("fpm_","").replace("_kernel",""),v["ms_per_step"]) for k,v in d["kernels"].items()))
+PY
