@@ -148,7 +148,7 @@ struct fpm_handle {
     std::vector<uint8_t> tpl0;    // level-0 copy for re-learning when MinReduceArea changes
     int tpl0_w = 0, tpl0_h = 0;
     std::vector<TplLevelHost> tpl;
-    DevBuf d_tpl, d_tsh, d_raw, d_rowfull;
+    DevBuf d_tpl, d_tsh, d_raw;
     // user rect (pure storage)
     int ur[4] = {0, 0, 0, 0};
     int has_ur = 0;
@@ -196,11 +196,11 @@ namespace {
         }                                                                                \
     } while (0)
 
-enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_ROWSUMS, K_ROWFIX, K_COUNT };
+enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_ROWSUMS, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"fpm_pyrdown_kernel", "fpm_warp_kernel(top)", "fpm_top_score_kernel", "fpm_top_peaks_kernel",
                                            "fpm_collect_sort_kernel", "fpm_refine_prep_kernel", "fpm_warp_kernel(roi)",
                                            "fpm_corr_rows_kernel", "fpm_refine_finalize_kernel", "fpm_final_kernel",
-                                           "fpm_corr_mma_kernel", "fpm_row_sums_kernel", "fpm_row_fix_kernel"};
+                                           "fpm_corr_mma_kernel", "fpm_row_sums_kernel"};
 
 cudaEvent_t prof_event(fpm_handle* h)
 {
@@ -350,7 +350,7 @@ bool mma_usable(const fpm_handle* h, int tw)
 
 // raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
 int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
-                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* row_full)
+                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (ne + MM_M - 1) / MM_M;
@@ -375,12 +375,6 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
        fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw + FPM_ROI_PAD, rows_per_cta,
                                                                            h->d_raw.as<int32_t>()));
     const int n_rows = ne * rh;
-    if (row_full) {
-        // the warp kernel already accumulated the full-row sums: only the 7 shifted windows are derived here
-        KL(K_ROWFIX, (double)n_rows * (64.0 + 8 + 56),
-           fpm_row_fix_kernel<<<(n_rows + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh, ne, row_full, rowS, rowQ));
-        return FPM_OK;
-    }
     KL(K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD),
        fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh, n_rows, rowS, rowQ));
     return FPM_OK;
@@ -572,7 +566,7 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         KL(K_WARP_TOP, 2.0 * njobs * (double)p.maxW * p.maxH,
            fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), 1, h->levels[top],
                                                                h->d_rot.as<uint8_t>(), rpitch, rot_stride, h->border, tiles_x,
-                                                               level_vec_ok(h->levels[top]), nullptr, 0));
+                                                               level_vec_ok(h->levels[top])));
     }
     {
         size_t smem = top_score_smem(t.w, t.h);
@@ -670,25 +664,17 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
                fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
                                                                              h->d_jobs_ref.as<FpmWarpJob>()));
-            const bool use_mma = mma_usable(h, t.w);
-            int* row_full = nullptr;
-            if (use_mma) {
-                const size_t rf_bytes = 2 * (size_t)ne * (t.h + FPM_ROI_PAD) * sizeof(int);
-                CK(h->d_rowfull.ensure(rf_bytes));
-                CK(cudaMemsetAsync(h->d_rowfull.p, 0, rf_bytes, h->stream));
-                row_full = h->d_rowfull.as<int>();
-            }
             const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
             dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
             // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
             KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
                fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
                                                                     h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
-                                                                    level_vec_ok(L), row_full, ne));
+                                                                    level_vec_ok(L)));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
-            if (use_mma) {
+            if (mma_usable(h, t.w)) {
                 int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
-                                          t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), row_full);
+                                          t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
                 if (rcm) return rcm;
             } else {
                 dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
@@ -888,7 +874,7 @@ void fpm_destroy(fpm_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
-    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_rowfull, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
                       &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
@@ -1281,7 +1267,7 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     const int tiles_x = (dp + WA_TW - 1) / WA_TW;
     dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
     fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), 1, s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
-                                                        tiles_x, level_vec_ok(s), nullptr, 0);
+                                                        tiles_x, level_vec_ok(s));
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1350,7 +1336,7 @@ int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois, int ne, const uint
     int32_t* dS = h->d_dbg[3].as<int32_t>();
     int32_t* dQ = dS + (size_t)ne * rh * FPM_NSHIFT;
     int e_pad = 0;
-    int rc = launch_corr_mma(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, &e_pad, dS, dQ, nullptr);
+    int rc = launch_corr_mma(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, &e_pad, dS, dQ);
     if (rc) return rc;
     std::vector<int32_t> raw((size_t)rh * e_pad * MM_N);
     CK(cudaMemcpyAsync(raw.data(), h->d_raw.p, raw.size() * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -161,8 +161,7 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 
 __global__ void __launch_bounds__(WA_THREADS)
 fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, uint8_t* __restrict__ dst,
-                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok,
-                int* __restrict__ row_full /* optional: [2][jobs][dh] running row sums / sums of squares */, int n_jobs_total)
+                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok)
 {
     const int g0 = blockIdx.y * group;
     const FpmWarpJob& jb0 = jobs[g0];
@@ -241,9 +240,8 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     fpm_cp_async_wait<0>();
     __syncthreads();
     const int xg = tid & 15;
-    const bool live = tx0 + 4 * xg < dpitch;           // this thread's 4 columns exist in the (padded) output row
+    if (tx0 + 4 * xg >= dpitch) return;
     const bool fast = staged && inside && (4 * xg + 3 < ncols);
-    const unsigned halfmask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;     // the 16 lanes that share an output row
     for (int j = 0; j < group; j++) {
         if (!jobs[g0 + j].valid) continue;
         uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride;
@@ -268,7 +266,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                     const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
                     pack |= (uint32_t)v << (8 * k);
                 }
-            } else if (live) {
+            } else {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if (4 * xg + k < ncols) {
@@ -299,40 +297,8 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                     }
                 }
             }
-            if (live) *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
-            if (row_full) {
-                // running sums of the whole output row (padding pixels are 0): one REDUX per 16 lanes, one RED per tile row
-                const unsigned rs = __reduce_add_sync(halfmask, __dp4a(pack, 0x01010101u, 0u));
-                const unsigned rq = __reduce_add_sync(halfmask, __dp4a(pack, pack, 0u));
-                if (xg == 0) {
-                    const size_t ri = (size_t)(g0 + j) * dh + ty0 + row;
-                    atomicAdd(row_full + ri, (int)rs);
-                    atomicAdd(row_full + (size_t)n_jobs_total * dh + ri, (int)rq);
-                }
-            }
+            *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
         }
-    }
-}
-
-// window row sums from the running full-row sums (MMA path): one thread per ROI row.
-//   S_c = sum_{x=c}^{c+w-1} row[x]: S_0 = full - sum(tail 6), S_c = S_{c-1} - row[c-1] + row[w+c-1]   (same for squares)
-__global__ void fpm_row_fix_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, int tw, int rh, int n_jobs,
-                                   const int* __restrict__ row_full, int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
-{
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_jobs * rh) return;
-    const int e = g / rh, y = g - e * rh;
-    const uint8_t* rb = roi + (size_t)e * roi_stride + (size_t)y * rpitch;
-    int s = row_full[g], q = row_full[(size_t)n_jobs * rh + g];
-    int hb[6], tb[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) { hb[k] = rb[k]; tb[k] = rb[tw + k]; s -= tb[k]; q -= tb[k] * tb[k]; }
-    rowS[(size_t)g * FPM_NSHIFT] = s; rowQ[(size_t)g * FPM_NSHIFT] = q;
-#pragma unroll
-    for (int c = 1; c < FPM_NSHIFT; c++) {
-        s += tb[c - 1] - hb[c - 1];
-        q += tb[c - 1] * tb[c - 1] - hb[c - 1] * hb[c - 1];
-        rowS[(size_t)g * FPM_NSHIFT + c] = s; rowQ[(size_t)g * FPM_NSHIFT + c] = q;
     }
 }
 
