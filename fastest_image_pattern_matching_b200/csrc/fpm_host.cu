@@ -128,7 +128,8 @@ struct TopPlan {                  // cached per (source size, parameters)
 
 struct fpm_handle {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     // parameters (src/TemplateMatcher.cpp:28-39)
@@ -210,18 +211,18 @@ cudaEvent_t prof_event(fpm_handle* h)
     return e;
 }
 
-inline void prof_begin(fpm_handle* h)
+inline void prof_begin(fpm_handle* h, cudaStream_t st = nullptr)
 {
     if (!h->profile) return;
     h->prof_cur = prof_event(h);
-    cudaEventRecord(h->prof_cur, h->stream);
+    cudaEventRecord(h->prof_cur, st ? st : h->stream);
 }
 
-inline void prof_end(fpm_handle* h, int kid, double work)
+inline void prof_end(fpm_handle* h, int kid, double work, cudaStream_t st = nullptr)
 {
     if (!h->profile) return;
     cudaEvent_t b = prof_event(h);
-    cudaEventRecord(b, h->stream);
+    cudaEventRecord(b, st ? st : h->stream);
     h->prof_pending.push_back({kid, h->prof_cur, b, work});
 }
 
@@ -229,6 +230,7 @@ void prof_collect(fpm_handle* h)
 {
     if (h->prof_pending.empty()) return;
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->aux_stream);
     for (auto& r : h->prof_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, r.a, r.b);
@@ -370,13 +372,22 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
         CK(cudaFuncSetAttribute(fpm_corr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
         h->mma_attr_set = true;
     }
+    // the window row sums only depend on the ROI patches: they run on the auxiliary stream, concurrently with the
+    // tensor-core kernel (which leaves most of every SM idle), and are joined before the finalize kernel
+    const int n_rows = ne * rh;
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    prof_begin(h, h->aux_stream);
+    fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->aux_stream>>>(roi, rpitch, roi_stride, tw, rh,
+                                                                                                     n_rows, rowS, rowQ);
+    prof_end(h, K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD), h->aux_stream);
+    CKL();
+    CK(cudaEventRecord(h->ev_join, h->aux_stream));
     dim3 grid(chunks, m_tiles);
     KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
        fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw + FPM_ROI_PAD, rows_per_cta,
                                                                            h->d_raw.as<int32_t>()));
-    const int n_rows = ne * rh;
-    KL(K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD),
-       fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh, n_rows, rowS, rowQ));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     return FPM_OK;
 }
 
@@ -855,7 +866,8 @@ fpm_handle* fpm_create(int device)
     fpm_handle* h = new fpm_handle();
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return nullptr;
     }
@@ -865,6 +877,8 @@ fpm_handle* fpm_create(int device)
     }
     cudaEventCreate(&h->ev_t0);
     cudaEventCreate(&h->ev_t1);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     return h;
 }
 
@@ -874,6 +888,7 @@ void fpm_destroy(fpm_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->aux_stream);
     DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
@@ -885,8 +900,10 @@ void fpm_destroy(fpm_handle* h)
     cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     prof_collect(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
+    cudaStreamDestroy(h->aux_stream);
     delete h;
 }
 
