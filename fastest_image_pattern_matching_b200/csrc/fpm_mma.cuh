@@ -286,16 +286,27 @@ fpm_row_sums_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stri
         uint4 v[RS_ROWS];
 #pragma unroll
         for (int k = 0; k < RS_ROWS; k++) v[k] = reinterpret_cast<const uint4*>(rb[k])[i];
-        const int rem = tw - 16 * i;                       // valid bytes in this chunk (>= 1)
+        if (i < n16 - 1) {
+            // full 16-byte chunk: no masking
 #pragma unroll
-        for (int k = 0; k < RS_ROWS; k++) {
-            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+            for (int k = 0; k < RS_ROWS; k++) {
+                s[k] = __dp4a(v[k].x, 0x01010101u, s[k]); q[k] = __dp4a(v[k].x, v[k].x, q[k]);
+                s[k] = __dp4a(v[k].y, 0x01010101u, s[k]); q[k] = __dp4a(v[k].y, v[k].y, q[k]);
+                s[k] = __dp4a(v[k].z, 0x01010101u, s[k]); q[k] = __dp4a(v[k].z, v[k].z, q[k]);
+                s[k] = __dp4a(v[k].w, 0x01010101u, s[k]); q[k] = __dp4a(v[k].w, v[k].w, q[k]);
+            }
+        } else {
+            const int rem = tw - 16 * i;                   // valid bytes in the last chunk (1..16)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int nb = rem - 4 * j;                // valid bytes in this word
-                const uint32_t m = nb >= 4 ? w[j] : (nb <= 0 ? 0u : (w[j] & (0xffffffffu >> (8 * (4 - nb)))));
-                s[k] = __dp4a(m, 0x01010101u, s[k]);
-                q[k] = __dp4a(m, m, q[k]);
+            for (int k = 0; k < RS_ROWS; k++) {
+                const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int nb = rem - 4 * j;            // valid bytes in this word
+                    const uint32_t m = nb >= 4 ? w[j] : (nb <= 0 ? 0u : (w[j] & (0xffffffffu >> (8 * (4 - nb)))));
+                    s[k] = __dp4a(m, 0x01010101u, s[k]);
+                    q[k] = __dp4a(m, m, q[k]);
+                }
             }
         }
     }

@@ -1,4 +1,4 @@
-python -m pytest tests -q -m gpu 2>&1 | tail -3
+python -m pytest tests -q -m gpu 2>&1 | tail -2
 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/b.json 2> gpurun_out/b.err
 python - <<PY
 import json
