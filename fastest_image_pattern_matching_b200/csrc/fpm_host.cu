@@ -350,13 +350,15 @@ bool mma_usable(const fpm_handle* h, int tw)
     return h->use_tc >= 2 ? true : tw >= 64;
 }
 
-// tensor-core row sums for the `ne` ROI patches in `roi`: raw[y][e_pad][64] (eval e at column block e_base + e) plus the
-// window row sums rowS/rowQ (already offset by the caller).  d_raw must hold rh * e_pad * 64 ints.
+// raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
 int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
-                    int ne, int e_base, int e_pad, int32_t* rowS, int32_t* rowQ)
+                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (ne + MM_M - 1) / MM_M;
+    const int e_pad = m_tiles * MM_M;
+    *e_pad_out = e_pad;
+    CK(h->d_raw.ensure((size_t)rh * e_pad * MM_N * sizeof(int32_t)));
     CUtensorMap map_a, map_b;
     int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)rpitch, (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
     if (rc) return rc;
@@ -370,14 +372,22 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
         CK(cudaFuncSetAttribute(fpm_corr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
         h->mma_attr_set = true;
     }
+    // the window row sums only depend on the ROI patches: they run on the auxiliary stream, concurrently with the
+    // tensor-core kernel (which leaves most of every SM idle), and are joined before the finalize kernel
     const int n_rows = ne * rh;
-    KL(K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD),
-       fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->stream>>>(roi, rpitch, roi_stride, tw, rh,
-                                                                                                    n_rows, rowS, rowQ));
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    prof_begin(h, h->aux_stream);
+    fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->aux_stream>>>(roi, rpitch, roi_stride, tw, rh,
+                                                                                                     n_rows, rowS, rowQ);
+    prof_end(h, K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD), h->aux_stream);
+    CKL();
+    CK(cudaEventRecord(h->ev_join, h->aux_stream));
     dim3 grid(chunks, m_tiles);
     KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
-       fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_base, e_pad, rh, tw + FPM_ROI_PAD,
-                                                                           rows_per_cta, h->d_raw.as<int32_t>()));
+       fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw + FPM_ROI_PAD, rows_per_cta,
+                                                                           h->d_raw.as<int32_t>()));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     return FPM_OK;
 }
 
@@ -643,16 +653,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         wave_cands = std::min(wave_cands, n);
         const int wave_evals = wave_cands * n_ang;
         CK(h->d_jobs_ref.ensure((size_t)wave_evals * sizeof(FpmWarpJob)));
-        const bool use_mma = mma_usable(h, t.w);
-        // tensor-core path: ROI sub-waves sized to stay L2 resident (see below); one M tile = 128 evals
-        int sub_cands = wave_cands;
-        if (use_mma) {
-            const size_t l2_budget = (size_t)56 << 20;
-            sub_cands = (int)std::max<size_t>(1, l2_budget / (roi_stride * n_ang));
-            if (sub_cands * n_ang > MM_M) sub_cands = std::max(1, (sub_cands * n_ang / MM_M) * MM_M / n_ang);   // ~ whole M tiles
-            sub_cands = std::min(sub_cands, wave_cands);
-        }
-        CK(h->d_roi.ensure(roi_stride * (use_mma ? (size_t)sub_cands * n_ang : (size_t)wave_evals)));
+        CK(h->d_roi.ensure(roi_stride * wave_evals));
         CK(h->d_rowsum.ensure((size_t)wave_evals * t.h * FPM_NCELL * 4));
         CK(h->d_rowS.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
         CK(h->d_rowQ.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
@@ -675,34 +676,18 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
                                                                              h->d_jobs_ref.as<FpmWarpJob>()));
             const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
-            const int wtiles = wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH);
+            dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
+            // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
+            KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
+               fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
+                                                                    h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
+                                                                    level_vec_ok(L)));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
-            if (use_mma) {
-                // Tensor-core path.  The ROI patches are produced and consumed in sub-waves of <= ~56 MB, so that the
-                // patches written by the warp kernel are still in L2 (126 MB) when the row-sum and MMA kernels read them
-                // and the buffer is overwritten by the next sub-wave before it is ever evicted to HBM.
-                raw_epad = (int)align_up(ne, MM_M);
-                CK(h->d_raw.ensure((size_t)(t.h + FPM_ROI_PAD) * raw_epad * MM_N * sizeof(int32_t)));
-                for (int cs = 0; cs < nc; cs += sub_cands) {
-                    const int ncs = std::min(sub_cands, nc - cs), nes = ncs * n_ang, e_base = cs * n_ang;
-                    dim3 wgrid(wtiles, ncs);                // one CTA = one tile of the n_ang ROIs of a candidate
-                    KL(K_WARP_ROI, 2.0 * nes * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
-                       fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>() + e_base, n_ang, L,
-                                                                            h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
-                                                                            level_vec_ok(L)));
-                    int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
-                                              t.w, t.h, nes, e_base, raw_epad,
-                                              h->d_rowS.as<int32_t>() + (size_t)e_base * (t.h + FPM_ROI_PAD) * FPM_NSHIFT,
-                                              h->d_rowQ.as<int32_t>() + (size_t)e_base * (t.h + FPM_ROI_PAD) * FPM_NSHIFT);
-                    if (rcm) return rcm;
-                }
+            if (mma_usable(h, t.w)) {
+                int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                          t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
+                if (rcm) return rcm;
             } else {
-                dim3 wgrid(wtiles, nc);
-                // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
-                KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
-                   fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
-                                                                        h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
-                                                                        level_vec_ok(L)));
                 dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
                 // algorithmic MACs: 49 * w * h per eval
                 KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
@@ -1367,9 +1352,8 @@ int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois, int ne, const uint
     CKL();
     int32_t* dS = h->d_dbg[3].as<int32_t>();
     int32_t* dQ = dS + (size_t)ne * rh * FPM_NSHIFT;
-    const int e_pad = (int)align_up(ne, MM_M);
-    CK(h->d_raw.ensure((size_t)rh * e_pad * MM_N * sizeof(int32_t)));
-    int rc = launch_corr_mma(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, 0, e_pad, dS, dQ);
+    int e_pad = 0;
+    int rc = launch_corr_mma(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, &e_pad, dS, dQ);
     if (rc) return rc;
     std::vector<int32_t> raw((size_t)rh * e_pad * MM_N);
     CK(cudaMemcpyAsync(raw.data(), h->d_raw.p, raw.size() * 4, cudaMemcpyDeviceToHost, h->stream));

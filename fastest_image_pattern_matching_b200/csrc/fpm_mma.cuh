@@ -145,11 +145,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 }  // namespace fpm_ptx
 
-// grid: (row_chunks, m_tiles); CTA (bx, by) handles ROI rows [bx*rows_per_cta, ...) of evals [128*by, 128*by+128) of the
-// ROI buffer (n_evals patches); eval e is written to raw[y][e_base + e] (e_pad evals per ROI row in total)
+// grid: (row_chunks, m_tiles); CTA (bx, by) handles ROI rows [bx*rows_per_cta, ...) of evals [128*by, 128*by+128)
 __global__ void __launch_bounds__(MM_THREADS, 1)
 fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    int n_evals, int e_base, int e_pad, int rh, int k_bytes, int rows_per_cta, int32_t* __restrict__ raw)
+                    int n_evals, int e_pad, int rh, int k_bytes, int rows_per_cta, int32_t* __restrict__ raw)
 {
     using namespace fpm_ptx;
     extern __shared__ uint8_t mm_smem_raw[];
@@ -246,7 +245,7 @@ fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));             // 4 arrivals (one per epilogue warp)
                 if (store) {
-                    uint4* o = reinterpret_cast<uint4*>(raw + ((size_t)y * e_pad + e_base + e0 + m) * MM_N);
+                    uint4* o = reinterpret_cast<uint4*>(raw + ((size_t)y * e_pad + e0 + m) * MM_N);
 #pragma unroll
                     for (int c = 0; c < MM_N / 4; c++) o[c] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                 }
