@@ -451,3 +451,38 @@ def test_mfc_compat_result_convention(matcher, golden_cases):
         assert abs(m.ptRT[0] - rt[0]) < 1e-9 and abs(m.ptRT[1] - rt[1]) < 1e-9
         assert abs(m.ptRB[0] - rb[0]) < 1e-9 and abs(m.ptRB[1] - rb[1]) < 1e-9
         assert abs(m.ptCenter[0] - q.ptCenter[0]) < 1e-3
+
+
+# ---------------- randomized differential test: GPU vs live oracle on small random scenes ----------------
+def _random_scene(seed):
+    from fastest_image_pattern_matching_b200 import synth
+    rng = np.random.default_rng(seed)
+    W, H = int(rng.integers(300, 900)), int(rng.integers(240, 700))
+    tw, th = int(rng.integers(24, 140)), int(rng.integers(20, 120))
+    tpl = synth.background(tw, th, seed + 7, float(rng.uniform(1.0, 3.0)))
+    tpl = cv2.normalize(tpl, None, 0, 255, cv2.NORM_MINMAX)
+    cv2.circle(tpl, (tw // 3, th // 3), max(3, min(tw, th) // 5), 255, -1)
+    cv2.rectangle(tpl, (tw // 2, th // 2), (tw - 3, th - 3), 0, -1)
+    src = synth.background(W, H, seed + 13, float(rng.uniform(1.5, 4.0)))
+    k = int(rng.integers(1, 5))
+    tol = float(rng.choice([0.0, 15.0, 45.0, 180.0]))
+    for _ in range(k):
+        a = float(rng.uniform(-tol, tol)) if tol > 0 else 0.0
+        cx, cy = float(rng.uniform(0.15 * W, 0.85 * W)), float(rng.uniform(0.15 * H, 0.85 * H))
+        synth.paste_rotated(src, tpl, cx, cy, a)
+    params = dict(max_pos=int(rng.integers(1, 8)), score=float(rng.choice([0.5, 0.7, 0.85])), tolerance_angle=tol,
+                  min_reduce_area=int(rng.choice([64, 256, 1024])), max_overlap=float(rng.choice([0.0, 0.3, 0.8])))
+    return src, tpl, params
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_scenes_match_live_oracle(matcher, seed):
+    src, tpl, params = _random_scene(1000 + seed)
+    configure(matcher, params)
+    assert matcher.learnPattern(tpl)
+    got = matcher.match(src)
+    om = configure(O.OracleMatcher(), params)
+    om.learn_pattern(tpl)
+    want = om.match(src)
+    ties = len({r.score for r in want}) != len(want)
+    assert_results_match(got, want, ordered=not ties)
