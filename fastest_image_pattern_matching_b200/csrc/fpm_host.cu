@@ -297,8 +297,8 @@ CorrCfg corr_config(int tpl_h)
 
 inline size_t top_score_smem(int tw, int th)
 {
-    size_t nwt = (tw + 3) / 4, pww = (TS_TILE + tw - 1 + 3) / 4 + 2;
-    return 4 * ((size_t)th * nwt + (size_t)(TS_TILE + th - 1) * pww);
+    size_t nwt = (tw + 3) / 4, pww = TS_TW / 4 + nwt + 1;
+    return 4 * ((size_t)th * nwt + (size_t)(TS_TH + th - 1) * pww);
 }
 
 inline int level_vec_ok(const FpmLevel& L)
@@ -584,8 +584,8 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         if (smem > 200 * 1024) { h->err = "top-layer template too large for the score kernel"; return FPM_ERR_LIMIT; }
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((maxRW + TS_TILE - 1) / TS_TILE, (maxRH + TS_TILE - 1) / TS_TILE, njobs);
-        dim3 block(TS_TILE, TS_TILE);
+        dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, njobs);
+        dim3 block(TS_THREADS);
         KL(K_TOP_SCORE, (double)njobs * maxRW * maxRH * t.w * t.h,      // MACs
            fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->d_rot.as<uint8_t>(), rpitch,
                                                                   rot_stride, tpl_level_dev(h, top), h->d_score.as<float>(),
@@ -1391,7 +1391,7 @@ int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* 
     size_t smem = top_score_smem(t.w, t.h);
     if (smem > 200 * 1024) { h->err = "template too large"; return FPM_ERR_LIMIT; }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((RW + TS_TILE - 1) / TS_TILE, (RH + TS_TILE - 1) / TS_TILE, 1), block(TS_TILE, TS_TILE);
+    dim3 grid((RW + TS_TW - 1) / TS_TW, (RH + TS_TH - 1) / TS_TH, 1), block(TS_THREADS);
     fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<uint8_t>(), rp, 0,
                                                            tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0);
     CKL();

@@ -56,23 +56,12 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
             for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
                 fpm_cp_async16(&s_in[r][16 * c], g);
         }
-    } else if (vec == 16) {
+    } else if (vec == 16 && xs >= 0 && xs + 16 * nch <= sw) {
+        // top / bottom border tile: only the row index needs reflecting, columns are all inside
         const int c = tid & 31;
         if (c < nch) {
-            const int x = xs + 16 * c;
-            const bool xin = x >= 0 && x + 15 < sw;
-            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
-                const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
-                if (xin) {
-                    fpm_cp_async16(&s_in[r][16 * c], row + x);
-                } else if (16 * c + 15 >= need_lo) {
-                    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-                    for (int k = 0; k < 16; k++)
-                        w[k >> 2] |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * (k & 3));
-                    *reinterpret_cast<uint4*>(&s_in[r][16 * c]) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
+                fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + xs + 16 * c);
         }
     } else {
         const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
@@ -80,7 +69,7 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
             const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
             for (int wc = w_lo + (tid & 63); wc <= w_hi; wc += 64) {
                 const int x = xs + 4 * wc;
-                if (vec == 4 && x >= 0 && x + 3 < sw) {
+                if (vec >= 4 && x >= 0 && x + 3 < sw) {
                     fpm_cp_async4(&s_in[r][4 * wc], row + x, true);
                 } else {
                     uint32_t v = 0;
@@ -332,13 +321,16 @@ __device__ __forceinline__ float fpm_ccoeff_epilogue(float numerator, double wsu
 
 // =====================================================================================
 // K4+K7  top-layer dense score map: exact integer TM_CCORR numerator, exact window sum / sqsum,
-// CCOEFF_NORMED epilogue.  One CTA = 16x16 scores; image patch + template in shared memory as
-// 32-bit words (rows zero padded); every thread walks its window 4 pixels at a time: the patch
-// words are re-aligned with a funnel shift and fed to dp4a (numerator, sum, sum of squares).
+// CCOEFF_NORMED epilogue.  One CTA = 64x16 scores, 4 horizontally adjacent scores per thread; image
+// patch + template in shared memory as 32-bit words (rows zero padded).  Per template word a thread
+// loads one patch word and one template word and feeds the 4 byte-shifted windows (funnel shifts by
+// 0/8/16/24 bits) to dp4a: numerator, window sum and window sum of squares, all exact.
 // =====================================================================================
-#define TS_TILE 16
+#define TS_TW 64
+#define TS_TH 16
+#define TS_THREADS 256
 
-__global__ void __launch_bounds__(TS_TILE * TS_TILE)
+__global__ void __launch_bounds__(TS_THREADS)
 fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restrict__ rot, int rpitch,
                      size_t rot_job_stride, FpmTplLevel tpl, float* __restrict__ score, int spitch,
                      size_t score_job_stride)
@@ -347,16 +339,16 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
     const FpmWarpJob& jb = jobs[blockIdx.z];
     const int tw = tpl.w, th = tpl.h;
     const int RW = jb.dw - tw + 1, RH = jb.dh - th + 1;
-    const int x0 = blockIdx.x * TS_TILE, y0 = blockIdx.y * TS_TILE;
+    const int x0 = blockIdx.x * TS_TW, y0 = blockIdx.y * TS_TH;
     if (!jb.valid || RW <= 0 || RH <= 0 || x0 >= RW || y0 >= RH) return;
     const int nwt = (tw + 3) / 4;                          // template words per row
-    const int ph = TS_TILE + th - 1;
-    const int pww = (TS_TILE + tw - 1 + 3) / 4 + 2;        // patch words per row (+1 for the shifted read)
+    const int ph = TS_TH + th - 1;
+    const int pww = TS_TW / 4 + nwt + 1;                   // patch words per row
     uint32_t* s_t = reinterpret_cast<uint32_t*>(smem);     // th * nwt
     uint32_t* s_p = s_t + th * nwt;                        // ph * pww
-    const int tid = threadIdx.y * TS_TILE + threadIdx.x;
+    const int tid = threadIdx.x;
     const uint8_t* __restrict__ r = rot + (size_t)blockIdx.z * rot_job_stride;
-    for (int i = tid; i < th * nwt; i += TS_TILE * TS_TILE) {
+    for (int i = tid; i < th * nwt; i += TS_THREADS) {
         int yy = i / nwt, xw = i - yy * nwt;
         uint32_t v = 0;
 #pragma unroll
@@ -364,7 +356,7 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
             if (4 * xw + k < tw) v |= (uint32_t)tpl.ptr[yy * tpl.pitch + 4 * xw + k] << (8 * k);
         s_t[i] = v;
     }
-    for (int i = tid; i < ph * pww; i += TS_TILE * TS_TILE) {
+    for (int i = tid; i < ph * pww; i += TS_THREADS) {
         int yy = i / pww, xw = i - yy * pww;
         int gy = y0 + yy;
         uint32_t v = 0;
@@ -378,32 +370,45 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
         s_p[i] = v;
     }
     __syncthreads();
-    const int ox = x0 + threadIdx.x, oy = y0 + threadIdx.y;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int ox = x0 + 4 * tx, oy = y0 + ty;
     if (ox >= RW || oy >= RH) return;
     float* out = score + (size_t)blockIdx.z * score_job_stride + (size_t)oy * spitch + ox;
-    if (tpl.result_equal1) { *out = 1.0f; return; }
-    const int wo = threadIdx.x >> 2, sh = 8 * (threadIdx.x & 3);
+    if (tpl.result_equal1) {
+        for (int k = 0; k < 4 && ox + k < RW; k++) out[k] = 1.0f;
+        return;
+    }
     const int tail = tw & 3;
     const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
-    long long num = 0, wsum = 0, wsq = 0;
+    long long num[4] = {0, 0, 0, 0}, wsum[4] = {0, 0, 0, 0}, wsq[4] = {0, 0, 0, 0};
     for (int yy = 0; yy < th; yy++) {
-        const uint32_t* prow = s_p + (threadIdx.y + yy) * pww + wo;
+        const uint32_t* prow = s_p + (ty + yy) * pww + tx;
         const uint32_t* trow = s_t + yy * nwt;
-        uint32_t a = 0, b = 0, c = 0;
+        uint32_t a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
         uint32_t lo = prow[0];
         for (int xw = 0; xw < nwt; xw++) {
             const uint32_t hi = prow[xw + 1];
-            uint32_t p = __funnelshift_r(lo, hi, sh);
-            if (xw == nwt - 1) p &= tailbm;
-            a = __dp4a(p, trow[xw], a);
-            b = __dp4a(p, 0x01010101u, b);
-            c = __dp4a(p, p, c);
+            const uint32_t t = trow[xw];
+            const uint32_t m = (xw == nwt - 1) ? tailbm : 0xffffffffu;
+            uint32_t p[4];
+            p[0] = lo & m;
+            p[1] = __funnelshift_r(lo, hi, 8) & m;
+            p[2] = __funnelshift_r(lo, hi, 16) & m;
+            p[3] = __funnelshift_r(lo, hi, 24) & m;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                a[k] = __dp4a(p[k], t, a[k]);
+                b[k] = __dp4a(p[k], 0x01010101u, b[k]);
+                c[k] = __dp4a(p[k], p[k], c[k]);
+            }
             lo = hi;
         }
-        num += a; wsum += b; wsq += c;                     // per-row s32 sums, s64 across rows
+#pragma unroll
+        for (int k = 0; k < 4; k++) { num[k] += a[k]; wsum[k] += b[k]; wsq[k] += c[k]; }   // per-row s32, s64 across rows
     }
     // TM_CCORR result cell is a float32 (cv::matchTemplate output depth), here the rounded exact sum
-    *out = fpm_ccoeff_epilogue((float)num, (double)wsum, (double)wsq, tpl.mean, tpl.norm, tpl.inv_area);
+    for (int k = 0; k < 4 && ox + k < RW; k++)
+        out[k] = fpm_ccoeff_epilogue((float)num[k], (double)wsum[k], (double)wsq[k], tpl.mean, tpl.norm, tpl.inv_area);
 }
 
 // =====================================================================================
