@@ -44,8 +44,8 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
     const int nout_cols = min(PD_TW, dst.w - ox0);
     const int nin_rows = 2 * nout_rows + 3;
     const int sw = src.w, sh = src.h;
-    // smem columns actually read by the horizontal pass: words 3 .. (nout_cols+1)/2 + 4
-    const int need_lo = 12, need_hi = 4 * ((nout_cols + 1) / 2 + 4) + 3;
+    // smem bytes actually read by the horizontal pass: 12 .. 8*ceil(nout_cols/4)+19
+    const int need_lo = 12, need_hi = 8 * ((nout_cols + 3) / 4) + 19;
 
     const int nch = (need_hi + 16) / 16;                         // 16-byte chunks per row (<= 18)
     const bool interior = ys >= 0 && ys + nin_rows <= sh && xs >= 0 && xs + 16 * nch <= sw;
@@ -85,41 +85,50 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
     fpm_cp_async_wait<0>();
     __syncthreads();
 
-    // horizontal pass: outputs 2k, 2k+1 have their centres at smem bytes 4k+16, 4k+18
+    // horizontal pass: 4 outputs per thread and row; output 4k+j has its centre at smem byte 8k+16+2j, so its
+    // first four taps are an (un)shifted word and the fifth is a single byte of the next word
     {
-        const int k = tid & 63;
-        if (2 * k < nout_cols) {
-            for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&s_in[r][4 * k + 12]);
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 16), 0x04060401u, (w1 >> 16) & 255u);
-                const uint32_t h1 = __dp4a(w1, 0x04060401u, w2 & 255u);
-                s_h[r][k] = h0 | (h1 << 16);
+        const int k = tid & 31;
+        if (4 * k < nout_cols) {
+            const uint32_t W = 0x04060401u;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
+                const uint8_t* b = &s_in[r][8 * k + 12];
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(b);
+                const uint2 w12 = *reinterpret_cast<const uint2*>(b + 4);
+                const uint32_t w3 = *reinterpret_cast<const uint32_t*>(b + 12);
+                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w12.x, 16), W, (w12.x >> 16) & 255u);
+                const uint32_t h1 = __dp4a(w12.x, W, w12.y & 255u);
+                const uint32_t h2 = __dp4a(__funnelshift_r(w12.x, w12.y, 16), W, (w12.y >> 16) & 255u);
+                const uint32_t h3 = __dp4a(w12.y, W, w3 & 255u);
+                *reinterpret_cast<uint2*>(&s_h[r][2 * k]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
             }
         }
     }
     __syncthreads();
 
-    // vertical pass: 4 outputs (two packed pairs) per thread
+    // vertical pass: 8 outputs (four packed pairs) per thread and row
     {
-        const int g = tid & 31;
-        if (4 * g < nout_cols) {
-            for (int oy = tid >> 5; oy < nout_rows; oy += PD_THREADS / 32) {
-                uint32_t o[2];
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int c = 2 * g + q;
-                    const uint32_t a = s_h[2 * oy][c] + s_h[2 * oy + 4][c];
-                    const uint32_t b = s_h[2 * oy + 1][c] + s_h[2 * oy + 3][c];
-                    const uint32_t v = a + 4u * b + 6u * s_h[2 * oy + 2][c] + 0x00800080u;
-                    o[q] = (v >> 8) & 0x00ff00ffu;
-                }
-                const uint32_t pack = (o[0] & 255u) | ((o[0] >> 8) & 0xff00u) | ((o[1] & 255u) << 16) | ((o[1] & 0x00ff0000u) << 8);
-                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 4 * g;
-                if (4 * g + 3 < nout_cols) {
-                    *reinterpret_cast<uint32_t*>(op) = pack;
+        const int g = tid & 15;
+        if (8 * g < nout_cols) {
+            for (int oy = tid >> 4; oy < nout_rows; oy += PD_THREADS / 16) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(&s_h[2 * oy][4 * g]);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 1][4 * g]);
+                const uint4 r2 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 2][4 * g]);
+                const uint4 r3 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 3][4 * g]);
+                const uint4 r4 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 4][4 * g]);
+                const uint32_t R = 0x00800080u, M = 0x00ff00ffu;
+                const uint32_t v0 = ((r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + R) >> 8) & M;
+                const uint32_t v1 = ((r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + R) >> 8) & M;
+                const uint32_t v2 = ((r0.z + r4.z + 4u * (r1.z + r3.z) + 6u * r2.z + R) >> 8) & M;
+                const uint32_t v3 = ((r0.w + r4.w + 4u * (r1.w + r3.w) + 6u * r2.w + R) >> 8) & M;
+                // bytes: v0.lo v0.hi v1.lo v1.hi | v2.lo v2.hi v3.lo v3.hi
+                const uint32_t p0 = __byte_perm(v0, v1, 0x6420), p1 = __byte_perm(v2, v3, 0x6420);
+                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 8 * g;
+                if (8 * g + 7 < nout_cols && (dst.pitch & 7) == 0) {
+                    *reinterpret_cast<uint2*>(op) = make_uint2(p0, p1);
                 } else {
-                    for (int k = 0; k < 4 && 4 * g + k < nout_cols; k++) op[k] = (uint8_t)(pack >> (8 * k));
+                    const unsigned long long pk = (unsigned long long)p0 | ((unsigned long long)p1 << 32);
+                    for (int q = 0; q < 8 && 8 * g + q < nout_cols; q++) op[q] = (uint8_t)(pk >> (8 * q));
                 }
             }
         }
