@@ -607,7 +607,7 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         double thresh = h->score;
         for (int l = 0; l < top; l++) thresh *= 0.9;          // vecLayerScore, :153-156
         KL(K_TOP_PEAKS, 4.0 * njobs * maxRW * maxRH,
-           fpm_top_peaks_kernel<<<njobs, PK_THREADS, 0, h->stream>>>(
+           fpm_top_peaks_kernel<<<njobs, (maxRW * maxRH <= 16384) ? 128 : PK_THREADS, 0, h->stream>>>(
                h->d_jobs_top.as<FpmWarpJob>(), h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
                h->d_blkv.as<float>(), h->d_blkl.as<int>(), blk_stride, thresh, h->max_overlap, max_picks,
                h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>()));

@@ -501,7 +501,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     const int job = blockIdx.x;
     const FpmWarpJob& jb = jobs[job];
     const int cols = jb.dw - tw + 1, rows = jb.dh - th + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = PK_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     if (!jb.valid || cols <= 0 || rows <= 0) { if (tid == 0) pick_count[job] = 0; return; }
     float* __restrict__ map = score + (size_t)job * score_job_stride;
     float* bval = blk_val + (size_t)job * blk_stride;
@@ -533,7 +533,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                 int px0 = max(sx, 0), py0 = max(sy, 0), px1 = min(sx + rw, cols), py1 = min(sy + rh, rows);
                 int pw = px1 - px0, ph = py1 - py0;
                 if (pw > 0 && ph > 0)
-                    for (int i = tid; i < pw * ph; i += PK_THREADS) {
+                    for (int i = tid; i < pw * ph; i += nthreads) {
                         int yy = i / pw, xx = i - yy * pw;
                         map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
                     }
@@ -553,7 +553,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
         }
         // argmax over the block table
         float best = -INFINITY; int bk = 0x7fffffff, bl = 0x7fffffff;
-        for (int k = tid; k < g.nblocks; k += PK_THREADS) {
+        for (int k = tid; k < g.nblocks; k += nthreads) {
             float v = bval[k]; int l = bloc[k];
             bool better = (v > best) || (v == best && (mode ? (k < bk) : (l < bl)));
             if (better) { best = v; bk = k; bl = l; }
@@ -1031,16 +1031,16 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                 rstride = FPM_NCELL;
             }
             float numf;
-            // loads are issued 8 at a time (independent), the additions stay in template-row order
+            // loads are issued 16 at a time (independent), the additions stay in template-row order
             if (use_chain) {
                 float acc = 0.0f;
                 int tr = 0;
-                for (; tr + 8 <= th; tr += 8) {
-                    int v[8];
+                for (; tr + 16 <= th; tr += 16) {
+                    int v[16];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = rs[(size_t)(tr + k) * rstride];
+                    for (int k = 0; k < 16; k++) v[k] = rs[(size_t)(tr + k) * rstride];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
+                    for (int k = 0; k < 16; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
                 }
                 for (; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * rstride]));
                 numf = acc;
