@@ -19,23 +19,22 @@
 
 // =====================================================================================
 // K1  pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, (s+128)>>8, out ((w+1)/2,(h+1)/2)
-// HBM-bound: reads W*H, writes W*H/4.  One CTA = 128x64 outputs.  The 131 input rows x 288 B of the tile
-// are staged in shared memory with 128-bit cp.async (LDGSTS); after ONE barrier every thread walks 19 staged
-// rows for its 4 output columns x 8 output rows: the horizontal taps of a row are one dp4a (weights 1,4,6,4)
-// plus one byte per output, the five most recent horizontal rows live in registers as two 16-bit lanes packed
-// per 32-bit word (sums < 65536, no carry crosses lanes) and every second row one packed 32-bit store leaves.
+// HBM-bound: reads W*H, writes W*H/4.  One CTA = 128x32 outputs.  The 67 input rows x 288 B of the
+// tile are staged in shared memory with 128-bit (or 32-bit) coalesced loads; the horizontal taps are
+// one dp4a (weights 1,4,6,4) + one byte per output, the vertical taps run on two 16-bit lanes packed
+// in a 32-bit register (sums < 65536, so no carry crosses lanes).
 // =====================================================================================
 #define PD_TW 128
-#define PD_TH 64
+#define PD_TH 32
 #define PD_IH (2 * PD_TH + 3)
 #define PD_IW (2 * PD_TW + 32)     // staged input columns [2*ox0-16, 2*ox0+2*TW+16), 16-byte chunks
 #define PD_THREADS 256
-#define PD_RB 8                    // output rows per thread
 
 __global__ void __launch_bounds__(PD_THREADS)
 fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 {
     __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
+    __shared__ __align__(16) uint32_t s_h[PD_IH][PD_TW / 2];     // two u16 horizontal sums per word
     const int tid = threadIdx.x;
     const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
     const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
@@ -86,42 +85,50 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
     fpm_cp_async_wait<0>();
     __syncthreads();
 
-    // fused horizontal + vertical pass: thread (k, rb) owns outputs 4k..4k+3 of rows 8rb..8rb+7; output 4k+j of a row
-    // has its centre at staged byte 8k+16+2j, so its first four taps are an (un)shifted word and the fifth one byte
+    // horizontal pass: 4 outputs per thread and row; output 4k+j has its centre at smem byte 8k+16+2j, so its
+    // first four taps are an (un)shifted word and the fifth is a single byte of the next word
     {
-        const int k = tid & 31, rb = tid >> 5;
-        const int oyb = rb * PD_RB;
-        if (4 * k < nout_cols && oyb < nout_rows) {
-            const uint32_t W = 0x04060401u, R = 0x00800080u, M = 0x00ff00ffu;
-            const int nr = min(PD_RB, nout_rows - oyb);
-            const uint8_t* b = &s_in[2 * oyb][8 * k + 12];
-            uint8_t* op = d + (size_t)(oy0 + oyb) * dst.pitch + ox0 + 4 * k;
-            const bool full = 4 * k + 3 < nout_cols;
-            uint32_t hA[5], hB[5];
-#pragma unroll
-            for (int t = 0; t < 2 * PD_RB + 3; t++) {
-                if (t <= 2 * nr + 2) {
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(b + t * PD_IW);
-                    const uint2 w12 = *reinterpret_cast<const uint2*>(b + t * PD_IW + 4);
-                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(b + t * PD_IW + 12);
-                    const uint32_t h0 = __dp4a(__funnelshift_r(w0, w12.x, 16), W, (w12.x >> 16) & 255u);
-                    const uint32_t h1 = __dp4a(w12.x, W, w12.y & 255u);
-                    const uint32_t h2 = __dp4a(__funnelshift_r(w12.x, w12.y, 16), W, (w12.y >> 16) & 255u);
-                    const uint32_t h3 = __dp4a(w12.y, W, w3 & 255u);
-                    hA[t % 5] = h0 | (h1 << 16);
-                    hB[t % 5] = h2 | (h3 << 16);
-                    if (t >= 4 && (t & 1) == 0) {
-                        // window rows t-4 .. t, weights 1 4 6 4 1
-                        const uint32_t va = ((hA[(t + 1) % 5] + hA[t % 5] + 4u * (hA[(t + 2) % 5] + hA[(t + 4) % 5]) + 6u * hA[(t + 3) % 5] + R) >> 8) & M;
-                        const uint32_t vb = ((hB[(t + 1) % 5] + hB[t % 5] + 4u * (hB[(t + 2) % 5] + hB[(t + 4) % 5]) + 6u * hB[(t + 3) % 5] + R) >> 8) & M;
-                        const uint32_t pack = __byte_perm(va, vb, 0x6420);
-                        uint8_t* o = op + (size_t)((t - 4) / 2) * dst.pitch;
-                        if (full) {
-                            *reinterpret_cast<uint32_t*>(o) = pack;
-                        } else {
-                            for (int q = 0; q < 4 && 4 * k + q < nout_cols; q++) o[q] = (uint8_t)(pack >> (8 * q));
-                        }
-                    }
+        const int k = tid & 31;
+        if (4 * k < nout_cols) {
+            const uint32_t W = 0x04060401u;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
+                const uint8_t* b = &s_in[r][8 * k + 12];
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(b);
+                const uint2 w12 = *reinterpret_cast<const uint2*>(b + 4);
+                const uint32_t w3 = *reinterpret_cast<const uint32_t*>(b + 12);
+                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w12.x, 16), W, (w12.x >> 16) & 255u);
+                const uint32_t h1 = __dp4a(w12.x, W, w12.y & 255u);
+                const uint32_t h2 = __dp4a(__funnelshift_r(w12.x, w12.y, 16), W, (w12.y >> 16) & 255u);
+                const uint32_t h3 = __dp4a(w12.y, W, w3 & 255u);
+                *reinterpret_cast<uint2*>(&s_h[r][2 * k]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+            }
+        }
+    }
+    __syncthreads();
+
+    // vertical pass: 8 outputs (four packed pairs) per thread and row
+    {
+        const int g = tid & 15;
+        if (8 * g < nout_cols) {
+            for (int oy = tid >> 4; oy < nout_rows; oy += PD_THREADS / 16) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(&s_h[2 * oy][4 * g]);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 1][4 * g]);
+                const uint4 r2 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 2][4 * g]);
+                const uint4 r3 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 3][4 * g]);
+                const uint4 r4 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 4][4 * g]);
+                const uint32_t R = 0x00800080u, M = 0x00ff00ffu;
+                const uint32_t v0 = ((r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + R) >> 8) & M;
+                const uint32_t v1 = ((r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + R) >> 8) & M;
+                const uint32_t v2 = ((r0.z + r4.z + 4u * (r1.z + r3.z) + 6u * r2.z + R) >> 8) & M;
+                const uint32_t v3 = ((r0.w + r4.w + 4u * (r1.w + r3.w) + 6u * r2.w + R) >> 8) & M;
+                // bytes: v0.lo v0.hi v1.lo v1.hi | v2.lo v2.hi v3.lo v3.hi
+                const uint32_t p0 = __byte_perm(v0, v1, 0x6420), p1 = __byte_perm(v2, v3, 0x6420);
+                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 8 * g;
+                if (8 * g + 7 < nout_cols && (dst.pitch & 7) == 0) {
+                    *reinterpret_cast<uint2*>(op) = make_uint2(p0, p1);
+                } else {
+                    const unsigned long long pk = (unsigned long long)p0 | ((unsigned long long)p1 << 32);
+                    for (int q = 0; q < 8 && 8 * g + q < nout_cols; q++) op[q] = (uint8_t)(pk >> (8 * q));
                 }
             }
         }
