@@ -139,7 +139,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
-    bool mma_attr_set = false, pd_attr_set = false;
+    bool mma_attr_set = false;
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
     int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
     // template
@@ -263,19 +263,10 @@ int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& dst, int 
 {
     auto aligned = [&](int a) { return ((reinterpret_cast<uintptr_t>(src.ptr) % a) == 0) && (src.pitch % a == 0) && (src.img_stride % a == 0); };
     const int vec_ok = aligned(16) ? 16 : (aligned(4) ? 4 : 1);
-    const int tiles_x = (dst.w + PD_TW - 1) / PD_TW, tiles_y = (dst.h + PD_TH - 1) / PD_TH;
-    const long long n_tiles_ll = (long long)tiles_x * tiles_y * batch;
-    if (n_tiles_ll > 0x7fffffff) { h->err = "pyramid level too large"; return FPM_ERR_LIMIT; }
-    const int n_tiles = (int)n_tiles_ll;
-    if (!h->pd_attr_set) {
-        CK(cudaFuncSetAttribute(fpm_pyrdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM_BYTES));
-        h->pd_attr_set = true;
-    }
-    // persistent CTAs: 4 per SM fit the 55.7 KB of shared memory each needs
-    const int grid = std::min(n_tiles, 148 * 4);
+    dim3 grid((dst.w + PD_TW - 1) / PD_TW, (dst.h + PD_TH - 1) / PD_TH, batch);
     // algorithmic bytes: every source pixel read once, every destination pixel written once
     KL(K_PYRDOWN, (double)batch * ((double)src.w * src.h + (double)dst.w * dst.h),
-       fpm_pyrdown_kernel<<<grid, PD_THREADS, PD_SMEM_BYTES, h->stream>>>(src, dst, vec_ok, tiles_x, tiles_y, n_tiles));
+       fpm_pyrdown_kernel<<<grid, PD_THREADS, 0, h->stream>>>(src, dst, vec_ok));
     return FPM_OK;
 }
 

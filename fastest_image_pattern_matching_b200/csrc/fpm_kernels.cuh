@@ -29,139 +29,109 @@
 #define PD_IH (2 * PD_TH + 3)
 #define PD_IW (2 * PD_TW + 32)     // staged input columns [2*ox0-16, 2*ox0+2*TW+16), 16-byte chunks
 #define PD_THREADS 256
-#define PD_SMEM_BYTES (2 * PD_IH * PD_IW + PD_IH * (PD_TW / 2) * 4)
 
-// Persistent CTAs: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the flattened
-// (image, tile row, tile column) space with TWO input buffers: the cp.async copies of tile i+1 are in flight
-// while tile i goes through the horizontal and vertical passes, so loads and arithmetic overlap inside a CTA.
 __global__ void __launch_bounds__(PD_THREADS)
-fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec, int tiles_x, int tiles_y, int n_tiles)
+fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 {
-    extern __shared__ __align__(16) uint8_t pd_smem[];
-    uint8_t* s_in2 = pd_smem;                                                   // [2][PD_IH][PD_IW]
-    uint32_t (*s_h)[PD_TW / 2] = reinterpret_cast<uint32_t (*)[PD_TW / 2]>(pd_smem + 2 * PD_IH * PD_IW);   // [PD_IH][64]
+    __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
+    __shared__ __align__(16) uint32_t s_h[PD_IH][PD_TW / 2];     // two u16 horizontal sums per word
     const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
+    const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
+    uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
+    const int xs = 2 * ox0 - 16, ys = 2 * oy0 - 2;
+    const int nout_rows = min(PD_TH, dst.h - oy0);
+    const int nout_cols = min(PD_TW, dst.w - ox0);
+    const int nin_rows = 2 * nout_rows + 3;
     const int sw = src.w, sh = src.h;
+    // smem bytes actually read by the horizontal pass: 12 .. 8*ceil(nout_cols/4)+19
+    const int need_lo = 12, need_hi = 8 * ((nout_cols + 3) / 4) + 19;
 
-    // stage the input rows of tile `t` into buffer `buf` (asynchronously where the tile allows it)
-    auto stage = [&](int t, int buf) {
-        const int img = t / (tiles_x * tiles_y), rem = t - img * (tiles_x * tiles_y);
-        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-        const int ox0 = tx * PD_TW, oy0 = ty * PD_TH;
-        const uint8_t* __restrict__ s = src.ptr + (size_t)img * src.img_stride;
-        uint8_t (*s_in)[PD_IW] = reinterpret_cast<uint8_t (*)[PD_IW]>(s_in2 + (size_t)buf * PD_IH * PD_IW);
-        const int xs = 2 * ox0 - 16, ys = 2 * oy0 - 2;
-        const int nout_rows = min(PD_TH, dst.h - oy0), nout_cols = min(PD_TW, dst.w - ox0);
-        const int nin_rows = 2 * nout_rows + 3;
-        // smem bytes actually read by the horizontal pass: 12 .. 8*ceil(nout_cols/4)+19
-        const int need_lo = 12, need_hi = 8 * ((nout_cols + 3) / 4) + 19;
-        const int nch = (need_hi + 16) / 16;                         // 16-byte chunks per row (<= 18)
-        const bool interior = ys >= 0 && ys + nin_rows <= sh && xs >= 0 && xs + 16 * nch <= sw;
-        if (interior && vec == 16) {
-            const int c = tid & 31;
-            if (c < nch) {
-                const uint8_t* g = s + (size_t)(ys + (tid >> 5)) * src.pitch + xs + 16 * c;
-                for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
-                    fpm_cp_async16(&s_in[r][16 * c], g);
-            }
-        } else if (vec == 16 && xs >= 0 && xs + 16 * nch <= sw) {
-            // top / bottom border tile: only the row index needs reflecting, columns are all inside
-            const int c = tid & 31;
-            if (c < nch) {
-                for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
-                    fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + xs + 16 * c);
-            }
-        } else {
-            const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
-            for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
-                const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
-                for (int wc = w_lo + (tid & 63); wc <= w_hi; wc += 64) {
-                    const int x = xs + 4 * wc;
-                    if (vec >= 4 && x >= 0 && x + 3 < sw) {
-                        fpm_cp_async4(&s_in[r][4 * wc], row + x, true);
-                    } else {
-                        uint32_t v = 0;
+    const int nch = (need_hi + 16) / 16;                         // 16-byte chunks per row (<= 18)
+    const bool interior = ys >= 0 && ys + nin_rows <= sh && xs >= 0 && xs + 16 * nch <= sw;
+    if (interior && vec == 16) {
+        const int c = tid & 31;
+        if (c < nch) {
+            const uint8_t* g = s + (size_t)(ys + (tid >> 5)) * src.pitch + xs + 16 * c;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
+                fpm_cp_async16(&s_in[r][16 * c], g);
+        }
+    } else if (vec == 16 && xs >= 0 && xs + 16 * nch <= sw) {
+        // top / bottom border tile: only the row index needs reflecting, columns are all inside
+        const int c = tid & 31;
+        if (c < nch) {
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
+                fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + xs + 16 * c);
+        }
+    } else {
+        const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
+        for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
+            const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
+            for (int wc = w_lo + (tid & 63); wc <= w_hi; wc += 64) {
+                const int x = xs + 4 * wc;
+                if (vec >= 4 && x >= 0 && x + 3 < sw) {
+                    fpm_cp_async4(&s_in[r][4 * wc], row + x, true);
+                } else {
+                    uint32_t v = 0;
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * k);
-                        *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
-                    }
+                    for (int k = 0; k < 4; k++)
+                        v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * k);
+                    *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
                 }
             }
         }
-        fpm_cp_async_commit();
-    };
+    }
+    fpm_cp_async_commit();
+    fpm_cp_async_wait<0>();
+    __syncthreads();
 
-    int t = blockIdx.x;
-    if (t >= n_tiles) return;
-    stage(t, 0);
-    for (int it = 0; t < n_tiles; t += gridDim.x, it++) {
-        const int tn = t + gridDim.x;
-        if (tn < n_tiles) {
-            stage(tn, (it + 1) & 1);          // that buffer was last read by the horizontal pass of iteration it-1
-            fpm_cp_async_wait<1>();
-        } else {
-            fpm_cp_async_wait<0>();
+    // horizontal pass: 4 outputs per thread and row; output 4k+j has its centre at smem byte 8k+16+2j, so its
+    // first four taps are an (un)shifted word and the fifth is a single byte of the next word
+    {
+        const int k = tid & 31;
+        if (4 * k < nout_cols) {
+            const uint32_t W = 0x04060401u;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
+                const uint8_t* b = &s_in[r][8 * k + 12];
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(b);
+                const uint2 w12 = *reinterpret_cast<const uint2*>(b + 4);
+                const uint32_t w3 = *reinterpret_cast<const uint32_t*>(b + 12);
+                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w12.x, 16), W, (w12.x >> 16) & 255u);
+                const uint32_t h1 = __dp4a(w12.x, W, w12.y & 255u);
+                const uint32_t h2 = __dp4a(__funnelshift_r(w12.x, w12.y, 16), W, (w12.y >> 16) & 255u);
+                const uint32_t h3 = __dp4a(w12.y, W, w3 & 255u);
+                *reinterpret_cast<uint2*>(&s_h[r][2 * k]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+            }
         }
-        __syncthreads();                      // tile `t` is staged; the vertical pass of the previous tile is done
-        const int img = t / (tiles_x * tiles_y), rem = t - img * (tiles_x * tiles_y);
-        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-        const int ox0 = tx * PD_TW, oy0 = ty * PD_TH;
-        uint8_t* __restrict__ d = dst.ptr + (size_t)img * dst.img_stride;
-        const int nout_rows = min(PD_TH, dst.h - oy0), nout_cols = min(PD_TW, dst.w - ox0);
-        const int nin_rows = 2 * nout_rows + 3;
-        const uint8_t (*s_in)[PD_IW] = reinterpret_cast<const uint8_t (*)[PD_IW]>(s_in2 + (size_t)(it & 1) * PD_IH * PD_IW);
+    }
+    __syncthreads();
 
-        // horizontal pass: 4 outputs per thread and row; output 4k+j has its centre at smem byte 8k+16+2j, so its
-        // first four taps are an (un)shifted word and the fifth is a single byte of the next word
-        {
-            const int k = tid & 31;
-            if (4 * k < nout_cols) {
-                const uint32_t W = 0x04060401u;
-                for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
-                    const uint8_t* b = &s_in[r][8 * k + 12];
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(b);
-                    const uint2 w12 = *reinterpret_cast<const uint2*>(b + 4);
-                    const uint32_t w3 = *reinterpret_cast<const uint32_t*>(b + 12);
-                    const uint32_t h0 = __dp4a(__funnelshift_r(w0, w12.x, 16), W, (w12.x >> 16) & 255u);
-                    const uint32_t h1 = __dp4a(w12.x, W, w12.y & 255u);
-                    const uint32_t h2 = __dp4a(__funnelshift_r(w12.x, w12.y, 16), W, (w12.y >> 16) & 255u);
-                    const uint32_t h3 = __dp4a(w12.y, W, w3 & 255u);
-                    *reinterpret_cast<uint2*>(&s_h[r][2 * k]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    // vertical pass: 8 outputs (four packed pairs) per thread and row
+    {
+        const int g = tid & 15;
+        if (8 * g < nout_cols) {
+            for (int oy = tid >> 4; oy < nout_rows; oy += PD_THREADS / 16) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(&s_h[2 * oy][4 * g]);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 1][4 * g]);
+                const uint4 r2 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 2][4 * g]);
+                const uint4 r3 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 3][4 * g]);
+                const uint4 r4 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 4][4 * g]);
+                const uint32_t R = 0x00800080u, M = 0x00ff00ffu;
+                const uint32_t v0 = ((r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + R) >> 8) & M;
+                const uint32_t v1 = ((r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + R) >> 8) & M;
+                const uint32_t v2 = ((r0.z + r4.z + 4u * (r1.z + r3.z) + 6u * r2.z + R) >> 8) & M;
+                const uint32_t v3 = ((r0.w + r4.w + 4u * (r1.w + r3.w) + 6u * r2.w + R) >> 8) & M;
+                // bytes: v0.lo v0.hi v1.lo v1.hi | v2.lo v2.hi v3.lo v3.hi
+                const uint32_t p0 = __byte_perm(v0, v1, 0x6420), p1 = __byte_perm(v2, v3, 0x6420);
+                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 8 * g;
+                if (8 * g + 7 < nout_cols && (dst.pitch & 7) == 0) {
+                    *reinterpret_cast<uint2*>(op) = make_uint2(p0, p1);
+                } else {
+                    const unsigned long long pk = (unsigned long long)p0 | ((unsigned long long)p1 << 32);
+                    for (int q = 0; q < 8 && 8 * g + q < nout_cols; q++) op[q] = (uint8_t)(pk >> (8 * q));
                 }
             }
         }
-        __syncthreads();
-
-        // vertical pass: 8 outputs (four packed pairs) per thread and row
-        {
-            const int g = tid & 15;
-            if (8 * g < nout_cols) {
-                for (int oy = tid >> 4; oy < nout_rows; oy += PD_THREADS / 16) {
-                    const uint4 r0 = *reinterpret_cast<const uint4*>(&s_h[2 * oy][4 * g]);
-                    const uint4 r1 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 1][4 * g]);
-                    const uint4 r2 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 2][4 * g]);
-                    const uint4 r3 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 3][4 * g]);
-                    const uint4 r4 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 4][4 * g]);
-                    const uint32_t R = 0x00800080u, M = 0x00ff00ffu;
-                    const uint32_t v0 = ((r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + R) >> 8) & M;
-                    const uint32_t v1 = ((r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + R) >> 8) & M;
-                    const uint32_t v2 = ((r0.z + r4.z + 4u * (r1.z + r3.z) + 6u * r2.z + R) >> 8) & M;
-                    const uint32_t v3 = ((r0.w + r4.w + 4u * (r1.w + r3.w) + 6u * r2.w + R) >> 8) & M;
-                    // bytes: v0.lo v0.hi v1.lo v1.hi | v2.lo v2.hi v3.lo v3.hi
-                    const uint32_t p0 = __byte_perm(v0, v1, 0x6420), p1 = __byte_perm(v2, v3, 0x6420);
-                    uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 8 * g;
-                    if (8 * g + 7 < nout_cols && (dst.pitch & 7) == 0) {
-                        *reinterpret_cast<uint2*>(op) = make_uint2(p0, p1);
-                    } else {
-                        const unsigned long long pk = (unsigned long long)p0 | ((unsigned long long)p1 << 32);
-                        for (int q = 0; q < 8 && 8 * g + q < nout_cols; q++) op[q] = (uint8_t)(pk >> (8 * q));
-                    }
-                }
-            }
-        }
-        // no barrier needed here: the next iteration's stage() writes the OTHER input buffer, and its
-        // horizontal pass (which overwrites s_h) starts only after the barrier at the top of the loop
     }
 }
 
