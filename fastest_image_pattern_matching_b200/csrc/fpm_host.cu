@@ -140,6 +140,8 @@ struct fpm_handle {
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
     bool mma_attr_set = false;
+    int stop_layer1 = 0, bitwise_not = 0, tol_range = 0;   // MFC-only modes (MatchTool/MatchToolDlg.cpp:788-816, :936)
+    double tol_r[4] = {0, 0, 0, 0};
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
     int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
     // template
@@ -149,7 +151,7 @@ struct fpm_handle {
     std::vector<uint8_t> tpl0;    // level-0 copy for re-learning when MinReduceArea changes
     int tpl0_w = 0, tpl0_h = 0;
     std::vector<TplLevelHost> tpl;
-    DevBuf d_tpl, d_tsh, d_raw;
+    DevBuf d_tpl, d_tsh, d_raw, d_inv;
     // user rect (pure storage)
     int ur[4] = {0, 0, 0, 0};
     int has_ur = 0;
@@ -498,7 +500,10 @@ void angle_schedule(const fpm_handle* h, int top, std::vector<double>& angles)
     const TplLevelHost& t = h->tpl[top];
     double dAngleStep = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
     angles.clear();
-    if (h->tol_angle < FPM_VISION_TOLERANCE) {
+    if (h->tol_range) {                                       // MatchTool/MatchToolDlg.cpp:805-816
+        for (double a = h->tol_r[0]; a < h->tol_r[1] + dAngleStep; a += dAngleStep) angles.push_back(a);
+        for (double a = h->tol_r[2]; a < h->tol_r[3] + dAngleStep; a += dAngleStep) angles.push_back(a);
+    } else if (h->tol_angle < FPM_VISION_TOLERANCE) {
         angles.push_back(0.0);
     } else {
         for (double a = 0; a < h->tol_angle + dAngleStep; a += dAngleStep) angles.push_back(a);
@@ -626,21 +631,22 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
     CK(cudaMemsetAsync(counters + CNT_REFINED, 0, sizeof(int), h->stream));
     *n_refined_out = 0;
     if (n_cands == 0) return FPM_OK;
-    if (top == 0) {
+    const int stop = h->stop_layer1 ? 1 : 0;                  // iStopLayer, MatchToolDlg.cpp:936
+    if (top <= stop) {
         fpm_cands_to_refined_kernel<<<(n_cands + 255) / 256, 256, 0, h->stream>>>(h->d_cand[0].as<FpmCand>(), n_cands, top,
                                                                                h->d_refined.as<FpmRefined>(), counters + CNT_REFINED);
         CKL();
         *n_refined_out = n_cands;
         return FPM_OK;
     }
-    const int n_ang = (h->tol_angle < FPM_VISION_TOLERANCE) ? 1 : 3;
+    const int n_ang = (!h->tol_range && h->tol_angle < FPM_VISION_TOLERANCE) ? 1 : 3;
     CK(h->d_cand[1].ensure((size_t)n_cands * sizeof(FpmCand)));
     int cur = 0, n = n_cands;
     double layer_score[FPM_MAX_LEVELS + 1];
     layer_score[0] = h->score;
     for (int l = 1; l <= top; l++) layer_score[l] = layer_score[l - 1] * 0.9;
     if (h->trace) h->tr_evals.assign(top + 1, std::vector<double>());
-    for (int layer = top - 1; layer >= 0 && n > 0; layer--) {
+    for (int layer = top - 1; layer >= stop && n > 0; layer--) {
         const TplLevelHost& t = h->tpl[layer];
         const FpmLevel& L = h->levels[layer];
         const double step = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
@@ -699,7 +705,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
                    cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,
                    h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
-                   L.h, layer_score[layer], h->use_simd, layer == 0 ? 1 : 0, h->subpixel, h->d_cand[cur ^ 1].as<FpmCand>(),
+                   L.h, layer_score[layer], h->use_simd, layer == stop ? 1 : 0, stop ? 2 : 1, (h->subpixel && layer == 0) ? 1 : 0,
+                   h->d_cand[cur ^ 1].as<FpmCand>(),
                    counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
                    h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr));
         }
@@ -718,7 +725,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                     rows.push_back(e.locx); rows.push_back(e.locy);
                 }
         }
-        n = (layer == 0) ? 0 : hc[CNT_NEXT];
+        n = (layer == stop) ? 0 : hc[CNT_NEXT];
         *n_refined_out = hc[CNT_REFINED];
         cur ^= 1;
     }
@@ -743,9 +750,12 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
     CK(h->d_rescnt.ensure((size_t)batch * sizeof(int)));
     CK(h->h_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev) + (size_t)batch * sizeof(int)));
     (void)n_refined;
+    // NMS rectangle size: pyramid[iStopLayer] * (iStopLayer == 0 ? 1 : 2)  (src/TemplateMatcher.cpp:376-377)
+    const int stop_l = std::min(h->stop_layer1 ? 1 : 0, (int)h->tpl.size() - 1);
+    const int nms_w = h->tpl[stop_l].w * (h->stop_layer1 ? 2 : 1), nms_h = h->tpl[stop_l].h * (h->stop_layer1 ? 2 : 1);
     KL(K_FINAL, 0,
        fpm_final_kernel<<<batch, FN_THREADS, 0, h->stream>>>(h->d_refined.as<FpmRefined>(), counters + CNT_REFINED, h->score,
-                                                             h->max_overlap, h->tpl[0].w, h->tpl[0].h,
+                                                             h->max_overlap, nms_w, nms_h, h->tpl[0].w, h->tpl[0].h,
                                                              h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
                                                              h->d_del.as<int>(), h->d_idmap.as<int>(),
                                                              h->d_pairs.as<unsigned char>(), pair_cap, h->mfc_compat, h->max_pos,
@@ -773,6 +783,7 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
 int match_guards(fpm_handle* h, int w, int hgt)
 {
     int tw = h->tpl0_w, th = h->tpl0_h;
+    if (h->tol_range && (h->tol_r[0] >= h->tol_r[1] || h->tol_r[2] >= h->tol_r[3])) return 1;   // "left value must be smaller"
     if ((tw < w && th > hgt) || (tw > w && th < hgt)) return 1;
     if ((long long)tw * th > (long long)w * hgt) return 1;
     return 0;
@@ -798,6 +809,15 @@ int match_device(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt,
     CK(h->d_counters.ensure(CNT_N * sizeof(int)));
     CK(h->h_counts.ensure((CNT_N + batch) * sizeof(int)));
     CK(cudaMemsetAsync(h->d_counters.p, 0, CNT_N * sizeof(int), h->stream));
+    if (h->bitwise_not) {
+        const int ipitch = (int)align_up(w, 128);
+        const size_t iimg = (size_t)ipitch * hgt;
+        CK(h->d_inv.ensure(iimg * batch));
+        dim3 ig((w / 4 + 128) / 128, hgt, batch);
+        fpm_invert_kernel<<<ig, 128, 0, h->stream>>>(d_src, w, hgt, stride, frame_stride, h->d_inv.as<uint8_t>(), ipitch, iimg);
+        CKL();
+        d_src = h->d_inv.as<uint8_t>(); stride = ipitch; frame_stride = iimg;
+    }
     rc = build_pyramid(h, d_src, batch, w, hgt, stride, frame_stride, top);
     if (rc) return rc;
     rc = make_top_plan(h, top, batch, 0, -1);
@@ -889,7 +909,7 @@ void fpm_destroy(fpm_handle* h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->aux_stream);
-    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
                       &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
@@ -926,6 +946,11 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_H2D_CHUNK: h->h2d_chunk = (int)v; break;
     case FPM_PARAM_TENSOR_CORES: h->use_tc = (int)v; break;
     case FPM_PARAM_MFC_COMPAT: h->mfc_compat = v != 0; break;
+    case FPM_PARAM_STOP_LAYER1: h->stop_layer1 = v != 0; break;
+    case FPM_PARAM_BITWISE_NOT: h->bitwise_not = v != 0; break;
+    case FPM_PARAM_TOLERANCE_RANGE: h->tol_range = v != 0; h->plan.valid = false; break;
+    case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
+        h->tol_r[param - FPM_PARAM_TOLERANCE1] = v; h->plan.valid = false; break;
     default: h->err = "unknown parameter"; return FPM_ERR_INVALID;
     }
     return FPM_OK;
@@ -948,6 +973,11 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_H2D_CHUNK: return h->h2d_chunk;
     case FPM_PARAM_TENSOR_CORES: return h->use_tc;
     case FPM_PARAM_MFC_COMPAT: return h->mfc_compat;
+    case FPM_PARAM_STOP_LAYER1: return h->stop_layer1;
+    case FPM_PARAM_BITWISE_NOT: return h->bitwise_not;
+    case FPM_PARAM_TOLERANCE_RANGE: return h->tol_range;
+    case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
+        return h->tol_r[param - FPM_PARAM_TOLERANCE1];
     default: return 0;
     }
 }
@@ -1138,6 +1168,15 @@ int fpm_stage_top(fpm_handle* h, const uint8_t* src, int width, int height, int 
     const int top = (int)h->tpl.size() - 1;
     CK(h->d_counters.ensure(CNT_N * sizeof(int)));
     CK(h->h_counts.ensure((CNT_N + 1) * sizeof(int)));
+    if (h->bitwise_not) {
+        const int ipitch = (int)align_up(width, 128);
+        const size_t iimg = (size_t)ipitch * height;
+        CK(h->d_inv.ensure(iimg));
+        dim3 ig((width / 4 + 128) / 128, height, 1);
+        fpm_invert_kernel<<<ig, 128, 0, h->stream>>>(d_src, width, height, pitch, img, h->d_inv.as<uint8_t>(), ipitch, iimg);
+        CKL();
+        d_src = h->d_inv.as<uint8_t>(); pitch = ipitch; img = iimg;
+    }
     rc = build_pyramid(h, d_src, 1, width, height, pitch, img, top);
     if (rc) return rc;
     rc = make_top_plan(h, top, 1, a0, a1);

@@ -1000,7 +1000,7 @@ __global__ void __launch_bounds__(RF_THREADS)
 fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double angle_step,
                            const int32_t* __restrict__ rowsum, int raw_epad, const int32_t* __restrict__ rowS,
                            const int32_t* __restrict__ rowQ, FpmTplLevel tpl, int lvl_w, int lvl_h,
-                           double layer_score, int use_chain, int is_last, int subpixel,
+                           double layer_score, int use_chain, int is_last, int out_scale, int subpixel,
                            FpmCand* __restrict__ next, int* __restrict__ next_count,
                            FpmRefined* __restrict__ refined, int* __restrict__ refined_count,
                            FpmEvalTrace* __restrict__ trace, float* __restrict__ trace_scores)
@@ -1118,7 +1118,7 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
     if (is_last) {
         FpmRefined o;
         o.angle = new_angle; o.score = (double)s_best[bi];
-        o.ptx = (double)rx; o.pty = (double)ry;
+        o.ptx = (double)(rx * (float)out_scale); o.pty = (double)(ry * (float)out_scale);   // pt * (iStopLayer == 0 ? 1 : 2), :357
         o.img = c.img; o.id = c.id;
         refined[atomicAdd(refined_count, 1)] = o;
     } else {
@@ -1130,7 +1130,20 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
     }
 }
 
-// top == 0: the top-layer picks are final (src/TemplateMatcher.cpp:272-276)
+// m_ckBitwiseNot (MatchTool/MatchToolDlg.cpp:788-794): the match runs on 255 - src
+__global__ void fpm_invert_kernel(const uint8_t* __restrict__ src, int w, int h, int spitch, size_t simg,
+                                  uint8_t* __restrict__ dst, int dpitch, size_t dimg)
+{
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * simg + (size_t)y * spitch + x;
+    uint8_t* d = dst + (size_t)blockIdx.z * dimg + (size_t)y * dpitch + x;
+    uint32_t v = 0;
+    for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)(255 - s[k]) << (8 * k);
+    *reinterpret_cast<uint32_t*>(d) = v;                 // dpitch is a multiple of 128: the padded tail is ours
+}
+
+// top <= stop layer: the top-layer picks are final (src/TemplateMatcher.cpp:272-276)
 __global__ void fpm_cands_to_refined_kernel(const FpmCand* __restrict__ cands, int n, int top,
                                             FpmRefined* __restrict__ refined, int* __restrict__ refined_count)
 {
@@ -1169,7 +1182,7 @@ __device__ __forceinline__ void fpm_corners(double ptx, double pty, double angle
 
 __global__ void __launch_bounds__(FN_THREADS)
 fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__ refined_count,
-                 double score_thresh, double max_overlap, int tpl_w, int tpl_h,
+                 double score_thresh, double max_overlap, int nms_w, int nms_h, int tpl_w, int tpl_h,
                  unsigned long long* __restrict__ key_scratch, int key_stride,
                  FpmRRect* __restrict__ rect_scratch, int* __restrict__ del_scratch,
                  int* __restrict__ idmap_scratch, unsigned char* __restrict__ pair_scratch, int pair_cap,
@@ -1211,7 +1224,7 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
     for (int i = tid; i < m; i += FN_THREADS) {
         const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
         float lt[2], rt[2], lb[2], rb[2];
-        fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
+        fpm_corners(r.ptx, r.pty, r.angle, nms_w, nms_h, lt, rt, lb, rb);
         rects[i] = fpm_rrect_from3(lt[0], lt[1], rt[0], rt[1], rb[0], rb[1]);
         del[i] = 0;
     }

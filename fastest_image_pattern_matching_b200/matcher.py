@@ -95,6 +95,17 @@ class TemplateMatcher:
     def setH2DChunk(self, v: int): self._set(L.PARAM_H2D_CHUNK, v)
     def setTensorCores(self, v: int): self._set(L.PARAM_TENSOR_CORES, v)
     def setMfcCompat(self, v: bool): self._set(L.PARAM_MFC_COMPAT, 1 if v else 0)
+    def setStopLayer1(self, v: bool): self._set(L.PARAM_STOP_LAYER1, 1 if v else 0)
+    def setBitwiseNot(self, v: bool): self._set(L.PARAM_BITWISE_NOT, 1 if v else 0)
+
+    def setToleranceRange(self, rng):
+        """rng = (t1, t2, t3, t4) enables the MFC two-range sweep, None disables it"""
+        if rng is None:
+            self._set(L.PARAM_TOLERANCE_RANGE, 0)
+            return
+        for p, v in zip((L.PARAM_TOLERANCE1, L.PARAM_TOLERANCE2, L.PARAM_TOLERANCE3, L.PARAM_TOLERANCE4), rng):
+            self._set(p, v)
+        self._set(L.PARAM_TOLERANCE_RANGE, 1)
 
     def getLastExecutionTime(self) -> float:
         """seconds, like the reference (include/TemplateMatcher.h:40)"""

@@ -49,6 +49,11 @@ enum fpm_param {
     FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always */
     FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC result convention (MatchTool/MatchToolDlg.cpp:1085-1116): angle = -theta wrapped
                                       to [-180,180], results truncated to TargetNum, corners in double; default 0 = Qt port */
+    /* MFC-only modes of the upstream dialog, off by default (the Qt TemplateMatcher has none of them) */
+    FPM_PARAM_STOP_LAYER1 = 13,    /* m_bStopLayer1 (MatchToolDlg.cpp:936): stop the descent at layer 1, coordinates x2 */
+    FPM_PARAM_BITWISE_NOT = 14,    /* m_ckBitwiseNot (:788-794): match on 255 - source                                */
+    FPM_PARAM_TOLERANCE_RANGE = 15,/* m_bToleranceRange (:805-816): sweep [TOLERANCE1,TOLERANCE2] and [TOLERANCE3,TOLERANCE4] */
+    FPM_PARAM_TOLERANCE1 = 16, FPM_PARAM_TOLERANCE2 = 17, FPM_PARAM_TOLERANCE3 = 18, FPM_PARAM_TOLERANCE4 = 19,
     FPM_PARAM_COUNT_
 };
 

@@ -352,6 +352,11 @@ class OracleMatcher:
         self.sub_pixel = False
         self.last_time = 0.0
         self.td = TemplData()
+        # MFC-only modes of the upstream dialog (MatchTool/MatchToolDlg.cpp), off in the Qt port
+        self.tolerance_range = None       # (t1, t2, t3, t4): two angle ranges, :805-816
+        self.stop_layer1 = False          # m_bStopLayer1: stop the descent at layer 1, :936
+        self.bitwise_not = False          # m_ckBitwiseNot: match on 255 - src, :788-794
+        self.mfc_compat = False           # result convention of :1085-1116 (angle sign/wrap, TargetNum truncation)
         # oracle-only switches
         self.top_numerator = "exact"      # "exact" (integer) | "cv" (cv2.matchTemplate)
         self.trace = None                 # dict filled with intermediates when not None
@@ -453,7 +458,17 @@ class OracleMatcher:
         tp = self.td.pyramid[top]
         step = math.atan(2.0 / max(tp.shape[1], tp.shape[0])) * R2D
         angles = []
-        if self.tolerance_angle < VISION_TOLERANCE:
+        if self.tolerance_range is not None:                       # MatchToolDlg.cpp:805-816
+            t1, t2, t3, t4 = self.tolerance_range
+            a = t1
+            while a < t2 + step:
+                angles.append(a)
+                a += step
+            a = t3
+            while a < t4 + step:
+                angles.append(a)
+                a += step
+        elif self.tolerance_angle < VISION_TOLERANCE:
             angles.append(0.0)
         else:
             a = 0.0
@@ -481,6 +496,11 @@ class OracleMatcher:
         top = get_top_layer(t0w, t0h, int(math.sqrt(float(self.min_reduce_area))))
         if top >= len(td.pyramid):
             raise RuntimeError("MinReduceArea changed after learnPattern (reference would index out of range)")
+        if self.tolerance_range is not None and (self.tolerance_range[0] >= self.tolerance_range[1] or
+                                                 self.tolerance_range[2] >= self.tolerance_range[3]):
+            return []                                              # "left value must be smaller", :807-811
+        if self.bitwise_not:
+            src = 255 - src
         src_pyr = build_pyramid(np.ascontiguousarray(src), top)
         if tr is not None:
             tr["src_pyr"] = src_pyr
@@ -530,7 +550,7 @@ class OracleMatcher:
             tr["refine"] = []
 
         dst_w, dst_h = size_pat
-        stop_layer = 0
+        stop_layer = 1 if self.stop_layer1 else 0
         all_res: List[MatchParameter] = []
         for ci, cand in enumerate(cands):
             r_angle = -cand.angle * D2R
@@ -547,7 +567,7 @@ class OracleMatcher:
                 tpl_l = td.pyramid[layer]
                 a_step = math.atan(2.0 / max(tpl_l.shape[1], tpl_l.shape[0])) * R2D
                 matched = cand.angle
-                if self.tolerance_angle < VISION_TOLERANCE:
+                if self.tolerance_range is None and self.tolerance_angle < VISION_TOLERANCE:
                     l_angles = [0.0]
                 else:
                     l_angles = [matched + a_step * i for i in (-1, 0, 1)]
@@ -608,8 +628,8 @@ class OracleMatcher:
                 all_res = all_res[:i]
                 break
 
-        dst_w = td.pyramid[stop_layer].shape[1]
-        dst_h = td.pyramid[stop_layer].shape[0]
+        dst_w = td.pyramid[stop_layer].shape[1] * (1 if stop_layer == 0 else 2)
+        dst_h = td.pyramid[stop_layer].shape[0] * (1 if stop_layer == 0 else 2)
         for r in all_res:
             lt, rt, lb, rb = self._corners(r, dst_w, dst_h)
             r.rect = cv2.RotatedRect((float(lt[0]), float(lt[1])), (float(rt[0]), float(rt[1])),
@@ -620,6 +640,24 @@ class OracleMatcher:
             return []
         iw, ih = td.pyramid[0].shape[1], td.pyramid[0].shape[0]
         out = []
+        if self.mfc_compat:                                        # MatchToolDlg.cpp:1085-1116
+            for i, r in enumerate(all_res):
+                a = -r.angle * D2R
+                ltx, lty = float(f32(r.pt[0])), float(f32(r.pt[1]))   # pt holds float values
+                rt = (ltx + iw * math.cos(a), lty - iw * math.sin(a))
+                lb = (ltx + ih * math.sin(a), lty + ih * math.cos(a))
+                rb = (rt[0] + ih * math.sin(a), rt[1] + ih * math.cos(a))
+                ang = -r.angle
+                if ang < -180:
+                    ang += 360
+                if ang > 180:
+                    ang -= 360
+                out.append(SingleTargetMatch(ptLT=(ltx, lty), ptRT=rt, ptRB=rb, ptLB=lb,
+                                             ptCenter=((ltx + rt[0] + rb[0] + lb[0]) / 4, (lty + rt[1] + rb[1] + lb[1]) / 4),
+                                             angle=ang, score=r.score))
+                if i + 1 == self.max_pos:
+                    break
+            return out
         for r in all_res:
             lt, rt, lb, rb = self._corners(r, iw, ih)
             four = f32(4.0)

@@ -541,3 +541,37 @@ def test_unaligned_device_frames(matcher, golden_cases):
         for i, w in enumerate(want):
             r = res[b * cap + i]
             assert abs(r.score - w["score"]) <= 1e-4 and abs(r.cx - w["cx"]) <= 0.05 and abs(r.cy - w["cy"]) <= 0.05
+
+
+# ---------------- MFC-only modes of the upstream dialog (MatchTool/MatchToolDlg.cpp) vs the oracle ----------------
+@pytest.mark.parametrize("mode", ["stop_layer1", "bitwise_not", "tolerance_range", "tolerance_range_invalid", "mfc_compat"])
+def test_mfc_only_modes(matcher, golden_cases, mode):
+    c = golden_cases["src8"]
+    tpl, src = get_image(c["tpl"]), get_image(c["src"])
+    om = configure(O.OracleMatcher(), c["params"])
+    configure(matcher, c["params"])
+    try:
+        if mode == "stop_layer1":
+            om.stop_layer1 = True
+            matcher.setStopLayer1(True)
+        elif mode == "bitwise_not":
+            om.bitwise_not = True
+            matcher.setBitwiseNot(True)
+            tpl = 255 - tpl
+        elif mode == "tolerance_range":
+            om.tolerance_range = (-30.0, 20.0, 40.0, 80.0)
+            matcher.setToleranceRange(om.tolerance_range)
+        elif mode == "tolerance_range_invalid":
+            om.tolerance_range = (30.0, 20.0, 40.0, 80.0)
+            matcher.setToleranceRange(om.tolerance_range)
+        elif mode == "mfc_compat":
+            om.mfc_compat = True
+            matcher.setMfcCompat(True)
+        om.learn_pattern(tpl)
+        assert matcher.learnPattern(tpl)
+        want = om.match(src)
+        got = matcher.match(src)
+    finally:
+        matcher.setStopLayer1(False); matcher.setBitwiseNot(False); matcher.setToleranceRange(None); matcher.setMfcCompat(False)
+    assert len(want) == {"stop_layer1": 3, "bitwise_not": 3, "tolerance_range": 2, "tolerance_range_invalid": 0, "mfc_compat": 3}[mode]
+    assert_results_match(got, want)
