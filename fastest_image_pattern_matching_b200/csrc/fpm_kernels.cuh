@@ -146,8 +146,8 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 // monotone in x and y, so the exact source bounding box of a tile follows from its 4 corners; the union box
 // (<= 160x160 px) is staged in shared memory with cp.async (odd word pitch: conflict-free gathers) and the
 // 4 bilinear taps of every pixel are gathered from shared memory -- a diagonal walk through global memory
-// would cost one L1 wavefront per lane.  32 pixels per thread and angle, packed 32-bit stores; padding
-// columns up to dpitch are written as zero.
+// would cost one L1 wavefront per lane.  32 pixels per thread and angle; padding columns up to dpitch are
+// written as zero.
 // =====================================================================================
 #define WA_TW 64
 #define WA_TH 128
@@ -237,38 +237,41 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     fpm_cp_async_commit();
     fpm_cp_async_wait<0>();
     __syncthreads();
-    const int xg = tid & 15;
-    if (tx0 + 4 * xg >= dpitch) return;
-    const bool fast = staged && inside && (4 * xg + 3 < ncols);
+    // Gather.  A warp owns one output row at a time and lane l the pixels l and l+32 of the tile row: neighbouring
+    // lanes read neighbouring source pixels (same word -> broadcast) or, for steep angles, neighbouring source rows
+    // (odd word pitch -> different banks), so the byte gathers are close to conflict-free at every angle.
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool fastw = staged && inside && ncols == WA_TW;     // whole tile row inside the image and the ROI: no predicates
     for (int j = 0; j < group; j++) {
         if (!jobs[g0 + j].valid) continue;
-        uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride;
-        int adj[4], bdj[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            adj[k] = s_ad[j][4 * xg + k] - (bx0 << 10);
-            bdj[k] = s_bd[j][4 * xg + k] - (by0 << 10);
-        }
-        for (int row = tid >> 4; row < nrows; row += WA_THREADS / 16) {
-            uint32_t pack = 0;
+        uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride + tx0;
+        const int adj0 = s_ad[j][lane] - (bx0 << 10), adj1 = s_ad[j][lane + 32] - (bx0 << 10);
+        const int bdj0 = s_bd[j][lane] - (by0 << 10), bdj1 = s_bd[j][lane + 32] - (by0 << 10);
+        for (int row = warp; row < nrows; row += WA_THREADS / 32) {
             const int X0 = s_X0[j][row], Y0 = s_Y0[j][row];
-            if (fast) {
+            uint8_t* drow = d + (size_t)(ty0 + row) * dpitch;
+            if (fastw) {
+                int v[2];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                for (int k = 0; k < 2; k++) {
+                    const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
                     const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
                     const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
                     const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
                     const int top = (p00 << 5) + ax * (p01 - p00);
                     const int bot = (p10 << 5) + ax * (p11 - p10);
-                    const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
-                    pack |= (uint32_t)v << (8 * k);
+                    v[k] = ((top << 5) + ay * (bot - top) + 512) >> 10;
                 }
+                drow[lane] = (uint8_t)v[0];
+                drow[lane + 32] = (uint8_t)v[1];
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (4 * xg + k < ncols) {
-                        const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                for (int k = 0; k < 2; k++) {
+                    const int col = lane + 32 * k;
+                    if (tx0 + col >= dpitch) continue;
+                    int v = 0;
+                    if (col < ncols) {
+                        const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
                         const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
                         const int lx = XX >> 10, ly = YY >> 10;              // relative to (bx0, by0)
                         const int sx = lx + bx0, sy = ly + by0;
@@ -290,12 +293,11 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                         }
                         const int top = (p00 << 5) + ax * (p01 - p00);
                         const int bot = (p10 << 5) + ax * (p11 - p10);
-                        const int v = ((top << 5) + ay * (bot - top) + 512) >> 10;
-                        pack |= (uint32_t)v << (8 * k);
+                        v = ((top << 5) + ay * (bot - top) + 512) >> 10;
                     }
+                    drow[col] = (uint8_t)v;                                  // padding columns are written as zero
                 }
             }
-            *reinterpret_cast<uint32_t*>(d + (size_t)(ty0 + row) * dpitch + tx0 + 4 * xg) = pack;
         }
     }
 }
