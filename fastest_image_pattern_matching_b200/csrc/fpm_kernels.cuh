@@ -139,24 +139,22 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 // K2/K3  warpAffine, u8 C1, INTER_LINEAR, BORDER_CONSTANT -- OpenCV's fixed-point path:
 //   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,
 //   X = (X0+adelta)>>5, sx = X>>5, ax = X&31, weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15
-//   == ((32-ay)*top + ay*bot + 512) >> 10 with top = (32-ax)*p00 + ax*p01   (same integers).
-// One job per output image (top-layer angle or refinement ROI).  One CTA = one 128x64 output tile of a
+//   == ((top<<5) + ay*(bot-top) + 512) >> 10 with top = (p00<<5) + ax*(p01-p00)   (same integers).
+// One job per output image (top-layer angle or refinement ROI).  One CTA = one 64x128 output tile of a
 // GROUP of jobs: the 3 angles of a refinement candidate are anchored at the same source point and differ by
 // less than ~4 px over the tile, so they share one staged source box.  The fixed-point map is separable and
 // monotone in x and y, so the exact source bounding box of a tile follows from its 4 corners; the union box
-// (<= 146x146 px) is staged in shared memory with cp.async (odd word pitch) TWICE: copy A as is, copy B shifted
-// by one byte, so that the horizontal tap pair (p[x], p[x+1]) of ANY x is one aligned 16-bit shared load
-// (A at even x, B at odd x).  Interpolation: two dp4a (pair x packed byte weights 32-ax, ax) and one dp2a
-// (top, bot x 32-ay, ay).  A warp owns one output row at a time, lane l the pixels l, l+32, l+64, l+96.
-// Padding columns up to dpitch are written as zero.
+// (<= 160x160 px) is staged in shared memory with cp.async (odd word pitch: conflict-free gathers) and the
+// 4 bilinear taps of every pixel are gathered from shared memory -- a diagonal walk through global memory
+// would cost one L1 wavefront per lane.  32 pixels per thread and angle; padding columns up to dpitch are
+// written as zero.
 // =====================================================================================
-#define WA_TW 128
-#define WA_TH 64
+#define WA_TW 64
+#define WA_TH 128
 #define WA_THREADS 256
-#define WA_BW 144     // staged box: max bytes per row actually used (36 words)
-#define WA_SW 148     // staged box pitch in bytes: 37 words (odd) -> rows fall in different banks
-#define WA_SH 146     // staged box: rows
-#define WA_COPY (WA_SH * WA_SW)
+#define WA_BW 160     // staged box: max bytes per row actually used (40 words)
+#define WA_SW 164     // staged box pitch in bytes: 41 words (odd) -> rows fall in different banks
+#define WA_SH 160     // staged box: rows
 #define WA_MAXG 3     // jobs per group
 
 __global__ void __launch_bounds__(WA_THREADS)
@@ -170,7 +168,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     const int tx0 = tile_x * WA_TW, ty0 = tile_y * WA_TH;
     if (!jb0.valid || ty0 >= dh || tx0 >= dpitch) return;
     __shared__ int s_ad[WA_MAXG][WA_TW], s_bd[WA_MAXG][WA_TW], s_X0[WA_MAXG][WA_TH], s_Y0[WA_MAXG][WA_TH];
-    __shared__ __align__(16) uint8_t s_src[2 * WA_COPY];         // copy A, then copy B (A shifted left by one byte)
+    __shared__ __align__(16) uint8_t s_src[WA_SH * WA_SW];
     const int tid = threadIdx.x;
     for (int i = tid; i < group * (WA_TW + WA_TH); i += WA_THREADS) {
         const int j = i / (WA_TW + WA_TH), k = i - j * (WA_TW + WA_TH);
@@ -194,7 +192,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
 
     // exact source box of the tile for every job of the group from the tile corners (X and Y are sums of
     // monotone functions of x and y), then the union
-    int bx0 = 0, by0 = 0, nwr = 0, nr = 0;
+    int bx0 = 0, by0 = 0;
     bool staged = false, inside = false;
     if (ncols > 0) {
         int Xmin = 0x7fffffff, Xmax = -0x7fffffff, Ymin = 0x7fffffff, Ymax = -0x7fffffff;
@@ -213,7 +211,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
         const int bx1 = min(sx1, sw - 1), by1 = min(sy1, sh - 1);
         staged = (bx1 - bx0 + 1 <= WA_BW) && (by1 - by0 + 1 <= WA_SH);
         if (staged && bx1 >= bx0 && by1 >= by0) {
-            nwr = (bx1 - bx0) / 4 + 1; nr = by1 - by0 + 1;               // nwr <= 36
+            const int nwr = (bx1 - bx0) / 4 + 1, nr = by1 - by0 + 1;      // nwr <= 40
             const int wc = tid & 63;
             if (wc < nwr) {
                 const int x = bx0 + 4 * wc;
@@ -239,56 +237,41 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     fpm_cp_async_commit();
     fpm_cp_async_wait<0>();
     __syncthreads();
-    const bool fastw = staged && inside && ncols == WA_TW;     // whole tile row inside the image and the ROI: no predicates
-    if (fastw) {
-        // copy B: B[r][x] = A[r][x+1]  (word i of B = bytes 1..4 of the word pair (i, i+1) of A)
-        const int wc = tid & 63;
-        if (wc < nwr) {
-            for (int r = tid >> 6; r < nr; r += WA_THREADS / 64) {
-                const uint32_t* a = reinterpret_cast<const uint32_t*>(s_src + r * WA_SW) + wc;
-                const uint32_t lo = a[0], hi = (wc + 1 < nwr) ? a[1] : 0u;
-                reinterpret_cast<uint32_t*>(s_src + WA_COPY + r * WA_SW)[wc] = __funnelshift_r(lo, hi, 8);
-            }
-        }
-        __syncthreads();
-    }
-    // Gather.  A warp owns one output row at a time and lane l the pixels l, l+32, l+64, l+96 of the tile row.
+    // Gather.  A warp owns one output row at a time and lane l the pixels l and l+32 of the tile row: neighbouring
+    // lanes read neighbouring source pixels (same word -> broadcast) or, for steep angles, neighbouring source rows
+    // (odd word pitch -> different banks), so the byte gathers are close to conflict-free at every angle.
     const int lane = tid & 31, warp = tid >> 5;
+    const bool fastw = staged && inside && ncols == WA_TW;     // whole tile row inside the image and the ROI: no predicates
     for (int j = 0; j < group; j++) {
         if (!jobs[g0 + j].valid) continue;
         uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride + tx0;
-        int adj[4], bdj[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            adj[k] = s_ad[j][lane + 32 * k] - (bx0 << 10);
-            bdj[k] = s_bd[j][lane + 32 * k] - (by0 << 10);
-        }
+        const int adj0 = s_ad[j][lane] - (bx0 << 10), adj1 = s_ad[j][lane + 32] - (bx0 << 10);
+        const int bdj0 = s_bd[j][lane] - (by0 << 10), bdj1 = s_bd[j][lane + 32] - (by0 << 10);
         for (int row = warp; row < nrows; row += WA_THREADS / 32) {
             const int X0 = s_X0[j][row], Y0 = s_Y0[j][row];
             uint8_t* drow = d + (size_t)(ty0 + row) * dpitch;
             if (fastw) {
+                int v[2];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
-                    const uint32_t wx = (uint32_t)((XX >> 5) & 31) * 255u + 32u;       // bytes (32-ax, ax)
-                    const uint32_t wy = (uint32_t)((YY >> 5) & 31) * 255u + 32u;       // bytes (32-ay, ay)
-                    const int off = (YY >> 10) * WA_SW + (XX >> 10);
-                    // even x: pair from copy A at off; odd x: pair from copy B at off-1 (both 2-byte aligned)
-                    const uint8_t* p = s_src + off + (off & 1) * (WA_COPY - 1);
-                    const uint32_t t01 = *reinterpret_cast<const unsigned short*>(p);
-                    const uint32_t b01 = *reinterpret_cast<const unsigned short*>(p + WA_SW);
-                    const uint32_t top = __dp4a(t01, wx, 0u), bot = __dp4a(b01, wx, 0u);
-                    const uint32_t v = __dp2a_lo(top | (bot << 16), wy, 512u) >> 10;
-                    drow[lane + 32 * k] = (uint8_t)v;
+                for (int k = 0; k < 2; k++) {
+                    const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
+                    const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
+                    const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
+                    const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
+                    const int top = (p00 << 5) + ax * (p01 - p00);
+                    const int bot = (p10 << 5) + ax * (p11 - p10);
+                    v[k] = ((top << 5) + ay * (bot - top) + 512) >> 10;
                 }
+                drow[lane] = (uint8_t)v[0];
+                drow[lane + 32] = (uint8_t)v[1];
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < 2; k++) {
                     const int col = lane + 32 * k;
                     if (tx0 + col >= dpitch) continue;
                     int v = 0;
                     if (col < ncols) {
-                        const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                        const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
                         const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
                         const int lx = XX >> 10, ly = YY >> 10;              // relative to (bx0, by0)
                         const int sx = lx + bx0, sy = ly + by0;
