@@ -607,6 +607,7 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         if (mode) blk_stride = (maxRW / t.w) * (maxRH / t.h) + 3;
         else blk_stride = ((maxRW + tile - 1) / tile) * ((maxRH + tile - 1) / tile);
         blk_stride = std::max(blk_stride, 1);
+        if (blk_stride > PK_SUP_MAX * 32) { h->err = "top-layer score map has too many blocks for the peak table"; return FPM_ERR_LIMIT; }
         CK(h->d_blkv.ensure((size_t)njobs * blk_stride * sizeof(float)));
         CK(h->d_blkl.ensure((size_t)njobs * blk_stride * sizeof(int)));
         double thresh = h->score;
@@ -1453,6 +1454,7 @@ int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw,
     int tile = 8;
     while ((long long)((cols + tile - 1) / tile) * ((rows + tile - 1) / tile) > 1024 && tile < 256) tile *= 2;
     int blk_stride = block_mode ? (cols / tw) * (rows / th) + 3 : ((cols + tile - 1) / tile) * ((rows + tile - 1) / tile);
+    if (blk_stride > PK_SUP_MAX * 32) { h->err = "score map has too many blocks for the peak table"; return FPM_ERR_LIMIT; }
     CK(h->d_dbg[1].ensure((size_t)blk_stride * 8));
     CK(h->d_dbg[3].ensure((size_t)max_picks * sizeof(FpmPick) + 16));
     CK(cudaMemcpy2DAsync(h->d_dbg[0].p, (size_t)sp * 4, score, (size_t)cols * 4, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, h->stream));

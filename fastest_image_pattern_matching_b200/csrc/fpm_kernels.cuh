@@ -492,7 +492,31 @@ __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, in
 }
 
 #define PK_THREADS 512
+#define PK_SUP_MAX 2048                 // super-table entries (32 blocks each) -> at most 65536 blocks per map
 
+// (value, block index, location) ordering of the greedy pick: larger value first; ties go to the
+// first block in table order (s_BlockMax::GetMaxValueLoc, mode 1) or to the first location in scan
+// order (cv::minMaxLoc, mode 0)
+__device__ __forceinline__ bool fpm_pick_better(int mode, float v, int k, int l, float bv, int bk, int bl)
+{
+    return (v > bv) || (v == bv && (mode ? (k < bk) : (l < bl)));
+}
+
+__device__ __forceinline__ void fpm_pick_warp_reduce(int mode, float& v, int& k, int& l)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int ok = __shfl_xor_sync(0xffffffffu, k, o);
+        int ol = __shfl_xor_sync(0xffffffffu, l, o);
+        if (fpm_pick_better(mode, ov, ok, ol, v, k, l)) { v = ov; k = ok; l = ol; }
+    }
+}
+
+// Greedy peak picking of one score map by one CTA.  Two-level maximum table: per block (global
+// scratch) and per 32 consecutive blocks (shared).  A pick repaints a rectangle, rescans only the
+// blocks that rectangle touches (found by index arithmetic, not by testing every block), refreshes
+// their super-entries and takes the argmax over the super-table with one warp.
 __global__ void __launch_bounds__(PK_THREADS)
 fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ score, int spitch,
                      size_t score_job_stride, int tw, int th, int mode, int tile,
@@ -509,8 +533,10 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     float* bval = blk_val + (size_t)job * blk_stride;
     int* bloc = blk_loc + (size_t)job * blk_stride;
     const FpmBlockGeom g = fpm_block_geom(mode, cols, rows, mode ? tw : tile, mode ? th : tile);
-    __shared__ float s_v[PK_THREADS / 32];
-    __shared__ int s_k[PK_THREADS / 32], s_loc[PK_THREADS / 32];
+    const int regular = g.ncol * g.nrow;
+    const int nsup = (g.nblocks + 31) >> 5;
+    __shared__ float s_sv[PK_SUP_MAX];
+    __shared__ int s_sk[PK_SUP_MAX], s_sl[PK_SUP_MAX];
     __shared__ float s_best_v;
     __shared__ int s_best_loc;
 
@@ -520,6 +546,15 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
         fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
         if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
     }
+    __syncthreads();
+    auto refresh_sup = [&](int s) {
+        int k = (s << 5) + lane;
+        float v = -INFINITY; int kk = 0x7fffffff, l = 0x7fffffff;
+        if (k < g.nblocks) { v = bval[k]; kk = k; l = bloc[k]; }
+        fpm_pick_warp_reduce(mode, v, kk, l);
+        if (lane == 0) { s_sv[s] = v; s_sk[s] = kk; s_sl[s] = l; }
+    };
+    for (int s = warp; s < nsup; s += nwarps) refresh_sup(s);
     __syncthreads();
 
     int npicks = 0;
@@ -531,53 +566,68 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
             int sy = (int)((double)lasty - (double)th * (1 - max_overlap));
             int rw = (int)(2 * (double)tw * (1 - max_overlap));
             int rh = (int)(2 * (double)th * (1 - max_overlap));
-            if (rw > 0 && rh > 0) {
-                int px0 = max(sx, 0), py0 = max(sy, 0), px1 = min(sx + rw, cols), py1 = min(sy + rh, rows);
-                int pw = px1 - px0, ph = py1 - py0;
-                if (pw > 0 && ph > 0)
-                    for (int i = tid; i < pw * ph; i += nthreads) {
-                        int yy = i / pw, xx = i - yy * pw;
-                        map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
-                    }
+            int px0 = max(sx, 0), py0 = max(sy, 0), px1 = min(sx + rw, cols), py1 = min(sy + rh, rows);
+            int pw = px1 - px0, ph = py1 - py0;
+            if (rw > 0 && rh > 0 && pw > 0 && ph > 0) {
+                for (int i = tid; i < pw * ph; i += nthreads) {
+                    int yy = i / pw, xx = i - yy * pw;
+                    map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
+                }
                 __syncthreads();
-                for (int k = warp; k < g.nblocks; k += nwarps) {
-                    int x, y, w, h;
-                    fpm_block_rect(g, k, cols, rows, x, y, w, h);
-                    int ix0 = max(x, sx), iy0 = max(y, sy), ix1 = min(x + w, sx + rw), iy1 = min(y + h, sy + rh);
-                    if (ix1 > ix0 && iy1 > iy0) {
-                        float v; int bx, by;
-                        fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
-                        if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
+                // blocks of the regular grid under the rectangle, plus the strips of mode 1
+                const int RX = g.ncol * g.bw, RY = g.nrow * g.bh;
+                int bx0 = px0 / g.bw, bx1 = min((px1 - 1) / g.bw, g.ncol - 1);
+                int by0 = py0 / g.bh, by1 = min((py1 - 1) / g.bh, g.nrow - 1);
+                int nbx = max(bx1 - bx0 + 1, 0), nby = max(by1 - by0 + 1, 0);
+                if (nbx == 0 || nby == 0) nbx = nby = 0;
+                const int nreg = nbx * nby;
+                const int hit_right = g.has_right && px1 > RX;
+                const int hit_bottom = g.has_bottom && py1 > RY && px0 < RX;
+                const int hit_corner = g.has_corner && px1 > RX && py1 > RY;
+                for (int idx = warp; idx < nreg + 3; idx += nwarps) {
+                    int k;
+                    if (idx < nreg) { int r = idx / nbx; k = (by0 + r) * g.ncol + bx0 + (idx - r * nbx); }
+                    else {
+                        int e = idx - nreg;
+                        if (e == 0) { if (!hit_right) continue; k = regular; }
+                        else if (e == 1) { if (!hit_bottom) continue; k = regular + g.has_right; }
+                        else { if (!hit_corner) continue; k = regular + g.has_right + g.has_bottom; }
                     }
+                    int x, y, w, h; float v; int bx, by;
+                    fpm_block_rect(g, k, cols, rows, x, y, w, h);
+                    fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
+                    if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
+                }
+                __syncthreads();
+                // super-entries over the touched block runs (a run of nbx blocks per grid row)
+                const int span = (nbx + 62) >> 5;
+                for (int idx = warp; idx < nby * span + 3; idx += nwarps) {
+                    int s;
+                    if (idx < nby * span) {
+                        int r = idx / span, j = idx - r * span;
+                        int k0 = (by0 + r) * g.ncol + bx0;
+                        s = (k0 >> 5) + j;
+                        if (s > ((k0 + nbx - 1) >> 5)) continue;
+                    } else {
+                        int k = regular + (idx - nby * span);
+                        if (k >= g.nblocks) continue;
+                        s = k >> 5;
+                    }
+                    refresh_sup(s);
                 }
                 __syncthreads();
             }
         }
-        // argmax over the block table
-        float best = -INFINITY; int bk = 0x7fffffff, bl = 0x7fffffff;
-        for (int k = tid; k < g.nblocks; k += nthreads) {
-            float v = bval[k]; int l = bloc[k];
-            bool better = (v > best) || (v == best && (mode ? (k < bk) : (l < bl)));
-            if (better) { best = v; bk = k; bl = l; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-            int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-            bool better = (ov > best) || (ov == best && (mode ? (ok < bk) : (ol < bl)));
-            if (better) { best = ov; bk = ok; bl = ol; }
-        }
-        if (lane == 0) { s_v[warp] = best; s_k[warp] = bk; s_loc[warp] = bl; }
-        __syncthreads();
-        if (tid == 0) {
-            float b = s_v[0]; int k0 = s_k[0], l0 = s_loc[0];
-            for (int w = 1; w < nwarps; w++) {
-                bool better = (s_v[w] > b) || (s_v[w] == b && (mode ? (s_k[w] < k0) : (s_loc[w] < l0)));
-                if (better) { b = s_v[w]; k0 = s_k[w]; l0 = s_loc[w]; }
+        // argmax over the super-table
+        if (warp == 0) {
+            float best = -INFINITY; int bk = 0x7fffffff, bl = 0x7fffffff;
+            for (int s = lane; s < nsup; s += 32)
+                if (fpm_pick_better(mode, s_sv[s], s_sk[s], s_sl[s], best, bk, bl)) { best = s_sv[s]; bk = s_sk[s]; bl = s_sl[s]; }
+            fpm_pick_warp_reduce(mode, best, bk, bl);
+            if (lane == 0) {
+                if (g.nblocks == 0) { best = -1.0f; bl = -1; }      // s_BlockMax::GetMaxValueLoc on empty
+                s_best_v = best; s_best_loc = bl;
             }
-            if (g.nblocks == 0) { b = -1.0f; l0 = -1; }      // s_BlockMax::GetMaxValueLoc on empty
-            s_best_v = b; s_best_loc = l0;
         }
         __syncthreads();
         float v = s_best_v; int loc = s_best_loc;
