@@ -62,6 +62,7 @@ SIGNATURES = {
     "fpm_dbg_warp_affine": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "fpm_dbg_corr_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "fpm_dbg_corr_rows_mma": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "fpm_dbg_corr_fused": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "fpm_dbg_top_score": (_i, [_vp, _vp, _i, _i, _vp]),
     "fpm_dbg_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _pi]),
     "fpm_dbg_rrect_overlap": (_i, [_vp, _vp, _d, _pi, _pd]),

@@ -139,7 +139,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
-    bool mma_attr_set = false;
+    bool mma_attr_set = false, fused_attr_set = false;
     int stop_layer1 = 0, bitwise_not = 0, tol_range = 0;   // MFC-only modes (MatchTool/MatchToolDlg.cpp:788-816, :936)
     double tol_r[4] = {0, 0, 0, 0};
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
@@ -151,7 +151,7 @@ struct fpm_handle {
     std::vector<uint8_t> tpl0;    // level-0 copy for re-learning when MinReduceArea changes
     int tpl0_w = 0, tpl0_h = 0;
     std::vector<TplLevelHost> tpl;
-    DevBuf d_tpl, d_tsh, d_raw, d_inv;
+    DevBuf d_tpl, d_tsh, d_raw, d_inv, d_numer, d_totS, d_totQ;
     // user rect (pure storage)
     int ur[4] = {0, 0, 0, 0};
     int has_ur = 0;
@@ -199,11 +199,11 @@ namespace {
         }                                                                                \
     } while (0)
 
-enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_ROWSUMS, K_COUNT };
+enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_CORR_FUSED, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"fpm_pyrdown_kernel", "fpm_warp_kernel(top)", "fpm_top_score_kernel", "fpm_top_peaks_kernel",
                                            "fpm_collect_sort_kernel", "fpm_refine_prep_kernel", "fpm_warp_kernel(roi)",
                                            "fpm_corr_rows_kernel", "fpm_refine_finalize_kernel", "fpm_final_kernel",
-                                           "fpm_corr_mma_kernel", "fpm_row_sums_kernel"};
+                                           "fpm_corr_mma_kernel", "fpm_corr_fused_kernel"};
 
 cudaEvent_t prof_event(fpm_handle* h)
 {
@@ -349,7 +349,45 @@ bool mma_usable(const fpm_handle* h, int tw)
 {
     if (h->use_tc == 0) return false;
     if (!get_encode_tiled()) return false;
-    return h->use_tc >= 2 ? true : tw >= 64;
+    return (h->use_tc == 2 || h->use_tc == 4) ? true : tw >= 64;
+}
+
+// The fused kernel keeps one CTA on 128 evals for all ROI rows: it wins when the evals fill the SMs and the rows are
+// short (then the row-split kernel is dominated by the 256 B of row dots per (eval, row) that it writes and the
+// finalize kernel reads back), and loses when a level has few evals and long rows.  Measured on B200: a fused CTA
+// streams its ROI patches at ~27 GB/s from HBM; the row-split path moves ~(row + 568) bytes per (eval, row) at ~5 TB/s.
+bool fused_pays(int ne, int rh, int rpitch, int k_bytes, int use_tc)
+{
+    (void)rh; (void)k_bytes;
+    if (use_tc == 4) return true;                                     // forced (tests)
+    const double m_tiles = (ne + MM_M - 1) / MM_M;
+    const double rounds = ceil(m_tiles / 148.0);
+    return m_tiles / rounds > 185.0 * rpitch / (rpitch + 568.0);
+}
+
+// fused tensor-core correlation: numerators (float chain), window totals and edge rows for `ne` ROI patches
+int launch_corr_fused(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
+                      int ne, int32_t* rowS, int32_t* rowQ)
+{
+    const int rh = th + FPM_ROI_PAD;
+    const int m_tiles = (ne + MM_M - 1) / MM_M;
+    CK(h->d_numer.ensure((size_t)ne * MM_N * sizeof(float)));
+    CK(h->d_totS.ensure((size_t)ne * FPM_NSHIFT * sizeof(long long)));
+    CK(h->d_totQ.ensure((size_t)ne * FPM_NSHIFT * sizeof(long long)));
+    CUtensorMap map_a, map_b;
+    int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)rpitch, (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
+    if (rc) return rc;
+    rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
+    if (rc) return rc;
+    if (!h->fused_attr_set) {
+        CK(cudaFuncSetAttribute(fpm_corr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FM_SMEM_BYTES));
+        h->fused_attr_set = true;
+    }
+    KL(K_CORR_FUSED, (double)ne * FPM_NCELL * (double)tw * th,
+       fpm_corr_fused_kernel<<<m_tiles, FM_THREADS, FM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, rh, tw, th, tw + FPM_ROI_PAD,
+                                                                               h->d_numer.as<float>(), rowS, rowQ,
+                                                                               h->d_totS.as<long long>(), h->d_totQ.as<long long>()));
+    return FPM_OK;
 }
 
 // raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
@@ -374,22 +412,10 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
         CK(cudaFuncSetAttribute(fpm_corr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
         h->mma_attr_set = true;
     }
-    // the window row sums only depend on the ROI patches: they run on the auxiliary stream, concurrently with the
-    // tensor-core kernel (which leaves most of every SM idle), and are joined before the finalize kernel
-    const int n_rows = ne * rh;
-    CK(cudaEventRecord(h->ev_fork, h->stream));
-    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-    prof_begin(h, h->aux_stream);
-    fpm_row_sums_kernel<<<(((n_rows + RS_ROWS - 1) / RS_ROWS) * 32 + 255) / 256, 256, 0, h->aux_stream>>>(roi, rpitch, roi_stride, tw, rh,
-                                                                                                     n_rows, rowS, rowQ);
-    prof_end(h, K_ROWSUMS, (double)n_rows * (tw + FPM_ROI_PAD), h->aux_stream);
-    CKL();
-    CK(cudaEventRecord(h->ev_join, h->aux_stream));
     dim3 grid(chunks, m_tiles);
     KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
-       fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw + FPM_ROI_PAD, rows_per_cta,
-                                                                           h->d_raw.as<int32_t>()));
-    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+       fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw, th, tw + FPM_ROI_PAD,
+                                                                           rows_per_cta, h->d_raw.as<int32_t>(), rowS, rowQ));
     return FPM_OK;
 }
 
@@ -690,7 +716,13 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                                                                     h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
                                                                     level_vec_ok(L)));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
-            if (mma_usable(h, t.w)) {
+            bool fused = false;                             // numerators + window totals straight from the fused tensor-core kernel
+            if (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3 && fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
+                int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                            t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
+                if (rcm) return rcm;
+                fused = true;
+            } else if (mma_usable(h, t.w)) {
                 int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
                                           t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
                 if (rcm) return rcm;
@@ -709,7 +741,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                    L.h, layer_score[layer], h->use_simd, layer == stop ? 1 : 0, stop ? 2 : 1, (h->subpixel && layer == 0) ? 1 : 0,
                    h->d_cand[cur ^ 1].as<FpmCand>(),
                    counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
-                   h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr));
+                   h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr,
+                   fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>()));
         }
         CK(cudaMemcpyAsync(hc, counters, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -910,7 +943,7 @@ void fpm_destroy(fpm_handle* h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->aux_stream);
-    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_numer, &h->d_totS, &h->d_totQ, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
                       &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
@@ -1406,6 +1439,60 @@ int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois, int ne, const uint
                 for (int c = 0; c < FPM_NSHIFT; c++)
                     rowsum[((size_t)e * th + tr) * FPM_NCELL + r * FPM_NSHIFT + c] =
                         raw[((size_t)(tr + r) * e_pad + e) * MM_N + c * 8 + (7 - r)];
+    return FPM_OK;
+}
+
+int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t* tpl, int tw, int th, float* numer,
+                       long long* winS, long long* winQ, int32_t* edge_rowS)
+{
+    if (!h || !rois || !tpl || !numer || !winS || !winQ || tw <= 0 || th <= 0 || ne <= 0) return FPM_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!get_encode_tiled()) { h->err = "cuTensorMapEncodeTiled not available"; return FPM_ERR_CUDA; }
+    const int rh = th + FPM_ROI_PAD, rw = tw + FPM_ROI_PAD;
+    const int rpitch = (int)align_up(rw, 16) + 16, tp = (int)align_up(tw, 16), bpitch = (int)align_up(tw + 8, 16);
+    const size_t roi_stride = (size_t)rpitch * rh;
+    CK(h->d_dbg[0].ensure(roi_stride * ne));
+    CK(h->d_dbg[1].ensure((size_t)tp * th + (size_t)8 * th * bpitch + 256));
+    CK(h->d_dbg[3].ensure(2 * (size_t)ne * rh * FPM_NSHIFT * 4));
+    CK(cudaMemsetAsync(h->d_dbg[0].p, 0, roi_stride * ne, h->stream));
+    CK(cudaMemsetAsync(h->d_dbg[1].p, 0, (size_t)tp * th, h->stream));
+    CK(cudaMemsetAsync(h->d_dbg[3].p, 0xff, 2 * (size_t)ne * rh * FPM_NSHIFT * 4, h->stream));   // rows the kernel must not need stay poisoned
+    for (int e = 0; e < ne; e++)
+        CK(cudaMemcpy2DAsync(h->d_dbg[0].as<uint8_t>() + e * roi_stride, rpitch, rois + (size_t)e * rh * rw, rw, rw, rh,
+                             cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_dbg[1].p, tp, tpl, tw, tw, th, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* tsh = h->d_dbg[1].as<uint8_t>() + align_up((size_t)tp * th, 256);
+    dim3 g((bpitch + 127) / 128, th, 8);
+    fpm_shift_template_kernel<<<g, 128, 0, h->stream>>>(h->d_dbg[1].as<uint8_t>(), tw, th, tp, tsh, bpitch);
+    CKL();
+    int32_t* dS = h->d_dbg[3].as<int32_t>();
+    int32_t* dQ = dS + (size_t)ne * rh * FPM_NSHIFT;
+    int rc = launch_corr_fused(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, dS, dQ);
+    if (rc) return rc;
+    std::vector<float> hn((size_t)ne * MM_N);
+    std::vector<long long> tS((size_t)ne * FPM_NSHIFT), tQ((size_t)ne * FPM_NSHIFT);
+    std::vector<int32_t> rS((size_t)ne * rh * FPM_NSHIFT), rQ((size_t)ne * rh * FPM_NSHIFT);
+    CK(cudaMemcpyAsync(hn.data(), h->d_numer.p, hn.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(tS.data(), h->d_totS.p, tS.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(tQ.data(), h->d_totQ.p, tQ.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rS.data(), dS, rS.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(rQ.data(), dQ, rQ.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (edge_rowS) memcpy(edge_rowS, rS.data(), rS.size() * 4);
+    // same window arithmetic as fpm_refine_finalize_kernel's fused branch
+    for (int e = 0; e < ne; e++)
+        for (int r = 0; r < FPM_NSHIFT; r++)
+            for (int c = 0; c < FPM_NSHIFT; c++) {
+                long long ws = tS[(size_t)e * FPM_NSHIFT + c], wq = tQ[(size_t)e * FPM_NSHIFT + c];
+                for (int y = 0; y < rh; y++)
+                    if (y < r || y >= r + th) {
+                        ws -= rS[((size_t)e * rh + y) * FPM_NSHIFT + c];
+                        wq -= rQ[((size_t)e * rh + y) * FPM_NSHIFT + c];
+                    }
+                const size_t o = (size_t)e * FPM_NCELL + r * FPM_NSHIFT + c;
+                numer[o] = hn[(size_t)e * MM_N + c * 8 + (7 - r)];
+                winS[o] = ws; winQ[o] = wq;
+            }
     return FPM_OK;
 }
 

@@ -1055,7 +1055,9 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                            double layer_score, int use_chain, int is_last, int out_scale, int subpixel,
                            FpmCand* __restrict__ next, int* __restrict__ next_count,
                            FpmRefined* __restrict__ refined, int* __restrict__ refined_count,
-                           FpmEvalTrace* __restrict__ trace, float* __restrict__ trace_scores)
+                           FpmEvalTrace* __restrict__ trace, float* __restrict__ trace_scores,
+                           const float* __restrict__ numer, const long long* __restrict__ totS,
+                           const long long* __restrict__ totQ)
 {
     const int ci = blockIdx.x;
     const int tid = threadIdx.x, j = tid >> 6, cell = tid & 63;
@@ -1070,6 +1072,17 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
         float sc;
         if (tpl.result_equal1) {
             sc = 1.0f;
+        } else if (numer) {
+            // fused tensor-core kernel: the float chain is already folded (column 8c + 7 - r), the window sums are
+            // the totals over all ROI rows minus the r rows above and the 6 - r rows below the window
+            const float numf = numer[(size_t)e * 64 + c * 8 + (7 - r)];
+            const int rh = th + FPM_ROI_PAD;
+            long long ws = totS[(size_t)e * FPM_NSHIFT + c], wq = totQ[(size_t)e * FPM_NSHIFT + c];
+            const int32_t* ps = rowS + (size_t)e * rh * FPM_NSHIFT + c;
+            const int32_t* pq = rowQ + (size_t)e * rh * FPM_NSHIFT + c;
+            for (int y = 0; y < r; y++) { ws -= ps[(size_t)y * FPM_NSHIFT]; wq -= pq[(size_t)y * FPM_NSHIFT]; }
+            for (int y = r + th; y < rh; y++) { ws -= ps[(size_t)y * FPM_NSHIFT]; wq -= pq[(size_t)y * FPM_NSHIFT]; }
+            sc = fpm_ccoeff_epilogue(numf, (double)ws, (double)wq, tpl.mean, tpl.norm, tpl.inv_area);
         } else {
             // row sums either as [e][tr][49] (dp4a kernel) or as raw[y][e_pad][64] with y = tr + r and
             // column 8c + 7 - r (tensor-core kernel); both walked in template-row order

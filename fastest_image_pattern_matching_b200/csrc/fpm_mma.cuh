@@ -18,8 +18,9 @@
 // Output layout "raw": raw[y][e][64] (one 256-byte line per (ROI row, eval)), consumed in ROI-row
 // order by fpm_refine_finalize_kernel, which keeps the reference's float32 accumulation order.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp id % 4), warps 6..9 = window statistics (fpm_mm_stats):
+// the 7 shifted row sums / square sums of every ROI row, computed from the A tiles while they are in shared memory.
 #pragma once
 #include <cuda.h>
 #include "fpm_common.cuh"
@@ -31,7 +32,7 @@
 #define MM_A_BYTES (MM_M * MM_KCHUNK)  // 16 KB
 #define MM_B_BYTES (MM_N * MM_KCHUNK)  // 8 KB
 #define MM_STAGE_BYTES (MM_A_BYTES + MM_B_BYTES)
-#define MM_THREADS 192
+#define MM_THREADS 320
 #define MM_TMEM_COLS 128               // two accumulator buffers of 64 columns
 #define MM_SMEM_BYTES (MM_STAGES * MM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 
@@ -141,14 +142,106 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v)
         : "r"(taddr)
         : "memory");
 }
+// shared-memory reads of TMA-filled stages: volatile asm, so they stay between the full-barrier wait and the
+// empty-barrier arrive no matter what the compiler knows about the pointer
+__device__ __forceinline__ uint4 lds128(uint32_t saddr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return (int)v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace fpm_ptx
 
+// Window statistics of the A tiles while they sit in shared memory (warps 6..9 of both tensor-core kernels):
+// thread m owns eval row m of the tile, walks its 128-byte rows chunk by chunk (the 128-byte swizzle permutes
+// 16-byte chunks inside a row: chunk j of row m lives at chunk j ^ (m & 7)) and produces, per ROI row, the 7
+// shifted window sums S_c = sum_{x<tw} roi[y][x+c] and square sums from the base sum over [0, tw) plus the
+// 6 head / 6 tail bytes.  kAllRows: store every row (row-split kernel); otherwise store only the first / last
+// 6 rows and return the totals over all rows (fused kernel).  Each consumed stage is released on empty_bar.
+template <bool kAllRows>
+__device__ __forceinline__ void fpm_mm_stats(uint32_t base_u32, uint32_t bar0, int m, int lane, int e, bool live,
+                                             int y_begin, int y_end, int rh, int tw, int th, int nk,
+                                             int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ,
+                                             long long* ts, long long* tq)
+{
+    using namespace fpm_ptx;
+    const uint32_t sw = (uint32_t)(m & 7);
+    int it = 0;
+    for (int y = y_begin; y < y_end; y++) {
+        uint32_t s0 = 0, q0 = 0;
+        int hd[6], tl[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { hd[i] = 0; tl[i] = 0; }
+        for (int k = 0; k < nk; k++, it++) {
+            const int s = it % MM_STAGES;
+            const uint32_t ph = (it / MM_STAGES) & 1;
+            mbar_wait(bar0 + 8u * s, ph);                                         // full_bar(s)
+            const uint32_t rowp = base_u32 + (uint32_t)s * MM_STAGE_BYTES + (uint32_t)m * MM_KCHUNK;
+            const int xb = k * MM_KCHUNK;
+            // chunks that hold window columns or the 6 tail bytes; every loaded value is consumed before the stage
+            // is released (no load may still be in flight when the empty barrier is signalled)
+            const int nj = min(MM_KCHUNK / 16, (tw + FPM_ROI_PAD - xb + 15) >> 4);
+            for (int j = 0; j < nj; j++) {
+                const uint4 v = lds128(rowp + (((uint32_t)j ^ sw) << 4));
+                const int rem = tw - (xb + 16 * j);                                 // window bytes in this chunk (may be <= 0)
+                if (k == 0 && j == 0) {
+                    hd[0] = v.x & 0xff; hd[1] = (v.x >> 8) & 0xff; hd[2] = (v.x >> 16) & 0xff; hd[3] = v.x >> 24;
+                    hd[4] = v.y & 0xff; hd[5] = (v.y >> 8) & 0xff;
+                }
+                if (rem >= 16) {
+                    s0 = __dp4a(v.x, 0x01010101u, s0); q0 = __dp4a(v.x, v.x, q0);
+                    s0 = __dp4a(v.y, 0x01010101u, s0); q0 = __dp4a(v.y, v.y, q0);
+                    s0 = __dp4a(v.z, 0x01010101u, s0); q0 = __dp4a(v.z, v.z, q0);
+                    s0 = __dp4a(v.w, 0x01010101u, s0); q0 = __dp4a(v.w, v.w, q0);
+                } else {
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        const int nb = rem - 4 * jj;
+                        const uint32_t mk = nb >= 4 ? w[jj] : (nb <= 0 ? 0u : (w[jj] & (0xffffffffu >> (8 * (4 - nb)))));
+                        s0 = __dp4a(mk, 0x01010101u, s0);
+                        q0 = __dp4a(mk, mk, q0);
+                    }
+                    // tail byte i sits at position rem + i of this chunk when that is inside [0, 16)
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        const int pos = rem + i;
+                        if (pos >= 0 && pos < 16) {
+                            const uint32_t wsel = pos < 8 ? (pos < 4 ? v.x : v.y) : (pos < 12 ? v.z : v.w);
+                            tl[i] = (int)__byte_perm(wsel, 0u, 0x4440u | (uint32_t)(pos & 3));
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8u * (MM_STAGES + s));              // empty_bar(s)
+        }
+        int sc = (int)s0, qc = (int)q0;
+        const bool store = live && (kAllRows || y < FPM_ROI_PAD || y >= th);
+        int32_t* ps = rowS + ((size_t)e * rh + y) * FPM_NSHIFT;
+        int32_t* pq = rowQ + ((size_t)e * rh + y) * FPM_NSHIFT;
+#pragma unroll
+        for (int c = 0; c < FPM_NSHIFT; c++) {
+            if (c > 0) { sc += tl[c - 1] - hd[c - 1]; qc += tl[c - 1] * tl[c - 1] - hd[c - 1] * hd[c - 1]; }
+            if (!kAllRows) { ts[c] += sc; tq[c] += qc; }
+            if (store) { ps[c] = sc; pq[c] = qc; }
+        }
+    }
+}
+
 // grid: (row_chunks, m_tiles); CTA (bx, by) handles ROI rows [bx*rows_per_cta, ...) of evals [128*by, 128*by+128)
 __global__ void __launch_bounds__(MM_THREADS, 1)
 fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    int n_evals, int e_pad, int rh, int k_bytes, int rows_per_cta, int32_t* __restrict__ raw)
+                    int n_evals, int e_pad, int rh, int tw, int th, int k_bytes, int rows_per_cta, int32_t* __restrict__ raw,
+                    int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
 {
     using namespace fpm_ptx;
     extern __shared__ uint8_t mm_smem_raw[];
@@ -173,7 +266,7 @@ fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        for (int s = 0; s < MM_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < MM_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1 + 4); }   // MMA commit + 4 statistics warps
         for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
         fence_barrier_init();
         fence_proxy_async();
@@ -225,6 +318,11 @@ fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     tc_commit(tfull_bar(buf));                           // accumulator of row y complete
                 }
             }
+        } else if (warp >= 6) {
+            // ===== window statistics: warps 6..9 =====
+            const int m = (warp - 6) * 32 + lane;
+            fpm_mm_stats<true>(base_u32, bar0, m, lane, e0 + m, (e0 + m) < n_evals, y_begin, y_end, rh, tw, th, nk, rowS, rowQ,
+                               nullptr, nullptr);
         } else {
             // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
             const int q = warp & 3;
@@ -257,75 +355,143 @@ fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, MM_TMEM_COLS);
 }
 
-// window row sums for the MMA path: rowS/rowQ[e][y][c] = sum_{x<w} S_e[y][x+c] (^2); one warp per ROI row,
-// 128-bit loads, warp-shuffle reduction; the 6 shifted windows follow from 6 head / 6 tail bytes through a
-// 3-step shuffle scan so that lanes 0..6 store the 7 values of the row with one coalesced store each.
-#define RS_ROWS 4        // ROI rows per warp: all their loads are issued before the first reduction
+// ---------------------------------------------------------------------------------------------
+// Fused variant: one CTA owns 128 evals for ALL ROI rows, so nothing but the 49 scores' numerators
+// and the window statistics leaves the SM.
+//   * epilogue warps keep the reference's float32 accumulation chain (MatchTemplate's
+//     `result += (float)IM_Conv_SIMD(row)` loop, src/TemplateMatcher.cpp:496-510) in registers:
+//     accumulator column 8c+jj of ROI row y is template row tr = y-7+jj of score (r = 7-jj, c), and y
+//     ascending is tr ascending, so acc[8c+jj] = fadd(acc[8c+jj], float(D_y[e][8c+jj])) walks exactly the
+//     reference's order; rows outside the template come back as 0 (TMA zero fill) and adding +0.0f is exact;
+//   * 4 statistics warps read the same A tiles from shared memory (one thread per eval row, swizzle
+//     undone per 16-byte chunk) for the window sums: 7 shifted sums / square sums per ROI row, their
+//     totals over all rows in 64 bit, and the first / last 6 rows per eval (all the 7x7 windows need).
+// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue, 6..9 = statistics.
+#define FM_THREADS 320
+#define FM_SMEM_BYTES MM_SMEM_BYTES
 
-__global__ void __launch_bounds__(256)
-fpm_row_sums_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, int tw, int rh, int n_rows_total,
-                    int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
+__global__ void __launch_bounds__(FM_THREADS, 1)
+fpm_corr_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      int n_evals, int rh, int tw, int th, int k_bytes, float* __restrict__ numer,
+                      int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ,
+                      long long* __restrict__ totS, long long* __restrict__ totQ)
 {
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int row0 = gw * RS_ROWS;
-    if (row0 >= n_rows_total) return;
-    const int n16 = (tw + 15) / 16;                       // 16-byte chunks covering the template width
-    const uint8_t* rb[RS_ROWS];
-    uint32_t s[RS_ROWS], q[RS_ROWS];
-    int hb[RS_ROWS], tb[RS_ROWS];
-#pragma unroll
-    for (int k = 0; k < RS_ROWS; k++) {
-        const int g = min(row0 + k, n_rows_total - 1);
-        const int e = g / rh, y = g - e * rh;
-        rb[k] = roi + (size_t)e * roi_stride + (size_t)y * rpitch;
-        s[k] = 0; q[k] = 0;
-        hb[k] = 0; tb[k] = 0;
-        if (lane >= 1 && lane <= 6) { hb[k] = rb[k][lane - 1]; tb[k] = rb[k][tw + lane - 1]; }
+    using namespace fpm_ptx;
+    extern __shared__ uint8_t mm_smem_raw[];
+    const uint32_t base_u32 = (smem_u32(mm_smem_raw) + 1023u) & ~1023u;
+    uint8_t* base = mm_smem_raw + (base_u32 - smem_u32(mm_smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + MM_STAGES * MM_STAGE_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (MM_STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * MM_STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * MM_STAGES + 2 + b); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MM_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e0 = blockIdx.x * MM_M;
+    const int nk = (k_bytes + MM_KCHUNK - 1) / MM_KCHUNK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < MM_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1 + 4); }   // MMA commit + 4 statistics warps
+        for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        fence_barrier_init();
+        fence_proxy_async();
     }
-    for (int i = lane; i < n16; i += 32) {
-        uint4 v[RS_ROWS];
-#pragma unroll
-        for (int k = 0; k < RS_ROWS; k++) v[k] = reinterpret_cast<const uint4*>(rb[k])[i];
-        if (i < n16 - 1) {
-            // full 16-byte chunk: no masking
-#pragma unroll
-            for (int k = 0; k < RS_ROWS; k++) {
-                s[k] = __dp4a(v[k].x, 0x01010101u, s[k]); q[k] = __dp4a(v[k].x, v[k].x, q[k]);
-                s[k] = __dp4a(v[k].y, 0x01010101u, s[k]); q[k] = __dp4a(v[k].y, v[k].y, q[k]);
-                s[k] = __dp4a(v[k].z, 0x01010101u, s[k]); q[k] = __dp4a(v[k].z, v[k].z, q[k]);
-                s[k] = __dp4a(v[k].w, 0x01010101u, s[k]); q[k] = __dp4a(v[k].w, v[k].w, q[k]);
-            }
-        } else {
-            const int rem = tw - 16 * i;                   // valid bytes in the last chunk (1..16)
-#pragma unroll
-            for (int k = 0; k < RS_ROWS; k++) {
-                const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int nb = rem - 4 * j;            // valid bytes in this word
-                    const uint32_t m = nb >= 4 ? w[j] : (nb <= 0 ? 0u : (w[j] & (0xffffffffu >> (8 * (4 - nb)))));
-                    s[k] = __dp4a(m, 0x01010101u, s[k]);
-                    q[k] = __dp4a(m, m, q[k]);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), MM_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int y = 0; y < rh; y++)
+                for (int k = 0; k < nk; k++, it++) {
+                    const int s = it % MM_STAGES;
+                    const uint32_t ph = (it / MM_STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), MM_STAGE_BYTES);
+                    const uint32_t sa = base_u32 + s * MM_STAGE_BYTES;
+                    tma_load_3d(sa, &map_a, full_bar(s), k * MM_KCHUNK, y, e0);
+                    tma_load_3d(sa + MM_A_BYTES, &map_b, full_bar(s), k * MM_KCHUNK, y - 7, 0);
                 }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int it = 0;
+            for (int y = 0; y < rh; y++) {
+                const int buf = y & 1;
+                const uint32_t tph = (y >> 1) & 1;
+                mbar_wait(tempty_bar(buf), tph ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + buf * MM_N;
+                for (int k = 0; k < nk; k++, it++) {
+                    const int s = it % MM_STAGES;
+                    const uint32_t ph = (it / MM_STAGES) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = base_u32 + s * MM_STAGE_BYTES;
+                    const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + MM_A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < MM_KCHUNK / 32; kk++)
+                        mma_i8(d_addr, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), MM_IDESC, (k | kk) ? 1u : 0u);
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(tfull_bar(buf));
             }
         }
-    }
+    } else if (warp < 6) {
+        // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4; float chain in registers =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        float acc[56];
 #pragma unroll
-    for (int k = 0; k < RS_ROWS; k++) {
+        for (int i = 0; i < 56; i++) acc[i] = 0.0f;
+        for (int y = 0; y < rh; y++) {
+            const int buf = y & 1;
+            const uint32_t tph = (y >> 1) & 1;
+            mbar_wait(tfull_bar(buf), tph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * MM_N;
+            uint32_t v[64];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s[k] += __shfl_xor_sync(0xffffffffu, s[k], o); q[k] += __shfl_xor_sync(0xffffffffu, q[k], o); }
-        // lane c in 1..6 contributes tail[c-1] - head[c-1]; inclusive scan over the lanes gives the shift-c correction
-        int ds = tb[k] - hb[k], dq = tb[k] * tb[k] - hb[k] * hb[k];
+            for (int c = 0; c < 4; c++) tmem_ld16(taddr + c * 16, v + c * 16);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            int a = __shfl_up_sync(0xffffffffu, ds, o), b = __shfl_up_sync(0xffffffffu, dq, o);
-            if (lane >= o) { ds += a; dq += b; }
+            for (int i = 0; i < 56; i++)
+                if (i & 7) acc[i] = __fadd_rn(acc[i], __int2float_rn((int)v[i]));      // jj = 0 is padding
         }
-        if (lane < FPM_NSHIFT && row0 + k < n_rows_total) {
-            rowS[(size_t)(row0 + k) * FPM_NSHIFT + lane] = (int32_t)s[k] + ds;
-            rowQ[(size_t)(row0 + k) * FPM_NSHIFT + lane] = (int32_t)q[k] + dq;
+        if (e0 + m < n_evals) {
+            float4* o = reinterpret_cast<float4*>(numer + (size_t)(e0 + m) * MM_N);
+#pragma unroll
+            for (int c = 0; c < 14; c++) o[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
+    } else {
+        // ===== window statistics: warps 6..9, thread = eval row m of the A tile =====
+        const int m = (warp - 6) * 32 + lane;
+        const int e = e0 + m;
+        const bool live = e < n_evals;
+        long long ts[FPM_NSHIFT], tq[FPM_NSHIFT];
+#pragma unroll
+        for (int c = 0; c < FPM_NSHIFT; c++) { ts[c] = 0; tq[c] = 0; }
+        fpm_mm_stats<false>(base_u32, bar0, m, lane, e, live, 0, rh, rh, tw, th, nk, rowS, rowQ, ts, tq);
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) { totS[(size_t)e * FPM_NSHIFT + c] = ts[c]; totQ[(size_t)e * FPM_NSHIFT + c] = tq[c]; }
         }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, MM_TMEM_COLS);
 }
 
 // pre-shifted template copies for the B operand: tsh[c][tr][x] = T[tr][x - c]  (0 outside the template)

@@ -264,6 +264,22 @@ class TemplateMatcher:
                                                     rowS.ctypes.data, rowQ.ctypes.data))
         return rowsum, rowS, rowQ
 
+    def dbgCorrFused(self, rois, tpl):
+        """fused tensor-core kernel: rois [ne, th+6, tw+6] u8 -> (numer [ne, 7, 7] f32, winS [ne, 7, 7] i64, winQ)"""
+        r = np.ascontiguousarray(np.asarray(rois, np.uint8))
+        t = np.ascontiguousarray(_as_u8_2d(tpl))
+        th, tw = t.shape
+        ne = r.shape[0]
+        assert r.shape == (ne, th + 6, tw + 6)
+        numer = np.zeros((ne, 7, 7), np.float32)
+        winS = np.zeros((ne, 7, 7), np.int64)
+        winQ = np.zeros((ne, 7, 7), np.int64)
+        edge = np.zeros((ne, th + 6, 7), np.int32)
+        self._check(self._lib.fpm_dbg_corr_fused(self._h, r.ctypes.data, ne, t.ctypes.data, tw, th, numer.ctypes.data,
+                                                 winS.ctypes.data, winQ.ctypes.data, edge.ctypes.data))
+        self.last_edge_rows = edge
+        return numer, winS, winQ
+
     def dbgTopScore(self, img) -> np.ndarray:
         s = np.ascontiguousarray(_as_u8_2d(img))
         lv = self.templateLevels()[-1]

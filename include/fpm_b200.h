@@ -46,7 +46,8 @@ enum fpm_param {
     FPM_PARAM_WORKSPACE_MB = 8,    /* refinement workspace budget per wave, default 4096 */
     FPM_PARAM_PROFILE = 9,         /* bracket every kernel launch with CUDA events (bench.py roofline) */
     FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
-    FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always */
+    FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always,
+                                      3 = like 1 but never the fused kernel (row dots to HBM, separate row sums), 4 = always fused */
     FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC result convention (MatchTool/MatchToolDlg.cpp:1085-1116): angle = -theta wrapped
                                       to [-180,180], results truncated to TargetNum, corners in double; default 0 = Qt port */
     /* MFC-only modes of the upstream dialog, off by default (the Qt TemplateMatcher has none of them) */
@@ -147,6 +148,11 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi /* (th+6)x(tw+6) */, con
                       int32_t* rowsum /* th*49 */, int32_t* rowS /* (th+6)*7 */, int32_t* rowQ /* (th+6)*7 */);
 int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois /* ne x (th+6)x(tw+6) */, int ne, const uint8_t* tpl, int tw, int th,
                           int32_t* rowsum /* ne*th*49 */, int32_t* rowS /* ne*(th+6)*7 */, int32_t* rowQ);
+/* fused tensor-core kernel: numer[ne*49] = float32 row-ordered accumulation of the row dots per (r,c) cell,
+ * winS/winQ[ne*49] = window sum / square sum of the ROI under the template at shift (r,c) */
+int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t* tpl, int tw, int th,
+                       float* numer, long long* winS, long long* winQ,
+                       int32_t* edge_rowS /* optional, ne*(th+6)*7: the stored first/last 6 rows, others -1 */);
 int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score /* (h-th+1)*(w-tw+1) */);
 int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw, int th, int block_mode,
                   double thresh, double max_overlap, int max_picks, double* picks /* max_picks*3: x,y,v */, int* n);
