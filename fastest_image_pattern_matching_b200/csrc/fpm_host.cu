@@ -404,8 +404,9 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     if (rc) return rc;
     rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
     if (rc) return rc;
-    // enough CTAs for ~2 waves of 148 SMs, at least 2 ROI rows per CTA
-    int chunks = std::max(1, (2 * 148 + m_tiles - 1) / m_tiles);
+    // at most 2 full waves of 148 SMs (one CTA per SM): a third, nearly empty wave would cost a whole CTA time;
+    // at least 2 ROI rows per CTA
+    int chunks = std::max(1, (2 * 148) / m_tiles);
     int rows_per_cta = std::max(2, (rh + chunks - 1) / chunks);
     chunks = (rh + rows_per_cta - 1) / rows_per_cta;
     if (!h->mma_attr_set) {                                  // per handle: the attribute is per device

@@ -1096,16 +1096,23 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                 rstride = FPM_NCELL;
             }
             float numf;
-            // loads are issued 16 at a time (independent), the additions stay in template-row order
+            // loads are issued 32 at a time (independent), the additions stay in template-row order
             if (use_chain) {
                 float acc = 0.0f;
                 int tr = 0;
-                for (; tr + 16 <= th; tr += 16) {
-                    int v[16];
+                for (; tr + 32 <= th; tr += 32) {
+                    int v[32];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) v[k] = rs[(size_t)(tr + k) * rstride];
+                    for (int k = 0; k < 32; k++) v[k] = rs[(size_t)(tr + k) * rstride];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
+                    for (int k = 0; k < 32; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
+                }
+                for (; tr + 8 <= th; tr += 8) {
+                    int v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = rs[(size_t)(tr + k) * rstride];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
                 }
                 for (; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * rstride]));
                 numf = acc;
