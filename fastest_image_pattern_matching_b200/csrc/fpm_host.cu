@@ -139,7 +139,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
-    bool mma_attr_set = false, fused_attr_set = false;
+    bool mma_attr_set = false, fused_attr_set = false, peaks_attr_set = false;
     int stop_layer1 = 0, bitwise_not = 0, tol_range = 0;   // MFC-only modes (MatchTool/MatchToolDlg.cpp:788-816, :936)
     double tol_r[4] = {0, 0, 0, 0};
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
@@ -306,6 +306,21 @@ inline size_t top_score_smem(int tw, int th)
 inline int level_vec_ok(const FpmLevel& L)
 {
     return ((reinterpret_cast<uintptr_t>(L.ptr) & 3) == 0) && (L.pitch % 4 == 0) && (L.img_stride % 4 == 0);
+}
+
+// room for the peak kernel's block table in shared memory (value + location per block); 0 = keep it in global scratch
+int peaks_smem_blocks(fpm_handle* h, int blk_stride)
+{
+    const int cap = 16384;                                   // 128 KB of dynamic shared memory next to the 24 KB static
+    if (blk_stride > cap) return 0;
+    if (!h->peaks_attr_set) {
+        if (cudaFuncSetAttribute(fpm_top_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8) != cudaSuccess) {
+            h->err = "cudaFuncSetAttribute(fpm_top_peaks_kernel) failed";
+            return -1;
+        }
+        h->peaks_attr_set = true;
+    }
+    return blk_stride;
 }
 
 // ---- tensor-core correlation (fpm_mma.cuh): TMA descriptors + launch -----------------------
@@ -639,11 +654,13 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         CK(h->d_blkl.ensure((size_t)njobs * blk_stride * sizeof(int)));
         double thresh = h->score;
         for (int l = 0; l < top; l++) thresh *= 0.9;          // vecLayerScore, :153-156
+        const int smem_blocks = peaks_smem_blocks(h, blk_stride);
+        if (smem_blocks < 0) return FPM_ERR_CUDA;
         KL(K_TOP_PEAKS, 4.0 * njobs * maxRW * maxRH,
-           fpm_top_peaks_kernel<<<njobs, (maxRW * maxRH <= 16384) ? 128 : PK_THREADS, 0, h->stream>>>(
+           fpm_top_peaks_kernel<<<njobs, (maxRW * maxRH <= 16384) ? 128 : PK_THREADS, (size_t)smem_blocks * 8, h->stream>>>(
                h->d_jobs_top.as<FpmWarpJob>(), h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
                h->d_blkv.as<float>(), h->d_blkl.as<int>(), blk_stride, thresh, h->max_overlap, max_picks,
-               h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>()));
+               h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), smem_blocks));
     }
     return FPM_OK;
 }
@@ -1551,8 +1568,11 @@ int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw,
     int* bl = reinterpret_cast<int*>(bv + blk_stride);
     FpmPick* dp = h->d_dbg[3].as<FpmPick>();
     int* dn = reinterpret_cast<int*>(dp + max_picks);
-    fpm_top_peaks_kernel<<<1, PK_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<float>(), sp, 0, tw, th,
-                                                          block_mode, tile, bv, bl, blk_stride, thresh, max_overlap, max_picks, dp, dn);
+    const int smem_blocks = peaks_smem_blocks(h, blk_stride);
+    if (smem_blocks < 0) return FPM_ERR_CUDA;
+    fpm_top_peaks_kernel<<<1, PK_THREADS, (size_t)smem_blocks * 8, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<float>(), sp, 0, tw, th,
+                                                                              block_mode, tile, bv, bl, blk_stride, thresh, max_overlap,
+                                                                              max_picks, dp, dn, smem_blocks);
     CKL();
     std::vector<FpmPick> hp(max_picks);
     int hn = 0;

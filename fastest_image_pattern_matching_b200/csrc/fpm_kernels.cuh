@@ -469,16 +469,25 @@ __device__ __forceinline__ void fpm_block_rect(const FpmBlockGeom& g, int k, int
     x = g.ncol * g.bw; y = g.nrow * g.bh; w = cols - x; h = rows - y;
 }
 
-// warp-cooperative scan of one block: max value, first location in row-major order
+// warp-cooperative scan of one block: max value, first location in row-major order.  The picks are a
+// latency chain (one CTA per map, hundreds of sequential picks), so the loads of a batch of 8 x 32 elements
+// are all issued before the first comparison.
 __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, int pitch, int x, int y,
                                                int w, int h, int lane, float& bv, int& bx, int& by)
 {
     float best = -INFINITY; int bidx = 0x7fffffff;
-    int n = w * h;
-    for (int i = lane; i < n; i += 32) {
-        int yy = i / w, xx = i - yy * w;
-        float v = map[(size_t)(y + yy) * pitch + x + xx];
-        if (v > best) { best = v; bidx = i; }
+    const int n = w * h;
+    for (int i0 = lane; i0 < n; i0 += 256) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + 32 * k;
+            const int yy = i / w, xx = i - yy * w;
+            v[k] = (i < n) ? map[(size_t)(y + yy) * pitch + x + xx] : -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (v[k] > best) { best = v[k]; bidx = i0 + 32 * k; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -522,7 +531,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                      size_t score_job_stride, int tw, int th, int mode, int tile,
                      float* __restrict__ blk_val, int* __restrict__ blk_loc, int blk_stride,
                      double thresh, double max_overlap, int max_picks,
-                     FpmPick* __restrict__ picks, int* __restrict__ pick_count)
+                     FpmPick* __restrict__ picks, int* __restrict__ pick_count, int smem_blocks)
 {
     const int job = blockIdx.x;
     const FpmWarpJob& jb = jobs[job];
@@ -530,9 +539,12 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     if (!jb.valid || cols <= 0 || rows <= 0) { if (tid == 0) pick_count[job] = 0; return; }
     float* __restrict__ map = score + (size_t)job * score_job_stride;
-    float* bval = blk_val + (size_t)job * blk_stride;
-    int* bloc = blk_loc + (size_t)job * blk_stride;
     const FpmBlockGeom g = fpm_block_geom(mode, cols, rows, mode ? tw : tile, mode ? th : tile);
+    // block table: in shared memory when the launch reserved room for it (smem_blocks), else in global scratch
+    extern __shared__ float pk_dyn[];
+    const bool tbl_smem = g.nblocks <= smem_blocks;
+    float* bval = tbl_smem ? pk_dyn : blk_val + (size_t)job * blk_stride;
+    int* bloc = tbl_smem ? reinterpret_cast<int*>(pk_dyn + smem_blocks) : blk_loc + (size_t)job * blk_stride;
     const int regular = g.ncol * g.nrow;
     const int nsup = (g.nblocks + 31) >> 5;
     __shared__ float s_sv[PK_SUP_MAX];
@@ -1252,6 +1264,16 @@ __device__ __forceinline__ void fpm_corners(double ptx, double pty, double angle
 
 #define FN_THREADS 256
 
+// two rotated rects whose centres are farther apart than the sum of their half diagonals (plus a margin that
+// dwarfs float rounding) cannot touch: rotatedRectangleIntersection would return INTERSECT_NONE -> keep both
+__device__ __forceinline__ bool fpm_rrect_far(const FpmRRect& a, const FpmRRect& b)
+{
+    const float dx = a.cx - b.cx, dy = a.cy - b.cy;
+    const float ra = 0.5f * sqrtf(a.w * a.w + a.h * a.h), rb = 0.5f * sqrtf(b.w * b.w + b.h * b.h);
+    const float lim = (ra + rb) * 1.001f + 1.0f;
+    return dx * dx + dy * dy > lim * lim;
+}
+
 __global__ void __launch_bounds__(FN_THREADS)
 fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__ refined_count,
                  double score_thresh, double max_overlap, int nms_w, int nms_h, int tpl_w, int tpl_h,
@@ -1308,62 +1330,75 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
         unsigned char* ov = pair_scratch + (size_t)img * pair_cap * pair_cap;
         for (int p = tid; p < m * m; p += FN_THREADS) {
             int i = p / m, k = p - i * m;
-            if (k > i) ov[p] = (unsigned char)fpm_rrect_overlap_decision(rects[i], rects[k], max_overlap, nullptr, nullptr);
+            if (k > i)
+                ov[p] = fpm_rrect_far(rects[i], rects[k])
+                            ? (unsigned char)0
+                            : (unsigned char)fpm_rrect_overlap_decision(rects[i], rects[k], max_overlap, nullptr, nullptr);
         }
         __syncthreads();
-        for (int i = 0; i < m - 1; i++) {
-            if (!del[i])
-                for (int k = i + 1 + tid; k < m; k += FN_THREADS)
-                    if (ov[i * m + k]) del[k] = 1;
-            __syncthreads();
+        // greedy pass by one warp: no CTA-wide barrier per survivor
+        if (tid < 32) {
+            for (int i = 0; i < m - 1; i++) {
+                if (!del[i])
+                    for (int k = i + 1 + tid; k < m; k += 32)
+                        if (ov[i * m + k]) del[k] = 1;
+                __syncwarp();
+            }
         }
+        __syncthreads();
     } else {
         for (int i = 0; i < m - 1; i++) {
             if (!del[i]) {
                 const FpmRRect ri = rects[i];
                 for (int k = i + 1 + tid; k < m; k += FN_THREADS)
-                    if (!del[k] && fpm_rrect_overlap_decision(ri, rects[k], max_overlap, nullptr, nullptr)) del[k] = 1;
+                    if (!del[k] && !fpm_rrect_far(ri, rects[k]) &&
+                        fpm_rrect_overlap_decision(ri, rects[k], max_overlap, nullptr, nullptr))
+                        del[k] = 1;
             }
             __syncthreads();
         }
     }
+    // survivor ranks by one thread (idmap is free again: rank of record i, or -1), conversion by all threads
     if (tid == 0) {
         int cnt = 0;
         for (int i = 0; i < m; i++) {
-            if (del[i]) continue;
-            if (cnt < result_cap) {
-                const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
-                FpmResultDev o;
-                o.score = r.score;
-                if (!mfc_compat) {
-                    // Qt TemplateMatcher conversion (src/TemplateMatcher.cpp:407-432): float corner math
-                    float lt[2], rt[2], lb[2], rb[2];
-                    fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
-                    o.angle = r.angle;
-                    o.cx = (double)((lt[0] + rt[0] + lb[0] + rb[0]) / 4.0f);
-                    o.cy = (double)((lt[1] + rt[1] + lb[1] + rb[1]) / 4.0f);
-                    o.ltx = lt[0]; o.lty = lt[1]; o.rtx = rt[0]; o.rty = rt[1];
-                    o.rbx = rb[0]; o.rby = rb[1]; o.lbx = lb[0]; o.lby = lb[1];
-                } else {
-                    // MFC CMatchToolDlg conversion (MatchTool/MatchToolDlg.cpp:1085-1099): double corner math,
-                    // angle negated and wrapped to [-180, 180]
-                    const double a = -r.angle * FPM_D2R, c = cos(a), sn = sin(a);
-                    o.ltx = r.ptx; o.lty = r.pty;
-                    o.rtx = o.ltx + tpl_w * c; o.rty = o.lty - tpl_w * sn;
-                    o.lbx = o.ltx + tpl_h * sn; o.lby = o.lty + tpl_h * c;
-                    o.rbx = o.rtx + tpl_h * sn; o.rby = o.rty + tpl_h * c;
-                    o.cx = (o.ltx + o.rtx + o.rbx + o.lbx) / 4;
-                    o.cy = (o.lty + o.rty + o.rby + o.lby) / 4;
-                    double ang = -r.angle;
-                    if (ang < -180) ang += 360;
-                    if (ang > 180) ang -= 360;
-                    o.angle = ang;
-                }
-                results[(size_t)img * result_cap + cnt] = o;
-            }
-            cnt++;
-            if (mfc_compat && cnt == max_pos) break;          // MatchToolDlg.cpp:1115-1116
+            const bool keep = !del[i] && !(mfc_compat && cnt >= max_pos);     // MatchToolDlg.cpp:1115-1116
+            idmap[i] = keep ? cnt : -1;
+            if (keep) cnt++;
         }
         result_count[img] = cnt;
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += FN_THREADS) {
+        const int rank = idmap[i];
+        if (rank < 0 || rank >= result_cap) continue;
+        const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
+        FpmResultDev o;
+        o.score = r.score;
+        if (!mfc_compat) {
+            // Qt TemplateMatcher conversion (src/TemplateMatcher.cpp:407-432): float corner math
+            float lt[2], rt[2], lb[2], rb[2];
+            fpm_corners(r.ptx, r.pty, r.angle, tpl_w, tpl_h, lt, rt, lb, rb);
+            o.angle = r.angle;
+            o.cx = (double)((lt[0] + rt[0] + lb[0] + rb[0]) / 4.0f);
+            o.cy = (double)((lt[1] + rt[1] + lb[1] + rb[1]) / 4.0f);
+            o.ltx = lt[0]; o.lty = lt[1]; o.rtx = rt[0]; o.rty = rt[1];
+            o.rbx = rb[0]; o.rby = rb[1]; o.lbx = lb[0]; o.lby = lb[1];
+        } else {
+            // MFC CMatchToolDlg conversion (MatchTool/MatchToolDlg.cpp:1085-1099): double corner math,
+            // angle negated and wrapped to [-180, 180]
+            const double a = -r.angle * FPM_D2R, c = cos(a), sn = sin(a);
+            o.ltx = r.ptx; o.lty = r.pty;
+            o.rtx = o.ltx + tpl_w * c; o.rty = o.lty - tpl_w * sn;
+            o.lbx = o.ltx + tpl_h * sn; o.lby = o.lty + tpl_h * c;
+            o.rbx = o.rtx + tpl_h * sn; o.rby = o.rty + tpl_h * c;
+            o.cx = (o.ltx + o.rtx + o.rbx + o.lbx) / 4;
+            o.cy = (o.lty + o.rty + o.rby + o.lby) / 4;
+            double ang = -r.angle;
+            if (ang < -180) ang += 360;
+            if (ang > 180) ang -= 360;
+            o.angle = ang;
+        }
+        results[(size_t)img * result_cap + rank] = o;
     }
 }
