@@ -469,24 +469,46 @@ __device__ __forceinline__ void fpm_block_rect(const FpmBlockGeom& g, int k, int
     x = g.ncol * g.bw; y = g.nrow * g.bh; w = cols - x; h = rows - y;
 }
 
-// warp-cooperative scan of one block: max value, first location in row-major order.  The picks are a
-// latency chain (one CTA per map, hundreds of sequential picks), so the loads of a batch of 8 x 32 elements
-// are all issued before the first comparison.
+// n / d for 0 <= n, n * d < 2^32, through one multiply-high (the pick loop is a latency chain: no IDIV on it)
+struct FpmFastDiv { uint32_t m; int d; };
+__device__ __forceinline__ FpmFastDiv fpm_fastdiv_make(int d)
+{
+    FpmFastDiv f; f.d = d;
+    f.m = d > 1 ? (uint32_t)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u;
+    return f;
+}
+__device__ __forceinline__ int fpm_fastdiv(int n, const FpmFastDiv& f) { return f.d > 1 ? (int)__umulhi((uint32_t)n, f.m) : n; }
+
+// per-lane walk over a w-wide block in steps of 32 elements: start (yy0, xx0) and step (q, r) with one carry;
+// dv.m != 0: multiply-high division by w is available (the regular block width), else a plain division is used
+struct FpmScanStep { int w, q, r, yy0, xx0; FpmFastDiv dv; };
+__device__ __forceinline__ FpmScanStep fpm_scan_step(int w, int lane, bool with_fastdiv)
+{
+    FpmScanStep s; s.w = w; s.q = 32 / w; s.r = 32 - s.q * w; s.yy0 = lane / w; s.xx0 = lane - s.yy0 * w;
+    if (with_fastdiv) s.dv = fpm_fastdiv_make(w); else { s.dv.m = 0; s.dv.d = w; }
+    return s;
+}
+
+// warp-cooperative scan of one block: max value, first location in row-major order.  The picks are a latency
+// chain (one CTA per map, hundreds of sequential picks), so the loads of a batch of NB x 32 elements are all
+// issued before the first comparison and nothing divides per element.
+template <int NB>
 __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, int pitch, int x, int y,
-                                               int w, int h, int lane, float& bv, int& bx, int& by)
+                                               int w, int h, int lane, const FpmScanStep& st, float& bv, int& bx, int& by)
 {
     float best = -INFINITY; int bidx = 0x7fffffff;
     const int n = w * h;
-    for (int i0 = lane; i0 < n; i0 += 256) {
-        float v[8];
+    int yy = st.yy0, xx = st.xx0;
+    for (int i0 = lane; i0 < n; i0 += 32 * NB) {
+        float v[NB];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int i = i0 + 32 * k;
-            const int yy = i / w, xx = i - yy * w;
-            v[k] = (i < n) ? map[(size_t)(y + yy) * pitch + x + xx] : -INFINITY;
+        for (int k = 0; k < NB; k++) {
+            v[k] = (i0 + 32 * k < n) ? map[(size_t)(y + yy) * pitch + x + xx] : -INFINITY;
+            xx += st.r; yy += st.q;
+            if (xx >= w) { xx -= w; yy++; }
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++)
+        for (int k = 0; k < NB; k++)
             if (v[k] > best) { best = v[k]; bidx = i0 + 32 * k; }
     }
 #pragma unroll
@@ -497,7 +519,8 @@ __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, in
     }
     bv = best;
     if (bidx == 0x7fffffff) bidx = 0;
-    by = y + bidx / w; bx = x + (bidx - (bidx / w) * w);
+    const int byy = st.dv.m ? fpm_fastdiv(bidx, st.dv) : bidx / w;
+    by = y + byy; bx = x + (bidx - byy * w);
 }
 
 #define PK_THREADS 512
@@ -505,7 +528,7 @@ __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, in
 
 // (value, block index, location) ordering of the greedy pick: larger value first; ties go to the
 // first block in table order (s_BlockMax::GetMaxValueLoc, mode 1) or to the first location in scan
-// order (cv::minMaxLoc, mode 0)
+// order (cv::minMaxLoc, mode 0).  Locations are packed (y << 16 | x): same order as y * cols + x.
 __device__ __forceinline__ bool fpm_pick_better(int mode, float v, int k, int l, float bv, int bk, int bl)
 {
     return (v > bv) || (v == bv && (mode ? (k < bk) : (l < bl)));
@@ -522,10 +545,10 @@ __device__ __forceinline__ void fpm_pick_warp_reduce(int mode, float& v, int& k,
     }
 }
 
-// Greedy peak picking of one score map by one CTA.  Two-level maximum table: per block (global
-// scratch) and per 32 consecutive blocks (shared).  A pick repaints a rectangle, rescans only the
-// blocks that rectangle touches (found by index arithmetic, not by testing every block), refreshes
-// their super-entries and takes the argmax over the super-table with one warp.
+// Greedy peak picking of one score map by one CTA.  Two-level maximum table: per block (shared memory, or
+// global scratch for very large maps) and per 32 consecutive blocks (shared).  A pick repaints a rectangle,
+// rescans only the blocks that rectangle touches (found by index arithmetic, not by testing every block),
+// refreshes their super-entries and takes the argmax over the super-table with one warp.
 __global__ void __launch_bounds__(PK_THREADS)
 fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ score, int spitch,
                      size_t score_job_stride, int tw, int th, int mode, int tile,
@@ -547,16 +570,24 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     int* bloc = tbl_smem ? reinterpret_cast<int*>(pk_dyn + smem_blocks) : blk_loc + (size_t)job * blk_stride;
     const int regular = g.ncol * g.nrow;
     const int nsup = (g.nblocks + 31) >> 5;
+    const FpmFastDiv div_bw = fpm_fastdiv_make(g.bw), div_bh = fpm_fastdiv_make(g.bh);
+    const FpmScanStep step_reg = fpm_scan_step(g.bw, lane, true);  // full-width blocks share one walk
     __shared__ float s_sv[PK_SUP_MAX];
     __shared__ int s_sk[PK_SUP_MAX], s_sl[PK_SUP_MAX];
     __shared__ float s_best_v;
     __shared__ int s_best_loc;
 
+    auto scan_to_table = [&](int k, int x, int y, int w, int h) {
+        float v; int bx, by;
+        const FpmScanStep st = (w == g.bw) ? step_reg : fpm_scan_step(w, lane, false);
+        if (w * h <= 64) fpm_scan_block<2>(map, spitch, x, y, w, h, lane, st, v, bx, by);   // small tiles (mode 0)
+        else fpm_scan_block<8>(map, spitch, x, y, w, h, lane, st, v, bx, by);
+        if (lane == 0) { bval[k] = v; bloc[k] = (by << 16) | bx; }
+    };
     for (int k = warp; k < g.nblocks; k += nwarps) {
-        int x, y, w, h; float v; int bx, by;
+        int x, y, w, h;
         fpm_block_rect(g, k, cols, rows, x, y, w, h);
-        fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
-        if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
+        scan_to_table(k, x, y, w, h);
     }
     __syncthreads();
     auto refresh_sup = [&](int s) {
@@ -569,27 +600,27 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     for (int s = warp; s < nsup; s += nwarps) refresh_sup(s);
     __syncthreads();
 
+    // getNextMaxLoc's rectangle (:1184-1222): constant size, origin follows the last pick
+    const double off_x = (double)tw * (1 - max_overlap), off_y = (double)th * (1 - max_overlap);
+    const int rw = (int)(2 * (double)tw * (1 - max_overlap));
+    const int rh = (int)(2 * (double)th * (1 - max_overlap));
+    const int RX = g.ncol * g.bw, RY = g.nrow * g.bh;
     int npicks = 0;
     int lastx = 0, lasty = 0;
     for (int it = 0; it < max_picks; it++) {
         if (it > 0) {
-            // getNextMaxLoc: paint the suppression rectangle, refresh the touched blocks
-            int sx = (int)((double)lastx - (double)tw * (1 - max_overlap));
-            int sy = (int)((double)lasty - (double)th * (1 - max_overlap));
-            int rw = (int)(2 * (double)tw * (1 - max_overlap));
-            int rh = (int)(2 * (double)th * (1 - max_overlap));
-            int px0 = max(sx, 0), py0 = max(sy, 0), px1 = min(sx + rw, cols), py1 = min(sy + rh, rows);
-            int pw = px1 - px0, ph = py1 - py0;
+            // paint the suppression rectangle, refresh the touched blocks
+            const int sx = (int)((double)lastx - off_x);
+            const int sy = (int)((double)lasty - off_y);
+            const int px0 = max(sx, 0), py0 = max(sy, 0), px1 = min(sx + rw, cols), py1 = min(sy + rh, rows);
+            const int pw = px1 - px0, ph = py1 - py0;
             if (rw > 0 && rh > 0 && pw > 0 && ph > 0) {
-                for (int i = tid; i < pw * ph; i += nthreads) {
-                    int yy = i / pw, xx = i - yy * pw;
-                    map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
-                }
+                for (int yy = warp; yy < ph; yy += nwarps)
+                    for (int xx = lane; xx < pw; xx += 32) map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
                 __syncthreads();
                 // blocks of the regular grid under the rectangle, plus the strips of mode 1
-                const int RX = g.ncol * g.bw, RY = g.nrow * g.bh;
-                int bx0 = px0 / g.bw, bx1 = min((px1 - 1) / g.bw, g.ncol - 1);
-                int by0 = py0 / g.bh, by1 = min((py1 - 1) / g.bh, g.nrow - 1);
+                const int bx0 = fpm_fastdiv(px0, div_bw), bx1 = min(fpm_fastdiv(px1 - 1, div_bw), g.ncol - 1);
+                const int by0 = fpm_fastdiv(py0, div_bh), by1 = min(fpm_fastdiv(py1 - 1, div_bh), g.nrow - 1);
                 int nbx = max(bx1 - bx0 + 1, 0), nby = max(by1 - by0 + 1, 0);
                 if (nbx == 0 || nby == 0) nbx = nby = 0;
                 const int nreg = nbx * nby;
@@ -597,18 +628,22 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                 const int hit_bottom = g.has_bottom && py1 > RY && px0 < RX;
                 const int hit_corner = g.has_corner && px1 > RX && py1 > RY;
                 for (int idx = warp; idx < nreg + 3; idx += nwarps) {
-                    int k;
-                    if (idx < nreg) { int r = idx / nbx; k = (by0 + r) * g.ncol + bx0 + (idx - r * nbx); }
-                    else {
-                        int e = idx - nreg;
+                    if (idx < nreg) {
+                        int r = 0, c = idx;
+                        while (c >= nbx) { c -= nbx; r++; }
+                        const int gx = bx0 + c, gy = by0 + r;
+                        const int x = gx * g.bw, y = gy * g.bh;
+                        scan_to_table(gy * g.ncol + gx, x, y, min(g.bw, cols - x), min(g.bh, rows - y));
+                    } else {
+                        const int e = idx - nreg;
+                        int k;
                         if (e == 0) { if (!hit_right) continue; k = regular; }
                         else if (e == 1) { if (!hit_bottom) continue; k = regular + g.has_right; }
                         else { if (!hit_corner) continue; k = regular + g.has_right + g.has_bottom; }
+                        int x, y, w, h;
+                        fpm_block_rect(g, k, cols, rows, x, y, w, h);
+                        scan_to_table(k, x, y, w, h);
                     }
-                    int x, y, w, h; float v; int bx, by;
-                    fpm_block_rect(g, k, cols, rows, x, y, w, h);
-                    fpm_scan_block(map, spitch, x, y, w, h, lane, v, bx, by);
-                    if (lane == 0) { bval[k] = v; bloc[k] = by * cols + bx; }
                 }
                 __syncthreads();
                 // super-entries over the touched block runs (a run of nbx blocks per grid row)
@@ -616,12 +651,13 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                 for (int idx = warp; idx < nby * span + 3; idx += nwarps) {
                     int s;
                     if (idx < nby * span) {
-                        int r = idx / span, j = idx - r * span;
-                        int k0 = (by0 + r) * g.ncol + bx0;
+                        int r = 0, j = idx;
+                        while (j >= span) { j -= span; r++; }
+                        const int k0 = (by0 + r) * g.ncol + bx0;
                         s = (k0 >> 5) + j;
                         if (s > ((k0 + nbx - 1) >> 5)) continue;
                     } else {
-                        int k = regular + (idx - nby * span);
+                        const int k = regular + (idx - nby * span);
                         if (k >= g.nblocks) continue;
                         s = k >> 5;
                     }
@@ -642,10 +678,10 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
             }
         }
         __syncthreads();
-        float v = s_best_v; int loc = s_best_loc;
+        const float v = s_best_v; const int loc = s_best_loc;
         __syncthreads();
         if ((double)v < thresh) break;
-        lastx = loc >= 0 ? loc % cols : -1; lasty = loc >= 0 ? loc / cols : -1;
+        lastx = loc >= 0 ? (loc & 0xffff) : -1; lasty = loc >= 0 ? (loc >> 16) : -1;
         if (tid == 0) { FpmPick p; p.x = lastx; p.y = lasty; p.v = v; picks[(size_t)job * max_picks + npicks] = p; }
         npicks++;
     }
