@@ -300,7 +300,7 @@ CorrCfg corr_config(int tpl_h)
 inline size_t top_score_smem(int tw, int th)
 {
     size_t nwt = (tw + 3) / 4, pww = TS_TW / 4 + nwt + 1;
-    return 4 * ((size_t)th * nwt + (size_t)(TS_TH + th - 1) * pww);
+    return 4 * ((size_t)th * nwt + (size_t)(TS_TH + th - 1) * (pww + 2 * TS_TW)) + 16;   // template, patch, row-window sums
 }
 
 inline int level_vec_ok(const FpmLevel& L)

@@ -381,6 +381,36 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
         s_p[i] = v;
     }
     __syncthreads();
+    const int tail = tw & 3;
+    const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
+    // Row-window sums of the patch, once per CTA: s_rs/s_rq[yy][x] = sum_{j<tw} P[yy][x+j] (^2).  Every score row
+    // that covers patch row yy reuses them, so the main loop only multiplies by the template (the zero padding of
+    // the template's last word masks the patch bytes beyond tw there).
+    uint32_t* s_rs = s_t + ((th * nwt + ph * pww + 3) & ~3);   // ph * TS_TW, 16-byte aligned
+    uint32_t* s_rq = s_rs + ph * TS_TW;
+    if (!tpl.result_equal1) {
+        for (int i = tid; i < ph * (TS_TW / 4); i += TS_THREADS) {
+            const int yy = i / (TS_TW / 4), xq = i - yy * (TS_TW / 4);
+            const uint32_t* prow = s_p + yy * pww + xq;
+            uint32_t b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+            uint32_t lo = prow[0];
+            for (int xw = 0; xw < nwt; xw++) {
+                const uint32_t hi = prow[xw + 1];
+                const uint32_t m = (xw == nwt - 1) ? tailbm : 0xffffffffu;
+                uint32_t p[4];
+                p[0] = lo & m;
+                p[1] = __funnelshift_r(lo, hi, 8) & m;
+                p[2] = __funnelshift_r(lo, hi, 16) & m;
+                p[3] = __funnelshift_r(lo, hi, 24) & m;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { b[k] = __dp4a(p[k], 0x01010101u, b[k]); c[k] = __dp4a(p[k], p[k], c[k]); }
+                lo = hi;
+            }
+            *reinterpret_cast<uint4*>(s_rs + yy * TS_TW + 4 * xq) = make_uint4(b[0], b[1], b[2], b[3]);
+            *reinterpret_cast<uint4*>(s_rq + yy * TS_TW + 4 * xq) = make_uint4(c[0], c[1], c[2], c[3]);
+        }
+        __syncthreads();
+    }
     const int tx = tid & 15, ty = tid >> 4;
     const int ox = x0 + 4 * tx, oy = y0 + ty;
     if (ox >= RW || oy >= RH) return;
@@ -389,33 +419,26 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
         for (int k = 0; k < 4 && ox + k < RW; k++) out[k] = 1.0f;
         return;
     }
-    const int tail = tw & 3;
-    const uint32_t tailbm = tail ? (0xffffffffu >> (8 * (4 - tail))) : 0xffffffffu;
     long long num[4] = {0, 0, 0, 0}, wsum[4] = {0, 0, 0, 0}, wsq[4] = {0, 0, 0, 0};
     for (int yy = 0; yy < th; yy++) {
         const uint32_t* prow = s_p + (ty + yy) * pww + tx;
         const uint32_t* trow = s_t + yy * nwt;
-        uint32_t a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+        uint32_t a[4] = {0, 0, 0, 0};
         uint32_t lo = prow[0];
         for (int xw = 0; xw < nwt; xw++) {
             const uint32_t hi = prow[xw + 1];
-            const uint32_t t = trow[xw];
-            const uint32_t m = (xw == nwt - 1) ? tailbm : 0xffffffffu;
-            uint32_t p[4];
-            p[0] = lo & m;
-            p[1] = __funnelshift_r(lo, hi, 8) & m;
-            p[2] = __funnelshift_r(lo, hi, 16) & m;
-            p[3] = __funnelshift_r(lo, hi, 24) & m;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                a[k] = __dp4a(p[k], t, a[k]);
-                b[k] = __dp4a(p[k], 0x01010101u, b[k]);
-                c[k] = __dp4a(p[k], p[k], c[k]);
-            }
+            const uint32_t t = trow[xw];                   // bytes beyond tw are 0 in the staged template
+            a[0] = __dp4a(lo, t, a[0]);
+            a[1] = __dp4a(__funnelshift_r(lo, hi, 8), t, a[1]);
+            a[2] = __dp4a(__funnelshift_r(lo, hi, 16), t, a[2]);
+            a[3] = __dp4a(__funnelshift_r(lo, hi, 24), t, a[3]);
             lo = hi;
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) { num[k] += a[k]; wsum[k] += b[k]; wsq[k] += c[k]; }   // per-row s32, s64 across rows
+        const uint4 rs = *reinterpret_cast<const uint4*>(s_rs + (ty + yy) * TS_TW + 4 * tx);
+        const uint4 rq = *reinterpret_cast<const uint4*>(s_rq + (ty + yy) * TS_TW + 4 * tx);
+        num[0] += a[0]; num[1] += a[1]; num[2] += a[2]; num[3] += a[3];   // per-row s32, s64 across rows
+        wsum[0] += rs.x; wsum[1] += rs.y; wsum[2] += rs.z; wsum[3] += rs.w;
+        wsq[0] += rq.x; wsq[1] += rq.y; wsq[2] += rq.z; wsq[3] += rq.w;
     }
     // TM_CCORR result cell is a float32 (cv::matchTemplate output depth), here the rounded exact sum
     for (int k = 0; k < 4 && ox + k < RW; k++)
