@@ -210,6 +210,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-steps-only", action="store_true",
+                    help="run only warm-up + timed device-resident steps and exit (clean launch list for ncu; prints no bench line)")
     ap.add_argument("--cpu-images", type=int, default=0, help="images per worker for the CPU baseline (0 = auto)")
     ap.add_argument("--h2d-chunk", type=int, default=0, help="frames per H2D chunk of the e2e path (0 = library default)")
     args = ap.parse_args()
@@ -253,7 +255,7 @@ def main():
 
     # ---------------- CPU baseline first (before CUDA is initialised in this process) ----------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.device_steps_only:
         cores = host_cores()
         workers = cores
         per_worker = args.cpu_images or 8
@@ -357,6 +359,15 @@ def main():
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
             return float(tmax[0]), float(tmax[1]), int(tsum[2])
         return ms, wall_ms, launches
+
+    if args.device_steps_only:
+        for i in range(max(args.warmup, 1) + K):
+            step_device(i)
+        torch.cuda.synchronize()
+        sys.stderr.write("device-steps-only: %d steps of %d frames done\n" % (max(args.warmup, 1) + K, B))
+        if dist:
+            dist.destroy_process_group()
+        return 0
 
     # sanity: every frame must yield the 3 pasted targets
     step_device(0)
