@@ -642,12 +642,14 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         // bCalMaxByBlock, src/TemplateMatcher.cpp:158-159
         const FpmLevel& L = h->levels[top];
         bool by_block = ((L.w * L.h) / (t.w * t.h) > 500) && h->max_pos > 10;
-        int mode = by_block ? 1 : 0;
+        int mode = by_block ? (h->mfc_compat ? 2 : 1) : 0;    // MFC s_BlockMax differs from the Qt port's (MatchToolDlg.h:109-213)
         int tile = 8;
         while ((long long)((maxRW + tile - 1) / tile) * ((maxRH + tile - 1) / tile) > 1024 && tile < 256) tile *= 2;
         int blk_stride;
-        if (mode) blk_stride = (maxRW / t.w) * (maxRH / t.h) + 3;
-        else blk_stride = ((maxRW + tile - 1) / tile) * ((maxRH + tile - 1) / tile);
+        const int tiles0 = ((maxRW + tile - 1) / tile) * ((maxRH + tile - 1) / tile);
+        if (mode == 1) blk_stride = (maxRW / t.w) * (maxRH / t.h) + 3;
+        else if (mode == 2) blk_stride = std::max((maxRW / (2 * t.w)) * (maxRH / (2 * t.h)) + 2, tiles0);   // an empty MFC table falls back to tiles
+        else blk_stride = tiles0;
         blk_stride = std::max(blk_stride, 1);
         if (blk_stride > PK_SUP_MAX * 32) { h->err = "top-layer score map has too many blocks for the peak table"; return FPM_ERR_LIMIT; }
         CK(h->d_blkv.ensure((size_t)njobs * blk_stride * sizeof(float)));
@@ -1558,7 +1560,8 @@ int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw,
     jb.dw = cols + tw - 1; jb.dh = rows + th - 1; jb.valid = 1;
     int tile = 8;
     while ((long long)((cols + tile - 1) / tile) * ((rows + tile - 1) / tile) > 1024 && tile < 256) tile *= 2;
-    int blk_stride = block_mode ? (cols / tw) * (rows / th) + 3 : ((cols + tile - 1) / tile) * ((rows + tile - 1) / tile);
+    const int tiles0 = ((cols + tile - 1) / tile) * ((rows + tile - 1) / tile);
+    int blk_stride = block_mode == 1 ? (cols / tw) * (rows / th) + 3 : (block_mode == 2 ? std::max((cols / (2 * tw)) * (rows / (2 * th)) + 2, tiles0) : tiles0);
     if (blk_stride > PK_SUP_MAX * 32) { h->err = "score map has too many blocks for the peak table"; return FPM_ERR_LIMIT; }
     CK(h->d_dbg[1].ensure((size_t)blk_stride * 8));
     CK(h->d_dbg[3].ensure((size_t)max_picks * sizeof(FpmPick) + 16));

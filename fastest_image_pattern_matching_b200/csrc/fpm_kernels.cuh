@@ -456,22 +456,41 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
 // =====================================================================================
 struct FpmPick { int x, y; float v; };
 
-struct FpmBlockGeom { int mode, bw, bh, ncol, nrow, nblocks, has_right, has_bottom, has_corner; };
+struct FpmBlockGeom { int mode, bw, bh, ncol, nrow, nblocks, has_right, has_bottom, has_corner, bottom_w; };
 
-__device__ __forceinline__ FpmBlockGeom fpm_block_geom(int mode, int cols, int rows, int bw, int bh)
+// mode 0: plain tiles of `tile` x `tile` (whole-map minMaxLoc semantics); mode 1: Qt s_BlockMax
+// (DataStructures.h:150-211: template-sized blocks, right strip, bottom strip, corner); mode 2: MFC s_BlockMax
+// (MatchTool/MatchToolDlg.h:109-175: 2x template blocks, right strip when the width has a residue, bottom strip
+// over the regular columns when both have one, over the full width when only the height has one; no corner; an
+// empty table -- fewer than one block in a dimension -- falls back to the whole-map search, :196-200)
+__device__ __forceinline__ FpmBlockGeom fpm_block_geom(int mode, int cols, int rows, int tw, int th, int tile)
 {
     FpmBlockGeom g;
-    g.mode = mode; g.bw = bw; g.bh = bh;
+    if (mode == 2 && (cols / (2 * tw) == 0 || rows / (2 * th) == 0)) mode = 0;
+    g.mode = mode;
     if (mode == 0) {
-        g.ncol = (cols + bw - 1) / bw; g.nrow = (rows + bh - 1) / bh;
+        g.bw = g.bh = tile;
+        g.ncol = (cols + tile - 1) / tile; g.nrow = (rows + tile - 1) / tile;
         g.has_right = g.has_bottom = g.has_corner = 0;
+        g.bottom_w = 0;
         g.nblocks = g.ncol * g.nrow;
-    } else {
-        g.ncol = cols / bw; g.nrow = rows / bh;
-        g.has_right = g.ncol * bw < cols;
-        g.has_bottom = (g.nrow * bh < rows) && (g.ncol * bw > 0);
-        g.has_corner = (g.ncol * bw < cols) && (g.nrow * bh < rows);
+    } else if (mode == 1) {
+        g.bw = tw; g.bh = th;
+        g.ncol = cols / g.bw; g.nrow = rows / g.bh;
+        g.has_right = g.ncol * g.bw < cols;
+        g.has_bottom = (g.nrow * g.bh < rows) && (g.ncol * g.bw > 0);
+        g.has_corner = (g.ncol * g.bw < cols) && (g.nrow * g.bh < rows);
+        g.bottom_w = g.ncol * g.bw;
         g.nblocks = g.ncol * g.nrow + g.has_right + g.has_bottom + g.has_corner;
+    } else {
+        g.bw = 2 * tw; g.bh = 2 * th;
+        g.ncol = cols / g.bw; g.nrow = rows / g.bh;
+        const int hres = g.ncol * g.bw < cols, vres = g.nrow * g.bh < rows;
+        g.has_right = hres;
+        g.has_bottom = vres;                     // (the upstream else-branch would scan an empty Mat when !vres: absent here)
+        g.has_corner = 0;
+        g.bottom_w = (hres && vres) ? g.ncol * g.bw : cols;
+        g.nblocks = g.ncol * g.nrow + g.has_right + g.has_bottom;
     }
     return g;
 }
@@ -488,7 +507,7 @@ __device__ __forceinline__ void fpm_block_rect(const FpmBlockGeom& g, int k, int
     }
     k -= regular;
     if (g.has_right) { if (k == 0) { x = g.ncol * g.bw; y = 0; w = cols - x; h = rows; return; } k--; }
-    if (g.has_bottom) { if (k == 0) { x = 0; y = g.nrow * g.bh; w = g.ncol * g.bw; h = rows - y; return; } k--; }
+    if (g.has_bottom) { if (k == 0) { x = 0; y = g.nrow * g.bh; w = g.bottom_w; h = rows - y; return; } k--; }
     x = g.ncol * g.bw; y = g.nrow * g.bh; w = cols - x; h = rows - y;
 }
 
@@ -554,7 +573,8 @@ __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, in
 // order (cv::minMaxLoc, mode 0).  Locations are packed (y << 16 | x): same order as y * cols + x.
 __device__ __forceinline__ bool fpm_pick_better(int mode, float v, int k, int l, float bv, int bk, int bl)
 {
-    return (v > bv) || (v == bv && (mode ? (k < bk) : (l < bl)));
+    // MFC GetMaxValueLoc (MatchToolDlg.h:202-212) keeps the LAST maximal block (>=)
+    return (v > bv) || (v == bv && (mode == 0 ? (l < bl) : (mode == 1 ? (k < bk) : (k > bk && k != 0x7fffffff))));
 }
 
 __device__ __forceinline__ void fpm_pick_warp_reduce(int mode, float& v, int& k, int& l)
@@ -585,7 +605,8 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     if (!jb.valid || cols <= 0 || rows <= 0) { if (tid == 0) pick_count[job] = 0; return; }
     float* __restrict__ map = score + (size_t)job * score_job_stride;
-    const FpmBlockGeom g = fpm_block_geom(mode, cols, rows, mode ? tw : tile, mode ? th : tile);
+    const FpmBlockGeom g = fpm_block_geom(mode, cols, rows, tw, th, tile);
+    mode = g.mode;                                                // MFC tables that come out empty use the plain search
     // block table: in shared memory when the launch reserved room for it (smem_blocks), else in global scratch
     extern __shared__ float pk_dyn[];
     const bool tbl_smem = g.nblocks <= smem_blocks;
@@ -648,7 +669,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                 if (nbx == 0 || nby == 0) nbx = nby = 0;
                 const int nreg = nbx * nby;
                 const int hit_right = g.has_right && px1 > RX;
-                const int hit_bottom = g.has_bottom && py1 > RY && px0 < RX;
+                const int hit_bottom = g.has_bottom && py1 > RY && px0 < g.bottom_w;
                 const int hit_corner = g.has_corner && px1 > RX && py1 > RY;
                 for (int idx = warp; idx < nreg + 3; idx += nwarps) {
                     if (idx < nreg) {

@@ -48,8 +48,9 @@ enum fpm_param {
     FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
     FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always,
                                       3 = like 1 but never the fused kernel (row dots to HBM, separate row sums), 4 = always fused */
-    FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC result convention (MatchTool/MatchToolDlg.cpp:1085-1116): angle = -theta wrapped
-                                      to [-180,180], results truncated to TargetNum, corners in double; default 0 = Qt port */
+    FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC conventions: result (MatchTool/MatchToolDlg.cpp:1085-1116: angle = -theta wrapped
+                                      to [-180,180], results truncated to TargetNum, corners in double) and s_BlockMax
+                                      (MatchToolDlg.h:109-213: 2x template blocks, last maximal block wins); default 0 = Qt port */
     /* MFC-only modes of the upstream dialog, off by default (the Qt TemplateMatcher has none of them) */
     FPM_PARAM_STOP_LAYER1 = 13,    /* m_bStopLayer1 (MatchToolDlg.cpp:936): stop the descent at layer 1, coordinates x2 */
     FPM_PARAM_BITWISE_NOT = 14,    /* m_ckBitwiseNot (:788-794): match on 255 - source                                */
@@ -154,6 +155,7 @@ int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t
                        float* numer, long long* winS, long long* winQ,
                        int32_t* edge_rowS /* optional, ne*(th+6)*7: the stored first/last 6 rows, others -1 */);
 int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score /* (h-th+1)*(w-tw+1) */);
+/* block_mode: 0 = whole-map minMaxLoc, 1 = Qt s_BlockMax (DataStructures.h:150-245), 2 = MFC s_BlockMax (MatchToolDlg.h:109-213) */
 int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw, int th, int block_mode,
                   double thresh, double max_overlap, int max_picks, double* picks /* max_picks*3: x,y,v */, int* n);
 /* host-side (CPU) evaluation of the NMS pair decision -- geometry code shared with the device */

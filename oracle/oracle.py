@@ -326,6 +326,47 @@ class BlockMax:
         return best[4], best[5]
 
 
+class BlockMaxMFC(BlockMax):
+    """s_BlockMax of the upstream MFC dialog (MatchTool/MatchToolDlg.h:89-213): blocks of 2x the template size,
+    right strip when the width leaves a residue, bottom strip over the regular columns when both dimensions do and
+    over the full width otherwise, no corner block; GetMaxValueLoc keeps the LAST maximal block (>=, :206) and an
+    empty table (less than one block in a dimension) searches the whole map (:196-200)."""
+
+    def __init__(self, mat, size_tpl):
+        self.mat = mat
+        bw, bh = 2 * size_tpl[0], 2 * size_tpl[1]
+        rows, cols = mat.shape
+        ncol, nrow = cols // bw, rows // bh
+        self.blocks = []
+        if ncol == 0 or nrow == 0:
+            return
+
+        def add(x, y, w, h):
+            v, (mx, my) = _min_max_loc(mat[y:y + h, x:x + w])
+            self.blocks.append([x, y, w, h, v, (x + mx, y + my)])
+
+        for y in range(nrow):
+            for x in range(ncol):
+                add(x * bw, y * bh, bw, bh)
+        hres, vres = cols % bw != 0, rows % bh != 0
+        if hres and vres:
+            add(ncol * bw, 0, cols - ncol * bw, rows)
+            add(0, nrow * bh, ncol * bw, rows - nrow * bh)
+        elif hres:
+            add(ncol * bw, 0, cols - ncol * bw, rows)
+        elif vres:                      # upstream's else-branch; with no residue at all it would scan an empty Mat
+            add(0, nrow * bh, cols, rows - nrow * bh)
+
+    def get_max(self):
+        if not self.blocks:
+            return _min_max_loc(self.mat)
+        best = self.blocks[0]
+        for b in self.blocks[1:]:
+            if b[4] >= best[4]:
+                best = b
+        return best[4], best[5]
+
+
 def _trunc(v):
     return int(v)                       # C++ double -> int truncation toward zero
 
@@ -431,7 +472,7 @@ class OracleMatcher:
         """Returns [((x, y), value), ...]; `result` is painted in place like the reference does."""
         picks = []
         if cal_by_block:
-            bm = BlockMax(result, size_pat)
+            bm = BlockMaxMFC(result, size_pat) if self.mfc_compat else BlockMax(result, size_pat)
             val, loc = bm.get_max()
             if val < thresh:
                 return picks

@@ -169,6 +169,29 @@ def test_peaks_match_oracle(matcher, block, seed):
         assert (int(g[0]), int(g[1])) == loc and np.float32(g[2]) == np.float32(val)
 
 
+@pytest.mark.parametrize("shape", [(211, 300), (216, 288), (216, 300), (211, 288), (30, 300), (211, 17)])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_peaks_match_oracle_mfc_blocks(matcher, shape, seed):
+    """MFC s_BlockMax (MatchToolDlg.h:109-213): 2x template blocks, residue strips, last maximal block on ties,
+    whole-map search when the table is empty"""
+    rng = np.random.default_rng(100 + seed)
+    rows, cols = shape
+    score = rng.uniform(-0.2, 0.9, (rows, cols)).astype(np.float32)
+    score = cv2.GaussianBlur(score, (0, 0), 1.5)
+    for _ in range(12):
+        y, x = int(rng.integers(0, rows)), int(rng.integers(0, cols))
+        score[y, x] = 1.0
+    tw, th = 9, 9 if shape[0] == 216 else 7        # 216 = 12 * 18, 288 = 16 * 18: shapes without residue
+    om = O.OracleMatcher()
+    om.mfc_compat = True
+    om.max_pos, om.max_overlap = 20, 0.25 * seed
+    want = om.top_picks(score.copy(), (tw, th), 0.3, True)
+    got = matcher.dbgPeaks(score, tw, th, 2, 0.3, om.max_overlap, om.max_pos + 5)
+    assert len(got) == len(want)
+    for g, (loc, val) in zip(got, want):
+        assert (int(g[0]), int(g[1])) == loc and np.float32(g[2]) == np.float32(val)
+
+
 def test_peaks_nothing_above_threshold(matcher):
     score = np.full((20, 30), 0.1, np.float32)
     assert len(matcher.dbgPeaks(score, 5, 5, False, 0.5, 0.0, 10)) == 0
