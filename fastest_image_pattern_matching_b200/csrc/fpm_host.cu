@@ -14,10 +14,29 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-device state of a kernel, shared by every handle and host
+// thread (fpm_match_multi runs handles concurrently): the opt-in is only ever RAISED, under a lock, so one
+// thread can never shrink it below what another is about to launch with.
+cudaError_t ensure_dyn_smem(const void* func, int device, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> granted;
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = granted[std::make_pair(func, device)];
+    if (bytes <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 struct DevBuf {
     void* p = nullptr;
@@ -314,7 +333,7 @@ int peaks_smem_blocks(fpm_handle* h, int blk_stride)
     const int cap = 16384;                                   // 128 KB of dynamic shared memory next to the 24 KB static
     if (blk_stride > cap) return 0;
     if (!h->peaks_attr_set) {
-        if (cudaFuncSetAttribute(fpm_top_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8) != cudaSuccess) {
+        if (ensure_dyn_smem((const void*)fpm_top_peaks_kernel, h->device, (size_t)cap * 8) != cudaSuccess) {
             h->err = "cudaFuncSetAttribute(fpm_top_peaks_kernel) failed";
             return -1;
         }
@@ -330,16 +349,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 EncodeTiledFn get_encode_tiled()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised once, thread-safe (handles may run on several host threads)
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -395,7 +413,7 @@ int launch_corr_fused(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_
     rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
     if (rc) return rc;
     if (!h->fused_attr_set) {
-        CK(cudaFuncSetAttribute(fpm_corr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FM_SMEM_BYTES));
+        CK(ensure_dyn_smem((const void*)fpm_corr_fused_kernel, h->device, FM_SMEM_BYTES));
         h->fused_attr_set = true;
     }
     KL(K_CORR_FUSED, (double)ne * FPM_NCELL * (double)tw * th,
@@ -425,7 +443,7 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     int rows_per_cta = std::max(2, (rh + chunks - 1) / chunks);
     chunks = (rh + rows_per_cta - 1) / rows_per_cta;
     if (!h->mma_attr_set) {                                  // per handle: the attribute is per device
-        CK(cudaFuncSetAttribute(fpm_corr_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+        CK(ensure_dyn_smem((const void*)fpm_corr_mma_kernel, h->device, MM_SMEM_BYTES));
         h->mma_attr_set = true;
     }
     dim3 grid(chunks, m_tiles);
@@ -630,7 +648,7 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         size_t smem = top_score_smem(t.w, t.h);
         if (smem > 200 * 1024) { h->err = "top-layer template too large for the score kernel"; return FPM_ERR_LIMIT; }
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem));
         dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, njobs);
         dim3 block(TS_THREADS);
         KL(K_TOP_SCORE, (double)njobs * maxRW * maxRH * t.w * t.h,      // MACs
@@ -719,7 +737,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         const size_t smem = cc.smem;
         if (smem > 200 * 1024) { h->err = "correlation kernel shared memory limit"; return FPM_ERR_LIMIT; }
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(ensure_dyn_smem((const void*)fpm_corr_rows_kernel, h->device, smem));
         const FpmTplLevel td = tpl_level_dev(h, layer);
         const FpmCand* cands = h->d_cand[cur].as<FpmCand>();
         for (int c0 = 0; c0 < n; c0 += wave_cands) {
@@ -893,7 +911,7 @@ int match_device(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt,
         const FpmLevel& L = h->levels[top];
         size_t smem = use_smem ? (size_t)n_pad * 8 : 0;
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(fpm_collect_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(ensure_dyn_smem((const void*)fpm_collect_sort_kernel, h->device, smem));
         KL(K_COLLECT, 0,
            fpm_collect_sort_kernel<<<batch, CS_THREADS, smem, h->stream>>>(
                h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), p.n_ang, max_picks, h->d_angles.as<double>(),
@@ -1139,6 +1157,56 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
 int fpm_match(fpm_handle* h, const uint8_t* src, int width, int height, int stride, fpm_result* out, int cap, int* n)
 {
     return fpm_match_batch(h, src, 1, width, height, stride, (size_t)stride * (size_t)std::max(height, 0), out, cap, n);
+}
+
+// Multi-template matching ("NCC-based OCR", MatchTool/MatchToolDlg.cpp:727-750: LoadDst + Match per glyph).  Every
+// handle owns its stream and buffers, so the matches are independent: they are issued from a small pool of host
+// threads and overlap on the device (each single match is launch-latency bound, not throughput bound).
+int fpm_match_multi(fpm_handle* const* hs, int n_handles, const uint8_t* src, int width, int height, int stride,
+                    fpm_result* out, int cap, int* counts)
+{
+    if (!hs || n_handles <= 0 || !src || !out || !counts || cap < 0) return FPM_ERR_INVALID;
+    for (int i = 0; i < n_handles; i++)
+        if (!hs[i]) return FPM_ERR_INVALID;
+    const int n_threads = std::min(n_handles, 12);
+    std::vector<int> rc(n_handles, FPM_OK);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++)
+        pool.emplace_back([&, t]() {
+            for (int i = t; i < n_handles; i += n_threads)
+                rc[i] = fpm_match(hs[i], src, width, height, stride, out + (size_t)i * cap, cap, counts + i);
+        });
+    for (std::thread& th : pool) th.join();
+    for (int i = 0; i < n_handles; i++)
+        if (rc[i] != FPM_OK) return rc[i];
+    return FPM_OK;
+}
+
+// Text assembly of the OCR loop (MatchToolDlg.cpp:752-771): sort by y, every run of neighbours closer than
+// line_tol in y is a line sorted by x, newline where consecutive entries are farther apart than line_tol.
+// (std::sort there leaves ties unspecified; stable sorts here, like the oracle.)
+int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int n, double line_tol, char* out, int out_cap)
+{
+    if (n < 0 || !out || out_cap <= 0 || (n > 0 && (!cx || !cy || !labels))) return FPM_ERR_INVALID;
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; i++) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cy[a] < cy[b]; });
+    auto by_x = [&](int a, int b) { return cx[a] < cx[b]; };
+    int start = 0;
+    for (int i = 0; i + 1 < n; i++) {
+        if (fabs(cy[idx[i + 1]] - cy[idx[i]]) < line_tol) continue;
+        std::stable_sort(idx.begin() + start, idx.begin() + i + 1, by_x);
+        start = i + 1;
+    }
+    if (n > 0) std::stable_sort(idx.begin() + start, idx.end(), by_x);
+    std::string text;
+    for (int i = 0; i < n; i++) {
+        if (i > 0 && fabs(cy[idx[i]] - cy[idx[i - 1]]) > line_tol) text += '\n';
+        text += labels[idx[i]];
+    }
+    if ((int)text.size() + 1 > out_cap) return FPM_ERR_LIMIT;
+    memcpy(out, text.c_str(), text.size() + 1);
+    return (int)text.size();
 }
 
 double fpm_last_time_ms(const fpm_handle* h) { return h ? h->last_ms : 0; }
@@ -1406,7 +1474,7 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int
     const CorrCfg cc = corr_config(th);
     if (cc.smem > 200 * 1024) { h->err = "correlation kernel shared memory limit"; return FPM_ERR_LIMIT; }
     if (cc.smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(fpm_corr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc.smem));
+        CK(ensure_dyn_smem((const void*)fpm_corr_rows_kernel, h->device, cc.smem));
     int32_t* dS = h->d_dbg[3].as<int32_t>();
     int32_t* dQ = dS + (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT;
     dim3 grid(cc.blocks_y_rows, 1);
@@ -1537,7 +1605,7 @@ int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* 
     CK(cudaMemcpyAsync(h->d_dbg[2].p, &jb, sizeof(jb), cudaMemcpyHostToDevice, h->stream));
     size_t smem = top_score_smem(t.w, t.h);
     if (smem > 200 * 1024) { h->err = "template too large"; return FPM_ERR_LIMIT; }
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fpm_top_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem));
     dim3 grid((RW + TS_TW - 1) / TS_TW, (RH + TS_TH - 1) / TS_TH, 1), block(TS_THREADS);
     fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<uint8_t>(), rp, 0,
                                                            tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0);

@@ -349,3 +349,70 @@ def rrect_from3_host(p1, p2, p3):
     out = (C.c_float * 5)()
     lib.fpm_dbg_rrect_from3(pts, out)
     return tuple(out)
+
+
+# ---- multi-template matching ("NCC-based OCR", MatchTool/MatchToolDlg.cpp:718-770) --------------------------
+OCR_LETTERS = "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ"          # chLetters, :723-725
+
+
+def match_multi(matchers, sourceImage):
+    """The same host image matched by several learned TemplateMatcher handles of one device, concurrently
+    (fpm_match_multi).  Returns one result list per matcher."""
+    if not matchers:
+        return []
+    s = _as_u8_2d(sourceImage)
+    lib = matchers[0]._lib
+    n = len(matchers)
+    cap = min(m.result_capacity for m in matchers)
+    hs = (C.c_void_p * n)(*[m._h for m in matchers])
+    res = (L.fpm_result * (cap * n))()
+    counts = (C.c_int * n)()
+    rc = lib.fpm_match_multi(hs, n, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], res, cap, counts)
+    if rc != 0:
+        errs = [lib.fpm_last_error(m._h).decode() for m in matchers]
+        raise FpmError("fpm_match_multi error %d: %s" % (rc, "; ".join(e for e in errs if e)))
+    return [_convert(res[i * cap:(i + 1) * cap], min(counts[i], cap)) for i in range(n)]
+
+
+def ocr_assemble(centres, labels, line_tol: float = 10.0) -> str:
+    """fpm_ocr_assemble: centres [(cx, cy), ...] + one character each -> text lines (MatchToolDlg.cpp:752-771)."""
+    lib = L.load()
+    n = len(labels)
+    if n == 0:
+        return ""
+    cx = (C.c_double * n)(*[float(c[0]) for c in centres])
+    cy = (C.c_double * n)(*[float(c[1]) for c in centres])
+    lab = C.create_string_buffer("".join(labels).encode("ascii"), n + 1)
+    out = C.create_string_buffer(2 * n + 2)
+    rc = lib.fpm_ocr_assemble(cx, cy, lab, n, float(line_tol), out, len(out))
+    if rc < 0:
+        raise FpmError("fpm_ocr_assemble error %d" % rc)
+    return out.value.decode("ascii")
+
+
+class GlyphReader:
+    """One learned TemplateMatcher per glyph; read(image) = the upstream OCR loop: match every glyph, collect the
+    centres with their letter, assemble lines."""
+
+    def __init__(self, templates: dict, device: int = 0, result_capacity: int = 256, **params):
+        self.letters = [ch for ch in OCR_LETTERS if ch in templates] + sorted(k for k in templates if k not in OCR_LETTERS)
+        self.matchers = []
+        for ch in self.letters:
+            m = TemplateMatcher(device, result_capacity=result_capacity)
+            for k, v in params.items():
+                {"max_pos": m.setMaxPositions, "max_overlap": m.setMaxOverlap, "score": m.setScore,
+                 "tolerance_angle": m.setToleranceAngle, "min_reduce_area": m.setMinReduceArea, "use_simd": m.setUseSIMD,
+                 "sub_pixel": m.setSubPixelEstimation}[k](v)
+            if not m.learnPattern(templates[ch]):
+                raise FpmError("learnPattern failed for glyph %r" % ch)
+            self.matchers.append(m)
+
+    def read(self, sourceImage, line_tol: float = 10.0):
+        """Returns (text, {letter: [SingleTargetMatch, ...]})."""
+        per = match_multi(self.matchers, sourceImage)
+        centres, labels = [], []
+        for ch, res in zip(self.letters, per):
+            for r in res:
+                centres.append(r.ptCenter)
+                labels.append(ch)
+        return ocr_assemble(centres, labels, line_tol), dict(zip(self.letters, per))

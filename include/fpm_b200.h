@@ -98,6 +98,16 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
 int fpm_match_batch_device(fpm_handle* h, const uint8_t* d_src, int batch, int width, int height,
                            int stride, size_t frame_stride, fpm_result* out, int cap, int* n);
 
+/* Multi-template matching (the upstream "NCC-based OCR" loop, MatchTool/MatchToolDlg.cpp:727-750:
+ * one LoadDst + Match per glyph template): the same HOST image matched by n_handles learned handles of one
+ * device, concurrently.  out holds n_handles*cap records (handle i at out + i*cap), counts n_handles totals. */
+int fpm_match_multi(fpm_handle* const* hs, int n_handles, const uint8_t* src, int width, int height, int stride,
+                    fpm_result* out, int cap, int* counts);
+/* Text assembly of that loop (MatchToolDlg.cpp:752-771): centres + one label each -> lines (sorted by y, split where
+ * neighbours differ by more than line_tol (upstream: 10 px), each line sorted by x), '\n' between lines.
+ * Returns the text length, or FPM_ERR_LIMIT if out_cap is too small. */
+int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int n, double line_tol, char* out, int out_cap);
+
 /* getLastExecutionTime (include/TemplateMatcher.h:40), milliseconds of the last match call. */
 double fpm_last_time_ms(const fpm_handle* h);
 

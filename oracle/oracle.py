@@ -803,3 +803,51 @@ def _rr_tuple(r):
     if isinstance(r, tuple):
         return r
     return ((r.center[0], r.center[1]), (r.size[0], r.size[1]), r.angle)
+
+
+# --------------------------------------------------------------------------------------
+# multi-template "NCC-based OCR" (MatchTool/MatchToolDlg.cpp:718-770; dead code behind an early
+# return upstream, README.md:118-122 shows its output)
+# --------------------------------------------------------------------------------------
+OCR_LETTERS = "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ"          # chLetters, :723-725
+
+
+def ocr_assemble(vec_pos, tol=10.0):
+    """vec_pos: [((cx, cy), char), ...] -> text.  Sort by y (:752); every run of neighbours closer than dTol = 10 px
+    in y is one line, sorted by x (:756-763); a newline wherever consecutive entries differ by more than dTol (:765-771).
+    (std::sort leaves ties unspecified; stable sorts here.)"""
+    vec = sorted(vec_pos, key=lambda t: t[0][1])
+    if not vec:
+        return ""
+    start = 0
+    for i in range(len(vec) - 1):
+        if abs(vec[i + 1][0][1] - vec[i][0][1]) < tol:
+            continue
+        vec[start:i + 1] = sorted(vec[start:i + 1], key=lambda t: t[0][0])
+        start = i + 1
+    vec[start:] = sorted(vec[start:], key=lambda t: t[0][0])
+    out = []
+    pre = vec[0][0]
+    for pos, ch in vec:
+        if abs(pos[1] - pre[1]) > tol:
+            out.append("\n")
+        pre = pos
+        out.append(ch)
+    return "".join(out)
+
+
+def ocr_read(src, templates, params=None, tol=10.0):
+    """templates: {char: u8 image}; one learnPattern + match per glyph in OCR_LETTERS order (:727-750), centres
+    collected with their letter, then ocr_assemble.  Returns (text, {char: [SingleTargetMatch, ...]})."""
+    vec, per = [], {}
+    for ch in OCR_LETTERS:
+        if ch not in templates:
+            continue
+        m = OracleMatcher()
+        for k, v in (params or {}).items():
+            setattr(m, k, v)
+        assert m.learn_pattern(templates[ch])
+        res = m.match(src)
+        per[ch] = res
+        vec.extend((r.ptCenter, ch) for r in res)
+    return ocr_assemble(vec, tol), per

@@ -76,6 +76,27 @@ def run_case(src, tpl, params):
     return out
 
 
+OCR_PARAMS = dict(max_pos=70, score=0.85, tolerance_angle=0, min_reduce_area=256, max_overlap=0.0)
+
+
+def ocr_case():
+    """36 glyph templates of Test Images/M12 read on M12_D_Test.jpg (MatchToolDlg.cpp:718-770)."""
+    from oracle.oracle import OCR_LETTERS, ocr_read
+    os.makedirs(os.path.join(HERE, "images", "M12"), exist_ok=True)
+    tpls = {}
+    for ch in OCR_LETTERS:
+        img = cv2.imread(os.path.join(REF, "M12", ch + ".jpg"), cv2.IMREAD_GRAYSCALE)
+        assert img is not None, ch
+        cv2.imwrite(os.path.join(HERE, "images", "M12", ch + ".png"), img, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        tpls[ch] = img
+    src = cv2.imread(os.path.join(REF, "M12", "M12_D_Test.jpg"), cv2.IMREAD_GRAYSCALE)
+    cv2.imwrite(os.path.join(HERE, "images", "M12", "M12_D_Test.png"), src, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+    text, per = ocr_read(src, tpls, OCR_PARAMS)
+    return dict(params=OCR_PARAMS, src="M12/M12_D_Test", src_sha=sha(src), text=text,
+                results={ch: [dict(score=r.score, angle=r.angle, cx=r.ptCenter[0], cy=r.ptCenter[1], lt=list(r.ptLT), rt=list(r.ptRT),
+                                   rb=list(r.ptRB), lb=list(r.ptLB)) for r in res] for ch, res in per.items()})
+
+
 def main():
     os.makedirs(os.path.join(HERE, "images"), exist_ok=True)
     for f in FIXTURES:
@@ -89,6 +110,8 @@ def main():
         cases[name]["src"] = s
         cases[name]["tpl"] = t
         print(name, "->", len(cases[name]["results"]), "results,", cases[name]["n_candidates"], "candidates")
+    cases["ocr_m12"] = ocr_case()
+    print("ocr_m12 ->", repr(cases["ocr_m12"]["text"]))
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(cases, f, indent=1)
 
