@@ -316,6 +316,8 @@ def main():
         m.setH2DChunk(args.h2d_chunk)
     if os.environ.get("FPM_TC"):
         m.setTensorCores(int(os.environ["FPM_TC"]))
+    if os.environ.get("FPM_SPLIT") is not None:
+        m.setSplitBatch(int(os.environ["FPM_SPLIT"]))
     if os.environ.get("FPM_WS_MB"):
         m.setWorkspaceMB(float(os.environ["FPM_WS_MB"]))
     cap = m.result_capacity
@@ -395,12 +397,17 @@ def main():
     del scratch
 
     # per-kernel device time over the same K steps, CUDA events around every launch on the launch stream
+    # (whole batch on one handle here: with the two concurrent half-batches of the timed steps the event-bracketed
+    #  durations of overlapping kernels would not add up)
+    split_default = m.getSplitBatch()
+    m.setSplitBatch(0)
     m.setProfile(True)
     m.profileReset()
     for i in range(K):
         step_device(i)
     prof = m.profile()
     m.setProfile(False)
+    m.setSplitBatch(split_default)
 
     if rank != 0:
         if dist:
@@ -475,6 +482,7 @@ def main():
         "config": {"workload": args.workload, "src": "%dx%d" % (Wd, H), "tpl": wl["tpl"], "target_num": wl["max_pos"],
                    "score": wl["score"], "tolerance_angle": wl["tol"], "min_reduce_area": wl["mra"], "batch_per_gpu": B,
                    "global_batch": world * B, "sharding": "frames over ranks, no data-path collective",
+                   "concurrent_half_batches": bool(split_default and B >= split_default and wl["tol"] > 0),
                    "l2": "step input %.0f MB > 126 MB L2; two alternating frame sets" % (B * H * Wd / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * H * Wd, "d2h_bytes_per_step": B * cap * 96 + B * 4,
                 "ms_per_step": e2e_ms / K, "h2d_copy_only_GBps": h2d_gbps, "host_numa": numa,

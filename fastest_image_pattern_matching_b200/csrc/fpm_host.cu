@@ -159,6 +159,10 @@ struct fpm_handle {
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
     bool mma_attr_set = false, fused_attr_set = false, peaks_attr_set = false;
+    // concurrent half-batches (fpm_match_batch_device): a second handle with the same template and parameters
+    fpm_handle* twin = nullptr;
+    int split_batch = 32;          // FPM_PARAM_SPLIT_BATCH: smallest batch that is split in two (0 = never)
+    unsigned learn_gen = 0, twin_gen = 0;
     int stop_layer1 = 0, bitwise_not = 0, tol_range = 0;   // MFC-only modes (MatchTool/MatchToolDlg.cpp:788-816, :936)
     double tol_r[4] = {0, 0, 0, 0};
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
@@ -977,6 +981,7 @@ fpm_handle* fpm_create(int device)
 void fpm_destroy(fpm_handle* h)
 {
     if (!h) return;
+    if (h->twin) { fpm_destroy(h->twin); h->twin = nullptr; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
@@ -1020,6 +1025,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_MFC_COMPAT: h->mfc_compat = v != 0; break;
     case FPM_PARAM_STOP_LAYER1: h->stop_layer1 = v != 0; break;
     case FPM_PARAM_BITWISE_NOT: h->bitwise_not = v != 0; break;
+    case FPM_PARAM_SPLIT_BATCH: h->split_batch = (int)v; break;
     case FPM_PARAM_TOLERANCE_RANGE: h->tol_range = v != 0; h->plan.valid = false; break;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         h->tol_r[param - FPM_PARAM_TOLERANCE1] = v; h->plan.valid = false; break;
@@ -1047,6 +1053,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_MFC_COMPAT: return h->mfc_compat;
     case FPM_PARAM_STOP_LAYER1: return h->stop_layer1;
     case FPM_PARAM_BITWISE_NOT: return h->bitwise_not;
+    case FPM_PARAM_SPLIT_BATCH: return h->split_batch;
     case FPM_PARAM_TOLERANCE_RANGE: return h->tol_range;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         return h->tol_r[param - FPM_PARAM_TOLERANCE1];
@@ -1062,6 +1069,7 @@ int fpm_learn(fpm_handle* h, const uint8_t* tpl, int width, int height, int stri
     h->tpl0.resize((size_t)width * height);
     for (int y = 0; y < height; y++) memcpy(h->tpl0.data() + (size_t)y * width, tpl + (size_t)y * stride, width);
     h->tpl0_w = width; h->tpl0_h = height;
+    h->learn_gen++;
     return do_learn(h);
 }
 
@@ -1074,6 +1082,27 @@ void fpm_clear(fpm_handle* h)
     h->ur[0] = h->ur[1] = h->ur[2] = h->ur[3] = 0;
 }
 
+// second handle for the concurrent half-batches: same device, parameters and template as h
+int ensure_twin(fpm_handle* h)
+{
+    if (!h->twin) {
+        h->twin = fpm_create(h->device);
+        if (!h->twin) { h->err = "could not create the twin handle"; return FPM_ERR_CUDA; }
+        h->twin->split_batch = 0;
+        h->twin_gen = 0;
+    }
+    fpm_handle* t = h->twin;
+    for (int p = 0; p < FPM_PARAM_COUNT_; p++)
+        if (p != FPM_PARAM_TRACE && p != FPM_PARAM_SPLIT_BATCH && fpm_get_param(t, p) != fpm_get_param(h, p))
+            fpm_set_param(t, p, fpm_get_param(h, p));
+    if (h->twin_gen != h->learn_gen || !t->learned) {
+        int rc = fpm_learn(t, h->tpl0.data(), h->tpl0_w, h->tpl0_h, h->tpl0_w);
+        if (rc) { h->err = t->err; return rc; }
+        h->twin_gen = h->learn_gen;
+    }
+    return FPM_OK;
+}
+
 int fpm_match_batch_device(fpm_handle* h, const uint8_t* d_src, int batch, int width, int height, int stride,
                            size_t frame_stride, fpm_result* out, int cap, int* n)
 {
@@ -1084,7 +1113,26 @@ int fpm_match_batch_device(fpm_handle* h, const uint8_t* d_src, int batch, int w
     if (stride < width) { h->err = "stride < width"; return FPM_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
     auto t0 = std::chrono::high_resolution_clock::now();
-    int rc = match_device(h, d_src, batch, width, height, stride, frame_stride, out, cap, n);
+    int rc;
+    if (h->split_batch > 0 && batch >= h->split_batch && !h->trace && h->learned &&
+        (h->tol_range || h->tol_angle >= FPM_VISION_TOLERANCE)) {       // single-angle workloads gain nothing from it
+        // Two half-batches on two handles (own streams and buffers), issued from two host threads: while one half
+        // sits in a latency-bound stage (peak picking, the small pyramid levels, the per-layer counter read-back)
+        // the other half's kernels fill the device.
+        rc = ensure_twin(h);
+        if (rc) return rc;
+        const int b0 = batch / 2;
+        int rc2 = FPM_OK;
+        std::thread second([&]() {
+            rc2 = fpm_match_batch_device(h->twin, d_src + (size_t)b0 * frame_stride, batch - b0, width, height, stride, frame_stride,
+                                         out + (size_t)b0 * cap, cap, n + b0);
+        });
+        rc = match_device(h, d_src, b0, width, height, stride, frame_stride, out, cap, n);
+        second.join();
+        if (rc == FPM_OK && rc2 != FPM_OK) { rc = rc2; h->err = h->twin->err; }
+    } else {
+        rc = match_device(h, d_src, batch, width, height, stride, frame_stride, out, cap, n);
+    }
     prof_collect(h);
     auto t1 = std::chrono::high_resolution_clock::now();
     h->last_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -1227,7 +1275,7 @@ int fpm_get_user_rect(const fpm_handle* h, int* x, int* y, int* w, int* hgt)
     return h->has_ur;
 }
 
-long long fpm_launch_count(const fpm_handle* h) { return h ? h->launches : 0; }
+long long fpm_launch_count(const fpm_handle* h) { return h ? h->launches + (h->twin ? h->twin->launches : 0) : 0; }
 
 int fpm_tpl_levels(const fpm_handle* h) { return (h && h->learned) ? (int)h->tpl.size() : 0; }
 
@@ -1696,6 +1744,12 @@ int fpm_profile_get(fpm_handle* h, int kid, double* ms, long long* launches, dou
     if (ms) *ms = h->prof_ms[kid];
     if (launches) *launches = h->prof_launches[kid];
     if (work) *work = h->prof_work[kid];
+    if (h->twin) {                                           // the half-batches of the twin handle count too
+        prof_collect(h->twin);
+        if (ms) *ms += h->twin->prof_ms[kid];
+        if (launches) *launches += h->twin->prof_launches[kid];
+        if (work) *work += h->twin->prof_work[kid];
+    }
     return FPM_OK;
 }
 
@@ -1704,6 +1758,7 @@ void fpm_profile_reset(fpm_handle* h)
     if (!h) return;
     prof_collect(h);
     for (int i = 0; i < 16; i++) { h->prof_ms[i] = 0; h->prof_work[i] = 0; h->prof_launches[i] = 0; }
+    if (h->twin) fpm_profile_reset(h->twin);
 }
 
 // ---- trace access -----------------------------------------------------------------------

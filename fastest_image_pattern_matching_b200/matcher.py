@@ -91,6 +91,8 @@ class TemplateMatcher:
     def getUseSIMD(self) -> bool: return bool(self._get(L.PARAM_USE_SIMD))
     def getSubPixelEstimation(self) -> bool: return bool(self._get(L.PARAM_SUBPIXEL))
     def setTrace(self, v: bool): self._set(L.PARAM_TRACE, 1 if v else 0)
+    def setSplitBatch(self, v: int): self._set(L.PARAM_SPLIT_BATCH, int(v))
+    def getSplitBatch(self) -> int: return int(self._get(L.PARAM_SPLIT_BATCH))
     def setWorkspaceMB(self, v: float): self._set(L.PARAM_WORKSPACE_MB, v)
     def setH2DChunk(self, v: int): self._set(L.PARAM_H2D_CHUNK, v)
     def setTensorCores(self, v: int): self._set(L.PARAM_TENSOR_CORES, v)

@@ -264,6 +264,45 @@ def test_batch_equals_single(matcher, golden_cases):
     assert len(single[0]) == 3 and len(single[3]) == 0
 
 
+def test_device_batch_in_two_concurrent_halves_equals_single(matcher, golden_cases):
+    """fpm_match_batch_device splits large batches into two half-batches on two internal handles (FPM_PARAM_SPLIT_BATCH)"""
+    import ctypes as C
+    import torch
+    from fastest_image_pattern_matching_b200 import _lib as L
+    from fastest_image_pattern_matching_b200.matcher import _convert
+    c = golden_cases["src8"]
+    configure(matcher, c["params"])
+    matcher.learnPattern(get_image(c["tpl"]))
+    a, b = get_image("Src8"), get_image("Src9")
+    frames = np.stack([a, b, a, np.zeros_like(a), b])
+    single = [matcher.match(f) for f in frames]
+    d = torch.from_numpy(frames).cuda()
+    B, H, W = frames.shape
+    cap = matcher.result_capacity
+    try:
+        for split in (2, 0):
+            matcher.setSplitBatch(split)
+            res = (L.fpm_result * (cap * B))()
+            counts = (C.c_int * B)()
+            matcher.matchBatchRaw(d.data_ptr(), B, W, H, W, H * W, True, res, counts)
+            assert [counts[i] for i in range(B)] == [len(x) for x in single]
+            for i in range(B):
+                assert_results_match(_convert(res[i * cap:(i + 1) * cap], counts[i]), single[i], 0, 0, 0)
+        # the template learned later must reach the twin handle too
+        matcher.setSplitBatch(2)
+        c9 = golden_cases["src9"]
+        configure(matcher, c9["params"])
+        matcher.learnPattern(get_image(c9["tpl"]))
+        single9 = [matcher.match(f) for f in frames]
+        res = (L.fpm_result * (cap * B))()
+        counts = (C.c_int * B)()
+        matcher.matchBatchRaw(d.data_ptr(), B, W, H, W, H * W, True, res, counts)
+        for i in range(B):
+            assert_results_match(_convert(res[i * cap:(i + 1) * cap], counts[i]), single9[i], 0, 0, 0)
+    finally:
+        matcher.setSplitBatch(32)
+
+
 def test_small_workspace_waves_give_same_result(matcher, golden_cases):
     c = golden_cases["src8"]
     configure(matcher, c["params"])
