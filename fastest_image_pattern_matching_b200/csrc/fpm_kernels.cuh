@@ -63,6 +63,27 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
             for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
                 fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + xs + 16 * c);
         }
+    } else if (vec == 16) {
+        // left / right border tile.  Pass A: every 16-byte chunk that lies inside the image in x is one cp.async, as in
+        // the interior (rows through the reflection).  Pass B: the few needed bytes outside those chunks (4 on the left
+        // edge, the ragged tail on the right edge) are fetched one per thread through the column reflection.
+        const int c = tid & 31;
+        const int c_first = xs < 0 ? (-xs + 15) / 16 : 0;                    // first chunk with x >= 0
+        const int c_last = min(nch - 1, (sw - xs) / 16 - 1);                 // last chunk with x + 16 <= sw
+        if (c >= c_first && c <= c_last) {
+            const int x = xs + 16 * c;
+            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
+                fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + x);
+        }
+        int l0 = need_lo, l1, r0, r1 = need_hi + 1;                          // byte ranges [l0, l1) and [r0, r1) of a row
+        if (c_last < c_first) { l1 = r1; r0 = r1; }                          // no whole chunk at all
+        else { l1 = max(l0, min(16 * c_first, r1)); r0 = max(l1, 16 * (c_last + 1)); }
+        const int nl = l1 - l0, nb = nl + max(r1 - r0, 0);
+        for (int i = tid; i < nin_rows * nb; i += PD_THREADS) {
+            const int r = i / nb, k = i - r * nb;
+            const int b = k < nl ? l0 + k : r0 + (k - nl);
+            s_in[r][b] = __ldg(s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + fpm_reflect101(xs + b, sw));
+        }
     } else {
         const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
         for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
