@@ -285,6 +285,25 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                 }
                 drow[lane] = (uint8_t)v[0];
                 drow[lane + 32] = (uint8_t)v[1];
+            } else if (staged && inside) {
+                // partial-width tile (the last tile column of a ROI, or a ROI narrower than a tile) whose taps all lie
+                // inside the image: the fast arithmetic with a column predicate; padding columns are written as zero
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int col = lane + 32 * k;
+                    if (tx0 + col >= dpitch) continue;
+                    int v = 0;
+                    if (col < ncols) {
+                        const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
+                        const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
+                        const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
+                        const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
+                        const int top = (p00 << 5) + ax * (p01 - p00);
+                        const int bot = (p10 << 5) + ax * (p11 - p10);
+                        v = ((top << 5) + ay * (bot - top) + 512) >> 10;
+                    }
+                    drow[col] = (uint8_t)v;
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
