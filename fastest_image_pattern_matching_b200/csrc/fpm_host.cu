@@ -382,11 +382,19 @@ int make_map_3d(fpm_handle* h, CUtensorMap* map, const void* base, uint64_t d0, 
     return FPM_OK;
 }
 
+// which correlation path a template level takes: 0 = dp4a (fpm_corr_rows_kernel), 1 = tensor cores
 bool mma_usable(const fpm_handle* h, int tw)
 {
     if (h->use_tc == 0) return false;
     if (!get_encode_tiled()) return false;
     return (h->use_tc == 2 || h->use_tc == 4) ? true : tw >= 64;
+}
+
+// narrow levels (16 <= width < 64): the row-split tensor-core kernel does not beat dp4a there (256 B of row dots per
+// 22..70-byte ROI row), the fused kernel does as soon as the level has enough evals to fill the SMs
+bool mma_narrow_fused(const fpm_handle* h, int tw)
+{
+    return h->use_tc == 1 && h->use_simd && get_encode_tiled() && tw >= 16 && tw < 64;
 }
 
 // The fused kernel keeps one CTA on 128 evals for all ROI rows: it wins when the evals fill the SMs and the rows are
@@ -759,7 +767,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                                                                     level_vec_ok(L)));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
             bool fused = false;                             // numerators + window totals straight from the fused tensor-core kernel
-            if (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3 && fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
+            if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) &&
+                fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
                 int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
                                             t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
                 if (rcm) return rcm;

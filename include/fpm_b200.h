@@ -46,7 +46,8 @@ enum fpm_param {
     FPM_PARAM_WORKSPACE_MB = 8,    /* refinement workspace budget per wave, default 4096 */
     FPM_PARAM_PROFILE = 9,         /* bracket every kernel launch with CUDA events (bench.py roofline) */
     FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
-    FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64 (default), 2 = always,
+    FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64, and for width >= 16 when a level has
+                                      enough evals for the fused kernel (default), 2 = always,
                                       3 = like 1 but never the fused kernel (row dots to HBM, separate row sums), 4 = always fused */
     FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC conventions: result (MatchTool/MatchToolDlg.cpp:1085-1116: angle = -theta wrapped
                                       to [-180,180], results truncated to TargetNum, corners in double) and s_BlockMax
