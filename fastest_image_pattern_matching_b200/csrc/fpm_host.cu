@@ -663,10 +663,15 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
             CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem));
         dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, njobs);
         dim3 block(TS_THREADS);
+        // scores certainly below the top-layer threshold (vecLayerScore, :153-156) may be stored as estimates: the peak
+        // search cannot observe them.  Off (exact everywhere) when the threshold is not comfortably positive.
+        double top_thresh = h->score;
+        for (int l = 0; l < top; l++) top_thresh *= 0.9;
+        const float reject_below = top_thresh > 0.05 ? (float)(top_thresh - 0.01) : -INFINITY;
         KL(K_TOP_SCORE, (double)njobs * maxRW * maxRH * t.w * t.h,      // MACs
            fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->d_rot.as<uint8_t>(), rpitch,
                                                                   rot_stride, tpl_level_dev(h, top), h->d_score.as<float>(),
-                                                                  spitch, score_stride));
+                                                                  spitch, score_stride, reject_below));
     }
     {
         // bCalMaxByBlock, src/TemplateMatcher.cpp:158-159
@@ -1665,7 +1670,7 @@ int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* 
     CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem));
     dim3 grid((RW + TS_TW - 1) / TS_TW, (RH + TS_TH - 1) / TS_TH, 1), block(TS_THREADS);
     fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<uint8_t>(), rp, 0,
-                                                           tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0);
+                                                           tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0, -INFINITY);
     CKL();
     CK(cudaMemcpy2DAsync(score, (size_t)RW * 4, h->d_dbg[1].p, (size_t)sp * 4, (size_t)RW * 4, RH, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

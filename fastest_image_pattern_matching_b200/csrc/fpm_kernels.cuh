@@ -370,6 +370,24 @@ __device__ __forceinline__ float fpm_ccoeff_epilogue(float numerator, double wsu
     return (float)num;
 }
 
+// Top-layer variant with an early out.  The score map is only ever consumed by the greedy peak search, which
+// observes nothing below its threshold (a pick is taken only if value >= thresh and the search stops at the first
+// maximum below it), so a score that is certainly below the threshold may be stored as a float32 estimate instead
+// of the exact double-precision quotient: that skips the fp64 sqrt and division (about half of the kernel's
+// instructions for a 14x14 template).  The integer sums and the variance term stay exact; the estimate's error
+// (~1e-6) is far inside the 0.01 margin of reject_below.  reject_below = -inf gives the exact map everywhere.
+__device__ __forceinline__ float fpm_ccoeff_epilogue_top(float numerator, double wsum, double wsqsum, double tmean, double tnorm,
+                                                         double inv_area, float reject_below, float inv_tnorm_f)
+{
+    const double num = (double)numerator - wsum * tmean;
+    const double diff2 = wsqsum - (wsum * wsum) * inv_area;
+    if (diff2 > 1.0) {                                       // away from the degenerate-variance guard of :575-577
+        const float est = (float)num * rsqrtf((float)diff2) * inv_tnorm_f;
+        if (est < reject_below) return est;
+    }
+    return fpm_ccoeff_epilogue(numerator, wsum, wsqsum, tmean, tnorm, inv_area);
+}
+
 // =====================================================================================
 // K4+K7  top-layer dense score map: exact integer TM_CCORR numerator, exact window sum / sqsum,
 // CCOEFF_NORMED epilogue.  One CTA = 64x16 scores, 4 horizontally adjacent scores per thread; image
@@ -384,7 +402,7 @@ __device__ __forceinline__ float fpm_ccoeff_epilogue(float numerator, double wsu
 __global__ void __launch_bounds__(TS_THREADS)
 fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restrict__ rot, int rpitch,
                      size_t rot_job_stride, FpmTplLevel tpl, float* __restrict__ score, int spitch,
-                     size_t score_job_stride)
+                     size_t score_job_stride, float reject_below)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const FpmWarpJob& jb = jobs[blockIdx.z];
@@ -481,8 +499,10 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
         wsq[0] += rq.x; wsq[1] += rq.y; wsq[2] += rq.z; wsq[3] += rq.w;
     }
     // TM_CCORR result cell is a float32 (cv::matchTemplate output depth), here the rounded exact sum
+    const float inv_tnorm_f = 1.0f / (float)tpl.norm;
     for (int k = 0; k < 4 && ox + k < RW; k++)
-        out[k] = fpm_ccoeff_epilogue((float)num[k], (double)wsum[k], (double)wsq[k], tpl.mean, tpl.norm, tpl.inv_area);
+        out[k] = fpm_ccoeff_epilogue_top((float)num[k], (double)wsum[k], (double)wsq[k], tpl.mean, tpl.norm, tpl.inv_area,
+                                         reject_below, inv_tnorm_f);
 }
 
 // =====================================================================================
