@@ -417,6 +417,7 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
     uint32_t* s_p = s_t + th * nwt;                        // ph * pww
     const int tid = threadIdx.x;
     const uint8_t* __restrict__ r = rot + (size_t)blockIdx.z * rot_job_stride;
+    const bool word_ok = ((rpitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(r) & 3) == 0);    // x0 is a multiple of 64
     for (int i = tid; i < th * nwt; i += TS_THREADS) {
         int yy = i / nwt, xw = i - yy * nwt;
         uint32_t v = 0;
@@ -430,10 +431,13 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
         int gy = y0 + yy;
         uint32_t v = 0;
         if (gy < jb.dh) {
+            const int gx0 = x0 + 4 * xw;
+            if (word_ok && gx0 + 3 < jb.dw) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(r + (size_t)gy * rpitch + gx0));
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int gx = x0 + 4 * xw + k;
-                if (gx < jb.dw) v |= (uint32_t)r[(size_t)gy * rpitch + gx] << (8 * k);
+                for (int k = 0; k < 4; k++)
+                    if (gx0 + k < jb.dw) v |= (uint32_t)r[(size_t)gy * rpitch + gx0 + k] << (8 * k);
             }
         }
         s_p[i] = v;
@@ -477,26 +481,54 @@ fpm_top_score_kernel(const FpmWarpJob* __restrict__ jobs, const uint8_t* __restr
         for (int k = 0; k < 4 && ox + k < RW; k++) out[k] = 1.0f;
         return;
     }
-    long long num[4] = {0, 0, 0, 0}, wsum[4] = {0, 0, 0, 0}, wsq[4] = {0, 0, 0, 0};
-    for (int yy = 0; yy < th; yy++) {
-        const uint32_t* prow = s_p + (ty + yy) * pww + tx;
-        const uint32_t* trow = s_t + yy * nwt;
-        uint32_t a[4] = {0, 0, 0, 0};
-        uint32_t lo = prow[0];
-        for (int xw = 0; xw < nwt; xw++) {
-            const uint32_t hi = prow[xw + 1];
-            const uint32_t t = trow[xw];                   // bytes beyond tw are 0 in the staged template
-            a[0] = __dp4a(lo, t, a[0]);
-            a[1] = __dp4a(__funnelshift_r(lo, hi, 8), t, a[1]);
-            a[2] = __dp4a(__funnelshift_r(lo, hi, 16), t, a[2]);
-            a[3] = __dp4a(__funnelshift_r(lo, hi, 24), t, a[3]);
-            lo = hi;
+    unsigned long long num[4], wsum[4], wsq[4];
+    if ((long long)tw * th <= 66000) {
+        // every sum is at most 255^2 * w * h < 2^32: plain 32-bit accumulators across all template rows (the 64-bit
+        // adds of the general path cost as many instructions as the dp4a loop itself for a 14x14 template)
+        uint32_t a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+        for (int yy = 0; yy < th; yy++) {
+            const uint32_t* prow = s_p + (ty + yy) * pww + tx;
+            const uint32_t* trow = s_t + yy * nwt;
+            uint32_t lo = prow[0];
+            for (int xw = 0; xw < nwt; xw++) {
+                const uint32_t hi = prow[xw + 1];
+                const uint32_t t = trow[xw];               // bytes beyond tw are 0 in the staged template
+                a[0] = __dp4a(lo, t, a[0]);
+                a[1] = __dp4a(__funnelshift_r(lo, hi, 8), t, a[1]);
+                a[2] = __dp4a(__funnelshift_r(lo, hi, 16), t, a[2]);
+                a[3] = __dp4a(__funnelshift_r(lo, hi, 24), t, a[3]);
+                lo = hi;
+            }
+            const uint4 rs = *reinterpret_cast<const uint4*>(s_rs + (ty + yy) * TS_TW + 4 * tx);
+            const uint4 rq = *reinterpret_cast<const uint4*>(s_rq + (ty + yy) * TS_TW + 4 * tx);
+            b[0] += rs.x; b[1] += rs.y; b[2] += rs.z; b[3] += rs.w;
+            c[0] += rq.x; c[1] += rq.y; c[2] += rq.z; c[3] += rq.w;
         }
-        const uint4 rs = *reinterpret_cast<const uint4*>(s_rs + (ty + yy) * TS_TW + 4 * tx);
-        const uint4 rq = *reinterpret_cast<const uint4*>(s_rq + (ty + yy) * TS_TW + 4 * tx);
-        num[0] += a[0]; num[1] += a[1]; num[2] += a[2]; num[3] += a[3];   // per-row s32, s64 across rows
-        wsum[0] += rs.x; wsum[1] += rs.y; wsum[2] += rs.z; wsum[3] += rs.w;
-        wsq[0] += rq.x; wsq[1] += rq.y; wsq[2] += rq.z; wsq[3] += rq.w;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { num[k] = a[k]; wsum[k] = b[k]; wsq[k] = c[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { num[k] = 0; wsum[k] = 0; wsq[k] = 0; }
+        for (int yy = 0; yy < th; yy++) {
+            const uint32_t* prow = s_p + (ty + yy) * pww + tx;
+            const uint32_t* trow = s_t + yy * nwt;
+            uint32_t a[4] = {0, 0, 0, 0};
+            uint32_t lo = prow[0];
+            for (int xw = 0; xw < nwt; xw++) {
+                const uint32_t hi = prow[xw + 1];
+                const uint32_t t = trow[xw];
+                a[0] = __dp4a(lo, t, a[0]);
+                a[1] = __dp4a(__funnelshift_r(lo, hi, 8), t, a[1]);
+                a[2] = __dp4a(__funnelshift_r(lo, hi, 16), t, a[2]);
+                a[3] = __dp4a(__funnelshift_r(lo, hi, 24), t, a[3]);
+                lo = hi;
+            }
+            const uint4 rs = *reinterpret_cast<const uint4*>(s_rs + (ty + yy) * TS_TW + 4 * tx);
+            const uint4 rq = *reinterpret_cast<const uint4*>(s_rq + (ty + yy) * TS_TW + 4 * tx);
+            num[0] += a[0]; num[1] += a[1]; num[2] += a[2]; num[3] += a[3];   // per-row s32, s64 across rows
+            wsum[0] += rs.x; wsum[1] += rs.y; wsum[2] += rs.z; wsum[3] += rs.w;
+            wsq[0] += rq.x; wsq[1] += rq.y; wsq[2] += rq.z; wsq[3] += rq.w;
+        }
     }
     // TM_CCORR result cell is a float32 (cv::matchTemplate output depth), here the rounded exact sum
     const float inv_tnorm_f = 1.0f / (float)tpl.norm;
