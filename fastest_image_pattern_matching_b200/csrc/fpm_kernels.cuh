@@ -626,9 +626,13 @@ __device__ __forceinline__ FpmScanStep fpm_scan_step(int w, int lane, bool with_
 // warp-cooperative scan of one block: max value, first location in row-major order.  The picks are a latency
 // chain (one CTA per map, hundreds of sequential picks), so the loads of a batch of NB x 32 elements are all
 // issued before the first comparison and nothing divides per element.
+// Elements inside the rectangle [px0, px1) x [py0, py1) count as -1: that is the suppression rectangle of the pick in
+// flight, whose stores may not have landed yet (no barrier between painting and rescanning); pass an empty
+// rectangle to read the map as it is.
 template <int NB>
 __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, int pitch, int x, int y,
-                                               int w, int h, int lane, const FpmScanStep& st, float& bv, int& bx, int& by)
+                                               int w, int h, int lane, const FpmScanStep& st,
+                                               int px0, int py0, int px1, int py1, float& bv, int& bx, int& by)
 {
     float best = -INFINITY; int bidx = 0x7fffffff;
     const int n = w * h;
@@ -637,7 +641,9 @@ __device__ __forceinline__ void fpm_scan_block(const float* __restrict__ map, in
         float v[NB];
 #pragma unroll
         for (int k = 0; k < NB; k++) {
-            v[k] = (i0 + 32 * k < n) ? map[(size_t)(y + yy) * pitch + x + xx] : -INFINITY;
+            const int gx = x + xx, gy = y + yy;
+            const bool painted = gx >= px0 && gx < px1 && gy >= py0 && gy < py1;
+            v[k] = (i0 + 32 * k < n) ? (painted ? -1.0f : map[(size_t)gy * pitch + gx]) : -INFINITY;
             xx += st.r; yy += st.q;
             if (xx >= w) { xx -= w; yy++; }
         }
@@ -710,20 +716,38 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
     const FpmScanStep step_reg = fpm_scan_step(g.bw, lane, true);  // full-width blocks share one walk
     __shared__ float s_sv[PK_SUP_MAX];
     __shared__ int s_sk[PK_SUP_MAX], s_sl[PK_SUP_MAX];
-    __shared__ float s_best_v;
-    __shared__ int s_best_loc;
+    __shared__ float s_best_v[2];
+    __shared__ int s_best_loc[2];
 
-    auto scan_to_table = [&](int k, int x, int y, int w, int h) {
+    auto scan_to_table = [&](int k, int x, int y, int w, int h, int px0, int py0, int px1, int py1) {
         float v; int bx, by;
         const FpmScanStep st = (w == g.bw) ? step_reg : fpm_scan_step(w, lane, false);
-        if (w * h <= 64) fpm_scan_block<2>(map, spitch, x, y, w, h, lane, st, v, bx, by);   // small tiles (mode 0)
-        else fpm_scan_block<8>(map, spitch, x, y, w, h, lane, st, v, bx, by);
+        if (w * h <= 64) fpm_scan_block<2>(map, spitch, x, y, w, h, lane, st, px0, py0, px1, py1, v, bx, by);   // small tiles (mode 0)
+        else fpm_scan_block<8>(map, spitch, x, y, w, h, lane, st, px0, py0, px1, py1, v, bx, by);
         if (lane == 0) { bval[k] = v; bloc[k] = (by << 16) | bx; }
     };
-    for (int k = warp; k < g.nblocks; k += nwarps) {
+    // table build: one THREAD per regular block (a sequential scan needs ~4 instructions per element and no
+    // cross-lane reduction; the warp-cooperative scan is kept for the picks, where latency counts, and for the
+    // big irregular strips)
+    const int regular_seq = (g.bw * g.bh <= 256) ? regular : 0;   // big tiles stay warp-cooperative
+    for (int k = tid; k < regular_seq; k += nthreads) {
+        const int gy = k / g.ncol, gx = k - gy * g.ncol;
+        const int x = gx * g.bw, y = gy * g.bh;
+        const int w = min(g.bw, cols - x), h = min(g.bh, rows - y);
+        float best = -INFINITY; int bx = 0, by = 0;
+        for (int yy = 0; yy < h; yy++) {
+            const float* rowp = map + (size_t)(y + yy) * spitch + x;
+            for (int xx = 0; xx < w; xx++) {
+                const float v = rowp[xx];
+                if (v > best) { best = v; bx = xx; by = yy; }
+            }
+        }
+        bval[k] = best; bloc[k] = ((y + by) << 16) | (x + bx);
+    }
+    for (int k = regular_seq + warp; k < g.nblocks; k += nwarps) {
         int x, y, w, h;
         fpm_block_rect(g, k, cols, rows, x, y, w, h);
-        scan_to_table(k, x, y, w, h);
+        scan_to_table(k, x, y, w, h, 0, 0, 0, 0);
     }
     __syncthreads();
     auto refresh_sup = [&](int s) {
@@ -753,7 +777,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
             if (rw > 0 && rh > 0 && pw > 0 && ph > 0) {
                 for (int yy = warp; yy < ph; yy += nwarps)
                     for (int xx = lane; xx < pw; xx += 32) map[(size_t)(py0 + yy) * spitch + px0 + xx] = -1.0f;
-                __syncthreads();
+                // (no barrier: the rescans below treat the rectangle as painted without reading it)
                 // blocks of the regular grid under the rectangle, plus the strips of mode 1
                 const int bx0 = fpm_fastdiv(px0, div_bw), bx1 = min(fpm_fastdiv(px1 - 1, div_bw), g.ncol - 1);
                 const int by0 = fpm_fastdiv(py0, div_bh), by1 = min(fpm_fastdiv(py1 - 1, div_bh), g.nrow - 1);
@@ -769,7 +793,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                         while (c >= nbx) { c -= nbx; r++; }
                         const int gx = bx0 + c, gy = by0 + r;
                         const int x = gx * g.bw, y = gy * g.bh;
-                        scan_to_table(gy * g.ncol + gx, x, y, min(g.bw, cols - x), min(g.bh, rows - y));
+                        scan_to_table(gy * g.ncol + gx, x, y, min(g.bw, cols - x), min(g.bh, rows - y), px0, py0, px1, py1);
                     } else {
                         const int e = idx - nreg;
                         int k;
@@ -778,7 +802,7 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
                         else { if (!hit_corner) continue; k = regular + g.has_right + g.has_bottom; }
                         int x, y, w, h;
                         fpm_block_rect(g, k, cols, rows, x, y, w, h);
-                        scan_to_table(k, x, y, w, h);
+                        scan_to_table(k, x, y, w, h, px0, py0, px1, py1);
                     }
                 }
                 __syncthreads();
@@ -810,12 +834,11 @@ fpm_top_peaks_kernel(const FpmWarpJob* __restrict__ jobs, float* __restrict__ sc
             fpm_pick_warp_reduce(mode, best, bk, bl);
             if (lane == 0) {
                 if (g.nblocks == 0) { best = -1.0f; bl = -1; }      // s_BlockMax::GetMaxValueLoc on empty
-                s_best_v = best; s_best_loc = bl;
+                s_best_v[it & 1] = best; s_best_loc[it & 1] = bl;   // double-buffered: the next write is two barriers away
             }
         }
         __syncthreads();
-        const float v = s_best_v; const int loc = s_best_loc;
-        __syncthreads();
+        const float v = s_best_v[it & 1]; const int loc = s_best_loc[it & 1];
         if ((double)v < thresh) break;
         lastx = loc >= 0 ? (loc & 0xffff) : -1; lasty = loc >= 0 ? (loc >> 16) : -1;
         if (tid == 0) { FpmPick p; p.x = lastx; p.y = lasty; p.v = v; picks[(size_t)job * max_picks + npicks] = p; }
