@@ -1255,7 +1255,7 @@ __device__ void fpm_subpix(const double* sc27 /* [theta][y][x] */, double xm, do
 // =====================================================================================
 #define RF_THREADS 192
 
-__global__ void __launch_bounds__(RF_THREADS)
+__global__ void __launch_bounds__(RF_THREADS, 6)
 fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double angle_step,
                            const int32_t* __restrict__ rowsum, int raw_epad, const int32_t* __restrict__ rowS,
                            const int32_t* __restrict__ rowQ, FpmTplLevel tpl, int lvl_w, int lvl_h,
