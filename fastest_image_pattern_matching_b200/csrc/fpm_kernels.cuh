@@ -161,7 +161,7 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 //   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,
 //   X = (X0+adelta)>>5, sx = X>>5, ax = X&31, weights (32-ax)(32-ay)*32 ..., (sum + 16384) >> 15
 //   == ((top<<5) + ay*(bot-top) + 512) >> 10 with top = (p00<<5) + ax*(p01-p00)   (same integers).
-// One job per output image (top-layer angle or refinement ROI).  One CTA = one 64x128 output tile of a
+// One job per output image (top-layer angle or refinement ROI).  One CTA = one 128x64 output tile of a
 // GROUP of jobs: the 3 angles of a refinement candidate are anchored at the same source point and differ by
 // less than ~4 px over the tile, so they share one staged source box.  The fixed-point map is separable and
 // monotone in x and y, so the exact source bounding box of a tile follows from its 4 corners; the union box
@@ -170,8 +170,9 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 // would cost one L1 wavefront per lane.  32 pixels per thread and angle; padding columns up to dpitch are
 // written as zero.
 // =====================================================================================
-#define WA_TW 64
-#define WA_TH 128
+#define WA_TW 128
+#define WA_TH 64
+#define WA_PX (WA_TW / 32)   // pixels per lane and tile row
 #define WA_THREADS 256
 #define WA_BW 160     // staged box: max bytes per row actually used (40 words)
 #define WA_SW 164     // staged box pitch in bytes: 41 words (odd) -> rows fall in different banks
@@ -258,7 +259,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     fpm_cp_async_commit();
     fpm_cp_async_wait<0>();
     __syncthreads();
-    // Gather.  A warp owns one output row at a time and lane l the pixels l and l+32 of the tile row: neighbouring
+    // Gather.  A warp owns one output row at a time and lane l the pixels l, l+32, l+64, l+96 of the tile row: neighbouring
     // lanes read neighbouring source pixels (same word -> broadcast) or, for steep angles, neighbouring source rows
     // (odd word pitch -> different banks), so the byte gathers are close to conflict-free at every angle.
     const int lane = tid & 31, warp = tid >> 5;
@@ -266,16 +267,20 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     for (int j = 0; j < group; j++) {
         if (!jobs[g0 + j].valid) continue;
         uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride + tx0;
-        const int adj0 = s_ad[j][lane] - (bx0 << 10), adj1 = s_ad[j][lane + 32] - (bx0 << 10);
-        const int bdj0 = s_bd[j][lane] - (by0 << 10), bdj1 = s_bd[j][lane + 32] - (by0 << 10);
+        int adj[WA_PX], bdj[WA_PX];
+#pragma unroll
+        for (int k = 0; k < WA_PX; k++) {
+            adj[k] = s_ad[j][lane + 32 * k] - (bx0 << 10);
+            bdj[k] = s_bd[j][lane + 32 * k] - (by0 << 10);
+        }
         for (int row = warp; row < nrows; row += WA_THREADS / 32) {
             const int X0 = s_X0[j][row], Y0 = s_Y0[j][row];
             uint8_t* drow = d + (size_t)(ty0 + row) * dpitch;
             if (fastw) {
-                int v[2];
+                int v[WA_PX];
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
+                for (int k = 0; k < WA_PX; k++) {
+                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
                     const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
                     const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
                     const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
@@ -283,18 +288,18 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                     const int bot = (p10 << 5) + ax * (p11 - p10);
                     v[k] = ((top << 5) + ay * (bot - top) + 512) >> 10;
                 }
-                drow[lane] = (uint8_t)v[0];
-                drow[lane + 32] = (uint8_t)v[1];
+#pragma unroll
+                for (int k = 0; k < WA_PX; k++) drow[lane + 32 * k] = (uint8_t)v[k];
             } else if (staged && inside) {
                 // partial-width tile (the last tile column of a ROI, or a ROI narrower than a tile) whose taps all lie
                 // inside the image: the fast arithmetic with a column predicate; padding columns are written as zero
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
+                for (int k = 0; k < WA_PX; k++) {
                     const int col = lane + 32 * k;
                     if (tx0 + col >= dpitch) continue;
                     int v = 0;
                     if (col < ncols) {
-                        const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
+                        const int XX = X0 + adj[k], YY = Y0 + bdj[k];
                         const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
                         const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
                         const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
@@ -306,12 +311,12 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
+                for (int k = 0; k < WA_PX; k++) {
                     const int col = lane + 32 * k;
                     if (tx0 + col >= dpitch) continue;
                     int v = 0;
                     if (col < ncols) {
-                        const int XX = X0 + (k ? adj1 : adj0), YY = Y0 + (k ? bdj1 : bdj0);
+                        const int XX = X0 + adj[k], YY = Y0 + bdj[k];
                         const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
                         const int lx = XX >> 10, ly = YY >> 10;              // relative to (bx0, by0)
                         const int sx = lx + bx0, sy = ly + by0;
