@@ -24,7 +24,8 @@ def _templates():
 
 
 def test_oracle_reads_m12(ocr_case):
-    """known answer: the printed text of the reference's own OCR test image"""
+    """known answer: the printed text of the reference's own OCR test image (the full 36-glyph oracle read takes
+    ~0.16 s on one core of the GPU box, ~0.4 s here: the CPU figure quoted in profiles/README.md)"""
     assert ocr_case["text"] == KNOWN_TEXT
     # a 6-glyph subset keeps the CPU suite short; the full read is what make_golden.py ran
     sub = {ch: get_image("M12/" + ch) for ch in "TESDA1"}
