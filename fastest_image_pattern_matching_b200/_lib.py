@@ -40,6 +40,11 @@ SIGNATURES = {
     "fpm_match_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _vp, _i, _vp]),
     "fpm_match_multi": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp]),
     "fpm_ocr_assemble": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i]),
+    "fpm_ingest_bmp": (_i, [_vp, _vp, _sz, _pi, _pi]),
+    "fpm_ingest_rgb32": (_i, [_vp, _vp, _i, _i, _i]),
+    "fpm_ingested_pixels": (_i, [_vp, _vp]),
+    "fpm_match_ingested": (_i, [_vp, _vp, _i, _pi]),
+    "fpm_learn_ingested": (_i, [_vp]),
     "fpm_match_batch_device": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _vp, _i, _vp]),
     "fpm_last_time_ms": (_d, [_vp]),
     "fpm_set_user_rect": (None, [_vp, _i, _i, _i, _i]),

@@ -174,7 +174,8 @@ struct fpm_handle {
     std::vector<uint8_t> tpl0;    // level-0 copy for re-learning when MinReduceArea changes
     int tpl0_w = 0, tpl0_h = 0;
     std::vector<TplLevelHost> tpl;
-    DevBuf d_tpl, d_tsh, d_raw, d_inv, d_numer, d_totS, d_totQ;
+    DevBuf d_tpl, d_tsh, d_raw, d_inv, d_numer, d_totS, d_totQ, d_ingest_raw, d_ingest;
+    int ingest_w = 0, ingest_h = 0, ingest_pitch = 0;      // last ingested frame (device resident)
     // user rect (pure storage)
     int ur[4] = {0, 0, 0, 0};
     int has_ur = 0;
@@ -1000,7 +1001,7 @@ void fpm_destroy(fpm_handle* h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->aux_stream);
-    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_numer, &h->d_totS, &h->d_totQ, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_numer, &h->d_totS, &h->d_totQ, &h->d_ingest_raw, &h->d_ingest, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
                       &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
@@ -1269,6 +1270,103 @@ int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int
     if ((int)text.size() + 1 > out_cap) return FPM_ERR_LIMIT;
     memcpy(out, text.c_str(), text.size() + 1);
     return (int)text.size();
+}
+
+// ---- image ingest ---------------------------------------------------------------------
+namespace {
+uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint32_t rd16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+}  // namespace
+
+int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!file || nbytes < 54 || file[0] != 'B' || file[1] != 'M') { h->err = "not a BMP file"; return FPM_ERR_INVALID; }
+    const uint32_t off = rd32(file + 10), dib = rd32(file + 14);
+    if (dib < 40) { h->err = "unsupported BMP header (OS/2 core header)"; return FPM_ERR_INVALID; }
+    const int w = (int)rd32(file + 18);
+    int hs = (int)rd32(file + 22);
+    const int bpp = (int)rd16(file + 28);
+    const uint32_t comp = rd32(file + 30), clr_used = rd32(file + 46);
+    const int top_down = hs < 0;
+    const int hh = top_down ? -hs : hs;
+    if (w <= 0 || hh <= 0 || comp != 0 || (bpp != 8 && bpp != 24)) {
+        h->err = "unsupported BMP (only uncompressed 8-bit palettized and 24-bit BGR)";
+        return FPM_ERR_INVALID;
+    }
+    const uint32_t row_stride = (uint32_t)(((size_t)w * bpp + 31) / 32 * 4);
+    if ((size_t)off + (size_t)row_stride * hh > nbytes) { h->err = "truncated BMP"; return FPM_ERR_INVALID; }
+    FpmBmpLut lut;
+    memset(&lut, 0, sizeof(lut));
+    if (bpp == 8) {
+        const uint32_t n_pal = clr_used ? std::min<uint32_t>(clr_used, 256) : 256;
+        const size_t pal_off = 14 + (size_t)dib;
+        if (pal_off + (size_t)n_pal * 4 > nbytes) { h->err = "truncated BMP palette"; return FPM_ERR_INVALID; }
+        for (uint32_t i = 0; i < n_pal; i++) {                       // CvtPaletteToGray: same weights as the 24-bit path
+            const uint8_t* e = file + pal_off + (size_t)i * 4;
+            lut.g[i] = (uint8_t)(((uint32_t)e[0] * 1868u + (uint32_t)e[1] * 9617u + (uint32_t)e[2] * 4899u + 8192u) >> 14);
+        }
+    }
+    CK(cudaSetDevice(h->device));
+    CK(h->d_ingest_raw.ensure(nbytes));
+    const int pitch = (int)align_up(w, 128);
+    CK(h->d_ingest.ensure((size_t)pitch * hh));
+    CK(cudaMemcpyAsync(h->d_ingest_raw.p, file, nbytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((w + 255) / 256, hh);
+    fpm_ingest_bmp_kernel<<<grid, 256, 0, h->stream>>>(h->d_ingest_raw.as<uint8_t>(), off, row_stride, bpp, top_down, lut, w, hh,
+                                                       h->d_ingest.as<uint8_t>(), pitch);
+    CKL();
+    CK(cudaStreamSynchronize(h->stream));                             // the caller's file buffer is free again
+    h->ingest_w = w; h->ingest_h = hh; h->ingest_pitch = pitch;
+    if (width) *width = w;
+    if (height) *height = hh;
+    return FPM_OK;
+}
+
+int fpm_ingest_rgb32(fpm_handle* h, const uint32_t* pixels, int width, int height, int stride_bytes)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!pixels || width <= 0 || height <= 0 || stride_bytes < 4 * width || (stride_bytes & 3)) { h->err = "bad RGB32 frame"; return FPM_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const size_t nbytes = (size_t)stride_bytes * height;
+    CK(h->d_ingest_raw.ensure(nbytes));
+    const int pitch = (int)align_up(width, 128);
+    CK(h->d_ingest.ensure((size_t)pitch * height));
+    CK(cudaMemcpyAsync(h->d_ingest_raw.p, pixels, nbytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((width + 255) / 256, height);
+    fpm_ingest_rgb32_kernel<<<grid, 256, 0, h->stream>>>(h->d_ingest_raw.as<uint32_t>(), stride_bytes / 4, width, height,
+                                                         h->d_ingest.as<uint8_t>(), pitch);
+    CKL();
+    CK(cudaStreamSynchronize(h->stream));
+    h->ingest_w = width; h->ingest_h = height; h->ingest_pitch = pitch;
+    return FPM_OK;
+}
+
+int fpm_ingested_pixels(fpm_handle* h, uint8_t* out)
+{
+    if (!h || !out) return FPM_ERR_INVALID;
+    if (h->ingest_w <= 0) { h->err = "no ingested frame"; return FPM_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2D(out, (size_t)h->ingest_w, h->d_ingest.p, (size_t)h->ingest_pitch, (size_t)h->ingest_w, h->ingest_h, cudaMemcpyDeviceToHost));
+    return FPM_OK;
+}
+
+int fpm_match_ingested(fpm_handle* h, fpm_result* out, int cap, int* n)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (h->ingest_w <= 0) { h->err = "no ingested frame"; return FPM_ERR_INVALID; }
+    return fpm_match_batch_device(h, h->d_ingest.as<uint8_t>(), 1, h->ingest_w, h->ingest_h, h->ingest_pitch,
+                                  (size_t)h->ingest_pitch * h->ingest_h, out, cap, n);
+}
+
+int fpm_learn_ingested(fpm_handle* h)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (h->ingest_w <= 0) { h->err = "no ingested frame"; return FPM_ERR_INVALID; }
+    std::vector<uint8_t> px((size_t)h->ingest_w * h->ingest_h);
+    int rc = fpm_ingested_pixels(h, px.data());
+    if (rc) return rc;
+    return fpm_learn(h, px.data(), h->ingest_w, h->ingest_h, h->ingest_w);
 }
 
 double fpm_last_time_ms(const fpm_handle* h) { return h ? h->last_ms : 0; }

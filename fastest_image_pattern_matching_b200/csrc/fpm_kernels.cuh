@@ -1427,6 +1427,40 @@ __global__ void fpm_invert_kernel(const uint8_t* __restrict__ src, int w, int h,
     *reinterpret_cast<uint32_t*>(d) = v;                 // dpitch is a multiple of 128: the padded tail is ours
 }
 
+// ---- image ingest: decode on the device -------------------------------------------------
+// Uncompressed Windows BMP rows -> u8 grayscale like cv::imread(path, IMREAD_GRAYSCALE) (src/MatchToolDialog.cpp:314,341):
+// 8-bit indices go through a gray look-up table built from the palette, 24-bit BGR pixels through OpenCV's fixed-point
+// weights (B*1868 + G*9617 + R*4899 + 8192) >> 14 (both pinned against cv2.imdecode in tests/test_ingest.py).
+struct FpmBmpLut { uint8_t g[256]; };
+
+__global__ void fpm_ingest_bmp_kernel(const uint8_t* __restrict__ file, uint32_t data_off, uint32_t row_stride, int bpp,
+                                      int top_down, FpmBmpLut lut, int w, int h, uint8_t* __restrict__ dst, int dpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* row = file + data_off + (size_t)(top_down ? y : h - 1 - y) * row_stride;
+    uint8_t v;
+    if (bpp == 8) {
+        v = lut.g[row[x]];
+    } else {
+        const uint32_t b = row[3 * x], g = row[3 * x + 1], r = row[3 * x + 2];
+        v = (uint8_t)((b * 1868u + g * 9617u + r * 4899u + 8192u) >> 14);
+    }
+    dst[(size_t)y * dpitch + x] = v;
+}
+
+// Camera frame hand-off (src/MatchToolDialog.cpp:1557-1575: QImage::convertToFormat(Format_Grayscale8) of an RGB32 frame):
+// 0xAARRGGBB pixels -> qGray = (R*11 + G*16 + B*5) / 32 (Qt's documented integer formula; no Qt here to pin it against)
+__global__ void fpm_ingest_rgb32_kernel(const uint32_t* __restrict__ px, int spitch_words, int w, int h,
+                                        uint8_t* __restrict__ dst, int dpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint32_t p = px[(size_t)y * spitch_words + x];
+    const uint32_t r = (p >> 16) & 255u, g = (p >> 8) & 255u, b = p & 255u;
+    dst[(size_t)y * dpitch + x] = (uint8_t)((r * 11u + g * 16u + b * 5u) >> 5);
+}
+
 // top <= stop layer: the top-layer picks are final (src/TemplateMatcher.cpp:272-276)
 __global__ void fpm_cands_to_refined_kernel(const FpmCand* __restrict__ cands, int n, int top,
                                             FpmRefined* __restrict__ refined, int* __restrict__ refined_count)

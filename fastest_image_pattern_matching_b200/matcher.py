@@ -147,6 +147,37 @@ class TemplateMatcher:
         self._check(self._lib.fpm_match(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], res, cap, C.byref(n)))
         return _convert(res, min(n.value, cap))
 
+    # ---- image ingest: decode on the device, match without a pixel copy ----
+    def ingestBmp(self, file_bytes) -> tuple:
+        """BMP file image (bytes / uint8 array) -> device-resident grayscale frame; returns (width, height)."""
+        b = np.frombuffer(bytes(file_bytes), np.uint8) if not isinstance(file_bytes, np.ndarray) else np.ascontiguousarray(file_bytes, np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        self._check(self._lib.fpm_ingest_bmp(self._h, b.ctypes.data, b.size, C.byref(w), C.byref(h)))
+        self._ingest_shape = (h.value, w.value)
+        return w.value, h.value
+
+    def ingestRgb32(self, pixels) -> None:
+        """camera frame: [H, W] uint32 0xAARRGGBB (QImage::Format_RGB32) -> device-resident grayscale frame"""
+        p = np.ascontiguousarray(pixels, np.uint32)
+        self._check(self._lib.fpm_ingest_rgb32(self._h, p.ctypes.data, p.shape[1], p.shape[0], p.strides[0]))
+        self._ingest_shape = p.shape
+
+    def ingestedPixels(self) -> np.ndarray:
+        out = np.zeros(self._ingest_shape, np.uint8)
+        self._check(self._lib.fpm_ingested_pixels(self._h, out.ctypes.data))
+        return out
+
+    def matchIngested(self) -> List[SingleTargetMatch]:
+        cap = self.result_capacity
+        res = (L.fpm_result * cap)()
+        n = C.c_int(0)
+        self._check(self._lib.fpm_match_ingested(self._h, res, cap, C.byref(n)))
+        return _convert(res, min(n.value, cap))
+
+    def learnIngested(self) -> bool:
+        self._check(self._lib.fpm_learn_ingested(self._h))
+        return True
+
     def matchBatch(self, frames: np.ndarray) -> List[List[SingleTargetMatch]]:
         """frames: [B, H, W] uint8 in host memory (pinned for full PCIe speed)."""
         f = np.asarray(frames)

@@ -111,6 +111,20 @@ int fpm_match_multi(fpm_handle* const* hs, int n_handles, const uint8_t* src, in
  * Returns the text length, or FPM_ERR_LIMIT if out_cap is too small. */
 int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int n, double line_tol, char* out, int out_cap);
 
+/* Image ingest: decode on the device, match the device-resident frame without a pixel copy.
+ * fpm_ingest_bmp: an uncompressed Windows BMP file image (8-bit palettized or 24-bit BGR, bottom-up or top-down) in a
+ *   HOST buffer -> u8 grayscale frame owned by the handle, bit-identical to cv::imread(path, IMREAD_GRAYSCALE)
+ *   (src/MatchToolDialog.cpp:314 source, :341 template): (B*1868 + G*9617 + R*4899 + 8192) >> 14 on pixels / palette entries.
+ * fpm_ingest_rgb32: camera frame hand-off (src/MatchToolDialog.cpp:1557-1575, QImage::convertToFormat(Format_Grayscale8)):
+ *   0xAARRGGBB pixels -> (R*11 + G*16 + B*5) / 32.
+ * fpm_match_ingested / fpm_learn_ingested use the last ingested frame as source / template;
+ * fpm_ingested_pixels copies it back (width*height bytes). */
+int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
+int fpm_ingest_rgb32(fpm_handle* h, const uint32_t* pixels, int width, int height, int stride_bytes);
+int fpm_ingested_pixels(fpm_handle* h, uint8_t* out);
+int fpm_match_ingested(fpm_handle* h, fpm_result* out, int cap, int* n);
+int fpm_learn_ingested(fpm_handle* h);
+
 /* getLastExecutionTime (include/TemplateMatcher.h:40), milliseconds of the last match call. */
 double fpm_last_time_ms(const fpm_handle* h);
 

@@ -851,3 +851,19 @@ def ocr_read(src, templates, params=None, tol=10.0):
         per[ch] = res
         vec.extend((r.ptCenter, ch) for r in res)
     return ocr_assemble(vec, tol), per
+
+
+# --------------------------------------------------------------------------------------
+# image ingest (src/MatchToolDialog.cpp:314, :341, :1557-1575)
+# --------------------------------------------------------------------------------------
+def ingest_bmp(file_bytes):
+    """cv::imread(path, IMREAD_GRAYSCALE) on the file image (same OpenCV decoder through cv2.imdecode)."""
+    return cv2.imdecode(np.frombuffer(bytes(file_bytes), np.uint8), cv2.IMREAD_GRAYSCALE)
+
+
+def ingest_rgb32(pixels):
+    """QImage::convertToFormat(Format_Grayscale8) of an RGB32 frame: qGray = (R*11 + G*16 + B*5) / 32 (Qt's documented
+    formula; parity unpinned -- there is no Qt in this image to run the real conversion)."""
+    p = np.asarray(pixels, np.uint32)
+    r, g, b = (p >> 16) & 255, (p >> 8) & 255, p & 255
+    return ((r * 11 + g * 16 + b * 5) >> 5).astype(np.uint8)
