@@ -1497,6 +1497,7 @@ __device__ __forceinline__ void fpm_corners(double ptx, double pty, double angle
 }
 
 #define FN_THREADS 256
+#define FN_PAIR_MAX 512      // survivors per frame handled by the all-pairs bit matrix
 
 // two rotated rects whose centres are farther apart than the sum of their half diagonals (plus a margin that
 // dwarfs float rounding) cannot touch: rotatedRectangleIntersection would return INTERSECT_NONE -> keep both
@@ -1523,6 +1524,7 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
     int* del = del_scratch + (size_t)img * key_stride;
     int* idmap = idmap_scratch + (size_t)img * key_stride;
     __shared__ int s_n, s_cut;
+    __shared__ unsigned s_bits[FN_PAIR_MAX * (FN_PAIR_MAX / 32)];     // 32 KB: pair-decision bit rows of the NMS
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int i = tid; i < n_total; i += FN_THREADS)
@@ -1560,24 +1562,34 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
     // filterWithRotatedRect: scores are sorted descending so the later index always loses.
     // Small sets: all pair decisions are evaluated in parallel first (the geometry is the expensive,
     // latency-bound part), then the greedy pass only reads the byte matrix.
-    if (m <= pair_cap) {
-        unsigned char* ov = pair_scratch + (size_t)img * pair_cap * pair_cap;
-        for (int p = tid; p < m * m; p += FN_THREADS) {
-            int i = p / m, k = p - i * m;
-            if (k > i)
-                ov[p] = fpm_rrect_far(rects[i], rects[k])
-                            ? (unsigned char)0
-                            : (unsigned char)fpm_rrect_overlap_decision(rects[i], rects[k], max_overlap, nullptr, nullptr);
+    if (m <= pair_cap && m <= FN_PAIR_MAX) {
+        // Pair decisions as bit rows in shared memory (row i, bit k = "k must go if i stays"): a warp per row, one
+        // ballot per 32 columns.  The greedy pass is then a chain of register / shared-memory operations in ONE warp
+        // (lane l keeps the deletion bits of survivors 32 l .. 32 l + 31) instead of a chain of global-memory round trips.
+        const int nw = (m + 31) >> 5;
+        const int lane = tid & 31;
+        for (int i = tid >> 5; i < m; i += FN_THREADS / 32) {
+            const FpmRRect ri = rects[i];
+            for (int j = 0; j < nw; j++) {
+                bool hit = false;
+                const int k = 32 * j + lane;
+                if (k > i && k < m) {
+                    const FpmRRect rk = rects[k];
+                    hit = !fpm_rrect_far(ri, rk) && fpm_rrect_overlap_decision(ri, rk, max_overlap, nullptr, nullptr);
+                }
+                const unsigned w = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_bits[i * (FN_PAIR_MAX / 32) + j] = w;
+            }
         }
         __syncthreads();
-        // greedy pass by one warp: no CTA-wide barrier per survivor
         if (tid < 32) {
+            unsigned dw = 0;
             for (int i = 0; i < m - 1; i++) {
-                if (!del[i])
-                    for (int k = i + 1 + tid; k < m; k += 32)
-                        if (ov[i * m + k]) del[k] = 1;
-                __syncwarp();
+                const unsigned wi = __shfl_sync(0xffffffffu, dw, i >> 5);
+                if (!((wi >> (i & 31)) & 1u) && lane < nw) dw |= s_bits[i * (FN_PAIR_MAX / 32) + lane];
             }
+            if (lane < nw)
+                for (int bpos = 0; bpos < 32 && 32 * lane + bpos < m; bpos++) del[32 * lane + bpos] = (dw >> bpos) & 1u;
         }
         __syncthreads();
     } else {
