@@ -1525,6 +1525,9 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
     int* idmap = idmap_scratch + (size_t)img * key_stride;
     __shared__ int s_n, s_cut;
     __shared__ unsigned s_bits[FN_PAIR_MAX * (FN_PAIR_MAX / 32)];     // 32 KB: pair-decision bit rows of the NMS
+    __shared__ unsigned s_kept[FN_PAIR_MAX / 32];
+    __shared__ int s_base[FN_PAIR_MAX / 32 + 1];
+    bool bit_path = false;
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int i = tid; i < n_total; i += FN_THREADS)
@@ -1588,9 +1591,20 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
                 const unsigned wi = __shfl_sync(0xffffffffu, dw, i >> 5);
                 if (!((wi >> (i & 31)) & 1u) && lane < nw) dw |= s_bits[i * (FN_PAIR_MAX / 32) + lane];
             }
-            if (lane < nw)
-                for (int bpos = 0; bpos < 32 && 32 * lane + bpos < m; bpos++) del[32 * lane + bpos] = (dw >> bpos) & 1u;
+            // survivors and their ranks straight from the bit words: exclusive prefix of the per-word counts
+            const int left = m - 32 * lane;
+            const unsigned valid = lane < nw ? (left >= 32 ? 0xffffffffu : ((1u << left) - 1u)) : 0u;
+            const unsigned kept = ~dw & valid;
+            int incl = __popc(kept);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane < FN_PAIR_MAX / 32) { s_kept[lane] = kept; s_base[lane] = incl - __popc(kept); }
+            if (lane == 31) s_base[FN_PAIR_MAX / 32] = incl;          // total survivors
         }
+        bit_path = true;
         __syncthreads();
     } else {
         for (int i = 0; i < m - 1; i++) {
@@ -1604,19 +1618,32 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
             __syncthreads();
         }
     }
-    // survivor ranks by one thread (idmap is free again: rank of record i, or -1), conversion by all threads
-    if (tid == 0) {
-        int cnt = 0;
-        for (int i = 0; i < m; i++) {
-            const bool keep = !del[i] && !(mfc_compat && cnt >= max_pos);     // MatchToolDlg.cpp:1115-1116
-            idmap[i] = keep ? cnt : -1;
-            if (keep) cnt++;
+    // survivor ranks (from the bit words, or by one thread on the large-set path: idmap is free again and holds
+    // the rank of record i, or -1), conversion by all threads
+    if (!bit_path) {
+        if (tid == 0) {
+            int cnt = 0;
+            for (int i = 0; i < m; i++) {
+                const bool keep = !del[i] && !(mfc_compat && cnt >= max_pos);     // MatchToolDlg.cpp:1115-1116
+                idmap[i] = keep ? cnt : -1;
+                if (keep) cnt++;
+            }
+            result_count[img] = cnt;
         }
-        result_count[img] = cnt;
+        __syncthreads();
+    } else if (tid == 0) {
+        const int total = s_base[FN_PAIR_MAX / 32];
+        result_count[img] = (mfc_compat && total > max_pos) ? max_pos : total;
     }
-    __syncthreads();
     for (int i = tid; i < m; i += FN_THREADS) {
-        const int rank = idmap[i];
+        int rank;
+        if (bit_path) {
+            const unsigned kw = s_kept[i >> 5];
+            rank = ((kw >> (i & 31)) & 1u) ? s_base[i >> 5] + __popc(kw & ((1u << (i & 31)) - 1u)) : -1;
+            if (mfc_compat && rank >= max_pos) rank = -1;                         // MatchToolDlg.cpp:1115-1116
+        } else {
+            rank = idmap[i];
+        }
         if (rank < 0 || rank >= result_cap) continue;
         const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
         FpmResultDev o;
