@@ -885,6 +885,7 @@ __device__ __forceinline__ uint32_t fpm_desc_key(float f)
 // translation (:186) and rotate back into the un-rotated top layer (:265-266).
 // =====================================================================================
 #define CS_THREADS 1024
+#define CS_MAX_SMEM_ANGLES 1024     // angle sweeps up to this size keep their pick-count prefix in shared memory
 
 __global__ void __launch_bounds__(CS_THREADS)
 fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict__ pick_count,
@@ -900,10 +901,19 @@ fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict
     extern __shared__ unsigned long long s_keys[];
     const int img = blockIdx.x, tid = threadIdx.x;
     __shared__ int s_n, s_base;
-    int* s_off = off_scratch + (size_t)img * n_angles;     // prefix of pick counts
+    __shared__ int s_cnt[CS_MAX_SMEM_ANGLES], s_offs[CS_MAX_SMEM_ANGLES];
+    // prefix of the pick counts per angle: in shared memory (counts loaded in parallel, a short serial scan over
+    // shared memory) unless the sweep has more angles than fit; a serial loop over GLOBAL memory here and in the
+    // fill loop below used to be most of this kernel's time (one L2 round trip per angle)
+    const bool offs_smem = n_angles <= CS_MAX_SMEM_ANGLES;
+    int* s_off = offs_smem ? s_offs : off_scratch + (size_t)img * n_angles;
+    if (offs_smem) {
+        for (int a = tid; a < n_angles; a += CS_THREADS) s_cnt[a] = pick_count[img * n_angles + a];
+        __syncthreads();
+    }
     if (tid == 0) {
         int n = 0;
-        for (int a = 0; a < n_angles; a++) { s_off[a] = n; n += pick_count[img * n_angles + a]; }
+        for (int a = 0; a < n_angles; a++) { s_off[a] = n; n += offs_smem ? s_cnt[a] : pick_count[img * n_angles + a]; }
         s_n = n;
         s_base = atomicAdd(flat_counter, n);
     }
@@ -915,12 +925,23 @@ fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict
     unsigned long long* keys = use_smem ? s_keys : key_scratch + (size_t)img * key_stride;
     for (int i = tid; i < n_pad; i += CS_THREADS) keys[i] = ~0ull;
     __syncthreads();
-    for (int a = 0; a < n_angles; a++) {
-        int c = pick_count[img * n_angles + a];
-        for (int j = tid; j < c; j += CS_THREADS) {
-            const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
-            uint32_t order = (uint32_t)(a * max_picks + j);
-            keys[s_off[a] + j] = ((unsigned long long)fpm_desc_key(p.v) << 32) | order;
+    if (offs_smem) {
+        // one thread per (angle, pick slot): the few picks of all angles are fetched in parallel
+        for (int i = tid; i < n_angles * max_picks; i += CS_THREADS) {
+            const int a = i / max_picks, j = i - a * max_picks;
+            if (j < s_cnt[a]) {
+                const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+                keys[s_off[a] + j] = ((unsigned long long)fpm_desc_key(p.v) << 32) | (uint32_t)i;
+            }
+        }
+    } else {
+        for (int a = 0; a < n_angles; a++) {
+            int c = pick_count[img * n_angles + a];
+            for (int j = tid; j < c; j += CS_THREADS) {
+                const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+                uint32_t order = (uint32_t)(a * max_picks + j);
+                keys[s_off[a] + j] = ((unsigned long long)fpm_desc_key(p.v) << 32) | order;
+            }
         }
     }
     __syncthreads();
@@ -1498,6 +1519,7 @@ __device__ __forceinline__ void fpm_corners(double ptx, double pty, double angle
 
 #define FN_THREADS 256
 #define FN_PAIR_MAX 512      // survivors per frame handled by the all-pairs bit matrix
+#define FN_KEYS_SMEM 1024    // sort keys per frame kept in shared memory
 
 // two rotated rects whose centres are farther apart than the sum of their half diagonals (plus a margin that
 // dwarfs float rounding) cannot touch: rotatedRectangleIntersection would return INTERSECT_NONE -> keep both
@@ -1519,7 +1541,10 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
 {
     const int img = blockIdx.x, tid = threadIdx.x;
     const int n_total = *refined_count;
-    unsigned long long* keys = key_scratch + (size_t)img * key_stride;
+    // sort keys in shared memory when the per-frame capacity allows (a bitonic sort in global memory pays one L2 round
+    // trip per stage)
+    __shared__ unsigned long long s_keys[FN_KEYS_SMEM];
+    unsigned long long* keys = key_stride <= FN_KEYS_SMEM ? s_keys : key_scratch + (size_t)img * key_stride;
     FpmRRect* rects = rect_scratch + (size_t)img * key_stride;
     int* del = del_scratch + (size_t)img * key_stride;
     int* idmap = idmap_scratch + (size_t)img * key_stride;
