@@ -161,7 +161,7 @@ struct fpm_handle {
     bool mma_attr_set = false, fused_attr_set = false, peaks_attr_set = false;
     // concurrent half-batches (fpm_match_batch_device): a second handle with the same template and parameters
     fpm_handle* twin = nullptr;
-    int split_batch = 32;          // FPM_PARAM_SPLIT_BATCH: smallest batch that is split in two (0 = never)
+    int split_batch = 8;           // FPM_PARAM_SPLIT_BATCH: smallest batch that is split in two (0 = never)
     unsigned learn_gen = 0, twin_gen = 0;
     int stop_layer1 = 0, bitwise_not = 0, tol_range = 0;   // MFC-only modes (MatchTool/MatchToolDlg.cpp:788-816, :936)
     double tol_r[4] = {0, 0, 0, 0};

@@ -58,7 +58,7 @@ enum fpm_param {
     FPM_PARAM_TOLERANCE_RANGE = 15,/* m_bToleranceRange (:805-816): sweep [TOLERANCE1,TOLERANCE2] and [TOLERANCE3,TOLERANCE4] */
     FPM_PARAM_TOLERANCE1 = 16, FPM_PARAM_TOLERANCE2 = 17, FPM_PARAM_TOLERANCE3 = 18, FPM_PARAM_TOLERANCE4 = 19,
     FPM_PARAM_SPLIT_BATCH = 20,    /* fpm_match_batch_device: batches of at least this many frames run as two concurrent
-                                      half-batches on two internal handles (default 32, 0 = never) */
+                                      half-batches on two internal handles (default 8, 0 = never) */
     FPM_PARAM_COUNT_
 };
 

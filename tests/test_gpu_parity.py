@@ -300,7 +300,7 @@ def test_device_batch_in_two_concurrent_halves_equals_single(matcher, golden_cas
         for i in range(B):
             assert_results_match(_convert(res[i * cap:(i + 1) * cap], counts[i]), single9[i], 0, 0, 0)
     finally:
-        matcher.setSplitBatch(32)
+        matcher.setSplitBatch(8)
 
 
 def test_small_workspace_waves_give_same_result(matcher, golden_cases):
