@@ -157,3 +157,33 @@ def test_guards_and_edge_cases():
     assert m.learn_pattern(tpl)
     assert m.match(np.zeros((20, 100), np.uint8)) == []         # template taller than source
     assert m.match(np.zeros((30, 30), np.uint8)) == []          # template area larger
+
+
+@pytest.mark.parametrize("shape", [(211, 300), (216, 288), (90, 301)])
+def test_block_max_variants_agree_with_plain_search_without_ties(shape):
+    """on a tie-free score map the Qt s_BlockMax, the MFC s_BlockMax and the plain minMaxLoc path
+    return the identical ordered pick list (they can differ only on exact float ties)."""
+    rng = np.random.default_rng(shape[0])
+    n = shape[0] * shape[1]
+    score = rng.permutation(np.linspace(-0.2, 0.9, n).astype(np.float32)).reshape(shape)
+    assert len(np.unique(score)) == score.size                 # no ties
+    om = O.OracleMatcher()
+    om.max_pos, om.max_overlap = 25, 0.2
+    plain = om.top_picks(score.copy(), (9, 7), 0.3, False)
+    qt = om.top_picks(score.copy(), (9, 7), 0.3, True)
+    om.mfc_compat = True
+    mfc = om.top_picks(score.copy(), (9, 7), 0.3, True)
+    assert len(plain) > 5 and plain == qt == mfc
+
+
+def test_block_max_tie_rules_differ_as_documented():
+    """two equal maxima in different blocks: Qt keeps the FIRST maximal block (std::max_element, DataStructures.h:241-245),
+    MFC the LAST one (>=, MatchToolDlg.h:206)"""
+    score = np.zeros((60, 80), np.float32)
+    score[5, 6] = 1.0
+    score[50, 70] = 1.0
+    om = O.OracleMatcher()
+    om.max_pos, om.max_overlap = 1, 0.0
+    assert om.top_picks(score.copy(), (9, 7), 0.5, True)[0][0] == (6, 5)
+    om.mfc_compat = True
+    assert om.top_picks(score.copy(), (9, 7), 0.5, True)[0][0] == (70, 50)
