@@ -20,7 +20,7 @@ class fpm_result(C.Structure):
 
 PARAM_MAX_POSITIONS, PARAM_MAX_OVERLAP, PARAM_SCORE, PARAM_TOLERANCE_ANGLE, PARAM_MIN_REDUCE_AREA, \
     PARAM_USE_SIMD, PARAM_SUBPIXEL, PARAM_TRACE, PARAM_WORKSPACE_MB, PARAM_PROFILE, PARAM_H2D_CHUNK, PARAM_TENSOR_CORES, PARAM_MFC_COMPAT, PARAM_STOP_LAYER1, PARAM_BITWISE_NOT, PARAM_TOLERANCE_RANGE, \
-    PARAM_TOLERANCE1, PARAM_TOLERANCE2, PARAM_TOLERANCE3, PARAM_TOLERANCE4, PARAM_SPLIT_BATCH = range(21)
+    PARAM_TOLERANCE1, PARAM_TOLERANCE2, PARAM_TOLERANCE3, PARAM_TOLERANCE4, PARAM_SPLIT_BATCH, PARAM_SHARD_UPLOAD = range(22)
 
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 _pi, _pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -65,12 +65,22 @@ SIGNATURES = {
     "fpm_stage_sort_candidates": (_i, [_vp, _vp, _i, _vp]),
     "fpm_stage_refine": (_i, [_vp, _vp, _i, _vp, _i, _pi]),
     "fpm_stage_final": (_i, [_vp, _vp, _i, _vp, _i, _pi]),
+    "fpm_comm_available": (_i, []),
+    "fpm_comm_get_unique_id": (_i, [_vp]),
+    "fpm_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "fpm_comm_attach": (_i, [_vp, _vp, _i, _i]),
+    "fpm_comm_destroy": (None, [_vp]),
+    "fpm_match_sharded": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _pi]),
+    "fpm_match_sharded_virtual": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "fpm_shard_angle_range": (_i, [_i, _i, _i, _pi, _pi]),
+    "fpm_collective_count": (C.c_longlong, [_vp]),
     "fpm_dbg_pyrdown": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "fpm_dbg_warp_affine": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "fpm_dbg_corr_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "fpm_dbg_corr_rows_mma": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "fpm_dbg_corr_fused": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "fpm_dbg_top_score": (_i, [_vp, _vp, _i, _i, _vp]),
+    "fpm_dbg_top_score_production": (_i, [_vp, _vp, _i, _i, _vp, C.POINTER(C.c_float)]),
     "fpm_dbg_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _d, _i, _vp, _pi]),
     "fpm_dbg_rrect_overlap": (_i, [_vp, _vp, _d, _pi, _pd]),
     "fpm_dbg_rrect_from3": (_i, [_vp, _vp]),

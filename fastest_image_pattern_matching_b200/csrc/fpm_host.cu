@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -133,13 +134,13 @@ struct TplLevelHost {
     std::vector<uint8_t> pix;    // w*h
 };
 
-struct TopPlan {                  // cached per (source size, parameters)
-    int sw = 0, sh = 0, top = -1, batch = 0, a0 = 0, a1 = 0;
+struct TopPlan {                  // cached per (source size, parameters); always the WHOLE angle schedule
+    int sw = 0, sh = 0, top = -1, batch = 0;
     double tol = -1;
     std::vector<double> angles;   // full schedule
-    std::vector<float> ftx, fty;  // for [a0, a1)
+    std::vector<float> ftx, fty;  // canvas translation per angle
     int maxW = 0, maxH = 0;
-    int n_ang = 0;                // a1 - a0
+    int n_ang = 0;                // angles.size()
     bool valid = false;
 };
 
@@ -184,11 +185,20 @@ struct fpm_handle {
     DevBuf d_off, d_keys, d_cand[2], d_candcnt, d_toppt, d_counters, d_jobs_ref, d_roi, d_rowsum, d_rowS, d_rowQ;
     DevBuf d_pairs, d_refined, d_rects, d_del, d_idmap, d_results, d_rescnt, d_trace, d_trace_sc, d_dbg[4];
     PinnedBuf h_counts, h_results, h_stage;
+    // angle-sharded latency mode (fpm_match_sharded): this handle is rank sh_rank of sh_nranks
+    int sh_nranks = 1, sh_rank = 0;
+    void* nccl_comm = nullptr;     // ncclComm_t (created by fpm_comm_init or borrowed through fpm_comm_attach)
+    bool nccl_owned = false;
+    int shard_upload = 1;          // FPM_PARAM_SHARD_UPLOAD: host frame uploaded as 1/N row slices + NVLink allgather
+    DevBuf d_gpicks, d_grefined;   // allgather buffers: one fixed-size block per rank, consumed in place by the kernels
+    FpmRefined* ref_out = nullptr; // where run_refine appends (null: d_refined / counters[CNT_REFINED])
+    int* ref_cnt = nullptr;
+    struct ShardState { int top = 0, chunk = 0, n_all = 0, n_local = 0, seg_cap = 0, empty = 1; size_t pick_blk = 0, ref_blk = 0; } sh;
     std::vector<FpmLevel> levels; // source pyramid of the current batch
     TopPlan plan;
     std::string err;
     double last_ms = 0;
-    long long launches = 0;
+    long long launches = 0, collectives = 0;
     // per-kernel profiling (CUDA events on the launch stream)
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;
@@ -584,25 +594,24 @@ void angle_schedule(const fpm_handle* h, int top, std::vector<double>& angles)
     }
 }
 
-int make_top_plan(fpm_handle* h, int top, int batch, int a0, int a1)
+// The plan always covers the whole schedule (a few dozen doubles per angle); a partial sweep (stage API, angle-sharded
+// mode) runs a sub-range of its job list, so a cached plan can never truncate a later full sweep.
+int make_top_plan(fpm_handle* h, int top, int batch)
 {
     const FpmLevel& L = h->levels[top];
     TopPlan& p = h->plan;
-    if (p.valid && p.sw == L.w && p.sh == L.h && p.top == top && p.batch == batch && p.tol == h->tol_angle &&
-        p.a0 == a0 && (p.a1 == a1 || a1 < 0))
+    if (p.valid && p.sw == L.w && p.sh == L.h && p.top == top && p.batch == batch && p.tol == h->tol_angle)
         return FPM_OK;
+    p.valid = false;
     angle_schedule(h, top, p.angles);
-    if (a1 < 0) a1 = (int)p.angles.size();
-    a0 = std::max(0, std::min(a0, (int)p.angles.size()));
-    a1 = std::max(a0, std::min(a1, (int)p.angles.size()));
-    p.sw = L.w; p.sh = L.h; p.top = top; p.batch = batch; p.tol = h->tol_angle; p.a0 = a0; p.a1 = a1;
-    p.n_ang = a1 - a0;
+    p.sw = L.w; p.sh = L.h; p.top = top; p.batch = batch; p.tol = h->tol_angle;
+    p.n_ang = (int)p.angles.size();
     const TplLevelHost& t = h->tpl[top];
     float cx = (L.w - 1) / 2.0f, cy = (L.h - 1) / 2.0f;
     std::vector<FpmWarpJob> jobs((size_t)batch * std::max(p.n_ang, 1));
     p.ftx.assign(p.n_ang, 0.f); p.fty.assign(p.n_ang, 0.f);
     p.maxW = p.maxH = 1;
-    for (int a = a0; a < a1; a++) {
+    for (int a = 0; a < p.n_ang; a++) {
         FpmWarpJob jb;
         fpm_rotation_matrix(cx, cy, p.angles[a], jb.m);
         int bw, bh;
@@ -611,15 +620,15 @@ int make_top_plan(fpm_handle* h, int top, int batch, int a0, int a1)
         jb.m[2] += (double)fTx; jb.m[5] += (double)fTy;
         fpm_invert_affine(jb.m);
         jb.dw = bw; jb.dh = bh; jb.valid = (bw > 0 && bh > 0) ? 1 : 0;
-        p.ftx[a - a0] = fTx; p.fty[a - a0] = fTy;
+        p.ftx[a] = fTx; p.fty[a] = fTy;
         p.maxW = std::max(p.maxW, bw); p.maxH = std::max(p.maxH, bh);
-        for (int b = 0; b < batch; b++) { jb.src_img = b; jobs[(size_t)b * p.n_ang + (a - a0)] = jb; }
+        for (int b = 0; b < batch; b++) { jb.src_img = b; jobs[(size_t)b * p.n_ang + a] = jb; }
     }
     if (p.n_ang > 0) {
         CK(h->d_jobs_top.ensure(jobs.size() * sizeof(FpmWarpJob)));
         CK(cudaMemcpyAsync(h->d_jobs_top.p, jobs.data(), jobs.size() * sizeof(FpmWarpJob), cudaMemcpyHostToDevice, h->stream));
         CK(h->d_angles.ensure(p.n_ang * sizeof(double)));
-        CK(cudaMemcpyAsync(h->d_angles.p, p.angles.data() + a0, p.n_ang * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_angles.p, p.angles.data(), p.n_ang * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         CK(h->d_ftx.ensure(p.n_ang * sizeof(float)));
         CK(h->d_fty.ensure(p.n_ang * sizeof(float)));
         CK(cudaMemcpyAsync(h->d_ftx.p, p.ftx.data(), p.n_ang * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -630,49 +639,58 @@ int make_top_plan(fpm_handle* h, int top, int batch, int a0, int a1)
     return FPM_OK;
 }
 
-// ---- top-layer sweep: warp + score + peaks for every (image, angle) ---------------------
-// leaves picks in d_picks [batch*n_ang][max_picks], counts in d_pickcnt
-int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
+// threshold of the top layer, vecLayerScore[top] = Score * 0.9^top (src/TemplateMatcher.cpp:153-156)
+double top_layer_threshold(const fpm_handle* h, int top)
+{
+    double t = h->score;
+    for (int l = 0; l < top; l++) t *= 0.9;
+    return t;
+}
+
+// Scores certainly below the top-layer threshold may be stored as estimates (fpm_ccoeff_epilogue_top): the peak
+// search cannot observe them.  Off (exact everywhere) when the threshold is not comfortably positive.
+float top_reject_below(const fpm_handle* h, int top)
+{
+    const double t = top_layer_threshold(h, top);
+    return t > 0.05 ? (float)(t - 0.01) : -INFINITY;
+}
+
+// ---- top-layer sweep: warp + score + peaks for jobs [j0, j0 + nj) of the plan's (image, angle) list -----
+// picks go to picks_out[nj][max_picks], counts to cnt_out[nj]
+int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt_out)
 {
     TopPlan& p = h->plan;
-    const int njobs = batch * p.n_ang;
     const int max_picks = h->max_pos + FPM_MATCH_CANDIDATE_NUM;
-    *max_picks_out = max_picks;
-    if (njobs == 0) return FPM_OK;
+    if (nj <= 0) return FPM_OK;
     const TplLevelHost& t = h->tpl[top];
     const int rpitch = (int)align_up(p.maxW, 16);
     const size_t rot_stride = (size_t)rpitch * p.maxH;
     const int maxRW = std::max(p.maxW - t.w + 1, 1), maxRH = std::max(p.maxH - t.h + 1, 1);
     const int spitch = (int)align_up(maxRW, 4);
     const size_t score_stride = (size_t)spitch * maxRH;
-    CK(h->d_rot.ensure(rot_stride * njobs));
-    CK(h->d_score.ensure(score_stride * njobs * sizeof(float)));
-    CK(h->d_picks.ensure((size_t)njobs * max_picks * sizeof(FpmPick)));
-    CK(h->d_pickcnt.ensure((size_t)njobs * sizeof(int)));
-    {
+    CK(h->d_rot.ensure(rot_stride * nj));
+    CK(h->d_score.ensure(score_stride * nj * sizeof(float)));
+    const FpmWarpJob* jobs = h->d_jobs_top.as<FpmWarpJob>() + j0;
+    const int kMaxGridYZ = 65535;                              // gridDim.y / gridDim.z limit: larger sweeps run in chunks
+    const size_t smem_ts = top_score_smem(t.w, t.h);
+    if (smem_ts > 200 * 1024) { h->err = "top-layer template too large for the score kernel"; return FPM_ERR_LIMIT; }
+    if (smem_ts > 48 * 1024)
+        CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem_ts));
+    for (int c0 = 0; c0 < nj; c0 += kMaxGridYZ) {
+        const int nc = std::min(kMaxGridYZ, nj - c0);
         const int tiles_x = (rpitch + WA_TW - 1) / WA_TW;
-        dim3 grid(tiles_x * ((p.maxH + WA_TH - 1) / WA_TH), njobs);
-        KL(K_WARP_TOP, 2.0 * njobs * (double)p.maxW * p.maxH,
-           fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), 1, h->levels[top],
-                                                               h->d_rot.as<uint8_t>(), rpitch, rot_stride, h->border, tiles_x,
-                                                               level_vec_ok(h->levels[top])));
-    }
-    {
-        size_t smem = top_score_smem(t.w, t.h);
-        if (smem > 200 * 1024) { h->err = "top-layer template too large for the score kernel"; return FPM_ERR_LIMIT; }
-        if (smem > 48 * 1024)
-            CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem));
-        dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, njobs);
+        dim3 wgrid(tiles_x * ((p.maxH + WA_TH - 1) / WA_TH), nc);
+        KL(K_WARP_TOP, 2.0 * nc * (double)p.maxW * p.maxH,
+           fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(jobs + c0, 1, h->levels[top],
+                                                                h->d_rot.as<uint8_t>() + (size_t)c0 * rot_stride, rpitch, rot_stride,
+                                                                h->border, tiles_x, level_vec_ok(h->levels[top])));
+        dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, nc);
         dim3 block(TS_THREADS);
-        // scores certainly below the top-layer threshold (vecLayerScore, :153-156) may be stored as estimates: the peak
-        // search cannot observe them.  Off (exact everywhere) when the threshold is not comfortably positive.
-        double top_thresh = h->score;
-        for (int l = 0; l < top; l++) top_thresh *= 0.9;
-        const float reject_below = top_thresh > 0.05 ? (float)(top_thresh - 0.01) : -INFINITY;
-        KL(K_TOP_SCORE, (double)njobs * maxRW * maxRH * t.w * t.h,      // MACs
-           fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_jobs_top.as<FpmWarpJob>(), h->d_rot.as<uint8_t>(), rpitch,
-                                                                  rot_stride, tpl_level_dev(h, top), h->d_score.as<float>(),
-                                                                  spitch, score_stride, reject_below));
+        KL(K_TOP_SCORE, (double)nc * maxRW * maxRH * t.w * t.h,      // MACs
+           fpm_top_score_kernel<<<grid, block, smem_ts, h->stream>>>(jobs + c0, h->d_rot.as<uint8_t>() + (size_t)c0 * rot_stride, rpitch,
+                                                                     rot_stride, tpl_level_dev(h, top),
+                                                                     h->d_score.as<float>() + (size_t)c0 * score_stride,
+                                                                     spitch, score_stride, top_reject_below(h, top)));
     }
     {
         // bCalMaxByBlock, src/TemplateMatcher.cpp:158-159
@@ -688,36 +706,40 @@ int run_top(fpm_handle* h, int top, int batch, int* max_picks_out)
         else blk_stride = tiles0;
         blk_stride = std::max(blk_stride, 1);
         if (blk_stride > PK_SUP_MAX * 32) { h->err = "top-layer score map has too many blocks for the peak table"; return FPM_ERR_LIMIT; }
-        CK(h->d_blkv.ensure((size_t)njobs * blk_stride * sizeof(float)));
-        CK(h->d_blkl.ensure((size_t)njobs * blk_stride * sizeof(int)));
-        double thresh = h->score;
-        for (int l = 0; l < top; l++) thresh *= 0.9;          // vecLayerScore, :153-156
+        CK(h->d_blkv.ensure((size_t)nj * blk_stride * sizeof(float)));
+        CK(h->d_blkl.ensure((size_t)nj * blk_stride * sizeof(int)));
+        const double thresh = top_layer_threshold(h, top);
         const int smem_blocks = peaks_smem_blocks(h, blk_stride);
         if (smem_blocks < 0) return FPM_ERR_CUDA;
-        KL(K_TOP_PEAKS, 4.0 * njobs * maxRW * maxRH,
-           fpm_top_peaks_kernel<<<njobs, (maxRW * maxRH <= 16384) ? 128 : PK_THREADS, (size_t)smem_blocks * 8, h->stream>>>(
-               h->d_jobs_top.as<FpmWarpJob>(), h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
+        KL(K_TOP_PEAKS, 4.0 * nj * maxRW * maxRH,
+           fpm_top_peaks_kernel<<<nj, (maxRW * maxRH <= 16384) ? 128 : PK_THREADS, (size_t)smem_blocks * 8, h->stream>>>(
+               jobs, h->d_score.as<float>(), spitch, score_stride, t.w, t.h, mode, tile,
                h->d_blkv.as<float>(), h->d_blkl.as<int>(), blk_stride, thresh, h->max_overlap, max_picks,
-               h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), smem_blocks));
+               picks_out, cnt_out, smem_blocks));
     }
     return FPM_OK;
 }
 
-enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_N = 8 };
+enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_TOTAL = 3, CNT_N = 8 };
 
 // ---- refinement of a flat candidate list held in d_cand[0] ------------------------------
 int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
 {
     int* counters = h->d_counters.as<int>();
     int* hc = h->h_counts.as<int>();
-    CK(h->d_refined.ensure((size_t)std::max(n_cands, 1) * sizeof(FpmRefined)));
-    CK(cudaMemsetAsync(counters + CNT_REFINED, 0, sizeof(int), h->stream));
+    FpmRefined* ref_out = h->ref_out;
+    int* ref_cnt = h->ref_cnt ? h->ref_cnt : counters + CNT_REFINED;
+    if (!ref_out) {
+        CK(h->d_refined.ensure((size_t)std::max(n_cands, 1) * sizeof(FpmRefined)));
+        ref_out = h->d_refined.as<FpmRefined>();
+    }
+    CK(cudaMemsetAsync(ref_cnt, 0, sizeof(int), h->stream));
     *n_refined_out = 0;
     if (n_cands == 0) return FPM_OK;
     const int stop = h->stop_layer1 ? 1 : 0;                  // iStopLayer, MatchToolDlg.cpp:936
     if (top <= stop) {
         fpm_cands_to_refined_kernel<<<(n_cands + 255) / 256, 256, 0, h->stream>>>(h->d_cand[0].as<FpmCand>(), n_cands, top,
-                                                                               h->d_refined.as<FpmRefined>(), counters + CNT_REFINED);
+                                                                               ref_out, ref_cnt);
         CKL();
         *n_refined_out = n_cands;
         return FPM_OK;
@@ -735,15 +757,21 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         const double step = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
         const int rpitch = (int)align_up(t.w + FPM_ROI_PAD, 16) + 16;
         const size_t roi_stride = (size_t)rpitch * (t.h + FPM_ROI_PAD);
-        const size_t per_eval = roi_stride + (size_t)t.h * FPM_NCELL * 4 + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 +
-                                sizeof(FpmWarpJob);
+        // bytes per eval of one wave: ROI patch, window row sums, job record, and the row dots in the layout of the
+        // correlation path this level can take (dp4a [h][49], row-split tensor-core raw[h+6][64], or the fused kernel's
+        // 64 numerators + 14 window totals)
+        size_t per_eval = roi_stride + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 + sizeof(FpmWarpJob);
+        if (mma_usable(h, t.w) || mma_narrow_fused(h, t.w))
+            per_eval += std::max((size_t)(t.h + FPM_ROI_PAD) * MM_N * 4, (size_t)MM_N * 4 + 2 * FPM_NSHIFT * 8);
+        if (!mma_usable(h, t.w)) per_eval += (size_t)t.h * FPM_NCELL * 4;
         size_t budget = (size_t)(h->workspace_mb * 1024.0 * 1024.0);
         int wave_cands = (int)std::max<size_t>(1, budget / (per_eval * n_ang));
         wave_cands = std::min(wave_cands, n);
+        wave_cands = std::min(wave_cands, 65535);             // one candidate per gridDim.y slot of the ROI warp
         const int wave_evals = wave_cands * n_ang;
         CK(h->d_jobs_ref.ensure((size_t)wave_evals * sizeof(FpmWarpJob)));
         CK(h->d_roi.ensure(roi_stride * wave_evals));
-        CK(h->d_rowsum.ensure((size_t)wave_evals * t.h * FPM_NCELL * 4));
+        if (!mma_usable(h, t.w)) CK(h->d_rowsum.ensure((size_t)wave_evals * t.h * FPM_NCELL * 4));
         CK(h->d_rowS.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
         CK(h->d_rowQ.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
         if (h->trace) {
@@ -797,7 +825,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                    h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
                    L.h, layer_score[layer], h->use_simd, layer == stop ? 1 : 0, stop ? 2 : 1, (h->subpixel && layer == 0) ? 1 : 0,
                    h->d_cand[cur ^ 1].as<FpmCand>(),
-                   counters + CNT_NEXT, h->d_refined.as<FpmRefined>(), counters + CNT_REFINED,
+                   counters + CNT_NEXT, ref_out, ref_cnt,
                    h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr,
                    fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>()));
         }
@@ -824,9 +852,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
 }
 
 // ---- final stage: filterWithScore + NMS + conversion, results to host ---------------------
-int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_result* out, int cap, int* n_out)
+int run_final(fpm_handle* h, int batch, const FpmRefinedView& rv, int key_stride, fpm_result* out, int cap, int* n_out)
 {
-    int* counters = h->d_counters.as<int>();
     key_stride = std::max(key_stride, 1);
     int ks = 1;
     while (ks < key_stride) ks <<= 1;
@@ -840,12 +867,11 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
     CK(h->d_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev)));
     CK(h->d_rescnt.ensure((size_t)batch * sizeof(int)));
     CK(h->h_results.ensure((size_t)batch * rcap * sizeof(FpmResultDev) + (size_t)batch * sizeof(int)));
-    (void)n_refined;
     // NMS rectangle size: pyramid[iStopLayer] * (iStopLayer == 0 ? 1 : 2)  (src/TemplateMatcher.cpp:376-377)
     const int stop_l = std::min(h->stop_layer1 ? 1 : 0, (int)h->tpl.size() - 1);
     const int nms_w = h->tpl[stop_l].w * (h->stop_layer1 ? 2 : 1), nms_h = h->tpl[stop_l].h * (h->stop_layer1 ? 2 : 1);
     KL(K_FINAL, 0,
-       fpm_final_kernel<<<batch, FN_THREADS, 0, h->stream>>>(h->d_refined.as<FpmRefined>(), counters + CNT_REFINED, h->score,
+       fpm_final_kernel<<<batch, FN_THREADS, 0, h->stream>>>(rv, h->score,
                                                              h->max_overlap, nms_w, nms_h, h->tpl[0].w, h->tpl[0].h,
                                                              h->d_keys.as<unsigned long long>(), ks, h->d_rects.as<FpmRRect>(),
                                                              h->d_del.as<int>(), h->d_idmap.as<int>(),
@@ -866,6 +892,52 @@ int run_final(fpm_handle* h, int batch, int n_refined, int key_stride, fpm_resul
             o.ltx = r.ltx; o.lty = r.lty; o.rtx = r.rtx; o.rty = r.rty;
             o.rbx = r.rbx; o.rby = r.rby; o.lbx = r.lbx; o.lby = r.lby;
         }
+    }
+    return FPM_OK;
+}
+
+// candidate list: gather the picks of all angles, std::sort by score (:214), un-rotation (:265-266).  Leaves this
+// rank's candidates (all of them when shard_n == 1) in d_cand[0]; *n_all (optional) = size of the global list of image 0.
+int collect_candidates(fpm_handle* h, int top, int batch, const FpmPickView& pv, int n_angles, int shard_rank, int shard_n,
+                       int* n_cands, int* cand_stride_out, int* n_all)
+{
+    const int max_picks = h->max_pos + FPM_MATCH_CANDIDATE_NUM;
+    const int cand_stride = std::max(n_angles * max_picks, 1);
+    *cand_stride_out = cand_stride;
+    int n_pad = 1;
+    while (n_pad < cand_stride) n_pad <<= 1;
+    CK(h->d_cand[0].ensure((size_t)batch * cand_stride * sizeof(FpmCand)));
+    CK(h->d_candcnt.ensure((size_t)batch * sizeof(int)));
+    CK(h->d_off.ensure((size_t)batch * std::max(n_angles, 1) * sizeof(int)));
+    const int use_smem = (size_t)n_pad * 8 <= 96 * 1024;
+    if (!use_smem) CK(h->d_keys.ensure((size_t)batch * n_pad * sizeof(unsigned long long)));
+    if (h->trace) CK(h->d_toppt.ensure((size_t)batch * cand_stride * 4 * sizeof(float)));
+    int* counters = h->d_counters.as<int>();
+    {
+        const FpmLevel& L = h->levels[top];
+        size_t smem = use_smem ? (size_t)n_pad * 8 : 0;
+        if (smem > 48 * 1024)
+            CK(ensure_dyn_smem((const void*)fpm_collect_sort_kernel, h->device, smem));
+        KL(K_COLLECT, 0,
+           fpm_collect_sort_kernel<<<batch, CS_THREADS, smem, h->stream>>>(
+               pv, n_angles, max_picks, h->d_angles.as<double>(),
+               h->d_ftx.as<float>(), h->d_fty.as<float>(), (L.w - 1) / 2.0f, (L.h - 1) / 2.0f,
+               h->d_keys.as<unsigned long long>(), n_pad, use_smem, h->d_off.as<int>(), h->d_cand[0].as<FpmCand>(),
+               counters + CNT_FLAT, h->trace ? h->d_toppt.as<float>() : nullptr, cand_stride,
+               n_all ? counters + CNT_TOTAL : h->d_candcnt.as<int>(), 0, shard_rank, shard_n));
+    }
+    int* hc = h->h_counts.as<int>();
+    CK(cudaMemcpyAsync(hc, h->d_counters.p, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *n_cands = hc[CNT_FLAT];
+    if (n_all) *n_all = hc[CNT_TOTAL];
+    if (h->trace && !n_all) {
+        std::vector<float> tp((size_t)cand_stride * 4);
+        int n0 = 0;
+        CK(cudaMemcpy(&n0, h->d_candcnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tp.data(), h->d_toppt.p, (size_t)n0 * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+        h->tr_cands.clear();
+        for (int i = 0; i < n0 * 4; i++) h->tr_cands.push_back(tp[i]);
     }
     return FPM_OK;
 }
@@ -911,50 +983,193 @@ int match_device(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt,
     }
     rc = build_pyramid(h, d_src, batch, w, hgt, stride, frame_stride, top);
     if (rc) return rc;
-    rc = make_top_plan(h, top, batch, 0, -1);
-    if (rc) return rc;
-    int max_picks = 0;
-    rc = run_top(h, top, batch, &max_picks);
+    rc = make_top_plan(h, top, batch);
     if (rc) return rc;
     const TopPlan& p = h->plan;
-    const int cand_stride = std::max(p.n_ang * max_picks, 1);
-    int n_pad = 1;
-    while (n_pad < cand_stride) n_pad <<= 1;
-    CK(h->d_cand[0].ensure((size_t)batch * cand_stride * sizeof(FpmCand)));
-    CK(h->d_candcnt.ensure((size_t)batch * sizeof(int)));
-    CK(h->d_off.ensure((size_t)batch * std::max(p.n_ang, 1) * sizeof(int)));
-    const int use_smem = (size_t)n_pad * 8 <= 96 * 1024;
-    if (!use_smem) CK(h->d_keys.ensure((size_t)batch * n_pad * sizeof(unsigned long long)));
-    if (h->trace) CK(h->d_toppt.ensure((size_t)batch * cand_stride * 4 * sizeof(float)));
-    {
-        const FpmLevel& L = h->levels[top];
-        size_t smem = use_smem ? (size_t)n_pad * 8 : 0;
-        if (smem > 48 * 1024)
-            CK(ensure_dyn_smem((const void*)fpm_collect_sort_kernel, h->device, smem));
-        KL(K_COLLECT, 0,
-           fpm_collect_sort_kernel<<<batch, CS_THREADS, smem, h->stream>>>(
-               h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), p.n_ang, max_picks, h->d_angles.as<double>(),
-               h->d_ftx.as<float>(), h->d_fty.as<float>(), (L.w - 1) / 2.0f, (L.h - 1) / 2.0f,
-               h->d_keys.as<unsigned long long>(), n_pad, use_smem, h->d_off.as<int>(), h->d_cand[0].as<FpmCand>(),
-               h->d_counters.as<int>() + CNT_FLAT, h->trace ? h->d_toppt.as<float>() : nullptr, cand_stride,
-               h->d_candcnt.as<int>(), 0));
-    }
-    int* hc = h->h_counts.as<int>();
-    CK(cudaMemcpyAsync(hc, h->d_counters.p, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const int n_cands = hc[CNT_FLAT];
-    if (h->trace) {
-        std::vector<float> tp((size_t)cand_stride * 4);
-        int n0 = 0;
-        CK(cudaMemcpy(&n0, h->d_candcnt.p, sizeof(int), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(tp.data(), h->d_toppt.p, (size_t)n0 * 4 * sizeof(float), cudaMemcpyDeviceToHost));
-        h->tr_cands.clear();
-        for (int i = 0; i < n0 * 4; i++) h->tr_cands.push_back(tp[i]);
-    }
+    const int max_picks = h->max_pos + FPM_MATCH_CANDIDATE_NUM;
+    const int njobs = batch * p.n_ang;
+    CK(h->d_picks.ensure((size_t)std::max(njobs, 1) * max_picks * sizeof(FpmPick)));
+    CK(h->d_pickcnt.ensure((size_t)std::max(njobs, 1) * sizeof(int)));
+    rc = run_top(h, top, 0, njobs, h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>());
+    if (rc) return rc;
+    FpmPickView pv{h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>(), 0, 0};
+    int n_cands = 0, cand_stride = 0;
+    rc = collect_candidates(h, top, batch, pv, p.n_ang, 0, 1, &n_cands, &cand_stride, nullptr);
+    if (rc) return rc;
     int n_refined = 0;
+    h->ref_out = nullptr; h->ref_cnt = nullptr;
     rc = run_refine(h, top, n_cands, &n_refined);
     if (rc) return rc;
-    return run_final(h, batch, n_refined, cand_stride, out, cap, n_out);
+    FpmRefinedView rv{h->d_refined.as<FpmRefined>(), h->d_counters.as<int>() + CNT_REFINED, 0, 1, 0};
+    return run_final(h, batch, rv, cand_stride, out, cap, n_out);
+}
+
+// ---- angle-sharded latency mode: one frame, nranks GPUs -------------------------------------------
+// The work of TemplateMatcher::match shards in two places: the top-layer angle sweep (src/TemplateMatcher.cpp:162-211)
+// and the per-candidate descent (:262-371).  Each rank runs a contiguous chunk of the angle schedule, the pick lists are
+// exchanged with ONE allgather of fixed-size blocks (picks + counts), every rank sorts the identical global list
+// (:214) and refines candidates id % nranks == rank, the refined records are exchanged with a second allgather and
+// every rank runs the identical filter / NMS (:373-395).  Both gathered buffers are consumed in place by the kernels
+// (FpmPickView / FpmRefinedView): nothing but the final results and two counters ever reaches the host.
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;           // ncclUniqueId (ABI-stable: 128 opaque bytes)
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    bool ok = false;
+};
+
+const NcclApi& nccl_api()
+{
+    // resolved at run time: the library must load (and every single-GPU entry point must work) on a box without NCCL;
+    // in a torch process "libnccl.so.2" resolves to the copy torch has already loaded
+    static const NcclApi api = []() {
+        NcclApi a;
+        void* lib = nullptr;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) return a;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(lib, "ncclAllGather"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(dlsym(lib, "ncclGetVersion"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+
+// in-place allgather of one `bytes`-sized block per rank (own block already at buf + rank*bytes), on the handle's stream
+int shard_allgather(fpm_handle* h, void* buf, size_t bytes)
+{
+    if (h->sh_nranks <= 1) return FPM_OK;
+    if (!h->nccl_comm) { h->err = "angle-sharded match: no communicator (fpm_comm_init / fpm_comm_attach)"; return FPM_ERR_INVALID; }
+    const NcclApi& a = nccl_api();
+    const int r = a.AllGather(static_cast<const char*>(buf) + (size_t)h->sh_rank * bytes, buf, bytes, 0 /*ncclInt8*/, h->nccl_comm, h->stream);
+    if (r != 0) { h->err = std::string("ncclAllGather: ") + a.GetErrorString(r); return FPM_ERR_CUDA; }
+    h->collectives++;
+    return FPM_OK;
+}
+
+// contiguous chunk of the angle schedule per rank: rank r sweeps [r*chunk, min(A, (r+1)*chunk))
+inline int shard_chunk(int n_angles, int nranks) { return std::max(1, (n_angles + nranks - 1) / nranks); }
+
+// phase 1: source on the device (uploaded in 1/N row slices + allgather when it comes from the host), pyramid,
+// top-layer sweep of this rank's angles into its block of the gather buffer
+int shard_begin(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, int src_on_device)
+{
+    h->sh = fpm_handle::ShardState();
+    if (!h->learned) return FPM_OK;                          // :99-101 -> empty
+    int rc = ensure_learned_for_mra(h);
+    if (rc) return rc;
+    if (!src || w <= 0 || hgt <= 0) return FPM_OK;
+    if (stride < w) { h->err = "stride < width"; return FPM_ERR_INVALID; }
+    if (match_guards(h, w, hgt)) return FPM_OK;
+    const int N = h->sh_nranks, R = h->sh_rank;
+    const uint8_t* d_src = src;
+    int pitch = stride;
+    size_t img = (size_t)stride * hgt;
+    if (!src_on_device) {
+        const bool linear = (stride == w) && (w % 4 == 0);
+        pitch = linear ? w : (int)align_up(w, 128);
+        const int rows_per = (hgt + N - 1) / N;
+        img = (size_t)pitch * rows_per * N;                   // room for N equal row slices
+        CK(h->d_src.ensure(img));
+        const bool sliced = N > 1 && h->shard_upload && h->nccl_comm;
+        const int y0 = sliced ? std::min(hgt, R * rows_per) : 0, y1 = sliced ? std::min(hgt, y0 + rows_per) : hgt;
+        if (y1 > y0) {
+            if (linear)
+                CK(cudaMemcpyAsync(h->d_src.as<uint8_t>() + (size_t)y0 * pitch, src + (size_t)y0 * stride, (size_t)(y1 - y0) * pitch,
+                                   cudaMemcpyHostToDevice, h->stream));
+            else
+                CK(cudaMemcpy2DAsync(h->d_src.as<uint8_t>() + (size_t)y0 * pitch, pitch, src + (size_t)y0 * stride, stride, w, y1 - y0,
+                                     cudaMemcpyHostToDevice, h->stream));
+        }
+        if (sliced) {
+            rc = shard_allgather(h, h->d_src.p, (size_t)pitch * rows_per);
+            if (rc) return rc;
+        }
+        d_src = h->d_src.as<uint8_t>();
+    }
+    const int top = (int)h->tpl.size() - 1;
+    CK(h->d_counters.ensure(CNT_N * sizeof(int)));
+    CK(h->h_counts.ensure((CNT_N + 1) * sizeof(int)));
+    CK(cudaMemsetAsync(h->d_counters.p, 0, CNT_N * sizeof(int), h->stream));
+    if (h->bitwise_not) {
+        const int ipitch = (int)align_up(w, 128);
+        const size_t iimg = (size_t)ipitch * hgt;
+        CK(h->d_inv.ensure(iimg));
+        dim3 ig((w / 4 + 128) / 128, hgt, 1);
+        fpm_invert_kernel<<<ig, 128, 0, h->stream>>>(d_src, w, hgt, pitch, img, h->d_inv.as<uint8_t>(), ipitch, iimg);
+        CKL();
+        d_src = h->d_inv.as<uint8_t>(); pitch = ipitch; img = iimg;
+    }
+    rc = build_pyramid(h, d_src, 1, w, hgt, pitch, img, top);
+    if (rc) return rc;
+    rc = make_top_plan(h, top, 1);
+    if (rc) return rc;
+    const TopPlan& p = h->plan;
+    const int max_picks = h->max_pos + FPM_MATCH_CANDIDATE_NUM;
+    const int chunk = shard_chunk(p.n_ang, N);
+    const size_t blk = align_up((size_t)chunk * max_picks * sizeof(FpmPick) + (size_t)chunk * sizeof(int), 16);
+    CK(h->d_gpicks.ensure(blk * N));
+    uint8_t* mine = h->d_gpicks.as<uint8_t>() + (size_t)R * blk;
+    int* cnt = reinterpret_cast<int*>(mine + (size_t)chunk * max_picks * sizeof(FpmPick));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)chunk * sizeof(int), h->stream));      // angles past the schedule's end stay empty
+    const int a0 = std::min(p.n_ang, R * chunk), a1 = std::min(p.n_ang, a0 + chunk);
+    rc = run_top(h, top, a0, a1 - a0, reinterpret_cast<FpmPick*>(mine), cnt);
+    if (rc) return rc;
+    h->sh.top = top; h->sh.chunk = chunk; h->sh.pick_blk = blk; h->sh.empty = 0;
+    return FPM_OK;
+}
+
+int shard_exchange_picks(fpm_handle* h)
+{
+    if (h->sh.empty) return FPM_OK;
+    return shard_allgather(h, h->d_gpicks.p, h->sh.pick_blk);
+}
+
+// phase 2: identical global candidate list on every rank, this rank's share refined into its block of the second buffer
+int shard_mid(fpm_handle* h)
+{
+    if (h->sh.empty) return FPM_OK;
+    const int N = h->sh_nranks, R = h->sh_rank, top = h->sh.top;
+    FpmPickView pv{h->d_gpicks.as<FpmPick>(), nullptr, h->sh.chunk, h->sh.pick_blk};
+    int n_local = 0, cand_stride = 0, n_all = 0;
+    int rc = collect_candidates(h, top, 1, pv, h->sh.chunk * N, R, N, &n_local, &cand_stride, &n_all);
+    if (rc) return rc;
+    const int seg_cap = std::max(1, (n_all + N - 1) / N);
+    const size_t blk = align_up((size_t)seg_cap * sizeof(FpmRefined) + 8, 16);
+    CK(h->d_grefined.ensure(blk * N));
+    uint8_t* mine = h->d_grefined.as<uint8_t>() + (size_t)R * blk;
+    h->ref_out = reinterpret_cast<FpmRefined*>(mine);
+    h->ref_cnt = reinterpret_cast<int*>(mine + (size_t)seg_cap * sizeof(FpmRefined));
+    int n_refined = 0;
+    rc = run_refine(h, top, n_local, &n_refined);
+    h->ref_out = nullptr; h->ref_cnt = nullptr;
+    if (rc) return rc;
+    h->sh.n_all = n_all; h->sh.n_local = n_local; h->sh.seg_cap = seg_cap; h->sh.ref_blk = blk;
+    return FPM_OK;
+}
+
+int shard_exchange_refined(fpm_handle* h)
+{
+    if (h->sh.empty) return FPM_OK;
+    return shard_allgather(h, h->d_grefined.p, h->sh.ref_blk);
+}
+
+// phase 3: replicated filterWithScore + NMS + conversion straight from the gathered blocks
+int shard_end(fpm_handle* h, fpm_result* out, int cap, int* n)
+{
+    *n = 0;
+    if (h->sh.empty) return FPM_OK;
+    FpmRefinedView rv{h->d_grefined.as<FpmRefined>(), nullptr, h->sh.seg_cap, h->sh_nranks, h->sh.ref_blk};
+    return run_final(h, 1, rv, std::max(h->sh.n_all, 1), out, cap, n);
 }
 
 }  // namespace
@@ -997,11 +1212,12 @@ void fpm_destroy(fpm_handle* h)
 {
     if (!h) return;
     if (h->twin) { fpm_destroy(h->twin); h->twin = nullptr; }
+    fpm_comm_destroy(h);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->aux_stream);
-    DevBuf* bufs[] = {&h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_numer, &h->d_totS, &h->d_totQ, &h->d_ingest_raw, &h->d_ingest, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
+    DevBuf* bufs[] = {&h->d_gpicks, &h->d_grefined, &h->d_tpl, &h->d_tsh, &h->d_raw, &h->d_inv, &h->d_numer, &h->d_totS, &h->d_totQ, &h->d_ingest_raw, &h->d_ingest, &h->d_src, &h->d_pyr, &h->d_rot, &h->d_score, &h->d_blkv, &h->d_blkl, &h->d_picks, &h->d_pickcnt,
                       &h->d_jobs_top, &h->d_angles, &h->d_ftx, &h->d_fty, &h->d_off, &h->d_keys, &h->d_cand[0], &h->d_cand[1],
                       &h->d_candcnt, &h->d_toppt, &h->d_counters, &h->d_jobs_ref, &h->d_roi, &h->d_rowsum, &h->d_rowS, &h->d_rowQ,
                       &h->d_pairs, &h->d_refined, &h->d_rects, &h->d_del, &h->d_idmap, &h->d_results, &h->d_rescnt, &h->d_trace, &h->d_trace_sc,
@@ -1041,6 +1257,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_STOP_LAYER1: h->stop_layer1 = v != 0; break;
     case FPM_PARAM_BITWISE_NOT: h->bitwise_not = v != 0; break;
     case FPM_PARAM_SPLIT_BATCH: h->split_batch = (int)v; break;
+    case FPM_PARAM_SHARD_UPLOAD: h->shard_upload = v != 0; break;
     case FPM_PARAM_TOLERANCE_RANGE: h->tol_range = v != 0; h->plan.valid = false; break;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         h->tol_r[param - FPM_PARAM_TOLERANCE1] = v; h->plan.valid = false; break;
@@ -1069,6 +1286,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_STOP_LAYER1: return h->stop_layer1;
     case FPM_PARAM_BITWISE_NOT: return h->bitwise_not;
     case FPM_PARAM_SPLIT_BATCH: return h->split_batch;
+    case FPM_PARAM_SHARD_UPLOAD: return h->shard_upload;
     case FPM_PARAM_TOLERANCE_RANGE: return h->tol_range;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         return h->tol_r[param - FPM_PARAM_TOLERANCE1];
@@ -1200,18 +1418,27 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
         }
         return cudaEventRecord(h->ev_copy[k & 1], h->copy_stream);
     };
-    CK(enqueue_copy(0));
+    // every exit drains both streams: an H2D copy still in flight reads the caller's buffer
+    auto fail_cuda = [&](const char* what, cudaError_t e) {
+        h->err = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+        return FPM_ERR_CUDA;
+    };
+    cudaError_t ce = enqueue_copy(0);
+    if (ce != cudaSuccess) return fail_cuda("host->device copy", ce);
     int rc = FPM_OK;
     for (int k = 0; k < nchunks && rc == FPM_OK; k++) {
-        if (k + 1 < nchunks) CK(enqueue_copy(k + 1));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_copy[k & 1], 0));
+        if (k + 1 < nchunks && (ce = enqueue_copy(k + 1)) != cudaSuccess) return fail_cuda("host->device copy", ce);
+        if ((ce = cudaStreamWaitEvent(h->stream, h->ev_copy[k & 1], 0)) != cudaSuccess) return fail_cuda("cudaStreamWaitEvent", ce);
         int b0 = k * chunk, nb = std::min(chunk, batch - b0);
         rc = match_device(h, h->d_src.as<uint8_t>() + (size_t)(k & 1) * buf_bytes, nb, width, height, pitch, img,
                           out + (size_t)b0 * cap, cap, n + b0);
-        CK(cudaEventRecord(h->ev_done[k & 1], h->stream));
+        if (rc == FPM_OK && (ce = cudaEventRecord(h->ev_done[k & 1], h->stream)) != cudaSuccess) return fail_cuda("cudaEventRecord", ce);
         prof_collect(h);
     }
     cudaStreamSynchronize(h->copy_stream);
+    if (rc != FPM_OK) cudaStreamSynchronize(h->stream);
     auto t1 = std::chrono::high_resolution_clock::now();
     h->last_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     return rc;
@@ -1284,18 +1511,28 @@ int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width
     if (!file || nbytes < 54 || file[0] != 'B' || file[1] != 'M') { h->err = "not a BMP file"; return FPM_ERR_INVALID; }
     const uint32_t off = rd32(file + 10), dib = rd32(file + 14);
     if (dib < 40) { h->err = "unsupported BMP header (OS/2 core header)"; return FPM_ERR_INVALID; }
-    const int w = (int)rd32(file + 18);
-    int hs = (int)rd32(file + 22);
+    // untrusted header fields: everything is range-checked in 64 bits before it sizes a buffer or a kernel
+    const int64_t w64 = (int32_t)rd32(file + 18), hs64 = (int32_t)rd32(file + 22);
     const int bpp = (int)rd16(file + 28);
     const uint32_t comp = rd32(file + 30), clr_used = rd32(file + 46);
-    const int top_down = hs < 0;
-    const int hh = top_down ? -hs : hs;
-    if (w <= 0 || hh <= 0 || comp != 0 || (bpp != 8 && bpp != 24)) {
+    const int top_down = hs64 < 0;
+    const int64_t hh64 = top_down ? -hs64 : hs64;
+    if (w64 <= 0 || hh64 <= 0 || comp != 0 || (bpp != 8 && bpp != 24)) {
         h->err = "unsupported BMP (only uncompressed 8-bit palettized and 24-bit BGR)";
         return FPM_ERR_INVALID;
     }
-    const uint32_t row_stride = (uint32_t)(((size_t)w * bpp + 31) / 32 * 4);
-    if ((size_t)off + (size_t)row_stride * hh > nbytes) { h->err = "truncated BMP"; return FPM_ERR_INVALID; }
+    if (w64 > (1 << 20) || hh64 > 65535 || w64 * hh64 > (1ll << 30)) {          // OpenCV's CV_IO_MAX_IMAGE_PIXELS = 2^30; one grid row per image row
+        h->err = "BMP dimensions out of range";
+        return FPM_ERR_INVALID;
+    }
+    const int w = (int)w64, hh = (int)hh64;
+    const size_t row_stride = ((size_t)w * bpp + 31) / 32 * 4;
+    const size_t pal_end = 14 + (size_t)dib + (bpp == 8 ? (size_t)(clr_used ? std::min<uint32_t>(clr_used, 256) : 256) * 4 : 0);
+    if ((size_t)off < 14 + (size_t)dib || (size_t)off > nbytes || row_stride * (size_t)hh > nbytes - off) {
+        h->err = "truncated BMP";
+        return FPM_ERR_INVALID;
+    }
+    (void)pal_end;
     FpmBmpLut lut;
     memset(&lut, 0, sizeof(lut));
     if (bpp == 8) {
@@ -1313,7 +1550,7 @@ int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width
     CK(h->d_ingest.ensure((size_t)pitch * hh));
     CK(cudaMemcpyAsync(h->d_ingest_raw.p, file, nbytes, cudaMemcpyHostToDevice, h->stream));
     dim3 grid((w + 255) / 256, hh);
-    fpm_ingest_bmp_kernel<<<grid, 256, 0, h->stream>>>(h->d_ingest_raw.as<uint8_t>(), off, row_stride, bpp, top_down, lut, w, hh,
+    fpm_ingest_bmp_kernel<<<grid, 256, 0, h->stream>>>(h->d_ingest_raw.as<uint8_t>(), (size_t)off, row_stride, bpp, top_down, lut, w, hh,
                                                        h->d_ingest.as<uint8_t>(), pitch);
     CKL();
     CK(cudaStreamSynchronize(h->stream));                             // the caller's file buffer is free again
@@ -1326,7 +1563,10 @@ int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width
 int fpm_ingest_rgb32(fpm_handle* h, const uint32_t* pixels, int width, int height, int stride_bytes)
 {
     if (!h) return FPM_ERR_INVALID;
-    if (!pixels || width <= 0 || height <= 0 || stride_bytes < 4 * width || (stride_bytes & 3)) { h->err = "bad RGB32 frame"; return FPM_ERR_INVALID; }
+    if (!pixels || width <= 0 || height <= 0 || height > 65535 || width > (1 << 20) || stride_bytes < 4 * width || (stride_bytes & 3)) {
+        h->err = "bad RGB32 frame";
+        return FPM_ERR_INVALID;
+    }
     CK(cudaSetDevice(h->device));
     const size_t nbytes = (size_t)stride_bytes * height;
     CK(h->d_ingest_raw.ensure(nbytes));
@@ -1461,30 +1701,36 @@ int fpm_stage_top(fpm_handle* h, const uint8_t* src, int width, int height, int 
     }
     rc = build_pyramid(h, d_src, 1, width, height, pitch, img, top);
     if (rc) return rc;
-    rc = make_top_plan(h, top, 1, a0, a1);
-    if (rc) return rc;
-    int max_picks = 0;
-    rc = run_top(h, top, 1, &max_picks);
+    rc = make_top_plan(h, top, 1);
     if (rc) return rc;
     const TopPlan& p = h->plan;
-    if (p.n_ang == 0) return FPM_OK;
-    std::vector<FpmPick> picks((size_t)p.n_ang * max_picks);
-    std::vector<int> cnt(p.n_ang);
+    if (a1 < 0) a1 = p.n_ang;
+    a0 = std::max(0, std::min(a0, p.n_ang));
+    a1 = std::max(a0, std::min(a1, p.n_ang));
+    const int n_loc = a1 - a0;
+    if (n_loc == 0) return FPM_OK;
+    const int max_picks = h->max_pos + FPM_MATCH_CANDIDATE_NUM;
+    CK(h->d_picks.ensure((size_t)n_loc * max_picks * sizeof(FpmPick)));
+    CK(h->d_pickcnt.ensure((size_t)n_loc * sizeof(int)));
+    rc = run_top(h, top, a0, n_loc, h->d_picks.as<FpmPick>(), h->d_pickcnt.as<int>());
+    if (rc) return rc;
+    std::vector<FpmPick> picks((size_t)n_loc * max_picks);
+    std::vector<int> cnt(n_loc);
     CK(cudaMemcpyAsync(picks.data(), h->d_picks.p, picks.size() * sizeof(FpmPick), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(cnt.data(), h->d_pickcnt.p, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     int k = 0;
-    for (int a = 0; a < p.n_ang; a++)
+    for (int a = 0; a < n_loc; a++)
         for (int j = 0; j < cnt[a]; j++) {
             if (k < cap) {
                 const FpmPick& pk = picks[(size_t)a * max_picks + j];
                 double* r = rows + (size_t)k * 5;
                 // translation removed here like :186 (float arithmetic)
-                r[0] = p.a0 + a;
-                r[1] = (double)((float)pk.x - p.ftx[a]);
-                r[2] = (double)((float)pk.y - p.fty[a]);
+                r[0] = a0 + a;
+                r[1] = (double)((float)pk.x - p.ftx[a0 + a]);
+                r[2] = (double)((float)pk.y - p.fty[a0 + a]);
                 r[3] = pk.v;
-                r[4] = p.angles[p.a0 + a];
+                r[4] = p.angles[a0 + a];
             }
             k++;
         }
@@ -1531,6 +1777,7 @@ int fpm_stage_refine(fpm_handle* h, const double* cands, int n, double* rows, in
     CK(cudaMemcpyAsync(h->d_cand[0].p, cc.data(), cc.size() * sizeof(FpmCand), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     int n_ref = 0;
+    h->ref_out = nullptr; h->ref_cnt = nullptr;
     int rc = run_refine(h, top, n, &n_ref);
     if (rc) return rc;
     std::vector<FpmRefined> rr(std::max(n_ref, 1));
@@ -1565,7 +1812,128 @@ int fpm_stage_final(fpm_handle* h, const double* refined, int n, fpm_result* out
     CK(cudaMemcpyAsync(h->d_refined.p, rr.data(), rr.size() * sizeof(FpmRefined), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_counters.as<int>() + CNT_REFINED, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return run_final(h, 1, n, std::max(max_id + 1, n), out, cap, n_out);
+    FpmRefinedView rv{h->d_refined.as<FpmRefined>(), h->d_counters.as<int>() + CNT_REFINED, 0, 1, 0};
+    return run_final(h, 1, rv, std::max(max_id + 1, n), out, cap, n_out);
+}
+
+// ---- angle-sharded latency mode: communicator + whole-match entry points ---------------------------------
+int fpm_comm_available(void) { return nccl_api().ok ? 1 : 0; }
+
+int fpm_comm_get_unique_id(void* id)
+{
+    if (!id || !nccl_api().ok) return FPM_ERR_INVALID;
+    NcclApi::UniqueId u;
+    if (nccl_api().GetUniqueId(&u) != 0) return FPM_ERR_CUDA;
+    memcpy(id, &u, sizeof(u));
+    return FPM_OK;
+}
+
+void fpm_comm_destroy(fpm_handle* h)
+{
+    if (!h) return;
+    if (h->nccl_comm && h->nccl_owned) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        nccl_api().CommDestroy(h->nccl_comm);
+    }
+    h->nccl_comm = nullptr; h->nccl_owned = false; h->sh_nranks = 1; h->sh_rank = 0;
+}
+
+int fpm_comm_init(fpm_handle* h, int nranks, int rank, const void* id)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id) { h->err = "bad communicator arguments"; return FPM_ERR_INVALID; }
+    const NcclApi& a = nccl_api();
+    if (!a.ok) { h->err = "libnccl.so.2 could not be loaded"; return FPM_ERR_INVALID; }
+    fpm_comm_destroy(h);
+    CK(cudaSetDevice(h->device));
+    NcclApi::UniqueId u;
+    memcpy(&u, id, sizeof(u));
+    void* comm = nullptr;
+    const int r = a.CommInitRank(&comm, nranks, u, rank);
+    if (r != 0) { h->err = std::string("ncclCommInitRank: ") + a.GetErrorString(r); return FPM_ERR_CUDA; }
+    h->nccl_comm = comm; h->nccl_owned = true; h->sh_nranks = nranks; h->sh_rank = rank;
+    return FPM_OK;
+}
+
+int fpm_comm_attach(fpm_handle* h, void* nccl_comm, int nranks, int rank)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_comm)) { h->err = "bad communicator arguments"; return FPM_ERR_INVALID; }
+    if (nranks > 1 && !nccl_api().ok) { h->err = "libnccl.so.2 could not be loaded"; return FPM_ERR_INVALID; }
+    fpm_comm_destroy(h);
+    h->nccl_comm = nccl_comm; h->nccl_owned = false; h->sh_nranks = nranks; h->sh_rank = rank;
+    return FPM_OK;
+}
+
+int fpm_shard_angle_range(int n_angles, int nranks, int rank, int* a0, int* a1)
+{
+    if (n_angles < 0 || nranks < 1 || rank < 0 || rank >= nranks || !a0 || !a1) return FPM_ERR_INVALID;
+    const int chunk = shard_chunk(n_angles, nranks);
+    *a0 = std::min(n_angles, rank * chunk);
+    *a1 = std::min(n_angles, *a0 + chunk);
+    return FPM_OK;
+}
+
+long long fpm_collective_count(const fpm_handle* h) { return h ? h->collectives : 0; }
+
+int fpm_match_sharded(fpm_handle* h, const uint8_t* src, int width, int height, int stride, int src_on_device,
+                      fpm_result* out, int cap, int* n)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!n || cap < 0 || (cap > 0 && !out)) { h->err = "bad output arguments"; return FPM_ERR_INVALID; }
+    *n = 0;
+    CK(cudaSetDevice(h->device));
+    auto t0 = std::chrono::high_resolution_clock::now();
+    int rc = shard_begin(h, src, width, height, stride, src_on_device);
+    if (!rc) rc = shard_exchange_picks(h);
+    if (!rc) rc = shard_mid(h);
+    if (!rc) rc = shard_exchange_refined(h);
+    if (!rc) rc = shard_end(h, out, cap, n);
+    prof_collect(h);
+    if (rc) cudaStreamSynchronize(h->stream);
+    h->last_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    return rc;
+}
+
+// The same pipeline with `nranks` handles of ONE device playing the ranks and the two exchanges done as device-to-device
+// block copies: exercises the partitioning and the in-place consumption of the gathered buffers where only one GPU
+// (and no NCCL peer) is available.  Every rank's result list is returned (rank r at out + r*cap, n[r]).
+int fpm_match_sharded_virtual(fpm_handle* const* hs, int nranks, const uint8_t* src, int width, int height, int stride,
+                              fpm_result* out, int cap, int* n)
+{
+    if (!hs || nranks < 1 || !n || cap < 0 || (cap > 0 && !out)) return FPM_ERR_INVALID;
+    for (int r = 0; r < nranks; r++) {
+        if (!hs[r] || hs[r]->nccl_comm) return FPM_ERR_INVALID;
+        hs[r]->sh_nranks = nranks; hs[r]->sh_rank = r;
+        n[r] = 0;
+    }
+    auto exchange = [&](DevBuf fpm_handle::*buf, size_t fpm_handle::ShardState::*blk) -> int {
+        for (int r = 0; r < nranks; r++) {
+            fpm_handle* h = hs[r];
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        for (int q = 0; q < nranks; q++) {
+            fpm_handle* h = hs[q];
+            if (h->sh.empty) continue;
+            const size_t b = h->sh.*blk;
+            for (int r = 0; r < nranks; r++)
+                if (r != q && !hs[r]->sh.empty)
+                    CK(cudaMemcpyAsync((h->*buf).as<uint8_t>() + (size_t)r * b, (hs[r]->*buf).as<uint8_t>() + (size_t)r * b, b,
+                                       cudaMemcpyDeviceToDevice, h->stream));
+        }
+        return FPM_OK;
+    };
+    int rc = FPM_OK;
+    auto restore = [&]() { for (int r = 0; r < nranks; r++) { hs[r]->sh_nranks = 1; hs[r]->sh_rank = 0; } };
+    for (int r = 0; r < nranks && !rc; r++) { cudaSetDevice(hs[r]->device); rc = shard_begin(hs[r], src, width, height, stride, 0); }
+    if (!rc) rc = exchange(&fpm_handle::d_gpicks, &fpm_handle::ShardState::pick_blk);
+    for (int r = 0; r < nranks && !rc; r++) rc = shard_mid(hs[r]);
+    if (!rc) rc = exchange(&fpm_handle::d_grefined, &fpm_handle::ShardState::ref_blk);
+    for (int r = 0; r < nranks && !rc; r++) rc = shard_end(hs[r], out + (size_t)r * cap, cap, n + r);
+    for (int r = 0; r < nranks; r++) prof_collect(hs[r]);
+    restore();
+    return rc;
 }
 
 // ---- stage kernels for parity tests ----------------------------------------------------
@@ -1745,7 +2113,15 @@ int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t
 }
 
 // dense NCC map of `img` against the learned TOP-layer template
+int fpm_dbg_top_score_production(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score, float* reject_below);
 int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score)
+{
+    return fpm_dbg_top_score_production(h, img, w, hgt, score, nullptr);
+}
+
+// reject_below == null: the exact map everywhere.  Otherwise the kernel runs exactly as inside match() (scores certainly
+// below Score*0.9^top - 0.01 may be float32 estimates) and the bound in use is returned.
+int fpm_dbg_top_score_production(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score, float* reject_below)
 {
     if (!h || !img || !score) return FPM_ERR_INVALID;
     if (!h->learned) return FPM_ERR_NOT_LEARNED;
@@ -1768,8 +2144,10 @@ int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* 
     CK(ensure_dyn_smem((const void*)fpm_top_score_kernel, h->device, smem));
     dim3 grid((RW + TS_TW - 1) / TS_TW, (RH + TS_TH - 1) / TS_TH, 1), block(TS_THREADS);
     fpm_top_score_kernel<<<grid, block, smem, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), h->d_dbg[0].as<uint8_t>(), rp, 0,
-                                                           tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0, -INFINITY);
+                                                           tpl_level_dev(h, top), h->d_dbg[1].as<float>(), sp, 0,
+                                                           reject_below ? top_reject_below(h, top) : -INFINITY);
     CKL();
+    if (reject_below) *reject_below = top_reject_below(h, top);
     CK(cudaMemcpy2DAsync(score, (size_t)RW * 4, h->d_dbg[1].p, (size_t)sp * 4, (size_t)RW * 4, RH, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return FPM_OK;

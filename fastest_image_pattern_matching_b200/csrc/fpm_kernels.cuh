@@ -889,8 +889,34 @@ __device__ __forceinline__ uint32_t fpm_desc_key(float f)
 #define CS_THREADS 1024
 #define CS_MAX_SMEM_ANGLES 1024     // angle sweeps up to this size keep their pick-count prefix in shared memory
 
+// Where the picks of (image, angle) live.  Contiguous: picks[(img*n_angles + a)*max_picks], count[img*n_angles + a].
+// Segmented (angle-sharded mode, one image): the buffer is the result of an allgather of one fixed-size block per
+// rank, block r = { FpmPick[seg_angles][max_picks]; int count[seg_angles] } holding angles [r*seg_angles, (r+1)*seg_angles)
+// of the schedule, so the gathered buffer is consumed in place.
+struct FpmPickView {
+    const FpmPick* picks;
+    const int* count;
+    int seg_angles;             // 0 = contiguous
+    size_t seg_stride;          // bytes per rank block
+};
+__device__ __forceinline__ const FpmPick* fpm_pick_row(const FpmPickView& v, int img, int n_angles, int max_picks, int a)
+{
+    if (v.seg_angles == 0) return v.picks + ((size_t)img * n_angles + a) * max_picks;
+    const int r = a / v.seg_angles, l = a - r * v.seg_angles;
+    return reinterpret_cast<const FpmPick*>(reinterpret_cast<const char*>(v.picks) + (size_t)r * v.seg_stride) + (size_t)l * max_picks;
+}
+__device__ __forceinline__ int fpm_pick_count(const FpmPickView& v, int img, int n_angles, int max_picks, int a)
+{
+    if (v.seg_angles == 0) return v.count[img * n_angles + a];
+    const int r = a / v.seg_angles, l = a - r * v.seg_angles;
+    const char* blk = reinterpret_cast<const char*>(v.picks) + (size_t)r * v.seg_stride;
+    return reinterpret_cast<const int*>(blk + (size_t)v.seg_angles * max_picks * sizeof(FpmPick))[l];
+}
+
+// shard_n > 1 (angle-sharded mode): every rank sorts the identical global list and keeps candidates
+// id % shard_n == shard_rank (candidate k -> rank k mod N); cand_count still reports the global count.
 __global__ void __launch_bounds__(CS_THREADS)
-fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict__ pick_count,
+fpm_collect_sort_kernel(FpmPickView pv,
                         int n_angles, int max_picks, const double* __restrict__ angles,
                         const float* __restrict__ ftx, const float* __restrict__ fty,
                         float centre_x, float centre_y,
@@ -898,7 +924,7 @@ fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict
                         int* __restrict__ off_scratch,
                         FpmCand* __restrict__ cands_flat, int* __restrict__ flat_counter,
                         float* __restrict__ top_pt, int cand_stride,
-                        int* __restrict__ cand_count, int angle_idx_base)
+                        int* __restrict__ cand_count, int angle_idx_base, int shard_rank, int shard_n)
 {
     extern __shared__ unsigned long long s_keys[];
     const int img = blockIdx.x, tid = threadIdx.x;
@@ -910,14 +936,15 @@ fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict
     const bool offs_smem = n_angles <= CS_MAX_SMEM_ANGLES;
     int* s_off = offs_smem ? s_offs : off_scratch + (size_t)img * n_angles;
     if (offs_smem) {
-        for (int a = tid; a < n_angles; a += CS_THREADS) s_cnt[a] = pick_count[img * n_angles + a];
+        for (int a = tid; a < n_angles; a += CS_THREADS) s_cnt[a] = fpm_pick_count(pv, img, n_angles, max_picks, a);
         __syncthreads();
     }
     if (tid == 0) {
         int n = 0;
-        for (int a = 0; a < n_angles; a++) { s_off[a] = n; n += offs_smem ? s_cnt[a] : pick_count[img * n_angles + a]; }
+        for (int a = 0; a < n_angles; a++) { s_off[a] = n; n += offs_smem ? s_cnt[a] : fpm_pick_count(pv, img, n_angles, max_picks, a); }
         s_n = n;
-        s_base = atomicAdd(flat_counter, n);
+        const int mine = n > shard_rank ? (n - shard_rank + shard_n - 1) / shard_n : 0;
+        s_base = atomicAdd(flat_counter, mine);
     }
     __syncthreads();
     const int n = s_n;
@@ -932,15 +959,15 @@ fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict
         for (int i = tid; i < n_angles * max_picks; i += CS_THREADS) {
             const int a = i / max_picks, j = i - a * max_picks;
             if (j < s_cnt[a]) {
-                const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+                const FpmPick& p = fpm_pick_row(pv, img, n_angles, max_picks, a)[j];
                 keys[s_off[a] + j] = ((unsigned long long)fpm_desc_key(p.v) << 32) | (uint32_t)i;
             }
         }
     } else {
         for (int a = 0; a < n_angles; a++) {
-            int c = pick_count[img * n_angles + a];
+            int c = fpm_pick_count(pv, img, n_angles, max_picks, a);
             for (int j = tid; j < c; j += CS_THREADS) {
-                const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+                const FpmPick& p = fpm_pick_row(pv, img, n_angles, max_picks, a)[j];
                 uint32_t order = (uint32_t)(a * max_picks + j);
                 keys[s_off[a] + j] = ((unsigned long long)fpm_desc_key(p.v) << 32) | order;
             }
@@ -951,15 +978,17 @@ fpm_collect_sort_kernel(const FpmPick* __restrict__ picks, const int* __restrict
     for (int i = tid; i < n; i += CS_THREADS) {
         uint32_t order = (uint32_t)(keys[i] & 0xffffffffu);
         int a = order / max_picks, j = order - a * max_picks;
-        const FpmPick& p = picks[((size_t)img * n_angles + a) * max_picks + j];
+        const FpmPick& p = fpm_pick_row(pv, img, n_angles, max_picks, a)[j];
         float ptx = (float)p.x - ftx[a], pty = (float)p.y - fty[a];
-        FpmCand c;
-        c.angle = angles[a];
-        c.score = (double)p.v;
-        c.img = img; c.id = i;
-        double dRAngle = -c.angle * FPM_D2R;
-        fpm_pt_rotate(ptx, pty, centre_x, centre_y, dRAngle, &c.ptx, &c.pty);
-        cands_flat[base + i] = c;
+        if (i % shard_n == shard_rank) {
+            FpmCand c;
+            c.angle = angles[a];
+            c.score = (double)p.v;
+            c.img = img; c.id = i;
+            double dRAngle = -c.angle * FPM_D2R;
+            fpm_pt_rotate(ptx, pty, centre_x, centre_y, dRAngle, &c.ptx, &c.pty);
+            cands_flat[base + i / shard_n] = c;
+        }
         if (top_pt) {
             float* t = top_pt + ((size_t)img * cand_stride + i) * 4;
             t[0] = ptx; t[1] = pty; t[2] = p.v; t[3] = (float)(a + angle_idx_base);
@@ -1255,20 +1284,19 @@ __device__ void fpm_subpix(const double* sc27 /* [theta][y][x] */, double xm, do
         for (int k = 0; k < 27; k++) s += P[i * 27 + k] * sc27[k];
         Z[i] = s;
     }
-    // K1^-1 * K2, closed-form 3x3 inverse (cv::invert, n == 3)
-    double a00 = 2 * Z[0], a01 = Z[3], a02 = Z[4];
-    double a10 = Z[3], a11 = 2 * Z[1], a12 = Z[5];
-    double a20 = Z[4], a21 = Z[5], a22 = 2 * Z[2];
-    double d = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
-    double b0 = -Z[6], b1 = -Z[7], b2 = -Z[8];
+    // matK1.inv() * matK2 (:1066): OpenCV's matrix-expression layer evaluates inv(A) * B as cv::solve(A, B, DECOMP_LU)
+    // (MatOp_Invert::matmul), which for a 3x3 double system is this closed form (adjugate rows times b, then * 1/det);
+    // pinned bit-for-bit against cv2.solve on 2000 random systems (tests/test_oracle.py)
+    const double S00 = 2 * Z[0], S01 = Z[3], S02 = Z[4];
+    const double S10 = Z[3], S11 = 2 * Z[1], S12 = Z[5];
+    const double S20 = Z[4], S21 = Z[5], S22 = 2 * Z[2];
+    const double b0 = -Z[6], b1 = -Z[7], b2 = -Z[8];
+    double d = S00 * (S11 * S22 - S12 * S21) - S01 * (S10 * S22 - S12 * S20) + S02 * (S10 * S21 - S11 * S20);
     if (d != 0.) {
         d = 1. / d;
-        double t0 = (a11 * a22 - a12 * a21) * d, t1 = (a02 * a21 - a01 * a22) * d, t2 = (a01 * a12 - a02 * a11) * d;
-        double t3 = (a12 * a20 - a10 * a22) * d, t4 = (a00 * a22 - a02 * a20) * d, t5 = (a02 * a10 - a00 * a12) * d;
-        double t6 = (a10 * a21 - a11 * a20) * d, t7 = (a01 * a20 - a00 * a21) * d, t8 = (a00 * a11 - a01 * a10) * d;
-        *outx = t0 * b0 + t1 * b1 + t2 * b2;
-        *outy = t3 * b0 + t4 * b1 + t5 * b2;
-        *outa = (t6 * b0 + t7 * b1 + t8 * b2) * FPM_R2D;
+        *outx = ((S11 * S22 - S12 * S21) * b0 + (S02 * S21 - S01 * S22) * b1 + (S01 * S12 - S02 * S11) * b2) * d;
+        *outy = ((S12 * S20 - S10 * S22) * b0 + (S00 * S22 - S02 * S20) * b1 + (S02 * S10 - S00 * S12) * b2) * d;
+        *outa = (((S10 * S21 - S11 * S20) * b0 + (S01 * S20 - S00 * S21) * b1 + (S00 * S11 - S01 * S10) * b2) * d) * FPM_R2D;
     } else {
         *outx = 0; *outy = 0; *outa = 0;
     }
@@ -1456,7 +1484,7 @@ __global__ void fpm_invert_kernel(const uint8_t* __restrict__ src, int w, int h,
 // weights (B*1868 + G*9617 + R*4899 + 8192) >> 14 (both pinned against cv2.imdecode in tests/test_ingest.py).
 struct FpmBmpLut { uint8_t g[256]; };
 
-__global__ void fpm_ingest_bmp_kernel(const uint8_t* __restrict__ file, uint32_t data_off, uint32_t row_stride, int bpp,
+__global__ void fpm_ingest_bmp_kernel(const uint8_t* __restrict__ file, size_t data_off, size_t row_stride, int bpp,
                                       int top_down, FpmBmpLut lut, int w, int h, uint8_t* __restrict__ dst, int dpitch)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -1533,8 +1561,32 @@ __device__ __forceinline__ bool fpm_rrect_far(const FpmRRect& a, const FpmRRect&
     return dx * dx + dy * dy > lim * lim;
 }
 
+// Refined records of a call.  Contiguous: recs[0 .. *count).  Segmented (angle-sharded mode): the allgathered buffer of
+// one block per rank, block r = { FpmRefined[seg_cap]; int count; int pad }, consumed in place.
+struct FpmRefinedView {
+    const FpmRefined* recs;
+    const int* count;
+    int seg_cap;                // 0 = contiguous
+    int nseg;
+    size_t seg_stride;          // bytes per rank block
+};
+__device__ __forceinline__ int fpm_refined_slots(const FpmRefinedView& v) { return v.seg_cap ? v.seg_cap * v.nseg : *v.count; }
+__device__ __forceinline__ const FpmRefined& fpm_refined_at(const FpmRefinedView& v, int i)
+{
+    if (v.seg_cap == 0) return v.recs[i];
+    const int r = i / v.seg_cap, k = i - r * v.seg_cap;
+    return reinterpret_cast<const FpmRefined*>(reinterpret_cast<const char*>(v.recs) + (size_t)r * v.seg_stride)[k];
+}
+__device__ __forceinline__ bool fpm_refined_valid(const FpmRefinedView& v, int i)
+{
+    if (v.seg_cap == 0) return true;
+    const int r = i / v.seg_cap, k = i - r * v.seg_cap;
+    const char* blk = reinterpret_cast<const char*>(v.recs) + (size_t)r * v.seg_stride;
+    return k < *reinterpret_cast<const int*>(blk + (size_t)v.seg_cap * sizeof(FpmRefined));
+}
+
 __global__ void __launch_bounds__(FN_THREADS)
-fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__ refined_count,
+fpm_final_kernel(FpmRefinedView rv,
                  double score_thresh, double max_overlap, int nms_w, int nms_h, int tpl_w, int tpl_h,
                  unsigned long long* __restrict__ key_scratch, int key_stride,
                  FpmRRect* __restrict__ rect_scratch, int* __restrict__ del_scratch,
@@ -1542,7 +1594,7 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
                  int mfc_compat, int max_pos, FpmResultDev* __restrict__ results, int result_cap, int* __restrict__ result_count)
 {
     const int img = blockIdx.x, tid = threadIdx.x;
-    const int n_total = *refined_count;
+    const int n_total = fpm_refined_slots(rv);
     // sort keys in shared memory when the per-frame capacity allows (a bitonic sort in global memory pays one L2 round
     // trip per stage)
     __shared__ unsigned long long s_keys[FN_KEYS_SMEM];
@@ -1558,12 +1610,12 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
     if (tid == 0) s_n = 0;
     __syncthreads();
     for (int i = tid; i < n_total; i += FN_THREADS)
-        if (refined[i].img == img) {
+        if (fpm_refined_valid(rv, i) && fpm_refined_at(rv, i).img == img) {
             // ties: lower candidate id first (the oracle's stable sort order); id is unique per image
+            const FpmRefined& ri = fpm_refined_at(rv, i);
             int slot = atomicAdd(&s_n, 1);
-            keys[slot] = ((unsigned long long)fpm_desc_key((float)refined[i].score) << 32) |
-                         (unsigned long long)(uint32_t)refined[i].id;
-            idmap[refined[i].id] = i;
+            keys[slot] = ((unsigned long long)fpm_desc_key((float)ri.score) << 32) | (unsigned long long)(uint32_t)ri.id;
+            idmap[ri.id] = i;
         }
     __syncthreads();
     const int n = s_n;
@@ -1577,12 +1629,12 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
     for (int i = tid; i < n; i += FN_THREADS) {
         int idx = idmap[(uint32_t)(keys[i] & 0xffffffffu)];
         keys[i] = (keys[i] & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)idx;
-        if (refined[idx].score < score_thresh) atomicMin(&s_cut, i);
+        if (fpm_refined_at(rv, idx).score < score_thresh) atomicMin(&s_cut, i);
     }
     __syncthreads();
     const int m = s_cut;
     for (int i = tid; i < m; i += FN_THREADS) {
-        const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
+        const FpmRefined& r = fpm_refined_at(rv, (int)(uint32_t)(keys[i] & 0xffffffffu));
         float lt[2], rt[2], lb[2], rb[2];
         fpm_corners(r.ptx, r.pty, r.angle, nms_w, nms_h, lt, rt, lb, rb);
         rects[i] = fpm_rrect_from3(lt[0], lt[1], rt[0], rt[1], rb[0], rb[1]);
@@ -1672,7 +1724,7 @@ fpm_final_kernel(const FpmRefined* __restrict__ refined, const int* __restrict__
             rank = idmap[i];
         }
         if (rank < 0 || rank >= result_cap) continue;
-        const FpmRefined& r = refined[(uint32_t)(keys[i] & 0xffffffffu)];
+        const FpmRefined& r = fpm_refined_at(rv, (int)(uint32_t)(keys[i] & 0xffffffffu));
         FpmResultDev o;
         o.score = r.score;
         if (!mfc_compat) {

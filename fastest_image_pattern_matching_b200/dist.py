@@ -6,17 +6,22 @@ Two modes:
   i % world; every rank runs the whole pipeline on its frames; NO data-path collective.  The small
   per-frame result lists can be gathered to every rank afterwards (one all_gather of a padded tensor).
 
-* latency -- `match_angle_sharded`: ONE frame, replicated on every GPU (each rank builds the pyramid
-  redundantly, which is cheaper than exchanging it).  The top-layer angle schedule is split
-  contiguously over the ranks, the per-rank pick lists are exchanged with an all_gather, every rank
+* latency -- ONE frame, every rank holds (or uploads 1/N of) the same frame and builds the pyramid
+  redundantly, which is cheaper than exchanging it.  The top-layer angle schedule is split
+  contiguously over the ranks, the per-rank pick lists are exchanged with an allgather, every rank
   sorts the union identically (score descending, ties in (angle, pick) order like the oracle's stable
-  sort), candidate k is refined by rank k % world, the refined rows are exchanged with a second
-  all_gather and every rank runs the identical final filter/NMS.  Both payloads are a few KB:
-  latency-bound NCCL allgathers over NVLink.
+  sort), candidate k is refined by rank k % world, the refined records are exchanged with a second
+  allgather and every rank runs the identical final filter/NMS.
 
-The functions only need an "engine" with the stage API of `TemplateMatcher` (stageNumAngles,
-stageTop, stageSortCandidates, stageRefine, stageFinal), so the host logic is testable on CPU with a
-gloo group and a stand-in engine (tests/test_dist_cpu.py).
+  The product path is C++: `fpm_match_sharded` (csrc/fpm_host.cu) issues the two `ncclAllGather` calls on
+  device buffers that the sort / NMS kernels consume in place.  `init_sharded` only distributes the
+  128-byte ncclUniqueId through torch.distributed and `match_sharded` is a one-line call; nothing of the
+  data path runs in Python.
+
+  `match_angle_sharded` is the same schedule written against the stage API of `TemplateMatcher`
+  (stageNumAngles, stageTop, stageSortCandidates, stageRefine, stageFinal) with torch.distributed
+  all_gathers: the executable specification of the partitioning, testable on CPU with a gloo group and
+  a stand-in engine (tests/test_dist_cpu.py), and the cross-check of the C++ path on real GPUs.
 """
 from __future__ import annotations
 
@@ -31,10 +36,30 @@ def shard_indices(n: int, rank: int, world: int) -> List[int]:
 
 
 def angle_range(n_angles: int, rank: int, world: int):
-    """contiguous split of the top-layer angle schedule"""
-    per = (n_angles + world - 1) // world
+    """contiguous split of the top-layer angle schedule (same arithmetic as fpm_shard_angle_range)"""
+    per = max(1, (n_angles + world - 1) // world)
     a0 = min(n_angles, rank * per)
     return a0, min(n_angles, a0 + per)
+
+
+def init_sharded(matcher, dist=None):
+    """Collective: gives `matcher` (a TemplateMatcher on this rank's GPU) an NCCL communicator over the ranks of
+    the torch.distributed group.  Rank 0 creates the ncclUniqueId through the C ABI; torch.distributed only carries
+    the 128 bytes."""
+    from .matcher import comm_unique_id
+    if dist is None or not dist.is_initialized():
+        matcher.commInit(1, 0, comm_unique_id())
+        return 1
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    matcher.commInit(world, rank, box[0])
+    return world
+
+
+def match_sharded(matcher, src=None, **kw):
+    """Latency mode through the C++/NCCL path (fpm_match_sharded); identical result list on every rank."""
+    return matcher.matchSharded(src, **kw)
 
 
 def _all_gather_rows(rows: np.ndarray, ncols: int, dist, device) -> np.ndarray:

@@ -328,6 +328,38 @@ class TemplateMatcher:
                                             float(thresh), float(max_overlap), max_picks, picks.ctypes.data, C.byref(n)))
         return picks[:n.value]
 
+    def dbgTopScoreProduction(self, img):
+        """the top-layer map exactly as match() computes it; returns (map, reject_below)"""
+        s = np.ascontiguousarray(_as_u8_2d(img))
+        lv = self.templateLevels()[-1]
+        out = np.zeros((s.shape[0] - lv["h"] + 1, s.shape[1] - lv["w"] + 1), np.float32)
+        rb = C.c_float(0)
+        self._check(self._lib.fpm_dbg_top_score_production(self._h, s.ctypes.data, s.shape[1], s.shape[0], out.ctypes.data, C.byref(rb)))
+        return out, rb.value
+
+    # ---- angle-sharded latency mode: one handle per GPU, two NCCL allgathers on device buffers (fpm_match_sharded) ----
+    def setShardUpload(self, v: bool): self._set(L.PARAM_SHARD_UPLOAD, 1 if v else 0)
+    def collectiveCount(self) -> int: return int(self._lib.fpm_collective_count(self._h))
+
+    def commInit(self, nranks: int, rank: int, unique_id: bytes):
+        """collective: ncclCommInitRank on this handle's device with the 128-byte id made by comm_unique_id() on rank 0"""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.fpm_comm_init(self._h, nranks, rank, buf))
+
+    def commDestroy(self): self._lib.fpm_comm_destroy(self._h)
+
+    def matchSharded(self, sourceImage=None, ptr=None, shape=None, stride=None, on_device=False) -> List[SingleTargetMatch]:
+        """collective over the communicator's ranks: every rank passes the SAME frame and receives the same result list"""
+        cap = self.result_capacity
+        if not hasattr(self, "_res_buf"):
+            self._res_buf = (L.fpm_result * cap)()
+        res, n = self._res_buf, C.c_int(0)
+        if ptr is None:
+            s = _as_u8_2d(sourceImage)
+            ptr, shape, stride = s.ctypes.data, s.shape, s.strides[0]
+        self._check(self._lib.fpm_match_sharded(self._h, ptr, shape[1], shape[0], stride, 1 if on_device else 0, res, cap, C.byref(n)))
+        return _convert(res, min(n.value, cap))
+
     # ---- angle-sharded stage API ----
     def stageNumAngles(self, W, H) -> int: return self._lib.fpm_stage_num_angles(self._h, W, H)
 
@@ -382,6 +414,44 @@ def rrect_from3_host(p1, p2, p3):
     out = (C.c_float * 5)()
     lib.fpm_dbg_rrect_from3(pts, out)
     return tuple(out)
+
+
+def comm_available() -> bool:
+    return bool(L.load().fpm_comm_available())
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0 calls it and distributes the 128 bytes)"""
+    buf = C.create_string_buffer(128)
+    rc = L.load().fpm_comm_get_unique_id(buf)
+    if rc != 0:
+        raise FpmError("fpm_comm_get_unique_id failed (%d): libnccl.so.2 not loadable?" % rc)
+    return buf.raw
+
+
+def shard_angle_range(n_angles: int, nranks: int, rank: int):
+    a0, a1 = C.c_int(), C.c_int()
+    rc = L.load().fpm_shard_angle_range(n_angles, nranks, rank, C.byref(a0), C.byref(a1))
+    if rc != 0:
+        raise FpmError("fpm_shard_angle_range: bad arguments")
+    return a0.value, a1.value
+
+
+def match_sharded_virtual(matchers, sourceImage):
+    """fpm_match_sharded_virtual: the angle-sharded pipeline with the given handles of ONE device as the ranks;
+    returns one result list per rank (they must all be equal)."""
+    s = _as_u8_2d(sourceImage)
+    lib = matchers[0]._lib
+    n = len(matchers)
+    cap = min(m.result_capacity for m in matchers)
+    hs = (C.c_void_p * n)(*[m._h for m in matchers])
+    res = (L.fpm_result * (cap * n))()
+    counts = (C.c_int * n)()
+    rc = lib.fpm_match_sharded_virtual(hs, n, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], res, cap, counts)
+    if rc != 0:
+        errs = [lib.fpm_last_error(m._h).decode() for m in matchers]
+        raise FpmError("fpm_match_sharded_virtual error %d: %s" % (rc, "; ".join(e for e in errs if e)))
+    return [_convert(res[i * cap:(i + 1) * cap], min(counts[i], cap)) for i in range(n)]
 
 
 # ---- multi-template matching ("NCC-based OCR", MatchTool/MatchToolDlg.cpp:718-770) --------------------------

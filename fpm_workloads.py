@@ -1,6 +1,7 @@
-"""Seeded synthetic workloads of the BASELINE.json configs.
+"""Seeded synthetic workloads of the BASELINE.json configs for bench.py, tests/ and smoke().
 
-Data generation only (numpy + cv2, imported lazily); nothing here is on the matching path."""
+Bench / test infrastructure (it reads the fixtures under tests/golden/): deliberately NOT part of the
+fastest_image_pattern_matching_b200 package, which holds only what the matching path needs."""
 from __future__ import annotations
 
 import math
@@ -8,7 +9,7 @@ import os
 
 import numpy as np
 
-GOLDEN_IMAGES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "images")
+GOLDEN_IMAGES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "images")
 
 
 def load_fixture(name: str) -> np.ndarray:
@@ -28,10 +29,18 @@ def background(w: int, h: int, seed: int, sigma: float = 3.0) -> np.ndarray:
     return cv2.GaussianBlur(noise, (0, 0), sigma)
 
 
-def paste_rotated(dst: np.ndarray, tpl: np.ndarray, cx: float, cy: float, angle_deg: float) -> None:
-    """Paste `tpl` rotated by angle_deg (OpenCV sign) with its centre at (cx, cy), in place."""
+def paste_rotated(dst: np.ndarray, tpl: np.ndarray, cx: float, cy: float, angle_deg: float, fast: bool = False) -> None:
+    """Paste `tpl` rotated by angle_deg (OpenCV sign) with its centre at (cx, cy), in place.
+    fast: warp only the bounding box of the rotated template (bench frames; same picture up to fixed-point rounding --
+    the golden fixtures were made with the full-frame warp and keep it)."""
     import cv2
     th, tw = tpl.shape
+    if fast:
+        r = int(math.ceil(math.hypot(tw, th) / 2)) + 2
+        x0, y0 = max(0, int(cx) - r), max(0, int(cy) - r)
+        x1, y1 = min(dst.shape[1], int(cx) + r + 1), min(dst.shape[0], int(cy) + r + 1)
+        paste_rotated(dst[y0:y1, x0:x1], tpl, cx - x0, cy - y0, angle_deg)
+        return
     m = cv2.getRotationMatrix2D(((tw - 1) / 2.0, (th - 1) / 2.0), angle_deg, 1.0)
     m[0, 2] += cx - (tw - 1) / 2.0
     m[1, 2] += cy - (th - 1) / 2.0
@@ -46,7 +55,7 @@ def paste_rotated(dst: np.ndarray, tpl: np.ndarray, cx: float, cy: float, angle_
 CFG1_POSES = [(1725.857, 1045.433, -0.046), (2662.869, 1537.446, 119.979), (1768.936, 2098.494, -120.150)]
 
 
-def cfg1_source(seed: int = 7, tpl: np.ndarray | None = None, jitter: bool = False) -> np.ndarray:
+def cfg1_source(seed: int = 7, tpl: np.ndarray | None = None, jitter: bool = False, fast: bool = False) -> np.ndarray:
     """4024x3036 synthetic stand-in for the missing Src7.bmp: blurred noise + Dst7 at the README poses."""
     if tpl is None:
         tpl = load_fixture("Dst7")
@@ -55,7 +64,7 @@ def cfg1_source(seed: int = 7, tpl: np.ndarray | None = None, jitter: bool = Fal
     for (cx, cy, a) in CFG1_POSES:
         if jitter:
             cx += float(rng.uniform(-40, 40)); cy += float(rng.uniform(-40, 40)); a += float(rng.uniform(-25, 25))
-        paste_rotated(img, tpl, cx, cy, a)
+        paste_rotated(img, tpl, cx, cy, a, fast)
     return img
 
 
@@ -83,7 +92,7 @@ def synth_template(size: int, seed: int = 4) -> np.ndarray:
     return t
 
 
-def synth_frame(w: int, h: int, tpl: np.ndarray, seed: int, k: int = 4) -> np.ndarray:
+def synth_frame(w: int, h: int, tpl: np.ndarray, seed: int, k: int = 4, fast: bool = False) -> np.ndarray:
     """cfg4/cfg5 frame: blurred noise + k non-overlapping rotated instances of tpl."""
     img = background(w, h, seed, 3.0)
     rng = np.random.default_rng(seed + 5000)
@@ -97,5 +106,5 @@ def synth_frame(w: int, h: int, tpl: np.ndarray, seed: int, k: int = 4) -> np.nd
         if all(math.hypot(cx - x, cy - y) >= diag for x, y, _ in centres):
             centres.append((cx, cy, float(rng.uniform(-180, 180))))
     for cx, cy, a in centres:
-        paste_rotated(img, tpl, cx, cy, a)
+        paste_rotated(img, tpl, cx, cy, a, fast)
     return img

@@ -59,6 +59,8 @@ enum fpm_param {
     FPM_PARAM_TOLERANCE1 = 16, FPM_PARAM_TOLERANCE2 = 17, FPM_PARAM_TOLERANCE3 = 18, FPM_PARAM_TOLERANCE4 = 19,
     FPM_PARAM_SPLIT_BATCH = 20,    /* fpm_match_batch_device: batches of at least this many frames run as two concurrent
                                       half-batches on two internal handles (default 8, 0 = never) */
+    FPM_PARAM_SHARD_UPLOAD = 21,   /* fpm_match_sharded with a HOST frame: 1 (default) = every rank uploads 1/N of the rows over its own
+                                      PCIe link and the slices are allgathered over NVLink; 0 = every rank uploads the whole frame */
     FPM_PARAM_COUNT_
 };
 
@@ -168,6 +170,34 @@ int fpm_stage_sort_candidates(fpm_handle* h, const double* picks, int n, double*
 int fpm_stage_refine(fpm_handle* h, const double* cands, int n, double* rows, int cap, int* n_out);
 int fpm_stage_final(fpm_handle* h, const double* refined, int n, fpm_result* out, int cap, int* n_out);
 
+/* ---- angle-sharded latency mode across the GPUs of one box ----
+ * One process (or thread) per GPU, each with its own handle, same template and parameters on every rank.  The work of
+ * TemplateMatcher::match shards in two places -- the top-layer angle sweep (src/TemplateMatcher.cpp:162-211) and the
+ * per-candidate descent (:262-371) -- joined by two ncclAllGather calls on device buffers (pick lists, refined records)
+ * that the sort / NMS kernels consume in place; the result list is identical on every rank and bit-identical to
+ * fpm_match on one GPU.  NCCL is loaded at run time (dlopen libnccl.so.2): the library has no link-time dependency.
+ *   fpm_comm_get_unique_id: rank 0 creates the 128-byte ncclUniqueId; the caller distributes it (MPI, torch.distributed, a file...)
+ *   fpm_comm_init:          collective over all ranks: ncclCommInitRank on the handle's device
+ *   fpm_comm_attach:        use an existing ncclComm_t (borrowed, not destroyed by the handle)
+ *   fpm_match_sharded:      collective; src is this rank's copy of the SAME frame (host pointer, or a device pointer with
+ *                           src_on_device = 1).  A host frame is uploaded as 1/N row slices + one allgather (FPM_PARAM_SHARD_UPLOAD).
+ *   fpm_match_sharded_virtual: the same pipeline with nranks handles of ONE device as the ranks and device-to-device block
+ *                           copies as the exchange (tests the partitioning where a single GPU is available). */
+#define FPM_COMM_ID_BYTES 128
+int fpm_comm_available(void);
+int fpm_comm_get_unique_id(void* id /* FPM_COMM_ID_BYTES */);
+int fpm_comm_init(fpm_handle* h, int nranks, int rank, const void* id /* FPM_COMM_ID_BYTES */);
+int fpm_comm_attach(fpm_handle* h, void* nccl_comm /* ncclComm_t */, int nranks, int rank);
+void fpm_comm_destroy(fpm_handle* h);
+int fpm_match_sharded(fpm_handle* h, const uint8_t* src, int width, int height, int stride, int src_on_device,
+                      fpm_result* out, int cap, int* n);
+int fpm_match_sharded_virtual(fpm_handle* const* hs, int nranks, const uint8_t* src, int width, int height, int stride,
+                              fpm_result* out /* nranks*cap */, int cap, int* n /* nranks */);
+/* contiguous chunk [a0, a1) of an n_angles schedule swept by `rank` (host arithmetic, no device needed) */
+int fpm_shard_angle_range(int n_angles, int nranks, int rank, int* a0, int* a1);
+/* number of NCCL collectives issued by this handle since creation */
+long long fpm_collective_count(const fpm_handle* h);
+
 /* ---- stage kernels exposed for bit-exact parity tests (host pointers in and out) ---- */
 int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, uint8_t* dst /* ((w+1)/2)*((h+1)/2) */);
 int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, const double m[6] /* forward 2x3 */,
@@ -182,6 +212,9 @@ int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t
                        float* numer, long long* winS, long long* winQ,
                        int32_t* edge_rowS /* optional, ne*(th+6)*7: the stored first/last 6 rows, others -1 */);
 int fpm_dbg_top_score(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score /* (h-th+1)*(w-tw+1) */);
+/* the map exactly as match() computes it: scores certainly below reject_below = Score*0.9^top - 0.01 may be float32
+ * estimates (the peak search cannot observe them); *reject_below returns the bound in use (-inf: exact everywhere) */
+int fpm_dbg_top_score_production(fpm_handle* h, const uint8_t* img, int w, int hgt, float* score, float* reject_below);
 /* block_mode: 0 = whole-map minMaxLoc, 1 = Qt s_BlockMax (DataStructures.h:150-245), 2 = MFC s_BlockMax (MatchToolDlg.h:109-213) */
 int fpm_dbg_peaks(fpm_handle* h, const float* score, int cols, int rows, int tw, int th, int block_mode,
                   double thresh, double max_overlap, int max_picks, double* picks /* max_picks*3: x,y,v */, int* n);

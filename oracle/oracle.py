@@ -795,7 +795,11 @@ class OracleMatcher:
         z = cv2.gemm(cv2.gemm(cv2.invert(ata)[1], A, 1, None, 0, flags=cv2.GEMM_2_T), S, 1, None, 0).ravel()
         k1 = np.array([[2 * z[0], z[3], z[4]], [z[3], 2 * z[1], z[5]], [z[4], z[5], 2 * z[2]]])
         k2 = np.array([[-z[6]], [-z[7]], [-z[8]]])
-        d = cv2.gemm(cv2.invert(k1)[1], k2, 1, None, 0)
+        # matK1.inv() * matK2 (:1066): OpenCV's MatExpr layer turns inv(A) * B into cv::solve(A, B, DECOMP_LU)
+        # (modules/core/src/matop.cpp, MatOp_Invert::matmul), not invert-then-multiply
+        ok, d = cv2.solve(k1, k2, flags=cv2.DECOMP_LU)
+        if not ok:
+            d = np.zeros((3, 1))
         return float(d[0, 0]), float(d[1, 0]), float(d[2, 0]) * R2D
 
 

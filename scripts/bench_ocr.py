@@ -9,7 +9,8 @@ import sys
 import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from fastest_image_pattern_matching_b200 import GlyphReader, synth  # noqa: E402
+from fastest_image_pattern_matching_b200 import GlyphReader  # noqa: E402
+import fpm_workloads as synth  # noqa: E402
 from fastest_image_pattern_matching_b200.matcher import OCR_LETTERS  # noqa: E402
 
 case = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "cases.json")))["ocr_m12"]

@@ -12,7 +12,8 @@ import torch.distributed as dist
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
-from fastest_image_pattern_matching_b200 import TemplateMatcher, synth  # noqa: E402
+from fastest_image_pattern_matching_b200 import TemplateMatcher  # noqa: E402
+import fpm_workloads as synth  # noqa: E402
 from fastest_image_pattern_matching_b200 import dist as D  # noqa: E402
 
 

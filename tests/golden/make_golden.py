@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle.oracle import OracleMatcher  # noqa: E402
-from fastest_image_pattern_matching_b200 import synth  # noqa: E402
+import fpm_workloads as synth  # noqa: E402
 
 REF = "/root/reference/Test Images"
 FIXTURES = ["Src3.bmp", "Dst3.bmp", "Src4.bmp", "Dst4.bmp", "Src6.jpg", "Dst6.bmp", "Dst7.bmp", "Src8.bmp", "Dst8.bmp",

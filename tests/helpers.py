@@ -1,6 +1,6 @@
 import numpy as np
 
-from fastest_image_pattern_matching_b200 import synth
+import fpm_workloads as synth
 
 
 def get_image(name):

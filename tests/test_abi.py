@@ -153,7 +153,7 @@ def test_rotated_rect_geometry_degenerate_contacts(fpm_built):
 
 def test_synthetic_generators_are_deterministic(golden_cases):
     import hashlib
-    from fastest_image_pattern_matching_b200 import synth
+    import fpm_workloads as synth
     a = synth.cfg1_source()
     assert a.shape == (3036, 4024)
     assert hashlib.sha256(a.tobytes()).hexdigest()[:16] == golden_cases["cfg1_synth"]["src_sha"]

@@ -55,7 +55,7 @@ def test_cpp_shim_compiles_and_fails_loudly_without_gpu(tmp_path, fpm_built):
 
 @pytest.mark.gpu
 def test_cpp_shim_matches(tmp_path, fpm_built, golden_cases):
-    from fastest_image_pattern_matching_b200 import synth
+    import fpm_workloads as synth
     exe = _build(tmp_path, fpm_built)
     t, s = synth.load_fixture("Dst8"), synth.load_fixture("Src8")
     (tmp_path / "t.raw").write_bytes(t.tobytes())

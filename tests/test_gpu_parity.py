@@ -235,7 +235,7 @@ def test_match_against_golden(matcher, golden_cases, case):
 
 def test_match_equals_live_oracle_on_jittered_cfg1(matcher, golden_cases):
     """a pose set that is not in the golden file: oracle and GPU run on the same seeded input here."""
-    from fastest_image_pattern_matching_b200 import synth
+    import fpm_workloads as synth
     c = golden_cases["cfg1_synth"]
     tpl = get_image("Dst7")
     src = synth.cfg1_source(seed=21, tpl=tpl, jitter=True)
@@ -446,7 +446,7 @@ def test_angle_sharded_driver_single_rank(matcher, golden_cases):
 
 # ---------------- BASELINE.json configs 4 and 5 at full size, against the live oracle ----------------
 def _cfg45(matcher, W, H, T, seeds):
-    from fastest_image_pattern_matching_b200 import synth
+    import fpm_workloads as synth
     tpl = synth.synth_template(T, 4)
     frames = [synth.synth_frame(W, H, tpl, s, 4) for s in seeds]
     params = dict(max_pos=4, score=0.8, tolerance_angle=180, min_reduce_area=256, max_overlap=0.0)
@@ -517,7 +517,7 @@ def test_mfc_compat_result_convention(matcher, golden_cases):
 
 # ---------------- randomized differential test: GPU vs live oracle on small random scenes ----------------
 def _random_scene(seed):
-    from fastest_image_pattern_matching_b200 import synth
+    import fpm_workloads as synth
     rng = np.random.default_rng(seed)
     W, H = int(rng.integers(300, 900)), int(rng.integers(240, 700))
     tw, th = int(rng.integers(24, 140)), int(rng.integers(20, 120))

@@ -28,7 +28,7 @@ def test_known_answer_counts(golden_cases, oracle_lib, case, count):
 
 def test_cfg1_recovers_readme_poses(golden_cases):
     # README.md:47-49 poses (synthetic Src7: Dst7 pasted there); MFC angle sign = -Qt sign
-    from fastest_image_pattern_matching_b200.synth import CFG1_POSES
+    from fpm_workloads import CFG1_POSES
     res = golden_cases["cfg1_synth"]["results"]
     assert len(res) == 3
     for (cx, cy, a) in CFG1_POSES:

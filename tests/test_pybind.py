@@ -30,7 +30,7 @@ def test_pybind_builds_and_has_the_reference_surface(pymod):
 
 @pytest.mark.gpu
 def test_pybind_match(pymod, golden_cases):
-    from fastest_image_pattern_matching_b200 import synth
+    import fpm_workloads as synth
     m = pymod.TemplateMatcher(0)
     m.setMaxPositions(5); m.setScore(0.8); m.setToleranceAngle(180); m.setMaxOverlap(0.8)
     assert m.learnPattern(synth.load_fixture("Dst8"))
