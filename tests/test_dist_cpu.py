@@ -117,3 +117,17 @@ def test_partitions_cover_everything_once():
             assert seen == list(range(n))
             fr = sorted(sum((D.shard_indices(n, r, world) for r in range(world)), []))
             assert fr == list(range(n))
+
+
+def test_c_abi_partition_equals_python_specification():
+    """fpm_shard_angle_range (the arithmetic fpm_match_sharded uses) == dist.angle_range; chunks are equal-sized so the
+    allgathered blocks line up with the global angle index"""
+    from fastest_image_pattern_matching_b200 import dist as D
+    from fastest_image_pattern_matching_b200.matcher import shard_angle_range
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 5, 41, 47, 53, 64):
+            chunk = max(1, -(-n // world))
+            for r in range(world):
+                assert shard_angle_range(n, world, r) == D.angle_range(n, r, world)
+                a0, a1 = shard_angle_range(n, world, r)
+                assert a0 == min(n, r * chunk) and a1 - a0 <= chunk

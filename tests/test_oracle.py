@@ -187,3 +187,113 @@ def test_block_max_tie_rules_differ_as_documented():
     assert om.top_picks(score.copy(), (9, 7), 0.5, True)[0][0] == (6, 5)
     om.mfc_compat = True
     assert om.top_picks(score.copy(), (9, 7), 0.5, True)[0][0] == (70, 50)
+
+
+# ---------------- round 2: sub-pixel arithmetic pins (src/TemplateMatcher.cpp:1002-1072) ----------------
+def _det3(m):
+    return (m[0, 0] * (m[1, 1] * m[2, 2] - m[1, 2] * m[2, 1]) - m[0, 1] * (m[1, 0] * m[2, 2] - m[1, 2] * m[2, 0]) +
+            m[0, 2] * (m[1, 0] * m[2, 1] - m[1, 1] * m[2, 0]))
+
+
+def _solve3_closed_form(S, b):
+    """cv::solve(3x3, DECOMP_LU) for doubles -- the arithmetic fpm_subpix uses for K1^-1 K2"""
+    d = 1.0 / _det3(S)
+    t0 = ((S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * b[0] + (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * b[1] + (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * b[2]) * d
+    t1 = ((S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * b[0] + (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * b[1] + (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * b[2]) * d
+    t2 = ((S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * b[0] + (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * b[1] + (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * b[2]) * d
+    return np.array([t0, t1, t2])
+
+
+def test_cv_solve_3x3_closed_form_is_bit_exact():
+    """`matK1.inv() * matK2` (:1066) is evaluated by OpenCV's MatExpr layer as cv::solve(K1, K2, DECOMP_LU); for a 3x3
+    double system that is the adjugate closed form restated in fpm_subpix -- pinned bit for bit against cv2.solve"""
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        S = rng.normal(size=(3, 3))
+        S = S + S.T
+        b = rng.normal(size=3)
+        ok, x = cv2.solve(S, b.reshape(3, 1), flags=cv2.DECOMP_LU)
+        assert ok and np.array_equal(x.ravel(), _solve3_closed_form(S, b))
+
+
+def _lu_inverse(Ain):
+    """cv::invert(DECOMP_LU) for n > 3: hal::LU64f (LUImpl, partial pivoting, eps = 100*DBL_EPSILON) on [A | I]"""
+    A = Ain.copy()
+    m = A.shape[0]
+    B = np.eye(m)
+    eps = np.finfo(float).eps * 100
+    for i in range(m):
+        k = i
+        for j in range(i + 1, m):
+            if abs(A[j, i]) > abs(A[k, i]):
+                k = j
+        if abs(A[k, i]) < eps:
+            return np.zeros_like(B)
+        if k != i:
+            A[[i, k], i:] = A[[k, i], i:]
+            B[[i, k]] = B[[k, i]]
+        d = -1 / A[i, i]
+        for j in range(i + 1, m):
+            al = A[j, i] * d
+            for kk in range(i + 1, m):
+                A[j, kk] += al * A[i, kk]
+            for kk in range(m):
+                B[j, kk] += al * B[i, kk]
+    for i in range(m - 1, -1, -1):
+        for j in range(m):
+            s = B[i, j]
+            for k in range(i + 1, m):
+                s -= A[i, k] * B[k, j]
+            B[i, j] = s / A[i, i]
+    return B
+
+
+def test_subpixel_fit_is_well_inside_the_tolerance_in_fp64():
+    """The 10x10 normal equations mix pixels and radians (cond(AtA) ~ 1e10..1e11): a strictly sequential, FMA-free
+    restatement of the chain (= the GPU's fpm_subpix, compiled with -fmad=false) and cv2's own gemm/invert/solve (SIMD
+    dispatched, FMA contracted on this host) must agree far inside 0.05 px / 0.01 deg -- so the north_star tolerance
+    holds for sub-pixel mode too, whatever the host's OpenCV dispatch does."""
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for it in range(40):
+        xm, ym = float(rng.integers(1, 6)), float(rng.integers(1, 6))
+        tm, step = float(rng.uniform(-180, 180)), float(rng.uniform(0.1, 9.0))
+        A = np.zeros((27, 10))
+        S = np.zeros(27)
+        row = 0
+        peak = rng.uniform(0.8, 1.0)
+        for theta in range(3):
+            for y in (-1, 0, 1):
+                for x in (-1, 0, 1):
+                    dx, dy = xm + x, ym + y
+                    dt = (tm + (theta - 1) * step) * O.D2R
+                    A[row] = [dx * dx, dy * dy, dt * dt, dx * dy, dx * dt, dy * dt, dx, dy, dt, 1.0]
+                    S[row] = np.float32(peak - 0.01 * ((x - 0.2) ** 2 + (y + 0.3) ** 2) - 0.004 * (theta - 1.1) ** 2 + rng.normal(0, 1e-4))
+                    row += 1
+        # cv2 chain (the oracle's)
+        ata = cv2.gemm(A, A, 1, None, 0, flags=cv2.GEMM_1_T)
+        zc = cv2.gemm(cv2.gemm(cv2.invert(ata)[1], A, 1, None, 0, flags=cv2.GEMM_2_T), S.reshape(-1, 1), 1, None, 0).ravel()
+        # sequential chain (the GPU's)
+        AtA = np.zeros((10, 10))
+        for i in range(10):
+            for j in range(10):
+                s = 0.0
+                for k in range(27):
+                    s += A[k, i] * A[k, j]
+                AtA[i, j] = s
+        inv = _lu_inverse(AtA)
+        P = np.zeros((10, 27))
+        for i in range(10):
+            for j in range(27):
+                s = 0.0
+                for k in range(10):
+                    s += inv[i, k] * A[j, k]
+                P[i, j] = s
+        zg = np.array([sum(P[i, k] * S[k] for k in range(27)) for i in range(10)])
+        outs = []
+        for z in (zc, zg):
+            k1 = np.array([[2 * z[0], z[3], z[4]], [z[3], 2 * z[1], z[5]], [z[4], z[5], 2 * z[2]]])
+            d = _solve3_closed_form(k1, -z[6:9])
+            outs.append((d[0], d[1], d[2] * O.R2D))
+        worst = max(worst, abs(outs[0][0] - outs[1][0]), abs(outs[0][1] - outs[1][1]), abs(outs[0][2] - outs[1][2]))
+    assert worst < 1e-4, worst
