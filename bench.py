@@ -690,7 +690,6 @@ def run_latency(args, wl, rank, world, local_rank):
     # the single-GPU figures of the same run: rank 0 alone, the other ranks wait at the barrier
     one = {}
     if rank == 0:
-        m.commDestroy()
         one["device_resident"] = series(lambda: lib.fpm_match_batch_device(hnd, dev.data_ptr(), 1, Wd, H, Wd, H * Wd, out, cap, C.byref(n)), False)
         one["host_pinned"] = series(lambda: lib.fpm_match(hnd, pinned.data_ptr(), Wd, H, Wd, out, cap, C.byref(n)), False)
         one["host_pageable"] = series(lambda: lib.fpm_match(hnd, frame.ctypes.data, Wd, H, Wd, out, cap, C.byref(n)), False)

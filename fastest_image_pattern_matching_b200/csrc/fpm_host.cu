@@ -8,6 +8,7 @@
 #include "../../include/fpm_b200.h"
 #include "fpm_kernels.cuh"
 #include "fpm_mma.cuh"
+#include "fpm_fused.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -159,7 +160,7 @@ struct fpm_handle {
     int use_simd = 1, subpixel = 0, trace = 0;
     double workspace_mb = 4096;
     int h2d_chunk = 0;             // frames per H2D chunk in fpm_match_batch (0 = auto)
-    bool mma_attr_set = false, fused_attr_set = false, peaks_attr_set = false;
+    bool mma_attr_set = false, fused_attr_set = false, peaks_attr_set = false, warpmma_attr_set = false;
     // concurrent half-batches (fpm_match_batch_device): a second handle with the same template and parameters
     fpm_handle* twin = nullptr;
     int split_batch = 8;           // FPM_PARAM_SPLIT_BATCH: smallest batch that is split in two (0 = never)
@@ -233,11 +234,12 @@ namespace {
         }                                                                                \
     } while (0)
 
-enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_CORR_FUSED, K_COUNT };
+enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_TOTAL = 3, CNT_ERR = 4, CNT_N = 8 };
+enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_CORR_FUSED, K_CORR_WARP, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"fpm_pyrdown_kernel", "fpm_warp_kernel(top)", "fpm_top_score_kernel", "fpm_top_peaks_kernel",
                                            "fpm_collect_sort_kernel", "fpm_refine_prep_kernel", "fpm_warp_kernel(roi)",
                                            "fpm_corr_rows_kernel", "fpm_refine_finalize_kernel", "fpm_final_kernel",
-                                           "fpm_corr_mma_kernel", "fpm_corr_fused_kernel"};
+                                           "fpm_corr_mma_kernel", "fpm_corr_fused_kernel", "fpm_corr_warp_kernel"};
 
 cudaEvent_t prof_event(fpm_handle* h)
 {
@@ -398,14 +400,14 @@ bool mma_usable(const fpm_handle* h, int tw)
 {
     if (h->use_tc == 0) return false;
     if (!get_encode_tiled()) return false;
-    return (h->use_tc == 2 || h->use_tc == 4) ? true : tw >= 64;
+    return (h->use_tc == 2 || h->use_tc == 4) ? true : tw >= 64;     // modes 1, 3, 5, 6: large levels
 }
 
 // narrow levels (16 <= width < 64): the row-split tensor-core kernel does not beat dp4a there (256 B of row dots per
 // 22..70-byte ROI row), the fused kernel does as soon as the level has enough evals to fill the SMs
 bool mma_narrow_fused(const fpm_handle* h, int tw)
 {
-    return h->use_tc == 1 && h->use_simd && get_encode_tiled() && tw >= 16 && tw < 64;
+    return (h->use_tc == 1 || h->use_tc == 6) && h->use_simd && get_encode_tiled() && tw >= 16 && tw < 64;
 }
 
 // The fused kernel keeps one CTA on 128 evals for all ROI rows: it wins when the evals fill the SMs and the rows are
@@ -473,6 +475,65 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
        fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw, th, tw + FPM_ROI_PAD,
                                                                            rows_per_cta, h->d_raw.as<int32_t>(), rowS, rowQ));
+    return FPM_OK;
+}
+
+// ---- ROI warp fused into the tensor-core correlation's producer (fpm_fused.cuh) ----------------------------------
+// copy width the source level allows for the box staging (0 = not even word aligned: the kernel is not used)
+inline int level_copy_vec(const FpmLevel& L)
+{
+    const uintptr_t p = reinterpret_cast<uintptr_t>(L.ptr);
+    for (int v = 16; v >= 4; v >>= 1)
+        if (p % v == 0 && L.pitch % v == 0 && L.img_stride % v == 0) return v;
+    return 0;
+}
+
+// worst-case bytes of the source box of one visit (8 ROI rows x 128 columns, the 3 angles of a candidate, which are anchored
+// at the same point and at most ~6 px apart anywhere in the ROI) over all rotation angles
+bool fw_box_fits(int vec)
+{
+    static int worst[17] = {0};
+    if (!worst[vec]) {
+        double mx = 0;
+        for (int i = 0; i <= 360; i++) {
+            const double a = i * 0.25 * FPM_D2R, c = fabs(cos(a)), s = fabs(sin(a));
+            const double W = 127 * c + (FW_R - 1) * s + 3 + 8, H = 127 * s + (FW_R - 1) * c + 3 + 8;
+            const double pitch = floor((W + 2 * vec) / vec) * vec + 4;
+            mx = std::max(mx, pitch * (H + 1));
+        }
+        worst[vec] = (int)mx;
+    }
+    return worst[vec] <= FW_BOX_BYTES;
+}
+
+bool corr_warp_usable(const fpm_handle* h, int tw, int n_ang, const FpmLevel& L)
+{
+    if (h->use_tc != 6) return false;                        // opt-in: bit-identical, less DRAM traffic, but slower than warp + MMA today
+    if (n_ang != 3 || tw < 64 || !get_encode_tiled()) return false;
+    return level_copy_vec(L) >= 4 && fw_box_fits(4);       // the box is staged with 4-byte copies
+}
+
+// raw[y][tile*128 + slot][64] s32 + rowS/rowQ for the 3 angles of `nc` candidates, straight from the source level
+int launch_corr_warp(fpm_handle* h, const FpmLevel& L, const FpmWarpJob* jobs, const uint8_t* tsh, int bpitch, int tw, int th,
+                     int nc, int* e_pad_out, int32_t* rowS, int32_t* rowQ)
+{
+    const int rh = th + FPM_ROI_PAD;
+    const int m_tiles = (nc + FW_CANDS - 1) / FW_CANDS;
+    const int e_pad = m_tiles * FW_M;
+    *e_pad_out = e_pad;
+    CK(h->d_raw.ensure((size_t)rh * e_pad * MM_N * sizeof(int32_t)));
+    CUtensorMap map_b;
+    int rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
+    if (rc) return rc;
+    if (!h->warpmma_attr_set) {
+        CK(ensure_dyn_smem((const void*)fpm_corr_warp_kernel, h->device, FW_SMEM_BYTES));
+        h->warpmma_attr_set = true;
+    }
+    dim3 grid((rh + FW_R - 1) / FW_R, m_tiles);
+    KL(K_CORR_WARP, (double)nc * 3 * FPM_NCELL * (double)tw * th,
+       fpm_corr_warp_kernel<<<grid, FW_THREADS, FW_SMEM_BYTES, h->stream>>>(jobs, nc, L, level_copy_vec(L), map_b, rh, tw, th,
+                                                                            tw + FPM_ROI_PAD, e_pad, h->d_raw.as<int32_t>(), rowS, rowQ,
+                                                                            h->d_counters.as<int>() + CNT_ERR));
     return FPM_OK;
 }
 
@@ -720,7 +781,6 @@ int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt
     return FPM_OK;
 }
 
-enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_TOTAL = 3, CNT_N = 8 };
 
 // ---- refinement of a flat candidate list held in d_cand[0] ------------------------------
 int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
@@ -760,7 +820,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         // bytes per eval of one wave: ROI patch, window row sums, job record, and the row dots in the layout of the
         // correlation path this level can take (dp4a [h][49], row-split tensor-core raw[h+6][64], or the fused kernel's
         // 64 numerators + 14 window totals)
-        size_t per_eval = roi_stride + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 + sizeof(FpmWarpJob);
+        const bool warp_fused = corr_warp_usable(h, t.w, n_ang, L);
+        size_t per_eval = (warp_fused ? 0 : roi_stride) + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 + sizeof(FpmWarpJob);
         if (mma_usable(h, t.w) || mma_narrow_fused(h, t.w))
             per_eval += std::max((size_t)(t.h + FPM_ROI_PAD) * MM_N * 4, (size_t)MM_N * 4 + 2 * FPM_NSHIFT * 8);
         if (!mma_usable(h, t.w)) per_eval += (size_t)t.h * FPM_NCELL * 4;
@@ -770,7 +831,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         wave_cands = std::min(wave_cands, 65535);             // one candidate per gridDim.y slot of the ROI warp
         const int wave_evals = wave_cands * n_ang;
         CK(h->d_jobs_ref.ensure((size_t)wave_evals * sizeof(FpmWarpJob)));
-        CK(h->d_roi.ensure(roi_stride * wave_evals));
+        if (!warp_fused) CK(h->d_roi.ensure(roi_stride * wave_evals));
         if (!mma_usable(h, t.w)) CK(h->d_rowsum.ensure((size_t)wave_evals * t.h * FPM_NCELL * 4));
         CK(h->d_rowS.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
         CK(h->d_rowQ.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
@@ -792,6 +853,16 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
                fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
                                                                              h->d_jobs_ref.as<FpmWarpJob>()));
+            int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
+            int raw_tile_evals = 0;                         // evals per 128-row tile of raw (0 = contiguous)
+            bool fused = false;                             // numerators + window totals straight from the fused tensor-core kernel
+            if (warp_fused) {
+                // the ROI patches are produced inside the correlation kernel and never reach HBM
+                int rcm = launch_corr_warp(h, L, h->d_jobs_ref.as<FpmWarpJob>(), h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch, t.w, t.h, nc,
+                                           &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
+                if (rcm) return rcm;
+                raw_tile_evals = FW_TILE_EVALS;
+            } else {
             const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
             dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
             // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
@@ -799,8 +870,6 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
                                                                     h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
                                                                     level_vec_ok(L)));
-            int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
-            bool fused = false;                             // numerators + window totals straight from the fused tensor-core kernel
             if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) &&
                 fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
                 int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
@@ -819,6 +888,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                                                                                 cc.rb, cc.evals_per_cta, h->d_rowsum.as<int32_t>(),
                                                                                 h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>()));
             }
+            }
             KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
                fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
                    cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,
@@ -827,7 +897,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                    h->d_cand[cur ^ 1].as<FpmCand>(),
                    counters + CNT_NEXT, ref_out, ref_cnt,
                    h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr,
-                   fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>()));
+                   fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>(), raw_tile_evals));
         }
         CK(cudaMemcpyAsync(hc, counters, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -844,6 +914,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                     rows.push_back(e.locx); rows.push_back(e.locy);
                 }
         }
+        if (hc[CNT_ERR]) { h->err = "fpm_corr_warp_kernel: source box larger than its staging buffer"; return FPM_ERR_LIMIT; }
         n = (layer == stop) ? 0 : hc[CNT_NEXT];
         *n_refined_out = hc[CNT_REFINED];
         cur ^= 1;

@@ -177,7 +177,7 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 #define WA_PX (WA_TW / 32)   // pixels per lane and tile row
 #define WA_THREADS 256
 #define WA_BW 160     // staged box: max bytes per row actually used (40 words)
-#define WA_SW 164     // staged box pitch in bytes: 41 words (odd) -> rows fall in different banks
+#define WA_SW 260     // staged box pitch capacity in bytes.  The pitch in use is 65 or 63 words = +-1 (mod 32 banks), see below
 #define WA_SH 160     // staged box: rows
 #define WA_MAXG 3     // jobs per group
 
@@ -193,6 +193,12 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     if (!jb0.valid || ty0 >= dh || tx0 >= dpitch) return;
     __shared__ int s_ad[WA_MAXG][WA_TW], s_bd[WA_MAXG][WA_TW], s_X0[WA_MAXG][WA_TH], s_Y0[WA_MAXG][WA_TH];
     __shared__ __align__(16) uint8_t s_src[WA_SH * WA_SW];
+    // Bank of a staged byte = (row * pitch_words + x / 4) mod 32.  The 32 lanes of a gather walk a straight line through the
+    // box; with pitch_words = +1 (mod 32) the bank is row + x/4, strictly monotone along any line whose row and column move
+    // in the SAME direction, with -1 (mod 32) along any line where they move in opposite directions: no two lanes share a
+    // bank unless they share the word.  (41 words, the first choice, left 42 % of the wavefronts to bank conflicts and the
+    // kernel bound by the shared-memory pipe.)  The direction of the lanes' line is (m[0], m[3]) of the inverse matrix.
+    const int SW = (jb0.m[0] * jb0.m[3] >= 0) ? 260 : 252;
     const int tid = threadIdx.x;
     for (int i = tid; i < group * (WA_TW + WA_TH); i += WA_THREADS) {
         const int j = i / (WA_TW + WA_TH), k = i - j * (WA_TW + WA_TH);
@@ -240,14 +246,14 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
             if (wc < nwr) {
                 const int x = bx0 + 4 * wc;
                 const uint8_t* rowp = s + (size_t)(by0 + (tid >> 6)) * sp + x;
-                uint8_t* sp_out = s_src + (tid >> 6) * WA_SW + 4 * wc;
+                uint8_t* sp_out = s_src + (tid >> 6) * SW + 4 * wc;
                 if (vec_ok && x + 3 < sw) {
                     for (int r = tid >> 6; r < nr; r += WA_THREADS / 64, rowp += (size_t)(WA_THREADS / 64) * sp,
-                             sp_out += (WA_THREADS / 64) * WA_SW)
+                             sp_out += (WA_THREADS / 64) * SW)
                         fpm_cp_async4(sp_out, rowp, true);
                 } else {
                     for (int r = tid >> 6; r < nr; r += WA_THREADS / 64, rowp += (size_t)(WA_THREADS / 64) * sp,
-                             sp_out += (WA_THREADS / 64) * WA_SW) {
+                             sp_out += (WA_THREADS / 64) * SW) {
                         uint32_t v = 0;
 #pragma unroll
                         for (int k = 0; k < 4; k++)
@@ -266,6 +272,50 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
     // (odd word pitch -> different banks), so the byte gathers are close to conflict-free at every angle.
     const int lane = tid & 31, warp = tid >> 5;
     const bool fastw = staged && inside && ncols == WA_TW;     // whole tile row inside the image and the ROI: no predicates
+    if (fastw) {
+        // Hot path, kept free of everything that is not per-pixel work (it was 46 instructions per pixel with the path
+        // dispatch, the generic->shared address conversion and the 64-bit row pointer inside the row loop):
+        //   XX = X0 + adelta, YY = Y0 + bdelta;  fx = XX & 0x3e0 = 32*ax, fy = YY & 0x3e0 = 32*ay (one LOP each instead of
+        //   shift + mask);  top' = (p00 << 10) + fx*(p01 - p00) = 32*top, bot' likewise;
+        //   v = ((top' << 10) + fy*(bot' - top') + (512 << 10)) >> 20   -- the same integer as ((top<<5) + ay*(bot-top) + 512) >> 10
+        //   (all terms < 2^29).
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_src);
+        for (int j = 0; j < group; j++) {
+            if (!jobs[g0 + j].valid) continue;
+            int adj[WA_PX], bdj[WA_PX];
+#pragma unroll
+            for (int k = 0; k < WA_PX; k++) {
+                adj[k] = s_ad[j][lane + 32 * k] - (bx0 << 10);
+                bdj[k] = s_bd[j][lane + 32 * k] - (by0 << 10);
+            }
+            uint8_t* __restrict__ drow = dst + (size_t)(g0 + j) * dst_job_stride + tx0 + (size_t)(ty0 + warp) * dpitch + lane;
+            const size_t dstep = (size_t)(WA_THREADS / 32) * dpitch;
+            const int* pX0 = &s_X0[j][warp];
+            const int* pY0 = &s_Y0[j][warp];
+#pragma unroll 2
+            for (int row = warp; row < nrows; row += WA_THREADS / 32, drow += dstep, pX0 += WA_THREADS / 32, pY0 += WA_THREADS / 32) {
+                const int X0 = *pX0, Y0 = *pY0;
+                int v[WA_PX];
+#pragma unroll
+                for (int k = 0; k < WA_PX; k++) {
+                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+                    const int fx = XX & 0x3e0, fy = YY & 0x3e0;
+                    const uint32_t a = sbase + (uint32_t)((YY >> 10) * SW + (XX >> 10)), a2 = a + SW;
+                    int p00, p01, p10, p11;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a));
+                    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(a));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a2));
+                    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p11) : "r"(a2));
+                    const int top = (p00 << 10) + fx * (p01 - p00);
+                    const int dif = (p10 << 10) - top + fx * (p11 - p10);
+                    v[k] = ((top << 10) + (512 << 10) + fy * dif) >> 20;
+                }
+#pragma unroll
+                for (int k = 0; k < WA_PX; k++) drow[32 * k] = (uint8_t)v[k];
+            }
+        }
+        return;
+    }
     for (int j = 0; j < group; j++) {
         if (!jobs[g0 + j].valid) continue;
         uint8_t* __restrict__ d = dst + (size_t)(g0 + j) * dst_job_stride + tx0;
@@ -278,21 +328,7 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
         for (int row = warp; row < nrows; row += WA_THREADS / 32) {
             const int X0 = s_X0[j][row], Y0 = s_Y0[j][row];
             uint8_t* drow = d + (size_t)(ty0 + row) * dpitch;
-            if (fastw) {
-                int v[WA_PX];
-#pragma unroll
-                for (int k = 0; k < WA_PX; k++) {
-                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
-                    const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
-                    const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
-                    const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
-                    const int top = (p00 << 5) + ax * (p01 - p00);
-                    const int bot = (p10 << 5) + ax * (p11 - p10);
-                    v[k] = ((top << 5) + ay * (bot - top) + 512) >> 10;
-                }
-#pragma unroll
-                for (int k = 0; k < WA_PX; k++) drow[lane + 32 * k] = (uint8_t)v[k];
-            } else if (staged && inside) {
+            if (staged && inside) {
                 // partial-width tile (the last tile column of a ROI, or a ROI narrower than a tile) whose taps all lie
                 // inside the image: the fast arithmetic with a column predicate; padding columns are written as zero
 #pragma unroll
@@ -303,8 +339,8 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                     if (col < ncols) {
                         const int XX = X0 + adj[k], YY = Y0 + bdj[k];
                         const int ax = (XX >> 5) & 31, ay = (YY >> 5) & 31;
-                        const uint8_t* p = s_src + (YY >> 10) * WA_SW + (XX >> 10);
-                        const int p00 = p[0], p01 = p[1], p10 = p[WA_SW], p11 = p[WA_SW + 1];
+                        const uint8_t* p = s_src + (YY >> 10) * SW + (XX >> 10);
+                        const int p00 = p[0], p01 = p[1], p10 = p[SW], p11 = p[SW + 1];
                         const int top = (p00 << 5) + ax * (p01 - p00);
                         const int bot = (p10 << 5) + ax * (p11 - p10);
                         v = ((top << 5) + ay * (bot - top) + 512) >> 10;
@@ -326,11 +362,11 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, ui
                         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
                         int p00, p01, p10, p11;
                         if (staged) {
-                            const uint8_t* p = s_src + ly * WA_SW + lx;
+                            const uint8_t* p = s_src + ly * SW + lx;
                             p00 = (x0in && y0in) ? p[0] : border;
                             p01 = (x1in && y0in) ? p[1] : border;
-                            p10 = (x0in && y1in) ? p[WA_SW] : border;
-                            p11 = (x1in && y1in) ? p[WA_SW + 1] : border;
+                            p10 = (x0in && y1in) ? p[SW] : border;
+                            p11 = (x1in && y1in) ? p[SW + 1] : border;
                         } else {
                             const uint8_t* p = s + (ptrdiff_t)sy * sp + sx;
                             p00 = (x0in && y0in) ? __ldg(p) : border;
@@ -1320,7 +1356,7 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                            FpmRefined* __restrict__ refined, int* __restrict__ refined_count,
                            FpmEvalTrace* __restrict__ trace, float* __restrict__ trace_scores,
                            const float* __restrict__ numer, const long long* __restrict__ totS,
-                           const long long* __restrict__ totQ)
+                           const long long* __restrict__ totQ, int raw_tile_evals)
 {
     const int ci = blockIdx.x;
     const int tid = threadIdx.x, j = tid >> 6, cell = tid & 63;
@@ -1352,7 +1388,9 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
             const int32_t* rs;
             size_t rstride;
             if (raw_epad) {
-                rs = rowsum + ((size_t)r * raw_epad + e) * 64 + c * 8 + (7 - r);
+                // eval -> row of the raw buffer: contiguous, or 128-row tiles that hold raw_tile_evals evals each (fpm_corr_warp_kernel)
+                const int slot = raw_tile_evals ? (e / raw_tile_evals) * 128 + e % raw_tile_evals : e;
+                rs = rowsum + ((size_t)r * raw_epad + slot) * 64 + c * 8 + (7 - r);
                 rstride = (size_t)raw_epad * 64;
             } else {
                 rs = rowsum + (size_t)e * th * FPM_NCELL + cell;

@@ -74,6 +74,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// wait of a warp role that is expected to idle for a while: a spinning warp takes issue slots from the warps that do the
+// work (the spin loops of the idle roles were a quarter of all instructions issued by fpm_corr_warp_kernel)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void fence_barrier_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -48,7 +48,10 @@ enum fpm_param {
     FPM_PARAM_H2D_CHUNK = 10,      /* frames per host->device chunk in fpm_match_batch (0 = auto)      */
     FPM_PARAM_TENSOR_CORES = 11,   /* correlation: 0 = dp4a only, 1 = tcgen05 for template width >= 64, and for width >= 16 when a level has
                                       enough evals for the fused kernel (default), 2 = always,
-                                      3 = like 1 but never the fused kernel (row dots to HBM, separate row sums), 4 = always fused */
+                                      3 = like 1 but never the fused kernel (row dots to HBM, separate row sums), 4 = always fused,
+                                      5 = same as 1 (kept for A/B runs), 6 = like 1 with fpm_corr_warp_kernel on the large levels:
+                                      the rotated ROI rows are computed inside the tcgen05 producer and never reach HBM (bit-identical,
+                                      1.45 GB/step less DRAM traffic on cfg1, but slower than warp + MMA today: DESIGN.md section 3) */
     FPM_PARAM_MFC_COMPAT = 12,     /* 1: upstream MFC conventions: result (MatchTool/MatchToolDlg.cpp:1085-1116: angle = -theta wrapped
                                       to [-180,180], results truncated to TargetNum, corners in double) and s_BlockMax
                                       (MatchToolDlg.h:109-213: 2x template blocks, last maximal block wins); default 0 = Qt port */

@@ -266,3 +266,66 @@ def test_sharded_nccl_single_rank(matcher, golden_cases):
     finally:
         matcher.commDestroy()
     assert_results_match(matcher.match(src), want, 0, 0, 0)
+
+
+# ---------------- ROI warp fused into the tensor-core correlation (fpm_corr_warp_kernel) ----------------
+def _match_with_trace(m, src, mode):
+    m.setTensorCores(mode)
+    m.setTrace(True)
+    try:
+        res = m.match(src)
+        # candidates of a layer are appended with atomicAdd: order by (candidate id, angle) before comparing
+        ev = {}
+        for l in range(len(m.templateLevels()) - 1):
+            e = m.traceEvals(l)
+            ev[l] = e[np.lexsort((e[:, 1], e[:, 0]))] if len(e) else e
+    finally:
+        m.setTrace(False)
+        m.setTensorCores(1)
+    return res, ev
+
+
+@pytest.mark.parametrize("case", ["cfg1_synth", "cfg3_src6", "src8", "src4", "src9"])
+def test_warp_fused_correlation_is_bit_identical(matcher, golden_cases, case):
+    """the kernel that computes the rotated ROI rows inside the tcgen05 producer must reproduce the unfused path
+    (fpm_warp_kernel -> fpm_corr_mma_kernel) bit for bit: same per-eval scores and argmax at every layer, same results"""
+    c = golden_cases[case]
+    configure(matcher, c["params"])
+    tpl, src = get_image(c["tpl"]), get_image(c["src"])
+    assert matcher.learnPattern(tpl)
+    want, wev = _match_with_trace(matcher, src, 5)
+    got, gev = _match_with_trace(matcher, src, 6)
+    assert len(want) == len(c["results"])
+    for l in wev:
+        assert wev[l].shape == gev[l].shape, "layer %d: eval count" % l
+        assert np.array_equal(wev[l], gev[l]), "layer %d: per-eval (angle, score, argmax) records differ" % l
+    assert_results_match(got, want, 0, 0, 0)
+
+
+def test_warp_fused_correlation_edge_cases(matcher):
+    """ROI boxes that leave the image (border 0), a batch, unaligned device rows, odd template sizes"""
+    import torch
+    import fpm_workloads as synth
+    rng = np.random.default_rng(3)
+    for tw, th, W, H in [(96, 70, 640, 480), (131, 77, 701, 533), (200, 64, 1000, 300)]:
+        tpl = synth.background(tw, th, 11, 2.0)
+        tpl = np.ascontiguousarray(tpl)
+        frames = []
+        for i in range(3):
+            src = synth.background(W, H, 50 + i, 2.5)
+            synth.paste_rotated(src, tpl, tw * 0.45, th * 0.5, float(rng.uniform(-30, 30)))        # partly outside
+            synth.paste_rotated(src, tpl, W - tw * 0.4, H - th * 0.45, float(rng.uniform(140, 200)))
+            synth.paste_rotated(src, tpl, W * 0.5, H * 0.5, float(rng.uniform(-180, 180)))
+            frames.append(src)
+        params = dict(max_pos=6, score=0.5, tolerance_angle=180, min_reduce_area=256, max_overlap=0.3)
+        configure(matcher, params)
+        assert matcher.learnPattern(tpl)
+        for mode_pair in [(5, 6)]:
+            matcher.setTensorCores(mode_pair[0])
+            want = matcher.matchBatch(np.stack(frames))
+            matcher.setTensorCores(mode_pair[1])
+            got = matcher.matchBatch(np.stack(frames))
+            matcher.setTensorCores(1)
+            assert sum(len(w) for w in want) >= 3
+            for g, w in zip(got, want):
+                assert_results_match(g, w, 0, 0, 0)
