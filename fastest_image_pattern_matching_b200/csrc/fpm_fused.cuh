@@ -108,9 +108,14 @@ __device__ __forceinline__ void sts_u8(uint32_t saddr, int v)
 __global__ void __launch_bounds__(FW_THREADS, 1)
 fpm_corr_warp_kernel(const FpmWarpJob* __restrict__ jobs, int n_cands, FpmLevel src, int vec,
                      const __grid_constant__ CUtensorMap map_b, int rh, int tw, int th, int k_bytes, int e_pad,
-                     int32_t* __restrict__ raw, int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ, int* __restrict__ err_flag)
+                     int32_t* __restrict__ raw, int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ, int* __restrict__ err_flag,
+                     const int* __restrict__ n_cands_dev)
 {
     using namespace fpm_ptx;
+    if (n_cands_dev) {                                       // live candidates known only on the device
+        n_cands = min(n_cands, *n_cands_dev);
+        if ((int)blockIdx.y * FW_CANDS >= n_cands) return;
+    }
     extern __shared__ uint8_t fw_smem_raw[];
     const uint32_t base_u32 = (smem_u32(fw_smem_raw) + 1023u) & ~1023u;
     uint8_t* base = fw_smem_raw + (base_u32 - smem_u32(fw_smem_raw));

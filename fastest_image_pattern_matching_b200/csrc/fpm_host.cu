@@ -168,6 +168,9 @@ struct fpm_handle {
     int stop_layer1 = 0, bitwise_not = 0, tol_range = 0;   // MFC-only modes (MatchTool/MatchToolDlg.cpp:788-816, :936)
     double tol_r[4] = {0, 0, 0, 0};
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
+    int async_descent = -1;        // FPM_PARAM_ASYNC_DESCENT: -1 auto (batches < 8 frames), 0 never, 1 always
+    int cur_batch = 1;             // frames of the match in flight
+    bool err_check_pending = false;
     int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
     // template
     bool learned = false;
@@ -234,7 +237,8 @@ namespace {
         }                                                                                \
     } while (0)
 
-enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_TOTAL = 3, CNT_ERR = 4, CNT_N = 8 };
+// CNT_LAYER + l: candidates entering pyramid layer l (descent without host round trips)
+enum { CNT_FLAT = 0, CNT_NEXT = 1, CNT_REFINED = 2, CNT_TOTAL = 3, CNT_ERR = 4, CNT_LAYER = 8, CNT_N = 8 + FPM_MAX_LEVELS };
 enum { K_PYRDOWN = 0, K_WARP_TOP, K_TOP_SCORE, K_TOP_PEAKS, K_COLLECT, K_PREP, K_WARP_ROI, K_CORR, K_FINALIZE, K_FINAL, K_CORR_MMA, K_CORR_FUSED, K_CORR_WARP, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"fpm_pyrdown_kernel", "fpm_warp_kernel(top)", "fpm_top_score_kernel", "fpm_top_peaks_kernel",
                                            "fpm_collect_sort_kernel", "fpm_refine_prep_kernel", "fpm_warp_kernel(roi)",
@@ -425,7 +429,7 @@ bool fused_pays(int ne, int rh, int rpitch, int k_bytes, int use_tc)
 
 // fused tensor-core correlation: numerators (float chain), window totals and edge rows for `ne` ROI patches
 int launch_corr_fused(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
-                      int ne, int32_t* rowS, int32_t* rowQ)
+                      int ne, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr, int n_ang = 1)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (ne + MM_M - 1) / MM_M;
@@ -444,13 +448,14 @@ int launch_corr_fused(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_
     KL(K_CORR_FUSED, (double)ne * FPM_NCELL * (double)tw * th,
        fpm_corr_fused_kernel<<<m_tiles, FM_THREADS, FM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, rh, tw, th, tw + FPM_ROI_PAD,
                                                                                h->d_numer.as<float>(), rowS, rowQ,
-                                                                               h->d_totS.as<long long>(), h->d_totQ.as<long long>()));
+                                                                               h->d_totS.as<long long>(), h->d_totQ.as<long long>(),
+                                                                               n_cands_dev, n_ang));
     return FPM_OK;
 }
 
 // raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
 int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
-                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ)
+                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr, int n_ang = 1)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (ne + MM_M - 1) / MM_M;
@@ -463,8 +468,9 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
     if (rc) return rc;
     // at most 2 full waves of 148 SMs (one CTA per SM): a third, nearly empty wave would cost a whole CTA time;
-    // at least 2 ROI rows per CTA
-    int chunks = std::max(1, (2 * 148) / m_tiles);
+    // at least 2 ROI rows per CTA.  With the live count only known on the device (n_cands_dev) `ne` is the top-layer upper
+    // bound and nearly all tiles leave at once: the rows are split as if one tile were live.
+    int chunks = std::max(1, (2 * 148) / (n_cands_dev ? 1 : m_tiles));
     int rows_per_cta = std::max(2, (rh + chunks - 1) / chunks);
     chunks = (rh + rows_per_cta - 1) / rows_per_cta;
     if (!h->mma_attr_set) {                                  // per handle: the attribute is per device
@@ -474,7 +480,8 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     dim3 grid(chunks, m_tiles);
     KL(K_CORR_MMA, (double)ne * FPM_NCELL * (double)tw * th,
        fpm_corr_mma_kernel<<<grid, MM_THREADS, MM_SMEM_BYTES, h->stream>>>(map_a, map_b, ne, e_pad, rh, tw, th, tw + FPM_ROI_PAD,
-                                                                           rows_per_cta, h->d_raw.as<int32_t>(), rowS, rowQ));
+                                                                           rows_per_cta, h->d_raw.as<int32_t>(), rowS, rowQ,
+                                                                           n_cands_dev, n_ang));
     return FPM_OK;
 }
 
@@ -515,7 +522,7 @@ bool corr_warp_usable(const fpm_handle* h, int tw, int n_ang, const FpmLevel& L)
 
 // raw[y][tile*128 + slot][64] s32 + rowS/rowQ for the 3 angles of `nc` candidates, straight from the source level
 int launch_corr_warp(fpm_handle* h, const FpmLevel& L, const FpmWarpJob* jobs, const uint8_t* tsh, int bpitch, int tw, int th,
-                     int nc, int* e_pad_out, int32_t* rowS, int32_t* rowQ)
+                     int nc, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (nc + FW_CANDS - 1) / FW_CANDS;
@@ -533,7 +540,7 @@ int launch_corr_warp(fpm_handle* h, const FpmLevel& L, const FpmWarpJob* jobs, c
     KL(K_CORR_WARP, (double)nc * 3 * FPM_NCELL * (double)tw * th,
        fpm_corr_warp_kernel<<<grid, FW_THREADS, FW_SMEM_BYTES, h->stream>>>(jobs, nc, L, level_copy_vec(L), map_b, rh, tw, th,
                                                                             tw + FPM_ROI_PAD, e_pad, h->d_raw.as<int32_t>(), rowS, rowQ,
-                                                                            h->d_counters.as<int>() + CNT_ERR));
+                                                                            h->d_counters.as<int>() + CNT_ERR, n_cands_dev));
     return FPM_OK;
 }
 
@@ -744,7 +751,7 @@ int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt
         KL(K_WARP_TOP, 2.0 * nc * (double)p.maxW * p.maxH,
            fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(jobs + c0, 1, h->levels[top],
                                                                 h->d_rot.as<uint8_t>() + (size_t)c0 * rot_stride, rpitch, rot_stride,
-                                                                h->border, tiles_x, level_vec_ok(h->levels[top])));
+                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr));
         dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, nc);
         dim3 block(TS_THREADS);
         KL(K_TOP_SCORE, (double)nc * maxRW * maxRH * t.w * t.h,      // MACs
@@ -783,6 +790,35 @@ int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt
 
 
 // ---- refinement of a flat candidate list held in d_cand[0] ------------------------------
+// per-layer geometry and workspace of the refinement
+struct RefineLayer {
+    int rpitch; size_t roi_stride; bool warp_fused; size_t per_eval; double step;
+};
+RefineLayer refine_layer(const fpm_handle* h, int layer, int n_ang)
+{
+    const TplLevelHost& t = h->tpl[layer];
+    const FpmLevel& L = h->levels[layer];
+    RefineLayer r;
+    r.step = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
+    r.rpitch = (int)align_up(t.w + FPM_ROI_PAD, 16) + 16;
+    r.roi_stride = (size_t)r.rpitch * (t.h + FPM_ROI_PAD);
+    // bytes per eval of one wave: ROI patch, window row sums, job record, and the row dots in the layout of the
+    // correlation path this level can take (dp4a [h][49], row-split tensor-core raw[h+6][64], or the fused kernel's
+    // 64 numerators + 14 window totals)
+    r.warp_fused = corr_warp_usable(h, t.w, n_ang, L);
+    r.per_eval = (r.warp_fused ? 0 : r.roi_stride) + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 + sizeof(FpmWarpJob);
+    if (mma_usable(h, t.w) || mma_narrow_fused(h, t.w))
+        r.per_eval += std::max((size_t)(t.h + FPM_ROI_PAD) * MM_N * 4, (size_t)MM_N * 4 + 2 * FPM_NSHIFT * 8);
+    if (!mma_usable(h, t.w)) r.per_eval += (size_t)t.h * FPM_NCELL * 4;
+    return r;
+}
+
+// ---- refinement of a flat candidate list held in d_cand[0] ------------------------------
+// Two ways to walk down the pyramid (src/TemplateMatcher.cpp:279-368):
+//   * with a counter read-back per layer (grids sized to the live candidates; workspace waves; tracing), or
+//   * without any host round trip (single-frame latency): every layer is enqueued at once with grids sized to the
+//     TOP-layer candidate count -- the list can only shrink -- and every kernel reads the live count of its layer from
+//     device memory (counters[CNT_LAYER + layer]); surplus CTAs leave at once.
 int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
 {
     int* counters = h->d_counters.as<int>();
@@ -811,22 +847,21 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
     layer_score[0] = h->score;
     for (int l = 1; l <= top; l++) layer_score[l] = layer_score[l - 1] * 0.9;
     if (h->trace) h->tr_evals.assign(top + 1, std::vector<double>());
+    const size_t budget = (size_t)(h->workspace_mb * 1024.0 * 1024.0);
+    // the descent without host round trips needs every layer to fit one workspace wave at the top-layer count
+    bool async = !h->trace && n_cands <= 65535 && (h->async_descent == 1 || (h->async_descent < 0 && h->cur_batch < 8));
+    for (int layer = top - 1; layer >= stop && async; layer--)
+        if (refine_layer(h, layer, n_ang).per_eval * n_ang * (size_t)n_cands > budget) async = false;
+    if (async) CK(cudaMemsetAsync(counters + CNT_LAYER, 0, FPM_MAX_LEVELS * sizeof(int), h->stream));
     for (int layer = top - 1; layer >= stop && n > 0; layer--) {
         const TplLevelHost& t = h->tpl[layer];
         const FpmLevel& L = h->levels[layer];
-        const double step = atan(2.0 / std::max(t.w, t.h)) * FPM_R2D;
-        const int rpitch = (int)align_up(t.w + FPM_ROI_PAD, 16) + 16;
-        const size_t roi_stride = (size_t)rpitch * (t.h + FPM_ROI_PAD);
-        // bytes per eval of one wave: ROI patch, window row sums, job record, and the row dots in the layout of the
-        // correlation path this level can take (dp4a [h][49], row-split tensor-core raw[h+6][64], or the fused kernel's
-        // 64 numerators + 14 window totals)
-        const bool warp_fused = corr_warp_usable(h, t.w, n_ang, L);
-        size_t per_eval = (warp_fused ? 0 : roi_stride) + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 + sizeof(FpmWarpJob);
-        if (mma_usable(h, t.w) || mma_narrow_fused(h, t.w))
-            per_eval += std::max((size_t)(t.h + FPM_ROI_PAD) * MM_N * 4, (size_t)MM_N * 4 + 2 * FPM_NSHIFT * 8);
-        if (!mma_usable(h, t.w)) per_eval += (size_t)t.h * FPM_NCELL * 4;
-        size_t budget = (size_t)(h->workspace_mb * 1024.0 * 1024.0);
-        int wave_cands = (int)std::max<size_t>(1, budget / (per_eval * n_ang));
+        const RefineLayer rl = refine_layer(h, layer, n_ang);
+        const double step = rl.step;
+        const int rpitch = rl.rpitch;
+        const size_t roi_stride = rl.roi_stride;
+        const bool warp_fused = rl.warp_fused;
+        int wave_cands = (int)std::max<size_t>(1, budget / (rl.per_eval * n_ang));
         wave_cands = std::min(wave_cands, n);
         wave_cands = std::min(wave_cands, 65535);             // one candidate per gridDim.y slot of the ROI warp
         const int wave_evals = wave_cands * n_ang;
@@ -839,7 +874,10 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             CK(h->d_trace.ensure((size_t)n * n_ang * sizeof(FpmEvalTrace)));
             CK(cudaMemsetAsync(h->d_trace.p, 0, (size_t)n * n_ang * sizeof(FpmEvalTrace), h->stream));
         }
-        CK(cudaMemsetAsync(counters + CNT_NEXT, 0, sizeof(int), h->stream));
+        // live candidates of this layer / where the survivors are counted
+        const int* n_dev = !async ? nullptr : (layer == top - 1 ? counters + CNT_FLAT : counters + CNT_LAYER + layer);
+        int* next_cnt = !async ? counters + CNT_NEXT : counters + CNT_LAYER + std::max(layer - 1, 0);
+        if (!async) CK(cudaMemsetAsync(counters + CNT_NEXT, 0, sizeof(int), h->stream));
         const CorrCfg cc = corr_config(t.h);
         const size_t smem = cc.smem;
         if (smem > 200 * 1024) { h->err = "correlation kernel shared memory limit"; return FPM_ERR_LIMIT; }
@@ -852,42 +890,43 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
             const int ne = nc * n_ang;
             KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
                fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
-                                                                             h->d_jobs_ref.as<FpmWarpJob>()));
+                                                                             h->d_jobs_ref.as<FpmWarpJob>(), n_dev));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
             int raw_tile_evals = 0;                         // evals per 128-row tile of raw (0 = contiguous)
             bool fused = false;                             // numerators + window totals straight from the fused tensor-core kernel
             if (warp_fused) {
                 // the ROI patches are produced inside the correlation kernel and never reach HBM
                 int rcm = launch_corr_warp(h, L, h->d_jobs_ref.as<FpmWarpJob>(), h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch, t.w, t.h, nc,
-                                           &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
+                                           &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev);
                 if (rcm) return rcm;
                 raw_tile_evals = FW_TILE_EVALS;
             } else {
-            const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
-            dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
-            // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
-            KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
-               fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
-                                                                    h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
-                                                                    level_vec_ok(L)));
-            if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) &&
-                fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
-                int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
-                                            t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
-                if (rcm) return rcm;
-                fused = true;
-            } else if (mma_usable(h, t.w)) {
-                int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
-                                          t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>());
-                if (rcm) return rcm;
-            } else {
-                dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
-                // algorithmic MACs: 49 * w * h per eval
-                KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
-                   fpm_corr_rows_kernel<<<cgrid, cc.threads, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, ne,
-                                                                                cc.rb, cc.evals_per_cta, h->d_rowsum.as<int32_t>(),
-                                                                                h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>()));
-            }
+                const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
+                dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
+                // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
+                KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
+                   fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
+                                                                        h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
+                                                                        level_vec_ok(L), n_dev));
+                // (the one-CTA-per-128-evals kernel only pays for many LIVE evals: never with an upper-bound count)
+                if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) && (!async || h->use_tc == 4) &&
+                    fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
+                    int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                                t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
+                    if (rcm) return rcm;
+                    fused = true;
+                } else if (mma_usable(h, t.w)) {
+                    int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                              t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
+                    if (rcm) return rcm;
+                } else {
+                    dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
+                    // algorithmic MACs: 49 * w * h per eval
+                    KL(K_CORR, (double)ne * FPM_NCELL * (double)t.w * t.h,
+                       fpm_corr_rows_kernel<<<cgrid, cc.threads, smem, h->stream>>>(h->d_roi.as<uint8_t>(), rpitch, roi_stride, td, ne,
+                                                                                    cc.rb, cc.evals_per_cta, h->d_rowsum.as<int32_t>(),
+                                                                                    h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang));
+                }
             }
             KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
                fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
@@ -895,30 +934,33 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                    h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
                    L.h, layer_score[layer], h->use_simd, layer == stop ? 1 : 0, stop ? 2 : 1, (h->subpixel && layer == 0) ? 1 : 0,
                    h->d_cand[cur ^ 1].as<FpmCand>(),
-                   counters + CNT_NEXT, ref_out, ref_cnt,
+                   next_cnt, ref_out, ref_cnt,
                    h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr,
-                   fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>(), raw_tile_evals));
+                   fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>(), raw_tile_evals, n_dev));
         }
+        cur ^= 1;
+        if (async) continue;                                  // n stays the top-layer count: an upper bound of every layer's list
         CK(cudaMemcpyAsync(hc, counters, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         if (h->trace) {
+            const FpmCand* cands_done = h->d_cand[cur ^ 1].as<FpmCand>();
             std::vector<FpmEvalTrace> tr((size_t)n * n_ang);
-            std::vector<FpmCand> cc(n);
+            std::vector<FpmCand> cc2(n);
             CK(cudaMemcpy(tr.data(), h->d_trace.p, tr.size() * sizeof(FpmEvalTrace), cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(cc.data(), cands, cc.size() * sizeof(FpmCand), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(cc2.data(), cands_done, cc2.size() * sizeof(FpmCand), cudaMemcpyDeviceToHost));
             std::vector<double>& rows = h->tr_evals[layer];
             for (int i = 0; i < n; i++)
                 for (int j = 0; j < n_ang; j++) {
                     const FpmEvalTrace& e = tr[(size_t)i * n_ang + j];
-                    rows.push_back(cc[i].id); rows.push_back(e.angle); rows.push_back(e.score);
+                    rows.push_back(cc2[i].id); rows.push_back(e.angle); rows.push_back(e.score);
                     rows.push_back(e.locx); rows.push_back(e.locy);
                 }
         }
         if (hc[CNT_ERR]) { h->err = "fpm_corr_warp_kernel: source box larger than its staging buffer"; return FPM_ERR_LIMIT; }
         n = (layer == stop) ? 0 : hc[CNT_NEXT];
         *n_refined_out = hc[CNT_REFINED];
-        cur ^= 1;
     }
+    if (async) h->err_check_pending = true;                   // CNT_ERR is read back together with the results
     return FPM_OK;
 }
 
@@ -950,9 +992,14 @@ int run_final(fpm_handle* h, int batch, const FpmRefinedView& rv, int key_stride
                                                              h->d_results.as<FpmResultDev>(), rcap, h->d_rescnt.as<int>()));
     FpmResultDev* hr = h->h_results.as<FpmResultDev>();
     int* hn = reinterpret_cast<int*>(hr + (size_t)batch * rcap);
+    int* hc = h->h_counts.as<int>();
+    const bool check_err = h->err_check_pending && hc;
+    h->err_check_pending = false;
+    if (check_err) CK(cudaMemcpyAsync(hc + CNT_ERR, h->d_counters.as<int>() + CNT_ERR, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(hn, h->d_rescnt.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(hr, h->d_results.p, (size_t)batch * rcap * sizeof(FpmResultDev), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (check_err && hc[CNT_ERR]) { h->err = "fpm_corr_warp_kernel: source box larger than its staging buffer"; return FPM_ERR_LIMIT; }
     for (int b = 0; b < batch; b++) {
         n_out[b] = hn[b];
         int m = std::min(hn[b], cap);
@@ -1040,6 +1087,7 @@ int match_device(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt,
     if (rc) return rc;
     if (match_guards(h, w, hgt)) return FPM_OK;
     const int top = (int)h->tpl.size() - 1;
+    h->cur_batch = batch;
     CK(h->d_counters.ensure(CNT_N * sizeof(int)));
     CK(h->h_counts.ensure((CNT_N + batch) * sizeof(int)));
     CK(cudaMemsetAsync(h->d_counters.p, 0, CNT_N * sizeof(int), h->stream));
@@ -1168,6 +1216,7 @@ int shard_begin(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, i
         d_src = h->d_src.as<uint8_t>();
     }
     const int top = (int)h->tpl.size() - 1;
+    h->cur_batch = 1;
     CK(h->d_counters.ensure(CNT_N * sizeof(int)));
     CK(h->h_counts.ensure((CNT_N + 1) * sizeof(int)));
     CK(cudaMemsetAsync(h->d_counters.p, 0, CNT_N * sizeof(int), h->stream));
@@ -1329,6 +1378,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_BITWISE_NOT: h->bitwise_not = v != 0; break;
     case FPM_PARAM_SPLIT_BATCH: h->split_batch = (int)v; break;
     case FPM_PARAM_SHARD_UPLOAD: h->shard_upload = v != 0; break;
+    case FPM_PARAM_ASYNC_DESCENT: h->async_descent = (int)v; break;
     case FPM_PARAM_TOLERANCE_RANGE: h->tol_range = v != 0; h->plan.valid = false; break;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         h->tol_r[param - FPM_PARAM_TOLERANCE1] = v; h->plan.valid = false; break;
@@ -1358,6 +1408,7 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_BITWISE_NOT: return h->bitwise_not;
     case FPM_PARAM_SPLIT_BATCH: return h->split_batch;
     case FPM_PARAM_SHARD_UPLOAD: return h->shard_upload;
+    case FPM_PARAM_ASYNC_DESCENT: return h->async_descent;
     case FPM_PARAM_TOLERANCE_RANGE: return h->tol_range;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         return h->tol_r[param - FPM_PARAM_TOLERANCE1];
@@ -1759,6 +1810,7 @@ int fpm_stage_top(fpm_handle* h, const uint8_t* src, int width, int height, int 
         d_src = h->d_src.as<uint8_t>();
     }
     const int top = (int)h->tpl.size() - 1;
+    h->cur_batch = 1;
     CK(h->d_counters.ensure(CNT_N * sizeof(int)));
     CK(h->h_counts.ensure((CNT_N + 1) * sizeof(int)));
     if (h->bitwise_not) {
@@ -1846,11 +1898,21 @@ int fpm_stage_refine(fpm_handle* h, const double* cands, int n, double* rows, in
     }
     CK(h->d_cand[0].ensure(cc.size() * sizeof(FpmCand)));
     CK(cudaMemcpyAsync(h->d_cand[0].p, cc.data(), cc.size() * sizeof(FpmCand), cudaMemcpyHostToDevice, h->stream));
+    CK(h->d_counters.ensure(CNT_N * sizeof(int)));
+    CK(h->h_counts.ensure((CNT_N + 1) * sizeof(int)));
+    CK(cudaMemsetAsync(h->d_counters.p, 0, CNT_N * sizeof(int), h->stream));
+    CK(cudaMemcpyAsync(h->d_counters.as<int>() + CNT_FLAT, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));   // live count of the first layer
     CK(cudaStreamSynchronize(h->stream));
     int n_ref = 0;
     h->ref_out = nullptr; h->ref_cnt = nullptr;
+    h->cur_batch = 1;
     int rc = run_refine(h, top, n, &n_ref);
     if (rc) return rc;
+    h->err_check_pending = false;
+    CK(cudaMemcpyAsync(h->h_counts.p, h->d_counters.p, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_counts.as<int>()[CNT_ERR]) { h->err = "fpm_corr_warp_kernel: source box larger than its staging buffer"; return FPM_ERR_LIMIT; }
+    n_ref = h->h_counts.as<int>()[CNT_REFINED];
     std::vector<FpmRefined> rr(std::max(n_ref, 1));
     if (n_ref) {
         CK(cudaMemcpyAsync(rr.data(), h->d_refined.p, (size_t)n_ref * sizeof(FpmRefined), cudaMemcpyDeviceToHost, h->stream));
@@ -2044,7 +2106,7 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     const int tiles_x = (dp + WA_TW - 1) / WA_TW;
     dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
     fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), 1, s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
-                                                        tiles_x, level_vec_ok(s));
+                                                        tiles_x, level_vec_ok(s), nullptr);
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -2078,7 +2140,7 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int
     int32_t* dQ = dS + (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT;
     dim3 grid(cc.blocks_y_rows, 1);
     fpm_corr_rows_kernel<<<grid, cc.threads, cc.smem, h->stream>>>(h->d_dbg[0].as<uint8_t>(), rpitch, roi_bytes, td, 1, cc.rb,
-                                                                    cc.evals_per_cta, h->d_dbg[2].as<int32_t>(), dS, dQ);
+                                                                    cc.evals_per_cta, h->d_dbg[2].as<int32_t>(), dS, dQ, nullptr, 1);
     CKL();
     CK(cudaMemcpyAsync(rowsum, h->d_dbg[2].p, (size_t)th * FPM_NCELL * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(rowS, dS, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -183,8 +183,11 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 
 __global__ void __launch_bounds__(WA_THREADS)
 fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, uint8_t* __restrict__ dst,
-                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok)
+                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok, const int* __restrict__ n_groups_dev)
 {
+    // n_groups_dev (optional): number of live job groups, known only on the device (descent without a host round trip per layer:
+    // the grid covers an upper bound, the surplus CTAs leave at once)
+    if (n_groups_dev && (int)blockIdx.y >= *n_groups_dev) return;
     const int g0 = blockIdx.y * group;
     const FpmWarpJob& jb0 = jobs[g0];
     const int dw = jb0.dw, dh = jb0.dh;
@@ -1039,8 +1042,9 @@ fpm_collect_sort_kernel(FpmPickView pv,
 // =====================================================================================
 __global__ void fpm_refine_prep_kernel(const FpmCand* __restrict__ cands, int n_cands, int n_ang,
                                        double angle_step, int lvl_w, int lvl_h, int tpl_w, int tpl_h,
-                                       FpmWarpJob* __restrict__ jobs)
+                                       FpmWarpJob* __restrict__ jobs, const int* __restrict__ n_cands_dev)
 {
+    if (n_cands_dev) n_cands = min(n_cands, *n_cands_dev);
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cands * n_ang) return;
     int ci = e / n_ang, j = e - ci * n_ang;
@@ -1092,9 +1096,13 @@ __device__ __forceinline__ uint32_t fpm_u4(const uint4& v, int i) { return i == 
 __global__ void __launch_bounds__(CR_MAX_THREADS)
 fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_stride, FpmTplLevel tpl,
                      int n_evals, int rb, int evals_per_cta, int32_t* __restrict__ rowsum,
-                     int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
+                     int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ, const int* __restrict__ n_evals_dev, int n_ang)
 {
     extern __shared__ __align__(16) uint32_t smem_w[];
+    if (n_evals_dev) {                                       // live evals known only on the device (n_ang per candidate)
+        n_evals = min(n_evals, *n_evals_dev * n_ang);
+        if ((int)blockIdx.y * evals_per_cta >= n_evals) return;
+    }
     const int tw = tpl.w, th = tpl.h;
     const int rh = th + FPM_ROI_PAD;                       // ROI rows per eval
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -1356,9 +1364,10 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                            FpmRefined* __restrict__ refined, int* __restrict__ refined_count,
                            FpmEvalTrace* __restrict__ trace, float* __restrict__ trace_scores,
                            const float* __restrict__ numer, const long long* __restrict__ totS,
-                           const long long* __restrict__ totQ, int raw_tile_evals)
+                           const long long* __restrict__ totQ, int raw_tile_evals, const int* __restrict__ n_cands_dev)
 {
     const int ci = blockIdx.x;
+    if (n_cands_dev && ci >= *n_cands_dev) return;
     const int tid = threadIdx.x, j = tid >> 6, cell = tid & 63;
     __shared__ float s_sc[3][FPM_NCELL];
     __shared__ float s_best[3];

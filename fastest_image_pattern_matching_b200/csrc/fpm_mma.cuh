@@ -247,9 +247,13 @@ __device__ __forceinline__ void fpm_mm_stats(uint32_t base_u32, uint32_t bar0, i
 __global__ void __launch_bounds__(MM_THREADS, 1)
 fpm_corr_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     int n_evals, int e_pad, int rh, int tw, int th, int k_bytes, int rows_per_cta, int32_t* __restrict__ raw,
-                    int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ)
+                    int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ, const int* __restrict__ n_cands_dev, int n_ang)
 {
     using namespace fpm_ptx;
+    if (n_cands_dev) {                                       // live evals known only on the device; surplus tiles leave at once
+        n_evals = min(n_evals, *n_cands_dev * n_ang);
+        if ((int)blockIdx.y * MM_M >= n_evals) return;
+    }
     extern __shared__ uint8_t mm_smem_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles
     const uint32_t base_u32 = (smem_u32(mm_smem_raw) + 1023u) & ~1023u;
@@ -380,9 +384,13 @@ __global__ void __launch_bounds__(FM_THREADS, 1)
 fpm_corr_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       int n_evals, int rh, int tw, int th, int k_bytes, float* __restrict__ numer,
                       int32_t* __restrict__ rowS, int32_t* __restrict__ rowQ,
-                      long long* __restrict__ totS, long long* __restrict__ totQ)
+                      long long* __restrict__ totS, long long* __restrict__ totQ, const int* __restrict__ n_cands_dev, int n_ang)
 {
     using namespace fpm_ptx;
+    if (n_cands_dev) {
+        n_evals = min(n_evals, *n_cands_dev * n_ang);
+        if ((int)blockIdx.x * MM_M >= n_evals) return;
+    }
     extern __shared__ uint8_t mm_smem_raw[];
     const uint32_t base_u32 = (smem_u32(mm_smem_raw) + 1023u) & ~1023u;
     uint8_t* base = mm_smem_raw + (base_u32 - smem_u32(mm_smem_raw));

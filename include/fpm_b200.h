@@ -64,6 +64,8 @@ enum fpm_param {
                                       half-batches on two internal handles (default 8, 0 = never) */
     FPM_PARAM_SHARD_UPLOAD = 21,   /* fpm_match_sharded with a HOST frame: 1 (default) = every rank uploads 1/N of the rows over its own
                                       PCIe link and the slices are allgathered over NVLink; 0 = every rank uploads the whole frame */
+    FPM_PARAM_ASYNC_DESCENT = 22,  /* pyramid descent without a host round trip per layer (grids sized to the top-layer candidate count, live
+                                      counts read on the device): -1 = automatic (batches of fewer than 8 frames), 0 = never, 1 = always */
     FPM_PARAM_COUNT_
 };
 

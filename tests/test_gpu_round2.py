@@ -329,3 +329,30 @@ def test_warp_fused_correlation_edge_cases(matcher):
             assert sum(len(w) for w in want) >= 3
             for g, w in zip(got, want):
                 assert_results_match(g, w, 0, 0, 0)
+
+
+# ---------------- pyramid descent without host round trips ----------------
+@pytest.mark.parametrize("case", ["cfg1_synth", "cfg3_src6", "src8", "test4_src3", "src9_subpix", "cfg2_synth"])
+def test_async_descent_equals_synchronous_descent(matcher, golden_cases, case):
+    """single-frame latency path: all layers enqueued at once with grids sized to the top-layer count and the live counts read on
+    the device -- must return exactly what the per-layer read-back path returns (also through the opt-in fused kernel)"""
+    c = golden_cases[case]
+    configure(matcher, c["params"])
+    tpl, src = get_image(c["tpl"]), get_image(c["src"])
+    assert matcher.learnPattern(tpl)
+    try:
+        matcher.setAsyncDescent(0)
+        want = matcher.match(src)
+        assert len(want) == len(c["results"])
+        for mode in (1, 6):
+            matcher.setTensorCores(mode)
+            matcher.setAsyncDescent(1)
+            got = matcher.match(src)
+            ties = len({r.dMatchScore for r in want}) != len(want)
+            assert_results_match(got, want, 0, 0, 0, ordered=not ties)
+            got_b = matcher.matchBatch(np.stack([src, src, src]))          # forced on for a batch as well
+            for g in got_b:
+                assert_results_match(g, want, 0, 0, 0, ordered=not ties)
+    finally:
+        matcher.setAsyncDescent(-1)
+        matcher.setTensorCores(1)
