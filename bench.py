@@ -90,23 +90,29 @@ def _cpu_worker(args):
     import cv2
     import numpy as np  # noqa: F401
     cv2.setNumThreads(1)
-    from oracle.oracle import OracleMatcher
     tpl, frames = make_frames(min(n_images, 2), seed, workload)
-    m = OracleMatcher()
+    try:                                                # CPU Baseline A: the C++ restatement, the reference's Release flags
+        from oracle.cpu_match import CpuMatcher
+        m = CpuMatcher()
+        impl = "cpp"
+    except Exception:                                   # not built: the Python/cv2 oracle
+        from oracle.oracle import OracleMatcher
+        m = OracleMatcher()
+        impl = "python"
     m.max_pos, m.score, m.tolerance_angle, m.min_reduce_area, m.max_overlap = wl["max_pos"], wl["score"], wl["tol"], wl["mra"], wl["overlap"]
     m.learn_pattern(tpl)
-    m.match(frames[0])                                  # warm-up (page-in, cv2 init)
+    m.match(frames[0])                                  # warm-up (page-in)
     t0 = time.perf_counter()
     found = 0
     for i in range(n_images):
         found += len(m.match(frames[i % len(frames)]))
-    return time.perf_counter() - t0, found
+    return time.perf_counter() - t0, found, impl
 
 
 def cpu_throughput(wl, workers: int, images_per_worker: int, workload: str = "cfg1"):
     """images/sec of the CPU oracle with `workers` processes (one single-threaded matcher each)."""
     import multiprocessing as mp
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "libncc_rowdot.so"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "libncc_rowdot.so", "liboracle_cpu_match.so"], capture_output=True)
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
         t0 = time.perf_counter()
@@ -114,6 +120,8 @@ def cpu_throughput(wl, workers: int, images_per_worker: int, workload: str = "cf
         wall = time.perf_counter() - t0
     busy = max(r[0] for r in res)
     total = workers * images_per_worker
+    global CPU_IMPL_NAME
+    CPU_IMPL_NAME = CPU_IMPL_NAMES[res[0][2]]
     return total / busy, busy, wall, sum(r[1] for r in res)
 
 
@@ -240,7 +248,7 @@ def percentile(v, q):
 
 def run_reference_arm(args, wl, METRIC):
     cores = host_cores()
-    per_worker = max(1, args.cpu_images or 2)
+    per_worker = max(1, args.cpu_images or 8)
     vals, times = [], []
     for _ in range(max(args.steps, 1)):
         v, busy, wall, found = cpu_throughput(wl, cores, per_worker, args.workload)
@@ -263,7 +271,12 @@ def run_reference_arm(args, wl, METRIC):
     return 0
 
 
-CPU_IMPL_NAME = "Python/cv2 4.13 oracle + SSE2 IM_Conv_SIMD restatement"
+CPU_IMPL_NAMES = {
+    "cpp": "CPU Baseline A = oracle/cpu_match.cpp, a C++ restatement of TemplateMatcher::match with the reference's SSE2 IM_Conv_SIMD, "
+           "built with the reference's Release flags (-O3 -ffast-math -msse4.2 -mavx2 ...), over C++ models of the OpenCV calls",
+    "python": "Python/cv2 4.13 oracle + SSE2 IM_Conv_SIMD restatement",
+}
+CPU_IMPL_NAME = CPU_IMPL_NAMES["cpp"]
 
 
 def main():
@@ -309,7 +322,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.device_steps_only:
         cores = host_cores()
         workers = cores
-        per_worker = args.cpu_images or 8
+        per_worker = args.cpu_images or 48        # ~10 s of CPU work per core on cfg1
         v, busy, wall, found = cpu_throughput(wl, workers, per_worker, args.workload)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
                         "sample": "%d processes x %d frames of the workload (%.1f s); %s, "

@@ -297,3 +297,26 @@ def test_subpixel_fit_is_well_inside_the_tolerance_in_fp64():
             outs.append((d[0], d[1], d[2] * O.R2D))
         worst = max(worst, abs(outs[0][0] - outs[1][0]), abs(outs[0][1] - outs[1][1]), abs(outs[0][2] - outs[1][2]))
     assert worst < 1e-4, worst
+
+
+# ---------------- round 2: CPU Baseline A (oracle/cpu_match.cpp) against the Python oracle ----------------
+@pytest.mark.parametrize("case", ["test4_src3", "src8", "src9", "src9_subpix", "src4", "cfg1_synth", "cfg2_synth", "cfg3_src6"])
+def test_cpp_baseline_equals_python_oracle_results(golden_cases, case):
+    """the C++ restatement of match() (reference Release flags incl. -ffast-math, own models of the OpenCV calls) returns the
+    Python oracle's accepted set on every golden case, within the north_star tolerances"""
+    from oracle.cpu_match import CpuMatcher
+    from tests.helpers import get_image
+    c = golden_cases[case]
+    m = CpuMatcher()
+    for k, v in c["params"].items():
+        setattr(m, k, v)
+    assert m.learn_pattern(get_image(c["tpl"]))
+    rows = m.match(get_image(c["src"]))
+    want = c["results"]
+    assert len(rows) == len(want)
+    if len({r["score"] for r in want}) != len(want):          # exact ties: compare as sets by pose
+        rows = np.array(sorted(rows.tolist(), key=lambda r: (round(r[2] / 4), round(r[3] / 4))))
+        want = sorted(want, key=lambda r: (round(r["cx"] / 4), round(r["cy"] / 4)))
+    for r, w in zip(rows, want):
+        assert abs(r[0] - w["score"]) <= 1e-4 and abs(r[1] - w["angle"]) <= 0.01
+        assert abs(r[2] - w["cx"]) <= 0.05 and abs(r[3] - w["cy"]) <= 0.05
