@@ -199,6 +199,7 @@ struct fpm_handle {
     int* ref_cnt = nullptr;
     struct ShardState { int top = 0, chunk = 0, n_all = 0, n_local = 0, seg_cap = 0, empty = 1; size_t pick_blk = 0, ref_blk = 0; } sh;
     std::vector<FpmLevel> levels; // source pyramid of the current batch
+    const std::vector<FpmLevel>* shared_levels = nullptr;   // fpm_match_multi: the pyramid built once by the first handle
     TopPlan plan;
     std::string err;
     double last_ms = 0;
@@ -623,6 +624,10 @@ int do_learn(fpm_handle* h)
 // ---- source pyramid -----------------------------------------------------------------
 int build_pyramid(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt, int stride, size_t frame_stride, int top)
 {
+    if (h->shared_levels) {                                    // multi-template matching: one upload, one pyramid for all handles
+        if (h->shared_levels != &h->levels) h->levels.assign(h->shared_levels->begin(), h->shared_levels->begin() + top + 1);
+        return FPM_OK;
+    }
     h->levels.assign(top + 1, FpmLevel());
     h->levels[0] = FpmLevel{const_cast<uint8_t*>(d_src), w, hgt, stride, frame_stride};
     size_t off = 0;
@@ -1580,13 +1585,53 @@ int fpm_match_multi(fpm_handle* const* hs, int n_handles, const uint8_t* src, in
     if (!hs || n_handles <= 0 || !src || !out || !counts || cap < 0) return FPM_ERR_INVALID;
     for (int i = 0; i < n_handles; i++)
         if (!hs[i]) return FPM_ERR_INVALID;
+    for (int i = 0; i < n_handles; i++) counts[i] = 0;
+    if (width <= 0 || height <= 0) return FPM_OK;
+    if (stride < width) return FPM_ERR_INVALID;
+    // One upload and ONE source pyramid for all templates (the upstream loop re-reads the same image for every glyph,
+    // MatchToolDlg.cpp:727-750): the first handle uploads the frame and builds the pyramid down to the deepest top layer
+    // any template needs; the other handles' streams wait on its event and match against the shared levels.
+    bool share = true;
+    int max_top = 0;
+    for (int i = 0; i < n_handles; i++) {
+        fpm_handle* h = hs[i];
+        if (!h->learned || h->device != hs[0]->device || h->bitwise_not || h->trace) { share = false; break; }
+        if (ensure_learned_for_mra(h) != FPM_OK) { share = false; break; }
+        max_top = std::max(max_top, (int)h->tpl.size() - 1);
+    }
+    fpm_handle* lead = hs[0];
+    int pitch = 0;
+    size_t img = 0;
+    if (share) {
+        fpm_handle* h = lead;
+        CK(cudaSetDevice(h->device));
+        pitch = (int)align_up(width, 128);
+        img = align_up((size_t)pitch * height, 256);
+        CK(h->d_src.ensure(img));
+        CK(cudaMemcpy2DAsync(h->d_src.p, pitch, src, stride, width, height, cudaMemcpyHostToDevice, h->stream));
+        h->shared_levels = nullptr;
+        int rc = build_pyramid(h, h->d_src.as<uint8_t>(), 1, width, height, pitch, img, max_top);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+    }
     const int n_threads = std::min(n_handles, 12);
     std::vector<int> rc(n_handles, FPM_OK);
     std::vector<std::thread> pool;
     for (int t = 0; t < n_threads; t++)
         pool.emplace_back([&, t]() {
-            for (int i = t; i < n_handles; i += n_threads)
-                rc[i] = fpm_match(hs[i], src, width, height, stride, out + (size_t)i * cap, cap, counts + i);
+            for (int i = t; i < n_handles; i += n_threads) {
+                fpm_handle* h = hs[i];
+                if (!share) {
+                    rc[i] = fpm_match(h, src, width, height, stride, out + (size_t)i * cap, cap, counts + i);
+                    continue;
+                }
+                cudaSetDevice(h->device);
+                if (h != lead && cudaStreamWaitEvent(h->stream, lead->ev_fork, 0) != cudaSuccess) { rc[i] = FPM_ERR_CUDA; continue; }
+                h->shared_levels = &lead->levels;
+                rc[i] = match_device(h, lead->d_src.as<uint8_t>(), 1, width, height, pitch, img, out + (size_t)i * cap, cap, counts + i);
+                h->shared_levels = nullptr;
+                prof_collect(h);
+            }
         });
     for (std::thread& th : pool) th.join();
     for (int i = 0; i < n_handles; i++)
