@@ -756,7 +756,7 @@ int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt
         KL(K_WARP_TOP, 2.0 * nc * (double)p.maxW * p.maxH,
            fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(jobs + c0, 1, h->levels[top],
                                                                 h->d_rot.as<uint8_t>() + (size_t)c0 * rot_stride, rpitch, rot_stride,
-                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr));
+                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr, FpmRefineGeom{}));
         dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, nc);
         dim3 block(TS_THREADS);
         KL(K_TOP_SCORE, (double)nc * maxRW * maxRH * t.w * t.h,      // MACs
@@ -893,9 +893,10 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         for (int c0 = 0; c0 < n; c0 += wave_cands) {
             const int nc = std::min(wave_cands, n - c0);
             const int ne = nc * n_ang;
-            KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
-               fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
-                                                                             h->d_jobs_ref.as<FpmWarpJob>(), n_dev));
+            if (warp_fused)                                 // the warp-fused kernel stages the job matrices of its 42 candidates itself
+                KL(K_PREP, (double)ne * sizeof(FpmWarpJob),
+                   fpm_refine_prep_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(cands + c0, nc, n_ang, step, L.w, L.h, t.w, t.h,
+                                                                                 h->d_jobs_ref.as<FpmWarpJob>(), n_dev));
             int raw_epad = 0;                               // 0 = [e][tr][49] row sums, else raw[y][e_pad][64] from the tensor cores
             int raw_tile_evals = 0;                         // evals per 128-row tile of raw (0 = contiguous)
             bool fused = false;                             // numerators + window totals straight from the fused tensor-core kernel
@@ -910,9 +911,10 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                 dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
                 // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
                 KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
-                   fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(h->d_jobs_ref.as<FpmWarpJob>(), n_ang, L,
+                   fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(nullptr, n_ang, L,
                                                                         h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
-                                                                        level_vec_ok(L), n_dev));
+                                                                        level_vec_ok(L), n_dev,
+                                                                        FpmRefineGeom{cands + c0, n_ang, step, L.w, L.h, t.w, t.h}));
                 // (the one-CTA-per-128-evals kernel only pays for many LIVE evals: never with an upper-bound count)
                 if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) && (!async || h->use_tc == 4) &&
                     fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
@@ -933,15 +935,18 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                                                                                     h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang));
                 }
             }
-            KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
-               fpm_refine_finalize_kernel<<<nc, RF_THREADS, 0, h->stream>>>(
-                   cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,
-                   h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
-                   L.h, layer_score[layer], h->use_simd, layer == stop ? 1 : 0, stop ? 2 : 1, (h->subpixel && layer == 0) ? 1 : 0,
-                   h->d_cand[cur ^ 1].as<FpmCand>(),
-                   next_cnt, ref_out, ref_cnt,
-                   h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr,
-                   fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>(), raw_tile_evals, n_dev));
+            {
+                auto fin = fpm_refine_finalize_kernel;
+                KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
+                   fin<<<nc, RF_THREADS, 0, h->stream>>>(
+                       cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,
+                       h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), td, L.w,
+                       L.h, layer_score[layer], h->use_simd, layer == stop ? 1 : 0, stop ? 2 : 1, (h->subpixel && layer == 0) ? 1 : 0,
+                       h->d_cand[cur ^ 1].as<FpmCand>(),
+                       next_cnt, ref_out, ref_cnt,
+                       h->trace ? h->d_trace.as<FpmEvalTrace>() + (size_t)c0 * n_ang : nullptr, nullptr,
+                       fused ? h->d_numer.as<float>() : nullptr, h->d_totS.as<long long>(), h->d_totQ.as<long long>(), raw_tile_evals, n_dev));
+            }
         }
         cur ^= 1;
         if (async) continue;                                  // n stays the top-layer count: an upper bound of every layer's list
@@ -2151,7 +2156,7 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     const int tiles_x = (dp + WA_TW - 1) / WA_TW;
     dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
     fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), 1, s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
-                                                        tiles_x, level_vec_ok(s), nullptr);
+                                                        tiles_x, level_vec_ok(s), nullptr, FpmRefineGeom{});
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -181,14 +181,46 @@ fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
 #define WA_SH 160     // staged box: rows
 #define WA_MAXG 3     // jobs per group
 
+// getRotatedROI matrix of eval j of a candidate (src/TemplateMatcher.cpp:1074-1088), inverted like warpAffine does
+struct FpmRefineGeom { const FpmCand* cands; int n_ang; double angle_step; int lvl_w, lvl_h, tpl_w, tpl_h; };
+
+__device__ __forceinline__ FpmWarpJob fpm_refine_job(const FpmCand& c, int j, int n_ang, double angle_step, int lvl_w, int lvl_h,
+                                                     int tpl_w, int tpl_h)
+{
+    double angle = (n_ang == 1) ? 0.0 : c.angle + angle_step * (double)(j - 1);
+    float ptcx = (float)(lvl_w - 1) / 2.0f, ptcy = (float)(lvl_h - 1) / 2.0f;
+    float ltx = c.ptx * 2, lty = c.pty * 2;
+    float rx, ry;
+    fpm_pt_rotate(ltx, lty, ptcx, ptcy, angle * FPM_D2R, &rx, &ry);
+    FpmWarpJob jb;
+    fpm_rotation_matrix(ptcx, ptcy, angle, jb.m);
+    jb.m[2] -= (double)(rx - 3);
+    jb.m[5] -= (double)(ry - 3);
+    fpm_invert_affine(jb.m);
+    jb.src_img = c.img;
+    jb.dw = tpl_w + FPM_ROI_PAD; jb.dh = tpl_h + FPM_ROI_PAD;
+    jb.valid = 1;
+    return jb;
+}
+
 __global__ void __launch_bounds__(WA_THREADS)
-fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs, int group, FpmLevel src, uint8_t* __restrict__ dst,
-                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok, const int* __restrict__ n_groups_dev)
+fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs_g, int group, FpmLevel src, uint8_t* __restrict__ dst,
+                int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok, const int* __restrict__ n_groups_dev,
+                FpmRefineGeom geom)
 {
     // n_groups_dev (optional): number of live job groups, known only on the device (descent without a host round trip per layer:
     // the grid covers an upper bound, the surplus CTAs leave at once)
     if (n_groups_dev && (int)blockIdx.y >= *n_groups_dev) return;
     const int g0 = blockIdx.y * group;
+    // jobs: given (top-layer sweep, tests), or the ROI matrices of candidate blockIdx.y computed here from its record
+    // (geom.cands != null: one launch less per pyramid layer than a separate preparation kernel)
+    __shared__ FpmWarpJob jobs_s[WA_MAXG];
+    if (threadIdx.x < group)
+        jobs_s[threadIdx.x] = geom.cands ? fpm_refine_job(geom.cands[blockIdx.y], threadIdx.x, geom.n_ang, geom.angle_step, geom.lvl_w,
+                                                          geom.lvl_h, geom.tpl_w, geom.tpl_h)
+                                         : jobs_g[g0 + threadIdx.x];
+    __syncthreads();
+    const FpmWarpJob* jobs = jobs_s - g0;              // jobs[g0 + j] below
     const FpmWarpJob& jb0 = jobs[g0];
     const int dw = jb0.dw, dh = jb0.dh;
     const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
@@ -1048,21 +1080,7 @@ __global__ void fpm_refine_prep_kernel(const FpmCand* __restrict__ cands, int n_
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_cands * n_ang) return;
     int ci = e / n_ang, j = e - ci * n_ang;
-    const FpmCand c = cands[ci];
-    double angle = (n_ang == 1) ? 0.0 : c.angle + angle_step * (double)(j - 1);
-    float ptcx = (float)(lvl_w - 1) / 2.0f, ptcy = (float)(lvl_h - 1) / 2.0f;
-    float ltx = c.ptx * 2, lty = c.pty * 2;
-    float rx, ry;
-    fpm_pt_rotate(ltx, lty, ptcx, ptcy, angle * FPM_D2R, &rx, &ry);
-    FpmWarpJob jb;
-    fpm_rotation_matrix(ptcx, ptcy, angle, jb.m);
-    jb.m[2] -= (double)(rx - 3);
-    jb.m[5] -= (double)(ry - 3);
-    fpm_invert_affine(jb.m);
-    jb.src_img = c.img;
-    jb.dw = tpl_w + FPM_ROI_PAD; jb.dh = tpl_h + FPM_ROI_PAD;
-    jb.valid = 1;
-    jobs[e] = jb;
+    jobs[e] = fpm_refine_job(cands[ci], j, n_ang, angle_step, lvl_w, lvl_h, tpl_w, tpl_h);
 }
 
 // =====================================================================================
@@ -1373,7 +1391,56 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
     __shared__ float s_best[3];
     __shared__ int s_loc[3];
     __shared__ double s_scratch[27 + 270 + 100 + 100 + 270];
+    __shared__ unsigned long long s_totS[3][FPM_NSHIFT], s_totQ[3][FPM_NSHIFT];      // sums over ALL ROI rows per shift
+    __shared__ int s_edgeS[3][2 * FPM_ROI_PAD][FPM_NSHIFT], s_edgeQ[3][2 * FPM_ROI_PAD][FPM_NSHIFT];   // rows 0..5 and th..th+5
     const int th = tpl.h;
+    // Window sums of CCOEFF_Denominator.  The 49 windows of an eval share their rows: window (r, c) = total of column c over
+    // all th + 6 ROI rows minus the r rows above and the 6 - r rows below it.  The totals are gathered by all 64 threads of
+    // the eval (every thread a strided share of the rows, 14 loads per row in flight) instead of a 2*th-load serial loop
+    // per cell, which was most of this kernel's time at single-frame latency.
+    const bool coop_window = !tpl.result_equal1 && !numer;
+    if (coop_window) {
+        if (tid < 3 * FPM_NSHIFT) { s_totS[tid / FPM_NSHIFT][tid % FPM_NSHIFT] = 0; s_totQ[tid / FPM_NSHIFT][tid % FPM_NSHIFT] = 0; }
+        __syncthreads();
+        if (j < n_ang) {
+            const int e = ci * n_ang + j;
+            const int rh = th + FPM_ROI_PAD;
+            const int32_t* ps = rowS + (size_t)e * rh * FPM_NSHIFT;
+            const int32_t* pq = rowQ + (size_t)e * rh * FPM_NSHIFT;
+            long long ts[FPM_NSHIFT], tq[FPM_NSHIFT];
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) { ts[c] = 0; tq[c] = 0; }
+#pragma unroll 2
+            for (int y = cell; y < rh; y += 64) {
+                int a[FPM_NSHIFT], b[FPM_NSHIFT];
+#pragma unroll
+                for (int c = 0; c < FPM_NSHIFT; c++) { a[c] = ps[(size_t)y * FPM_NSHIFT + c]; b[c] = pq[(size_t)y * FPM_NSHIFT + c]; }
+#pragma unroll
+                for (int c = 0; c < FPM_NSHIFT; c++) { ts[c] += a[c]; tq[c] += b[c]; }
+                if (y < FPM_ROI_PAD) {
+#pragma unroll
+                    for (int c = 0; c < FPM_NSHIFT; c++) { s_edgeS[j][y][c] = a[c]; s_edgeQ[j][y][c] = b[c]; }
+                }
+                if (y >= th) {
+#pragma unroll
+                    for (int c = 0; c < FPM_NSHIFT; c++) { s_edgeS[j][FPM_ROI_PAD + y - th][c] = a[c]; s_edgeQ[j][FPM_ROI_PAD + y - th][c] = b[c]; }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < FPM_NSHIFT; c++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ts[c] += __shfl_xor_sync(0xffffffffu, ts[c], o);
+                    tq[c] += __shfl_xor_sync(0xffffffffu, tq[c], o);
+                }
+                if ((tid & 31) == 0) {
+                    atomicAdd(&s_totS[j][c], (unsigned long long)ts[c]);
+                    atomicAdd(&s_totQ[j][c], (unsigned long long)tq[c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
     if (j < n_ang && cell < FPM_NCELL) {
         const int e = ci * n_ang + j;
         const int r = cell / FPM_NSHIFT, c = cell - r * FPM_NSHIFT;
@@ -1432,20 +1499,9 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
                 for (int tr = 0; tr < th; tr++) acc += rs[(size_t)tr * rstride];
                 numf = (float)acc;
             }
-            const int32_t* ps = rowS + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;
-            const int32_t* pq = rowQ + ((size_t)e * (th + FPM_ROI_PAD) + r) * FPM_NSHIFT + c;
-            long long ws = 0, wq = 0;
-            {
-                int y = 0;
-                for (; y + 8 <= th; y += 8) {
-                    int a[8], b[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) { a[k] = ps[(size_t)(y + k) * FPM_NSHIFT]; b[k] = pq[(size_t)(y + k) * FPM_NSHIFT]; }
-#pragma unroll
-                    for (int k = 0; k < 8; k++) { ws += a[k]; wq += b[k]; }
-                }
-                for (; y < th; y++) { ws += ps[(size_t)y * FPM_NSHIFT]; wq += pq[(size_t)y * FPM_NSHIFT]; }
-            }
+            long long ws = (long long)s_totS[j][c], wq = (long long)s_totQ[j][c];
+            for (int y = 0; y < r; y++) { ws -= s_edgeS[j][y][c]; wq -= s_edgeQ[j][y][c]; }
+            for (int y = r; y < FPM_ROI_PAD; y++) { ws -= s_edgeS[j][FPM_ROI_PAD + y][c]; wq -= s_edgeQ[j][FPM_ROI_PAD + y][c]; }   // ROI rows th + r .. th + 5
             sc = fpm_ccoeff_epilogue(numf, (double)ws, (double)wq, tpl.mean, tpl.norm, tpl.inv_area);
         }
         s_sc[j][cell] = sc;
