@@ -1,7 +1,9 @@
 """Multi-GPU check, launched with torchrun (one rank per GPU, NCCL):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 scripts/multi_gpu_check.py
-Verifies on real GPUs that (a) the angle-sharded latency mode (two NCCL allgathers) returns on every rank
-exactly what a single GPU returns, and (b) frame sharding + gather reproduces the single-GPU results."""
+Verifies on real GPUs that (a) the angle-sharded latency mode returns on every rank exactly what a single GPU returns --
+through the C++/NCCL path (fpm_match_sharded: two ncclAllGather on device buffers) AND through the stage-API specification
+(dist.match_angle_sharded, torch.distributed allgathers) -- and (b) frame sharding + gather reproduces the single-GPU results.
+(bench.py --mode latency measures the C++ path; this script is the correctness check.)"""
 import os
 import sys
 import time
@@ -35,6 +37,16 @@ def main():
     dt = (time.perf_counter() - t0) * 1e3
     rows = D.results_to_rows(res)
     assert rows.shape == single.shape and np.array_equal(rows, single), "rank %d: angle-sharded != single GPU" % rank
+    D.init_sharded(m, dist)                                    # ncclCommInitRank through the C ABI
+    for on_dev in (False, True):
+        if on_dev:
+            d = torch.from_numpy(src).to(dev)
+            got = m.matchSharded(ptr=d.data_ptr(), shape=src.shape, stride=src.shape[1], on_device=True)
+        else:
+            got = m.matchSharded(src)
+        rows = D.results_to_rows(got)
+        assert rows.shape == single.shape and np.array_equal(rows, single), "rank %d: fpm_match_sharded != single GPU" % rank
+    assert m.collectiveCount() >= 5
     t0 = time.perf_counter(); m.match(src); dt1 = (time.perf_counter() - t0) * 1e3
     frames = [src, synth.load_fixture("Src8"), src, synth.load_fixture("Src9"), src]
     m8 = TemplateMatcher(local)
