@@ -75,6 +75,7 @@ SIGNATURES = {
     "fpm_shard_angle_range": (_i, [_i, _i, _i, _pi, _pi]),
     "fpm_collective_count": (C.c_longlong, [_vp]),
     "fpm_dbg_pyrdown": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "fpm_dbg_pyrdown2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "fpm_dbg_warp_affine": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "fpm_dbg_corr_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "fpm_dbg_corr_rows_mma": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

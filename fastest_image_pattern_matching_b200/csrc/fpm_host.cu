@@ -302,14 +302,62 @@ FpmTplLevel tpl_level_dev(const fpm_handle* h, int l)
     return d;
 }
 
-int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& dst, int batch)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+// One launch of the pyramid kernel: d1 = pyrDown(src) and, when d2 is given, d2 = pyrDown(d1) from the level-1 tile that is
+// still in shared memory (fpm_pyrdown.cuh).
+int launch_pyrdown(fpm_handle* h, const FpmLevel& src, const FpmLevel& d1, const FpmLevel* d2, int batch)
 {
-    auto aligned = [&](int a) { return ((reinterpret_cast<uintptr_t>(src.ptr) % a) == 0) && (src.pitch % a == 0) && (src.img_stride % a == 0); };
-    const int vec_ok = aligned(16) ? 16 : (aligned(4) ? 4 : 1);
-    dim3 grid((dst.w + PD_TW - 1) / PD_TW, (dst.h + PD_TH - 1) / PD_TH, batch);
-    // algorithmic bytes: every source pixel read once, every destination pixel written once
-    KL(K_PYRDOWN, (double)batch * ((double)src.w * src.h + (double)dst.w * dst.h),
-       fpm_pyrdown_kernel<<<grid, PD_THREADS, 0, h->stream>>>(src, dst, vec_ok));
+    auto aligned = [](const FpmLevel& L, int a) {
+        return ((reinterpret_cast<uintptr_t>(L.ptr) % a) == 0) && (L.pitch % a == 0) && (L.img_stride % a == 0);
+    };
+    Pd2Args a;
+    a.src = src; a.d1 = d1; a.d2 = d2 ? *d2 : FpmLevel{nullptr, 0, 0, 0, 0};
+    a.vec = aligned(src, 16) ? 16 : (aligned(src, 8) ? 8 : (aligned(src, 4) ? 4 : 1));
+    a.st1_vec = aligned(d1, 8) ? 1 : 0;
+    a.st2_vec = (d2 && aligned(*d2, 8)) ? 1 : 0;
+    dim3 grid((d1.w + PD2_TW - 1) / PD2_TW, (d1.h + PD2_TH - 1) / PD2_TH, batch);
+    // 16-byte aligned source: the staged tile of a CTA is one TMA load of the [batch][h][pitch/4] u32 view of the level
+    // (the row padding belongs to the tensor; the kernel never uses what it holds)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (a.vec >= 16) {
+        EncodeTiledFn enc = get_encode_tiled();
+        if (!enc) { h->err = "cuTensorMapEncodeTiled not available"; return FPM_ERR_CUDA; }
+        const cuuint64_t img = src.img_stride ? (cuuint64_t)src.img_stride : (cuuint64_t)src.pitch * src.h;
+        cuuint64_t dims[3] = {(cuuint64_t)src.pitch / 4, (cuuint64_t)src.h, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)src.pitch, img};
+        cuuint32_t box[3] = {(cuuint32_t)((d2 ? Pd2Cfg<true>::IP : Pd2Cfg<false>::IP) / 4), (cuuint32_t)(d2 ? Pd2Cfg<true>::IH : Pd2Cfg<false>::IH), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) a.vec = 8;                   // e.g. a stride beyond the descriptor's range: cp.async staging instead
+    }
+    // algorithmic bytes: every level of the chain read once and written once, also the level that stays on chip
+    double work = (double)batch * ((double)src.w * src.h + (double)d1.w * d1.h);
+    if (d2) {
+        work += (double)batch * ((double)d1.w * d1.h + (double)d2->w * d2->h);
+        CK(ensure_dyn_smem((const void*)fpm_pyrdown_kernel<true>, h->device, Pd2Cfg<true>::SMEM));
+        KL(K_PYRDOWN, work, fpm_pyrdown_kernel<true><<<grid, Pd2Cfg<true>::NT, Pd2Cfg<true>::SMEM, h->stream>>>(a, tmap));
+    } else {
+        CK(ensure_dyn_smem((const void*)fpm_pyrdown_kernel<false>, h->device, Pd2Cfg<false>::SMEM));
+        KL(K_PYRDOWN, work, fpm_pyrdown_kernel<false><<<grid, Pd2Cfg<false>::NT, Pd2Cfg<false>::SMEM, h->stream>>>(a, tmap));
+    }
+    return FPM_OK;
+}
+
+// levels[1..top] from levels[0], two levels per launch
+int launch_pyramid_chain(fpm_handle* h, const std::vector<FpmLevel>& lv, int top, int batch)
+{
+    for (int l = 1; l <= top;) {
+        const bool two = l + 1 <= top;
+        int rc = launch_pyrdown(h, lv[l - 1], lv[l], two ? &lv[l + 1] : nullptr, batch);
+        if (rc) return rc;
+        l += two ? 2 : 1;
+    }
     return FPM_OK;
 }
 
@@ -365,10 +413,6 @@ int peaks_smem_blocks(fpm_handle* h, int blk_stride)
 }
 
 // ---- tensor-core correlation (fpm_mma.cuh): TMA descriptors + launch -----------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 EncodeTiledFn get_encode_tiled()
 {
     // function-local static: initialised once, thread-safe (handles may run on several host threads)
@@ -566,10 +610,10 @@ int do_learn(fpm_handle* h)
     CK(cudaMemsetAsync(h->d_tpl.p, 0, off, h->stream));
     CK(cudaMemcpy2DAsync(h->d_tpl.as<uint8_t>() + h->tpl[0].dev_off, h->tpl[0].pitch, h->tpl0.data(), w0, w0, h0,
                          cudaMemcpyHostToDevice, h->stream));
-    for (int l = 1; l <= top; l++) {
-        FpmLevel s{h->d_tpl.as<uint8_t>() + h->tpl[l - 1].dev_off, h->tpl[l - 1].w, h->tpl[l - 1].h, h->tpl[l - 1].pitch, 0};
-        FpmLevel d{h->d_tpl.as<uint8_t>() + h->tpl[l].dev_off, h->tpl[l].w, h->tpl[l].h, h->tpl[l].pitch, 0};
-        int rc = launch_pyrdown(h, s, d, 1);
+    {
+        std::vector<FpmLevel> lv(top + 1);
+        for (int l = 0; l <= top; l++) lv[l] = FpmLevel{h->d_tpl.as<uint8_t>() + h->tpl[l].dev_off, h->tpl[l].w, h->tpl[l].h, h->tpl[l].pitch, 0};
+        int rc = launch_pyramid_chain(h, lv, top, 1);
         if (rc) return rc;
     }
     {
@@ -642,12 +686,8 @@ int build_pyramid(fpm_handle* h, const uint8_t* d_src, int batch, int w, int hgt
         off += img * batch;
     }
     CK(h->d_pyr.ensure(off + 256));
-    for (int l = 1; l <= top; l++) {
-        h->levels[l].ptr = h->d_pyr.as<uint8_t>() + offs[l];
-        int rc = launch_pyrdown(h, h->levels[l - 1], h->levels[l], batch);
-        if (rc) return rc;
-    }
-    return FPM_OK;
+    for (int l = 1; l <= top; l++) h->levels[l].ptr = h->d_pyr.as<uint8_t>() + offs[l];
+    return launch_pyramid_chain(h, h->levels, top, batch);
 }
 
 // ---- angle schedule + per-angle top-layer geometry (src/TemplateMatcher.cpp:130-173) -----
@@ -2122,17 +2162,28 @@ int fpm_match_sharded_virtual(fpm_handle* const* hs, int nranks, const uint8_t* 
 // ---- stage kernels for parity tests ----------------------------------------------------
 int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, uint8_t* dst)
 {
-    if (!h || !src || !dst || w <= 0 || hgt <= 0) return FPM_ERR_INVALID;
+    return fpm_dbg_pyrdown2(h, src, w, hgt, stride, 0, dst, nullptr);
+}
+
+// one launch: dst1 = pyrDown(src) and (dst2 != NULL) dst2 = pyrDown(dst1).  The device copy of src starts `misalign` bytes
+// past a 128-byte boundary and its pitch is a multiple of 128 plus `misalign`: 0 -> 16-byte cp.async, 8 -> 8-byte,
+// 4 -> 4-byte, odd -> byte loads.
+int fpm_dbg_pyrdown2(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, int misalign, uint8_t* dst1, uint8_t* dst2)
+{
+    if (!h || !src || !dst1 || w <= 0 || hgt <= 0 || misalign < 0 || misalign > 127) return FPM_ERR_INVALID;
     CK(cudaSetDevice(h->device));
-    int dw = (w + 1) / 2, dh = (hgt + 1) / 2;
-    int sp = (int)align_up(w, 128), dp = (int)align_up(dw, 128);
-    CK(h->d_dbg[0].ensure((size_t)sp * hgt));
-    CK(h->d_dbg[1].ensure((size_t)dp * dh));
-    CK(cudaMemcpy2DAsync(h->d_dbg[0].p, sp, src, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
-    FpmLevel s{h->d_dbg[0].as<uint8_t>(), w, hgt, sp, 0}, d{h->d_dbg[1].as<uint8_t>(), dw, dh, dp, 0};
-    int rc = launch_pyrdown(h, s, d, 1);
+    const int w1 = (w + 1) / 2, h1 = (hgt + 1) / 2, w2 = (w1 + 1) / 2, h2 = (h1 + 1) / 2;
+    const int sp = (int)align_up(w, 128) + misalign, p1 = (int)align_up(w1, 128), p2 = (int)align_up(w2, 128);
+    CK(h->d_dbg[0].ensure((size_t)sp * hgt + 128));
+    CK(h->d_dbg[1].ensure((size_t)p1 * h1));
+    CK(h->d_dbg[2].ensure((size_t)p2 * h2));
+    uint8_t* ds = h->d_dbg[0].as<uint8_t>() + misalign;
+    CK(cudaMemcpy2DAsync(ds, sp, src, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    FpmLevel s{ds, w, hgt, sp, 0}, d1{h->d_dbg[1].as<uint8_t>(), w1, h1, p1, 0}, d2{h->d_dbg[2].as<uint8_t>(), w2, h2, p2, 0};
+    int rc = launch_pyrdown(h, s, d1, dst2 ? &d2 : nullptr, 1);
     if (rc) return rc;
-    CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(dst1, w1, d1.ptr, p1, w1, h1, cudaMemcpyDeviceToHost, h->stream));
+    if (dst2) CK(cudaMemcpy2DAsync(dst2, w2, d2.ptr, p2, w2, h2, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return FPM_OK;
 }

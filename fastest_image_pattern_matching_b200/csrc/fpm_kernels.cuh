@@ -1,7 +1,7 @@
 // fpm_kernels.cuh -- hand-written sm_100a kernels for every stage of TemplateMatcher::match
 // (/root/reference/src/TemplateMatcher.cpp:97-437).  One kernel per reference stage:
 //
-//   fpm_pyrdown_kernel        cv::buildPyramid / pyrDown                     (:55, :124)
+//   fpm_pyrdown_kernel        cv::buildPyramid / pyrDown, 1 or 2 levels/launch (:55, :124)   [fpm_pyrdown.cuh]
 //   fpm_warp_kernel           cv::warpAffine INTER_LINEAR, BORDER_CONSTANT    (:175, :1089)
 //   fpm_top_score_kernel      matchTemplate(TM_CCORR) + CCOEFF_Denominator    (:177, :514, :527-598)
 //   fpm_top_peaks_kernel      minMaxLoc / s_BlockMax / getNextMaxLoc          (:179-210, :1196-1221)
@@ -18,146 +18,11 @@
 #pragma once
 #include "fpm_common.cuh"
 #include "fpm_geometry.cuh"
+#include "fpm_pyrdown.cuh"
 
 // =====================================================================================
-// K1  pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, (s+128)>>8, out ((w+1)/2,(h+1)/2)
-// HBM-bound: reads W*H, writes W*H/4.  One CTA = 128x32 outputs.  The 67 input rows x 288 B of the
-// tile are staged in shared memory with 128-bit (or 32-bit) coalesced loads; the horizontal taps are
-// one dp4a (weights 1,4,6,4) + one byte per output, the vertical taps run on two 16-bit lanes packed
-// in a 32-bit register (sums < 65536, so no carry crosses lanes).
+// K1  pyrDown: fpm_pyrdown.cuh (one or two pyramid levels per launch)
 // =====================================================================================
-#define PD_TW 128
-#define PD_TH 32
-#define PD_IH (2 * PD_TH + 3)
-#define PD_IW (2 * PD_TW + 32)     // staged input columns [2*ox0-16, 2*ox0+2*TW+16), 16-byte chunks
-#define PD_THREADS 256
-
-__global__ void __launch_bounds__(PD_THREADS)
-fpm_pyrdown_kernel(FpmLevel src, FpmLevel dst, int vec)
-{
-    __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
-    __shared__ __align__(16) uint32_t s_h[PD_IH][PD_TW / 2];     // two u16 horizontal sums per word
-    const int tid = threadIdx.x;
-    const int ox0 = blockIdx.x * PD_TW, oy0 = blockIdx.y * PD_TH;
-    const uint8_t* __restrict__ s = src.ptr + (size_t)blockIdx.z * src.img_stride;
-    uint8_t* __restrict__ d = dst.ptr + (size_t)blockIdx.z * dst.img_stride;
-    const int xs = 2 * ox0 - 16, ys = 2 * oy0 - 2;
-    const int nout_rows = min(PD_TH, dst.h - oy0);
-    const int nout_cols = min(PD_TW, dst.w - ox0);
-    const int nin_rows = 2 * nout_rows + 3;
-    const int sw = src.w, sh = src.h;
-    // smem bytes actually read by the horizontal pass: 12 .. 8*ceil(nout_cols/4)+19
-    const int need_lo = 12, need_hi = 8 * ((nout_cols + 3) / 4) + 19;
-
-    const int nch = (need_hi + 16) / 16;                         // 16-byte chunks per row (<= 18)
-    const bool interior = ys >= 0 && ys + nin_rows <= sh && xs >= 0 && xs + 16 * nch <= sw;
-    if (interior && vec == 16) {
-        const int c = tid & 31;
-        if (c < nch) {
-            const uint8_t* g = s + (size_t)(ys + (tid >> 5)) * src.pitch + xs + 16 * c;
-            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32, g += (size_t)(PD_THREADS / 32) * src.pitch)
-                fpm_cp_async16(&s_in[r][16 * c], g);
-        }
-    } else if (vec == 16 && xs >= 0 && xs + 16 * nch <= sw) {
-        // top / bottom border tile: only the row index needs reflecting, columns are all inside
-        const int c = tid & 31;
-        if (c < nch) {
-            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
-                fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + xs + 16 * c);
-        }
-    } else if (vec == 16) {
-        // left / right border tile.  Pass A: every 16-byte chunk that lies inside the image in x is one cp.async, as in
-        // the interior (rows through the reflection).  Pass B: the few needed bytes outside those chunks (4 on the left
-        // edge, the ragged tail on the right edge) are fetched one per thread through the column reflection.
-        const int c = tid & 31;
-        const int c_first = xs < 0 ? (-xs + 15) / 16 : 0;                    // first chunk with x >= 0
-        const int c_last = min(nch - 1, (sw - xs) / 16 - 1);                 // last chunk with x + 16 <= sw
-        if (c >= c_first && c <= c_last) {
-            const int x = xs + 16 * c;
-            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32)
-                fpm_cp_async16(&s_in[r][16 * c], s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + x);
-        }
-        int l0 = need_lo, l1, r0, r1 = need_hi + 1;                          // byte ranges [l0, l1) and [r0, r1) of a row
-        if (c_last < c_first) { l1 = r1; r0 = r1; }                          // no whole chunk at all
-        else { l1 = max(l0, min(16 * c_first, r1)); r0 = max(l1, 16 * (c_last + 1)); }
-        const int nl = l1 - l0, nb = nl + max(r1 - r0, 0);
-        for (int i = tid; i < nin_rows * nb; i += PD_THREADS) {
-            const int r = i / nb, k = i - r * nb;
-            const int b = k < nl ? l0 + k : r0 + (k - nl);
-            s_in[r][b] = __ldg(s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch + fpm_reflect101(xs + b, sw));
-        }
-    } else {
-        const int w_lo = need_lo / 4, w_hi = need_hi / 4;         // words 3 .. need_hi/4 (<= 68)
-        for (int r = tid >> 6; r < nin_rows; r += PD_THREADS / 64) {
-            const uint8_t* row = s + (size_t)fpm_reflect101(ys + r, sh) * src.pitch;
-            for (int wc = w_lo + (tid & 63); wc <= w_hi; wc += 64) {
-                const int x = xs + 4 * wc;
-                if (vec >= 4 && x >= 0 && x + 3 < sw) {
-                    fpm_cp_async4(&s_in[r][4 * wc], row + x, true);
-                } else {
-                    uint32_t v = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        v |= (uint32_t)__ldg(row + fpm_reflect101(x + k, sw)) << (8 * k);
-                    *reinterpret_cast<uint32_t*>(&s_in[r][4 * wc]) = v;
-                }
-            }
-        }
-    }
-    fpm_cp_async_commit();
-    fpm_cp_async_wait<0>();
-    __syncthreads();
-
-    // horizontal pass: 4 outputs per thread and row; output 4k+j has its centre at smem byte 8k+16+2j, so its
-    // first four taps are an (un)shifted word and the fifth is a single byte of the next word
-    {
-        const int k = tid & 31;
-        if (4 * k < nout_cols) {
-            const uint32_t W = 0x04060401u;
-            for (int r = tid >> 5; r < nin_rows; r += PD_THREADS / 32) {
-                const uint8_t* b = &s_in[r][8 * k + 12];
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(b);
-                const uint2 w12 = *reinterpret_cast<const uint2*>(b + 4);
-                const uint32_t w3 = *reinterpret_cast<const uint32_t*>(b + 12);
-                const uint32_t h0 = __dp4a(__funnelshift_r(w0, w12.x, 16), W, (w12.x >> 16) & 255u);
-                const uint32_t h1 = __dp4a(w12.x, W, w12.y & 255u);
-                const uint32_t h2 = __dp4a(__funnelshift_r(w12.x, w12.y, 16), W, (w12.y >> 16) & 255u);
-                const uint32_t h3 = __dp4a(w12.y, W, w3 & 255u);
-                *reinterpret_cast<uint2*>(&s_h[r][2 * k]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
-            }
-        }
-    }
-    __syncthreads();
-
-    // vertical pass: 8 outputs (four packed pairs) per thread and row
-    {
-        const int g = tid & 15;
-        if (8 * g < nout_cols) {
-            for (int oy = tid >> 4; oy < nout_rows; oy += PD_THREADS / 16) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(&s_h[2 * oy][4 * g]);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 1][4 * g]);
-                const uint4 r2 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 2][4 * g]);
-                const uint4 r3 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 3][4 * g]);
-                const uint4 r4 = *reinterpret_cast<const uint4*>(&s_h[2 * oy + 4][4 * g]);
-                const uint32_t R = 0x00800080u, M = 0x00ff00ffu;
-                const uint32_t v0 = ((r0.x + r4.x + 4u * (r1.x + r3.x) + 6u * r2.x + R) >> 8) & M;
-                const uint32_t v1 = ((r0.y + r4.y + 4u * (r1.y + r3.y) + 6u * r2.y + R) >> 8) & M;
-                const uint32_t v2 = ((r0.z + r4.z + 4u * (r1.z + r3.z) + 6u * r2.z + R) >> 8) & M;
-                const uint32_t v3 = ((r0.w + r4.w + 4u * (r1.w + r3.w) + 6u * r2.w + R) >> 8) & M;
-                // bytes: v0.lo v0.hi v1.lo v1.hi | v2.lo v2.hi v3.lo v3.hi
-                const uint32_t p0 = __byte_perm(v0, v1, 0x6420), p1 = __byte_perm(v2, v3, 0x6420);
-                uint8_t* op = d + (size_t)(oy0 + oy) * dst.pitch + ox0 + 8 * g;
-                if (8 * g + 7 < nout_cols && (dst.pitch & 7) == 0) {
-                    *reinterpret_cast<uint2*>(op) = make_uint2(p0, p1);
-                } else {
-                    const unsigned long long pk = (unsigned long long)p0 | ((unsigned long long)p1 << 32);
-                    for (int q = 0; q < 8 && 8 * g + q < nout_cols; q++) op[q] = (uint8_t)(pk >> (8 * q));
-                }
-            }
-        }
-    }
-}
-
 // =====================================================================================
 // K2/K3  warpAffine, u8 C1, INTER_LINEAR, BORDER_CONSTANT -- OpenCV's fixed-point path:
 //   AB_BITS=10, INTER_BITS=5, adelta/bdelta = cvRound(M*x*1024), X0 = cvRound((M01*y+M02)*1024)+16,

@@ -263,6 +263,16 @@ class TemplateMatcher:
         self._check(self._lib.fpm_dbg_pyrdown(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], out.ctypes.data))
         return out
 
+    def dbgPyrDown2(self, img, misalign=0, two=True):
+        """one launch of the pyramid kernel: (pyrDown(img), pyrDown(pyrDown(img))), or the first level only."""
+        s = _as_u8_2d(img)
+        h1, w1 = (s.shape[0] + 1) // 2, (s.shape[1] + 1) // 2
+        o1 = np.empty((h1, w1), np.uint8)
+        o2 = np.empty(((h1 + 1) // 2, (w1 + 1) // 2), np.uint8) if two else None
+        self._check(self._lib.fpm_dbg_pyrdown2(self._h, s.ctypes.data, s.shape[1], s.shape[0], s.strides[0], int(misalign),
+                                               o1.ctypes.data, o2.ctypes.data if two else None))
+        return (o1, o2) if two else o1
+
     def dbgWarpAffine(self, img, M, dsize, border=0) -> np.ndarray:
         s = _as_u8_2d(img)
         m = np.ascontiguousarray(np.asarray(M, np.float64).reshape(6))

@@ -205,6 +205,10 @@ long long fpm_collective_count(const fpm_handle* h);
 
 /* ---- stage kernels exposed for bit-exact parity tests (host pointers in and out) ---- */
 int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, uint8_t* dst /* ((w+1)/2)*((h+1)/2) */);
+/* one launch of the two-level pyramid kernel: dst1 = pyrDown(src), dst2 = pyrDown(dst1) (dst2 may be NULL: one level).
+   misalign: byte offset of the device copy of src past a 128-byte boundary, also added to its pitch (0 / 8 / 4 / odd select
+   the 16- / 8- / 4-byte cp.async and the byte staging paths). */
+int fpm_dbg_pyrdown2(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, int misalign, uint8_t* dst1, uint8_t* dst2);
 int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, const double m[6] /* forward 2x3 */,
                         int dw, int dh, int border, uint8_t* dst /* dw*dh */);
 int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi /* (th+6)x(tw+6) */, const uint8_t* tpl, int tw, int th,

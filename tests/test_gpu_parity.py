@@ -32,6 +32,28 @@ def test_pyrdown_unaligned_stride(matcher):
     assert np.array_equal(matcher.dbgPyrDown(view), cv2.pyrDown(np.ascontiguousarray(view)))
 
 
+@pytest.mark.parametrize("shape", [(7, 9), (1, 1), (2, 2), (5, 3), (3, 300), (101, 333), (259, 517), (129, 257), (130, 258),
+                                   (131, 261), (257, 1030), (1519, 2013), (3036, 4024)])
+def test_pyrdown_two_levels_per_launch_bit_exact(matcher, shape):
+    """fpm_pyrdown_kernel<TWO>: level 2 comes from the level-1 tile in shared memory (halo recomputed, REFLECT_101 fix-up)."""
+    rng = np.random.default_rng(shape[0] * 17 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    want1 = cv2.pyrDown(img)
+    want2 = cv2.pyrDown(want1)
+    for misalign in (0, 8, 4, 3):                      # 16- / 8- / 4-byte cp.async staging, byte staging
+        got1, got2 = matcher.dbgPyrDown2(img, misalign)
+        assert np.array_equal(got1, want1), (shape, misalign, int((got1 != want1).sum()))
+        assert np.array_equal(got2, want2), (shape, misalign, int((got2 != want2).sum()))
+        assert np.array_equal(matcher.dbgPyrDown2(img, misalign, two=False), want1), (shape, misalign)
+
+
+def test_pyrdown_saturated_image(matcher):
+    img = np.full((300, 700), 255, np.uint8)           # largest packed 16-bit sums (16 * 4080 + 128) must not carry
+    img[::3, ::5] = 0
+    got1, got2 = matcher.dbgPyrDown2(img)
+    assert np.array_equal(got1, cv2.pyrDown(img)) and np.array_equal(got2, cv2.pyrDown(cv2.pyrDown(img)))
+
+
 def test_source_pyramid_chain(matcher, golden_cases):
     c = golden_cases["src8"]
     src = get_image(c["src"])
