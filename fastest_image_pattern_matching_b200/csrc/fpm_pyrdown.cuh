@@ -93,21 +93,39 @@ FPM_HD PdRow pd_hsum(uint32_t wm, uint4 w, uint32_t wp)
     return r;
 }
 
-// one staged row: p = the 16 centre bytes (16-byte aligned).  edge_l / edge_r: the lane has no lane neighbour that
-// holds the adjacent chunk, so it reads the halo word itself.  The host build reads both halo words directly.
-FPM_HD PdRow pd_hrow(const uint8_t* p, bool edge_l, bool edge_r)
+// one staged row: p = the 16 centre bytes (16-byte aligned).  The halo words come from the neighbour lanes by shuffle.  A
+// lane without a neighbour that holds the adjacent chunk (edge: 1 = left, 2 = right; first / last group of a strip, lane
+// 0 / 31) reads its halo word itself -- ONE predicated load per row for the left and the right edge lanes together (two
+// loads cost 4.4 wavefronts per warp and row: the few active lanes sit in strips whose rows share their banks) and two
+// selects, no branch.  No lane has both edges (pd_no_double_edge).  The host build reads both words directly.
+FPM_HD PdRow pd_hrow(const uint8_t* p, int edge)
 {
     const uint4 w = *reinterpret_cast<const uint4*>(p);
 #ifdef __CUDA_ARCH__
     uint32_t wm = __shfl_up_sync(0xffffffffu, w.w, 1), wp = __shfl_down_sync(0xffffffffu, w.x, 1);
-    if (edge_l) wm = *reinterpret_cast<const uint32_t*>(p - 4);
-    if (edge_r) wp = *reinterpret_cast<const uint32_t*>(p + 16);
+    uint32_t v = 0;
+    const unsigned ea = (unsigned)__cvta_generic_to_shared(p) + (edge == 1 ? -4 : 16);
+    asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.s32 pe, %2, 0;\n\t@pe ld.shared.u32 %0, [%1];\n\t}" : "+r"(v) : "r"(ea), "r"(edge));
+    wm = edge == 1 ? v : wm;
+    wp = edge == 2 ? v : wp;
 #else
-    (void)edge_l; (void)edge_r;
+    (void)edge;
     const uint32_t wm = *reinterpret_cast<const uint32_t*>(p - 4), wp = *reinterpret_cast<const uint32_t*>(p + 16);
 #endif
     return pd_hsum(wm, w, wp);
 }
+
+// with ng groups per strip laid out over the lanes of nt / 32 warps, is there a lane that is both a left and a right edge?
+constexpr bool pd_no_double_edge(int ng, int nthreads, int nlive)
+{
+    for (int t = 0; t < nthreads; t++) {
+        const int id = t < nlive ? t : nlive - 1, g = id % ng, lane = t & 31;
+        if ((g == 0 || lane == 0) && (g == ng - 1 || lane == 31)) return false;
+    }
+    return true;
+}
+static_assert(pd_no_double_edge(18, 320, 18 * 17) && pd_no_double_edge(16, 256, 256) && pd_no_double_edge(PD2_G2, PD2_G2 * PD2_S2, PD2_G2 * PD2_S2),
+              "a lane with both halo words missing needs a second load in pd_hrow");
 
 FPM_HD uint32_t pd_vpair(uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t h4)
 {
@@ -275,10 +293,10 @@ FPM_HD void pd2_level1(int tid, const Pd2Tile<TWO>& t, int bz, const Pd2Args& a,
 #ifdef __CUDA_ARCH__
     if (!__any_sync(0xffffffffu, wanted)) return;           // the whole warp lies outside the needed area
     const int lane = tid & 31;
-    const bool edge_l = g == 0 || lane == 0, edge_r = g == C::NG - 1 || lane == 31;
+    const int edge = ((g == 0 || lane == 0) ? 1 : 0) | ((g == C::NG - 1 || lane == 31) ? 2 : 0);
 #else
     if (!wanted) return;
-    const bool edge_l = true, edge_r = true;
+    const int edge = 3;
 #endif
     const int c1 = t.X1 - C::GOFF + 8 * g, r1 = t.Y1 - C::ROFF + PD2_R * st;
     const uint8_t* p = s_in + (size_t)(2 * PD2_R * st) * C::IP + 16 * g + 16;
@@ -288,11 +306,11 @@ FPM_HD void pd2_level1(int tid, const Pd2Tile<TWO>& t, int bz, const Pd2Args& a,
     const bool full8 = a.st1_vec != 0 && c1 + 8 <= a.d1.w;
     uint8_t* drow = a.d1.ptr + (size_t)bz * a.d1.img_stride + (long long)r1 * a.d1.pitch;
     uint8_t* trow = s_l1 + (PD2_R * st) * C::L1P + 8 * g + 8;
-    PdRow h0 = pd_hrow(p, edge_l, edge_r), h1 = pd_hrow(p + C::IP, edge_l, edge_r), h2 = pd_hrow(p + 2 * C::IP, edge_l, edge_r);
+    PdRow h0 = pd_hrow(p, edge), h1 = pd_hrow(p + C::IP, edge), h2 = pd_hrow(p + 2 * C::IP, edge);
     uint2 o[PD2_R];
 #pragma unroll
     for (int j = 0; j < PD2_R; j++) {
-        const PdRow h3 = pd_hrow(p + (2 * j + 3) * C::IP, edge_l, edge_r), h4 = pd_hrow(p + (2 * j + 4) * C::IP, edge_l, edge_r);
+        const PdRow h3 = pd_hrow(p + (2 * j + 3) * C::IP, edge), h4 = pd_hrow(p + (2 * j + 4) * C::IP, edge);
         o[j] = pd_vert(h0, h1, h2, h3, h4);
         h0 = h2; h1 = h3; h2 = h4;
     }
@@ -352,20 +370,20 @@ FPM_HD void pd2_level2(int tid, int bx, int by, int bz, const Pd2Args& a, const 
 #ifdef __CUDA_ARCH__
     if (!__any_sync(0xffffffffu, wanted)) return;
     const int lane = tid & 31;
-    const bool edge_l = g == 0 || lane == 0, edge_r = g == PD2_G2 - 1 || lane == 31;
+    const int edge = ((g == 0 || lane == 0) ? 1 : 0) | ((g == PD2_G2 - 1 || lane == 31) ? 2 : 0);
 #else
     if (!wanted) return;
-    const bool edge_l = true, edge_r = true;
+    const int edge = 3;
 #endif
     const uint8_t* p = s_l1 + (2 * PD2_R2 * st) * C::L1P + 16 * g + 16;
     const int jhi = wanted ? min(PD2_R2, a.d2.h - r2) : 0;
     const bool full8 = a.st2_vec != 0 && c2 + 8 <= a.d2.w;
     uint8_t* drow = a.d2.ptr + (size_t)bz * a.d2.img_stride + (size_t)r2 * a.d2.pitch;
-    PdRow h0 = pd_hrow(p, edge_l, edge_r), h1 = pd_hrow(p + C::L1P, edge_l, edge_r), h2 = pd_hrow(p + 2 * C::L1P, edge_l, edge_r);
+    PdRow h0 = pd_hrow(p, edge), h1 = pd_hrow(p + C::L1P, edge), h2 = pd_hrow(p + 2 * C::L1P, edge);
     uint2 o[PD2_R2];
 #pragma unroll
     for (int j = 0; j < PD2_R2; j++) {
-        const PdRow h3 = pd_hrow(p + (2 * j + 3) * C::L1P, edge_l, edge_r), h4 = pd_hrow(p + (2 * j + 4) * C::L1P, edge_l, edge_r);
+        const PdRow h3 = pd_hrow(p + (2 * j + 3) * C::L1P, edge), h4 = pd_hrow(p + (2 * j + 4) * C::L1P, edge);
         o[j] = pd_vert(h0, h1, h2, h3, h4);
         h0 = h2; h1 = h3; h2 = h4;
     }
