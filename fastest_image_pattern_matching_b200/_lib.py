@@ -42,6 +42,9 @@ SIGNATURES = {
     "fpm_ocr_assemble": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i]),
     "fpm_ingest_bmp": (_i, [_vp, _vp, _sz, _pi, _pi]),
     "fpm_ingest_rgb32": (_i, [_vp, _vp, _i, _i, _i]),
+    "fpm_ingest_jpeg": (_i, [_vp, _vp, _sz, _pi, _pi]),
+    "fpm_ingest_image": (_i, [_vp, _vp, _sz, _pi, _pi]),
+    "fpm_dbg_jpeg_luma": (_i, [_vp, _sz, _pi, _pi, _pi, _pi, _vp, _vp, _sz, _vp, _i]),
     "fpm_ingested_pixels": (_i, [_vp, _vp]),
     "fpm_match_ingested": (_i, [_vp, _vp, _i, _pi]),
     "fpm_learn_ingested": (_i, [_vp]),

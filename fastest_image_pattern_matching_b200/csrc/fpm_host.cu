@@ -9,6 +9,7 @@
 #include "fpm_kernels.cuh"
 #include "fpm_mma.cuh"
 #include "fpm_fused.cuh"
+#include "fpm_jpeg.h"
 
 #include <algorithm>
 #include <chrono>
@@ -1769,6 +1770,69 @@ int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width
     h->ingest_w = w; h->ingest_h = hh; h->ingest_pitch = pitch;
     if (width) *width = w;
     if (height) *height = hh;
+    return FPM_OK;
+}
+
+// JPEG file image -> grayscale frame like cv::imread(path, IMREAD_GRAYSCALE): Huffman decoding on the host (fpm_jpeg.h), the
+// quantised luma coefficients go to the device, dequantisation + IDCT + range limit run there
+int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!file) { h->err = "null JPEG buffer"; return FPM_ERR_INVALID; }
+    fpm_jpeg::Luma im;
+    const std::string why = fpm_jpeg::decode_luma(file, nbytes, &im);
+    if (!why.empty()) { h->err = why; return FPM_ERR_INVALID; }
+    if (im.height > 65535 || im.width > 65535) { h->err = "JPEG too large"; return FPM_ERR_LIMIT; }
+    CK(cudaSetDevice(h->device));
+    const size_t cbytes = im.coef.size() * sizeof(int16_t);
+    CK(h->d_ingest_raw.ensure(cbytes));
+    const int pitch = (int)align_up(im.width, 128);
+    CK(h->d_ingest.ensure((size_t)pitch * im.height));
+    CK(cudaMemcpyAsync(h->d_ingest_raw.p, im.coef.data(), cbytes, cudaMemcpyHostToDevice, h->stream));
+    FpmJpegQuant qt;
+    memcpy(qt.q, im.quant, sizeof(qt.q));
+    const int nblk = im.bw * im.bh;
+    fpm_ingest_jpeg_idct_kernel<<<(nblk + 127) / 128, 128, 0, h->stream>>>(h->d_ingest_raw.as<int16_t>(), qt, im.bw, im.bh, im.width,
+                                                                           im.height, h->d_ingest.as<uint8_t>(), pitch);
+    CKL();
+    CK(cudaStreamSynchronize(h->stream));                             // the coefficient vector dies with this call
+    h->ingest_w = im.width; h->ingest_h = im.height; h->ingest_pitch = pitch;
+    if (width) *width = im.width;
+    if (height) *height = im.height;
+    return FPM_OK;
+}
+
+// what cv::imread does first: pick the decoder by the file's signature (two of the reference's "*.jpg" Test Images are BMP data)
+int fpm_ingest_image(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height)
+{
+    if (!h) return FPM_ERR_INVALID;
+    if (!file || nbytes < 2) { h->err = "empty image file"; return FPM_ERR_INVALID; }
+    if (file[0] == 'B' && file[1] == 'M') return fpm_ingest_bmp(h, file, nbytes, width, height);
+    if (file[0] == 0xFF && file[1] == 0xD8) return fpm_ingest_jpeg(h, file, nbytes, width, height);
+    h->err = "unsupported image file (not BMP or JPEG)";
+    return FPM_ERR_INVALID;
+}
+
+// host half of the JPEG ingest alone (no device): quantised luma coefficients [bh*bw][64] + the luma quantisation table, for
+// the CPU-side pin of the Huffman decoder against cv2 (tests/test_ingest.py).  coef may be NULL to query the sizes.
+int fpm_dbg_jpeg_luma(const uint8_t* file, size_t nbytes, int* width, int* height, int* bw, int* bh, uint16_t* quant /* 64 */,
+                      int16_t* coef, size_t coef_capacity, char* err, int err_capacity)
+{
+    fpm_jpeg::Luma im;
+    const std::string why = fpm_jpeg::decode_luma(file, nbytes, &im);
+    if (!why.empty()) {
+        if (err && err_capacity > 0) { strncpy(err, why.c_str(), err_capacity - 1); err[err_capacity - 1] = 0; }
+        return FPM_ERR_INVALID;
+    }
+    if (width) *width = im.width;
+    if (height) *height = im.height;
+    if (bw) *bw = im.bw;
+    if (bh) *bh = im.bh;
+    if (quant) memcpy(quant, im.quant, sizeof(im.quant));
+    if (coef) {
+        if (coef_capacity < im.coef.size()) return FPM_ERR_LIMIT;
+        memcpy(coef, im.coef.data(), im.coef.size() * sizeof(int16_t));
+    }
     return FPM_OK;
 }
 

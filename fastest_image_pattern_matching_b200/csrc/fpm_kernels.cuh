@@ -10,7 +10,7 @@
 //   fpm_corr_rows_kernel      IM_Conv_SIMD row dot products (dp4a)            (:461-483, :496-510)
 //   fpm_refine_finalize_kernel float row chain + CCOEFF_Denominator + argmax + pose update (:304-367)
 //   fpm_final_kernel          filterWithScore / RotatedRect / NMS / output    (:373-432)
-//   fpm_ingest_*_kernel       cv::imread(IMREAD_GRAYSCALE) of a BMP, camera RGB32 -> gray (MatchToolDialog.cpp:314, :1557)
+//   fpm_ingest_*_kernel       cv::imread(IMREAD_GRAYSCALE) of a BMP / JPEG (dequantisation + ISLOW IDCT), camera RGB32 -> gray (MatchToolDialog.cpp:314, :1557)
 // and, in fpm_mma.cuh, the tcgen05 versions of the row dot products (fpm_corr_mma_kernel, fpm_corr_fused_kernel).
 //
 // All integer work is exact; all double/float epilogues are written op-by-op (the library is
@@ -1478,6 +1478,88 @@ __global__ void fpm_ingest_rgb32_kernel(const uint32_t* __restrict__ px, int spi
     const uint32_t p = px[(size_t)y * spitch_words + x];
     const uint32_t r = (p >> 16) & 255u, g = (p >> 8) & 255u, b = p & 255u;
     dst[(size_t)y * dpitch + x] = (uint8_t)((r * 11u + g * 16u + b * 5u) >> 5);
+}
+
+// JPEG luma blocks -> u8 pixels: dequantisation + libjpeg's accurate integer IDCT (JDCT_ISLOW, jidctint.c: the decoder
+// behind cv::imread, 13-bit constants, 2 extra bits after the column pass, descale by 18 after the row pass) + the
+// post-IDCT range limit (10-bit wrap, +128, clamp).  One thread per 8x8 block; integer-exact, so the frame is bit-identical
+// to cv2.imdecode(IMREAD_GRAYSCALE) (tests/test_ingest.py).  The Huffman decoding happened on the host (fpm_jpeg.h).
+struct FpmJpegQuant { uint16_t q[64]; };
+
+__device__ __forceinline__ void fpm_idct_islow_1d(const int (&in)[8], int (&out)[8], int shift)
+{
+    // even part
+    int z2 = in[2], z3 = in[6];
+    int z1 = (z2 + z3) * 4433;                                       // FIX(0.541196100)
+    int tmp2 = z1 + z3 * -15137;                                     // FIX(1.847759065)
+    int tmp3 = z1 + z2 * 6270;                                       // FIX(0.765366865)
+    int tmp0 = (in[0] + in[4]) << 13, tmp1 = (in[0] - in[4]) << 13;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    // odd part
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * 9633;                                 // FIX(1.175875602)
+    tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;       // FIX(0.298631336, 2.053119869, 3.072711026, 1.501321110)
+    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;            // FIX(0.899976223, 2.562915447, 1.961570560, 0.390180644)
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    const int r = 1 << (shift - 1);
+    out[0] = (tmp10 + tmp3 + r) >> shift; out[7] = (tmp10 - tmp3 + r) >> shift;
+    out[1] = (tmp11 + tmp2 + r) >> shift; out[6] = (tmp11 - tmp2 + r) >> shift;
+    out[2] = (tmp12 + tmp1 + r) >> shift; out[5] = (tmp12 - tmp1 + r) >> shift;
+    out[3] = (tmp13 + tmp0 + r) >> shift; out[4] = (tmp13 - tmp0 + r) >> shift;
+}
+
+__global__ void __launch_bounds__(128)
+fpm_ingest_jpeg_idct_kernel(const int16_t* __restrict__ coef, FpmJpegQuant qt, int bw, int bh, int w, int h,
+                            uint8_t* __restrict__ dst, int dpitch)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bw * bh) return;
+    const int by = b / bw, bx = b - by * bw;
+    const uint4* c4 = reinterpret_cast<const uint4*>(coef + (size_t)b * 64);
+    int ws[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {                                       // row r of the block: 8 coefficients = one 16-byte load
+        const uint4 v = __ldg(c4 + r);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ws[r][2 * k] = (int)(int16_t)(u[k] & 0xffffu) * (int)qt.q[8 * r + 2 * k];
+            ws[r][2 * k + 1] = (int)(int16_t)(u[k] >> 16) * (int)qt.q[8 * r + 2 * k + 1];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {                                       // pass 1: columns, results scaled up by 4
+        int in[8], out[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) in[r] = ws[r][c];
+        fpm_idct_islow_1d(in, out, 13 - 2);
+#pragma unroll
+        for (int r = 0; r < 8; r++) ws[r][c] = out[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {                                       // pass 2: rows, descale, range limit
+        int out[8];
+        fpm_idct_islow_1d(ws[r], out, 13 + 2 + 3);
+        const int y = 8 * by + r;
+        if (y >= h) continue;
+        uint32_t px[2] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            int v = out[c] & 1023;                                      // libjpeg's range_limit table: 10-bit wrap,
+            v = v >= 512 ? v - 1024 : v;                                // signed, centre 128, clamp
+            v = min(255, max(0, v + 128));
+            px[c >> 2] |= (uint32_t)v << (8 * (c & 3));
+        }
+        uint8_t* o = dst + (size_t)y * dpitch + 8 * bx;
+        if (8 * bx + 8 <= w) {
+            *reinterpret_cast<uint2*>(o) = make_uint2(px[0], px[1]);    // dpitch is a multiple of 128
+        } else {
+            for (int c = 0; c < 8 && 8 * bx + c < w; c++) o[c] = (uint8_t)(px[c >> 2] >> (8 * (c & 3)));
+        }
+    }
 }
 
 // top <= stop layer: the top-layer picks are final (src/TemplateMatcher.cpp:272-276)

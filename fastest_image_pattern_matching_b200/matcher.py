@@ -156,6 +156,21 @@ class TemplateMatcher:
         self._ingest_shape = (h.value, w.value)
         return w.value, h.value
 
+    def _ingest_file(self, fn, file_bytes) -> tuple:
+        b = np.frombuffer(bytes(file_bytes), np.uint8) if not isinstance(file_bytes, np.ndarray) else np.ascontiguousarray(file_bytes, np.uint8)
+        w, h = C.c_int(0), C.c_int(0)
+        self._check(fn(self._h, b.ctypes.data, b.size, C.byref(w), C.byref(h)))
+        self._ingest_shape = (h.value, w.value)
+        return w.value, h.value
+
+    def ingestJpeg(self, file_bytes) -> tuple:
+        """baseline JPEG file image -> the grayscale frame cv::imread(IMREAD_GRAYSCALE) returns (luma, ISLOW IDCT on the device)"""
+        return self._ingest_file(self._lib.fpm_ingest_jpeg, file_bytes)
+
+    def ingestImage(self, file_bytes) -> tuple:
+        """BMP or JPEG by signature, like cv::imread"""
+        return self._ingest_file(self._lib.fpm_ingest_image, file_bytes)
+
     def ingestRgb32(self, pixels) -> None:
         """camera frame: [H, W] uint32 0xAARRGGBB (QImage::Format_RGB32) -> device-resident grayscale frame"""
         p = np.ascontiguousarray(pixels, np.uint32)

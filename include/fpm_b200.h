@@ -127,6 +127,13 @@ int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int
  * fpm_match_ingested / fpm_learn_ingested use the last ingested frame as source / template;
  * fpm_ingested_pixels copies it back (width*height bytes). */
 int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
+/* fpm_ingest_jpeg: a baseline / extended-sequential Huffman JPEG file image (8-bit, one scan, grayscale or YCbCr with any chroma
+ * subsampling, restart intervals) -> the frame cv::imread(path, IMREAD_GRAYSCALE) returns, bit for bit (luma only, libjpeg's
+ * ISLOW integer IDCT): the entropy decoding runs on the host, dequantisation + IDCT + range limit on the device.  Progressive,
+ * arithmetic, 12-bit, CMYK / RGB-coded and multi-scan files are rejected with FPM_ERR_INVALID and a message.
+ * fpm_ingest_image: BMP or JPEG by the file's signature, like cv::imread. */
+int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
+int fpm_ingest_image(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
 int fpm_ingest_rgb32(fpm_handle* h, const uint32_t* pixels, int width, int height, int stride_bytes);
 int fpm_ingested_pixels(fpm_handle* h, uint8_t* out);
 int fpm_match_ingested(fpm_handle* h, fpm_result* out, int cap, int* n);
@@ -205,6 +212,10 @@ long long fpm_collective_count(const fpm_handle* h);
 
 /* ---- stage kernels exposed for bit-exact parity tests (host pointers in and out) ---- */
 int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int stride, uint8_t* dst /* ((w+1)/2)*((h+1)/2) */);
+/* host half of fpm_ingest_jpeg alone (no device needed): quantised luma coefficients [bh*bw][64] in natural order + the luma
+   quantisation table; coef may be NULL to query the sizes */
+int fpm_dbg_jpeg_luma(const uint8_t* file, size_t nbytes, int* width, int* height, int* bw, int* bh, uint16_t* quant /* 64 */,
+                      int16_t* coef, size_t coef_capacity, char* err, int err_capacity);
 /* one launch of the two-level pyramid kernel: dst1 = pyrDown(src), dst2 = pyrDown(dst1) (dst2 may be NULL: one level).
    misalign: byte offset of the device copy of src past a 128-byte boundary, also added to its pitch (0 / 8 / 4 / odd select
    the 16- / 8- / 4-byte cp.async and the byte staging paths). */

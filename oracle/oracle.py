@@ -865,6 +865,40 @@ def ingest_bmp(file_bytes):
     return cv2.imdecode(np.frombuffer(bytes(file_bytes), np.uint8), cv2.IMREAD_GRAYSCALE)
 
 
+def ingest_image(file_bytes):
+    """cv::imread(path, IMREAD_GRAYSCALE) of a BMP or JPEG file image (src/MatchToolDialog.cpp:314, :341)."""
+    return cv2.imdecode(np.frombuffer(bytes(file_bytes), np.uint8), cv2.IMREAD_GRAYSCALE)
+
+
+def jpeg_idct_islow(coef, quant):
+    """libjpeg's accurate integer IDCT (jidctint.c jpeg_idct_islow, the JDCT_ISLOW default behind cv::imread) restated in
+    numpy: coef [n, 8, 8] quantised coefficients in natural order, quant [8, 8] -> [n, 8, 8] u8 samples.  Model of the
+    device kernel fpm_ingest_jpeg_idct_kernel; pinned against cv2.imdecode in tests/test_ingest.py."""
+    def pass1d(x, shift):                                   # x [..., 8] along the last axis
+        x = [x[..., k] for k in range(8)]
+        z2, z3 = x[2], x[6]
+        z1 = (z2 + z3) * 4433
+        tmp2 = z1 + z3 * -15137
+        tmp3 = z1 + z2 * 6270
+        tmp0, tmp1 = (x[0] + x[4]) << 13, (x[0] - x[4]) << 13
+        tmp10, tmp13, tmp11, tmp12 = tmp0 + tmp3, tmp0 - tmp3, tmp1 + tmp2, tmp1 - tmp2
+        tmp0, tmp1, tmp2, tmp3 = x[7], x[5], x[3], x[1]
+        z1, z2, z3, z4 = tmp0 + tmp3, tmp1 + tmp2, tmp0 + tmp2, tmp1 + tmp3
+        z5 = (z3 + z4) * 9633
+        tmp0, tmp1, tmp2, tmp3 = tmp0 * 2446, tmp1 * 16819, tmp2 * 25172, tmp3 * 12299
+        z1, z2, z3, z4 = z1 * -7373, z2 * -20995, z3 * -16069 + z5, z4 * -3196 + z5
+        tmp0, tmp1, tmp2, tmp3 = tmp0 + z1 + z3, tmp1 + z2 + z4, tmp2 + z2 + z3, tmp3 + z1 + z4
+        r = 1 << (shift - 1)
+        out = [tmp10 + tmp3, tmp11 + tmp2, tmp12 + tmp1, tmp13 + tmp0, tmp13 - tmp0, tmp12 - tmp1, tmp11 - tmp2, tmp10 - tmp3]
+        return np.stack([(o + r) >> shift for o in out], axis=-1)
+
+    d = np.asarray(coef, np.int64) * np.asarray(quant, np.int64)[None]
+    ws = pass1d(d.transpose(0, 2, 1), 13 - 2).transpose(0, 2, 1)           # pass 1 runs down the columns
+    out = pass1d(ws, 13 + 2 + 3) & 1023                                     # pass 2 along the rows; range_limit: 10-bit wrap
+    out = np.where(out >= 512, out - 1024, out) + 128
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def ingest_rgb32(pixels):
     """QImage::convertToFormat(Format_Grayscale8) of an RGB32 frame: qGray = (R*11 + G*16 + B*5) / 32 (Qt's documented
     formula; parity unpinned -- there is no Qt in this image to run the real conversion)."""

@@ -103,6 +103,10 @@ def main():
         img = cv2.imread(os.path.join(REF, f), cv2.IMREAD_GRAYSCALE)
         assert img is not None, f
         cv2.imwrite(os.path.join(HERE, "images", os.path.splitext(f)[0] + ".png"), img, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+        if f.endswith(".jpg"):                             # the JPEG file images themselves: fixtures of the JPEG ingest path
+            import shutil
+            os.makedirs(os.path.join(HERE, "jpeg"), exist_ok=True)
+            shutil.copyfile(os.path.join(REF, f), os.path.join(HERE, "jpeg", f))
     cases = {}
     for name, (s, t, params) in CASES.items():
         src, tpl = get_image(s), get_image(t)

@@ -57,6 +57,123 @@ def test_oracle_bmp_decode_pins():
     assert np.array_equal(O.ingest_bmp(cv2.imencode(".bmp", src8)[1]), src8)
 
 
+# ---------------- JPEG: Huffman decoding on the host, dequantisation + ISLOW IDCT on the device ----------------
+def _jpeg_cases():
+    rng = np.random.default_rng(21)
+    smooth = cv2.GaussianBlur(rng.integers(0, 256, (203, 317), dtype=np.uint8), (0, 0), 2.5)
+    noisy = rng.integers(0, 256, (64, 80), dtype=np.uint8)
+    col = cv2.GaussianBlur(rng.integers(0, 256, (131, 157, 3), dtype=np.uint8), (0, 0), 1.5)
+    extreme = np.zeros((40, 56), np.uint8)
+    extreme[::2, ::3] = 255                                  # ringing drives the IDCT output past [0, 255]: range limit
+    enc = lambda img, *p: bytes(cv2.imencode(".jpg", img, list(p))[1])
+    Q, SS, RST = cv2.IMWRITE_JPEG_QUALITY, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_RST_INTERVAL
+    return {
+        "gray_q95": enc(smooth, Q, 95),
+        "gray_q30_odd_size": enc(smooth[:201, :315], Q, 30),
+        "gray_noise_q100": enc(noisy, Q, 100),
+        "gray_extreme_q50": enc(extreme, Q, 50),
+        "gray_restart_7": enc(smooth, Q, 80, RST, 7),
+        "color_420": enc(col, Q, 90, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420),
+        "color_444": enc(col, Q, 85, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444),
+        "color_422_restart": enc(col[:130, :151], Q, 75, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, RST, 3),
+        "color_411": enc(col, Q, 60, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411),
+        "tiny_1x1": enc(np.full((1, 1), 77, np.uint8), Q, 90),
+    }
+
+
+def _host_luma(data):
+    """quantised luma coefficients through the library's host-side Huffman decoder (no device involved)"""
+    import ctypes as C
+    from fastest_image_pattern_matching_b200 import _lib as L
+    lib = L.load()
+    buf = np.frombuffer(data, np.uint8)
+    w, h, bw, bh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    quant = np.zeros(64, np.uint16)
+    err = C.create_string_buffer(256)
+    rc = lib.fpm_dbg_jpeg_luma(buf.ctypes.data, buf.size, C.byref(w), C.byref(h), C.byref(bw), C.byref(bh), quant.ctypes.data, None, 0, err, 256)
+    if rc != 0:
+        raise ValueError(err.value.decode())
+    coef = np.zeros((bh.value * bw.value, 8, 8), np.int16)
+    rc = lib.fpm_dbg_jpeg_luma(buf.ctypes.data, buf.size, None, None, None, None, None, coef.ctypes.data, coef.size, err, 256)
+    assert rc == 0
+    return w.value, h.value, bw.value, bh.value, quant.reshape(8, 8), coef
+
+
+@pytest.mark.parametrize("name", sorted(_jpeg_cases()))
+def test_jpeg_host_decoder_and_idct_model_equal_cv2(name):
+    """CPU pin: the library's Huffman decoder + the numpy restatement of libjpeg's ISLOW IDCT reproduce cv2.imdecode
+    (= the reference's cv::imread(IMREAD_GRAYSCALE)) bit for bit; the device kernel is then checked against the same frames"""
+    data = _jpeg_cases()[name]
+    want = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+    w, h, bw, bh, quant, coef = _host_luma(data)
+    assert (h, w) == want.shape
+    px = O.jpeg_idct_islow(coef, quant).reshape(bh, bw, 8, 8).transpose(0, 2, 1, 3).reshape(bh * 8, bw * 8)
+    assert np.array_equal(px[:h, :w], want)
+
+
+@pytest.mark.parametrize("name", ["Src6", "Dst10"])
+def test_jpeg_host_decoder_on_the_references_own_jpeg_files(name):
+    """the two real JPEG files among the reference's Test Images (committed as they are under tests/golden/jpeg by
+    make_golden.py): 4096x3000 grayscale baseline and 54x54 YCbCr 4:2:0"""
+    import os
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg", name + ".jpg"), "rb").read()
+    w, h, bw, bh, quant, coef = _host_luma(data)
+    px = O.jpeg_idct_islow(coef, quant).reshape(bh, bw, 8, 8).transpose(0, 2, 1, 3).reshape(bh * 8, bw * 8)[:h, :w]
+    assert np.array_equal(px, cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE))
+    assert np.array_equal(px, get_image(name))               # the decoded fixture every matching test uses
+
+
+def test_jpeg_host_decoder_rejects_what_it_cannot_decode():
+    rng = np.random.default_rng(5)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (48, 64), dtype=np.uint8), (0, 0), 2)
+    prog = bytes(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1])
+    good = bytes(cv2.imencode(".jpg", img)[1])
+    for bad, word in ((prog, "progressive"), (good[:200], "truncated"), (b"\x89PNG", "not a JPEG")):
+        with pytest.raises(ValueError) as e:
+            _host_luma(bad)
+        assert word in str(e.value), (word, str(e.value))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(_jpeg_cases()))
+def test_gpu_jpeg_ingest_bit_exact(matcher, name):
+    data = _jpeg_cases()[name]
+    want = O.ingest_image(data)
+    w, h = matcher.ingestJpeg(data)
+    assert (h, w) == want.shape
+    assert np.array_equal(matcher.ingestedPixels(), want)
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_image_sniffs_the_signature_and_rejects_progressive(matcher):
+    from fastest_image_pattern_matching_b200 import FpmError
+    for data in (_jpeg_cases()["color_420"], _cases()["bgr24"]):       # cv::imread picks the decoder by signature, not by suffix
+        matcher.ingestImage(data)
+        assert np.array_equal(matcher.ingestedPixels(), O.ingest_image(data))
+    img = np.zeros((16, 16), np.uint8)
+    with pytest.raises(FpmError):
+        matcher.ingestJpeg(bytes(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1]))
+    with pytest.raises(FpmError):
+        matcher.ingestImage(bytes(cv2.imencode(".png", img)[1]))
+
+
+@pytest.mark.gpu
+def test_gpu_jpeg_ingest_of_the_references_own_jpeg_files(matcher, golden_cases):
+    """Src6.jpg (4096x3000 grayscale baseline) and Dst10.jpg (54x54 YCbCr 4:2:0) of the reference's Test Images: the decoded
+    fixtures under tests/golden/images came from cv2.imread of the same files (make_golden.py)"""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg")
+    for name in ("Src6", "Dst10"):
+        path = os.path.join(here, name + ".jpg")
+        if not os.path.exists(path):
+            pytest.skip("JPEG fixture not present")
+        data = open(path, "rb").read()
+        w, h = matcher.ingestImage(data)
+        got = matcher.ingestedPixels()
+        assert np.array_equal(got, O.ingest_image(data))
+        assert np.array_equal(got, get_image(name))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(_cases()))
 def test_gpu_bmp_ingest_bit_exact(matcher, name):
