@@ -150,6 +150,7 @@ struct TopPlan {                  // cached per (source size, parameters); alway
 
 struct fpm_handle {
     int device = 0;
+    int num_sms = 148;             // cudaDevAttrMultiProcessorCount of the device (B200: 148); sizes the wave arithmetic
     cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -464,12 +465,12 @@ bool mma_narrow_fused(const fpm_handle* h, int tw)
 // short (then the row-split kernel is dominated by the 256 B of row dots per (eval, row) that it writes and the
 // finalize kernel reads back), and loses when a level has few evals and long rows.  Measured on B200: a fused CTA
 // streams its ROI patches at ~27 GB/s from HBM; the row-split path moves ~(row + 568) bytes per (eval, row) at ~5 TB/s.
-bool fused_pays(int ne, int rh, int rpitch, int k_bytes, int use_tc)
+bool fused_pays(int ne, int rh, int rpitch, int k_bytes, int use_tc, int num_sms)
 {
     (void)rh; (void)k_bytes;
     if (use_tc == 4) return true;                                     // forced (tests)
     const double m_tiles = (ne + MM_M - 1) / MM_M;
-    const double rounds = ceil(m_tiles / 148.0);
+    const double rounds = ceil(m_tiles / (double)num_sms);
     return m_tiles / rounds > 185.0 * rpitch / (rpitch + 568.0);
 }
 
@@ -513,10 +514,10 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     if (rc) return rc;
     rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
     if (rc) return rc;
-    // at most 2 full waves of 148 SMs (one CTA per SM): a third, nearly empty wave would cost a whole CTA time;
+    // at most 2 full waves of the SMs (148 on B200; one CTA per SM): a third, nearly empty wave would cost a whole CTA time;
     // at least 2 ROI rows per CTA.  With the live count only known on the device (n_cands_dev) `ne` is the top-layer upper
     // bound and nearly all tiles leave at once: the rows are split as if one tile were live.
-    int chunks = std::max(1, (2 * 148) / (n_cands_dev ? 1 : m_tiles));
+    int chunks = std::max(1, (2 * h->num_sms) / (n_cands_dev ? 1 : m_tiles));
     int rows_per_cta = std::max(2, (rh + chunks - 1) / chunks);
     chunks = (rh + rows_per_cta - 1) / rows_per_cta;
     if (!h->mma_attr_set) {                                  // per handle: the attribute is per device
@@ -958,7 +959,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                                                                         FpmRefineGeom{cands + c0, n_ang, step, L.w, L.h, t.w, t.h}));
                 // (the one-CTA-per-128-evals kernel only pays for many LIVE evals: never with an upper-bound count)
                 if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) && (!async || h->use_tc == 4) &&
-                    fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc)) {
+                    fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc, h->num_sms)) {
                     int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
                                                 t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
                     if (rcm) return rcm;
@@ -977,7 +978,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                 }
             }
             {
-                auto fin = fpm_refine_finalize_kernel;
+                // grids that leave most SMs idle (single frames): the deep-prefetch shape of the kernel
+                auto fin = nc <= 2 * h->num_sms ? fpm_refine_finalize_kernel<128, 8, 2> : fpm_refine_finalize_kernel<32, 2, 6>;
                 KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
                    fin<<<nc, RF_THREADS, 0, h->stream>>>(
                        cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,
@@ -1362,6 +1364,7 @@ fpm_handle* fpm_create(int device)
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
     fpm_handle* h = new fpm_handle();
     h->device = device;
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms <= 0) h->num_sms = 148;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -32,6 +32,22 @@ static const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 
 struct HuffTable {
     bool defined = false;
     std::vector<uint16_t> look;        // 16-bit prefix -> (length << 8) | symbol, 0 = invalid code
+    // AC tables: 16-bit prefix -> code AND value bits in one step when both fit the window:
+    // (value + 2048) << 12 | run << 8 | total bits (code + size); 0 = take the two-step path
+    std::vector<uint32_t> fast;
+    void build_fast()
+    {
+        fast.assign(65536, 0);
+        for (uint32_t w = 0; w < 65536; w++) {
+            const uint32_t e = look[w];
+            if (!e) continue;
+            const int len = e >> 8, r = (e >> 4) & 15, sz = e & 15;
+            if (sz == 0 || sz > 11 || len + sz > 16) continue;      // |value| <= 2047: value + 2048 stays a positive 12-bit field
+            int v = (int)((w >> (16 - len - sz)) & ((1u << sz) - 1));
+            if (v < (1 << (sz - 1))) v = v - (1 << sz) + 1;
+            fast[w] = ((uint32_t)(v + 2048) << 12) | ((uint32_t)r << 8) | (uint32_t)(len + sz);
+        }
+    }
     void build(const uint8_t counts[16], const uint8_t* symbols)
     {
         look.assign(65536, 0);
@@ -59,6 +75,16 @@ struct BitReader {
     BitReader(const uint8_t* b, const uint8_t* e) : p(b), end(e) {}
     void fill()
     {
+        // four bytes at once while none of them is 0xFF (no stuffing, no marker): the common case
+        while (nbits <= 32 && !marker && p + 4 <= end) {
+            uint32_t v;
+            memcpy(&v, p, 4);
+            if (((v & 0x7F7F7F7Fu) + 0x01010101u) & v & 0x80808080u) break;
+            v = __builtin_bswap32(v);
+            acc |= (uint64_t)v << (32 - nbits);
+            nbits += 32;
+            p += 4;
+        }
         while (nbits <= 56) {
             uint32_t byte = 0;
             if (!marker && p < end) {
@@ -150,6 +176,7 @@ inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
                 for (int z = 0; z < 16; z++) total += s[k + z];
                 if (total > 256 || k + 16 + total > sl) return "bad DHT segment";
                 (tc ? ac[th] : dc[th]).build(s + k, s + k + 16);
+                if (tc) ac[th].build_fast();
                 k += 16 + total;
             }
         } else if (m == 0xC0 || m == 0xC1) {                             // SOF0 / SOF1
@@ -239,7 +266,17 @@ inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
                         if (sz) pred[c] += extend(br.receive(sz), sz);
                         if (c == 0) blk[0] = (int16_t)pred[c];
                         for (int k = 1; k < 64;) {
-                            e = ha.look[br.peek16()];
+                            const uint32_t w16 = br.peek16();
+                            const uint32_t f = ha.fast[w16];
+                            if (f) {                                     // code + value bits inside the 16-bit window
+                                br.skip(f & 255);
+                                k += (f >> 8) & 15;
+                                if (k > 63) return "corrupt JPEG: coefficient index out of range";
+                                if (c == 0) blk[kZigzag[k]] = (int16_t)((int)(f >> 12) - 2048);
+                                k++;
+                                continue;
+                            }
+                            e = ha.look[w16];
                             if (!e) return "corrupt JPEG: bad Huffman code";
                             br.skip(e >> 8);
                             const int r = (e >> 4) & 15;
