@@ -978,8 +978,7 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                 }
             }
             {
-                // grids that leave most SMs idle (single frames): the deep-prefetch shape of the kernel
-                auto fin = nc <= 2 * h->num_sms ? fpm_refine_finalize_kernel<128, 8, 2> : fpm_refine_finalize_kernel<32, 2, 6>;
+                auto fin = fpm_refine_finalize_kernel;
                 KL(K_FINALIZE, (double)ne * ((double)t.h * FPM_NCELL * 4 + 2.0 * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4),
                    fin<<<nc, RF_THREADS, 0, h->stream>>>(
                        cands + c0, n_ang, step, raw_epad ? h->d_raw.as<int32_t>() : h->d_rowsum.as<int32_t>(), raw_epad,

@@ -1238,11 +1238,7 @@ __device__ void fpm_subpix(const double* sc27 /* [theta][y][x] */, double xm, do
 // =====================================================================================
 #define RF_THREADS 192
 
-// DEPTH = row sums a thread has in flight for the float chain (and 14 * WDEPTH loads of the window pass): the chain is a
-// sequence of memory round trips, th / DEPTH of them.  <32, 2, 6> is the throughput shape (6 CTAs per SM); <128, 8, 2> is for
-// grids that do not fill the GPU anyway (single-frame latency): 5 round trips instead of 18 for a 521-row template.
-template <int DEPTH, int WDEPTH, int MINB>
-__global__ void __launch_bounds__(RF_THREADS, MINB)
+__global__ void __launch_bounds__(RF_THREADS, 6)
 fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double angle_step,
                            const int32_t* __restrict__ rowsum, int raw_epad, const int32_t* __restrict__ rowS,
                            const int32_t* __restrict__ rowQ, FpmTplLevel tpl, int lvl_w, int lvl_h,
@@ -1279,7 +1275,7 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
             long long ts[FPM_NSHIFT], tq[FPM_NSHIFT];
 #pragma unroll
             for (int c = 0; c < FPM_NSHIFT; c++) { ts[c] = 0; tq[c] = 0; }
-#pragma unroll WDEPTH
+#pragma unroll 2
             for (int y = cell; y < rh; y += 64) {
                 int a[FPM_NSHIFT], b[FPM_NSHIFT];
 #pragma unroll
@@ -1346,22 +1342,21 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
             if (use_chain) {
                 float acc = 0.0f;
                 int tr = 0;
-                for (; tr + DEPTH <= th; tr += DEPTH) {
-                    int v[DEPTH];
+                for (; tr + 32 <= th; tr += 32) {
+                    int v[32];
 #pragma unroll
-                    for (int k = 0; k < DEPTH; k++) v[k] = rs[(size_t)(tr + k) * rstride];
+                    for (int k = 0; k < 32; k++) v[k] = rs[(size_t)(tr + k) * rstride];
 #pragma unroll
-                    for (int k = 0; k < DEPTH; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
+                    for (int k = 0; k < 32; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
                 }
-                // the tail in ONE more round trip: rows past the template are not loaded and not added
-                if (tr < th) {
-                    int v[DEPTH];
+                for (; tr + 8 <= th; tr += 8) {
+                    int v[8];
 #pragma unroll
-                    for (int k = 0; k < DEPTH; k++) v[k] = tr + k < th ? rs[(size_t)(tr + k) * rstride] : 0;
+                    for (int k = 0; k < 8; k++) v[k] = rs[(size_t)(tr + k) * rstride];
 #pragma unroll
-                    for (int k = 0; k < DEPTH; k++)
-                        if (tr + k < th) acc = __fadd_rn(acc, __int2float_rn(v[k]));
+                    for (int k = 0; k < 8; k++) acc = __fadd_rn(acc, __int2float_rn(v[k]));
                 }
+                for (; tr < th; tr++) acc = __fadd_rn(acc, __int2float_rn(rs[(size_t)tr * rstride]));
                 numf = acc;
             } else {
                 long long acc = 0;
