@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpm_b200.so")
 SOURCES = ["fpm_host.cu"]
-HEADERS = ["fpm_common.cuh", "fpm_geometry.cuh", "fpm_kernels.cuh", "fpm_mma.cuh"]
+HEADERS = ["fpm_common.cuh", "fpm_geometry.cuh", "fpm_kernels.cuh", "fpm_pyrdown.cuh", "fpm_mma.cuh", "fpm_fused.cuh", "fpm_jpeg.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",

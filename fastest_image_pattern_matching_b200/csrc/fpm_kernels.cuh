@@ -68,6 +68,34 @@ __device__ __forceinline__ FpmWarpJob fpm_refine_job(const FpmCand& c, int j, in
     return jb;
 }
 
+// hot loop of fpm_warp_kernel: the rows warp, warp + 8, ... of one job's tile; SWC = pitch of the staged box in bytes
+template <int SWC>
+__device__ __forceinline__ void fpm_warp_rows(uint32_t sbase, const int (&adj)[WA_PX], const int (&bdj)[WA_PX], const int* pX0,
+                                              const int* pY0, uint8_t* __restrict__ drow, size_t dstep, int warp, int nrows)
+{
+#pragma unroll 2
+    for (int row = warp; row < nrows; row += WA_THREADS / 32, drow += dstep, pX0 += WA_THREADS / 32, pY0 += WA_THREADS / 32) {
+        const int X0 = *pX0, Y0 = *pY0;
+        int v[WA_PX];
+#pragma unroll
+        for (int k = 0; k < WA_PX; k++) {
+            const int XX = X0 + adj[k], YY = Y0 + bdj[k];
+            const int fx = XX & 0x3e0, fy = YY & 0x3e0;
+            const uint32_t a = sbase + (uint32_t)((YY >> 10) * SWC + (XX >> 10));
+            int p00, p01, p10, p11;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a));
+            asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(a));
+            asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(p10) : "r"(a), "n"(SWC));
+            asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(p11) : "r"(a), "n"(SWC + 1));
+            const int top = (p00 << 10) + fx * (p01 - p00);
+            const int dif = (p10 << 10) - top + fx * (p11 - p10);
+            v[k] = ((top << 10) + (512 << 10) + fy * dif) >> 20;
+        }
+#pragma unroll
+        for (int k = 0; k < WA_PX; k++) drow[32 * k] = (uint8_t)v[k];
+    }
+}
+
 __global__ void __launch_bounds__(WA_THREADS)
 fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs_g, int group, FpmLevel src, uint8_t* __restrict__ dst,
                 int dpitch, size_t dst_job_stride, int border, int tiles_x, int vec_ok, const int* __restrict__ n_groups_dev,
@@ -192,27 +220,9 @@ fpm_warp_kernel(const FpmWarpJob* __restrict__ jobs_g, int group, FpmLevel src, 
             const size_t dstep = (size_t)(WA_THREADS / 32) * dpitch;
             const int* pX0 = &s_X0[j][warp];
             const int* pY0 = &s_Y0[j][warp];
-#pragma unroll 2
-            for (int row = warp; row < nrows; row += WA_THREADS / 32, drow += dstep, pX0 += WA_THREADS / 32, pY0 += WA_THREADS / 32) {
-                const int X0 = *pX0, Y0 = *pY0;
-                int v[WA_PX];
-#pragma unroll
-                for (int k = 0; k < WA_PX; k++) {
-                    const int XX = X0 + adj[k], YY = Y0 + bdj[k];
-                    const int fx = XX & 0x3e0, fy = YY & 0x3e0;
-                    const uint32_t a = sbase + (uint32_t)((YY >> 10) * SW + (XX >> 10)), a2 = a + SW;
-                    int p00, p01, p10, p11;
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(a));
-                    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(a));
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(a2));
-                    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p11) : "r"(a2));
-                    const int top = (p00 << 10) + fx * (p01 - p00);
-                    const int dif = (p10 << 10) - top + fx * (p11 - p10);
-                    v[k] = ((top << 10) + (512 << 10) + fy * dif) >> 20;
-                }
-#pragma unroll
-                for (int k = 0; k < WA_PX; k++) drow[32 * k] = (uint8_t)v[k];
-            }
+            // the pitch as a compile-time constant: the second row's taps become immediate offsets of the first row's address
+            if (SW == 260) fpm_warp_rows<260>(sbase, adj, bdj, pX0, pY0, drow, dstep, warp, nrows);
+            else fpm_warp_rows<252>(sbase, adj, bdj, pX0, pY0, drow, dstep, warp, nrows);
         }
         return;
     }
