@@ -171,6 +171,9 @@ struct fpm_handle {
     double tol_r[4] = {0, 0, 0, 0};
     int mfc_compat = 0;            // 1: MFC result convention (angle sign/wrap, TargetNum truncation, double corners)
     int async_descent = -1;        // FPM_PARAM_ASYNC_DESCENT: -1 auto (batches < 8 frames), 0 never, 1 always
+    int jpeg_device_huffman = 1;   // FPM_PARAM_JPEG_DEVICE_HUFFMAN
+    int jpeg_passes = 0;           // synchronisation passes of the last device-decoded JPEG scan (0: decoded on the host)
+    DevBuf d_jpeg;                 // unstuffed scan, tables, decoder states, DC values
     int cur_batch = 1;             // frames of the match in flight
     bool err_check_pending = false;
     int use_tc = 1;                // 0 = dp4a only, 1 = tcgen05 for large levels, 2 = tcgen05 wherever possible
@@ -1397,6 +1400,7 @@ void fpm_destroy(fpm_handle* h)
                       &h->d_dbg[0], &h->d_dbg[1], &h->d_dbg[2], &h->d_dbg[3]};
     for (DevBuf* b : bufs) b->release();
     h->h_counts.release(); h->h_results.release(); h->h_stage.release();
+    h->d_jpeg.release();
     for (int i = 0; i < 2; i++) { cudaEventDestroy(h->ev_copy[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     prof_collect(h);
@@ -1432,6 +1436,7 @@ int fpm_set_param(fpm_handle* h, int param, double v)
     case FPM_PARAM_SPLIT_BATCH: h->split_batch = (int)v; break;
     case FPM_PARAM_SHARD_UPLOAD: h->shard_upload = v != 0; break;
     case FPM_PARAM_ASYNC_DESCENT: h->async_descent = (int)v; break;
+    case FPM_PARAM_JPEG_DEVICE_HUFFMAN: h->jpeg_device_huffman = v != 0; break;
     case FPM_PARAM_TOLERANCE_RANGE: h->tol_range = v != 0; h->plan.valid = false; break;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         h->tol_r[param - FPM_PARAM_TOLERANCE1] = v; h->plan.valid = false; break;
@@ -1462,6 +1467,8 @@ double fpm_get_param(const fpm_handle* h, int param)
     case FPM_PARAM_SPLIT_BATCH: return h->split_batch;
     case FPM_PARAM_SHARD_UPLOAD: return h->shard_upload;
     case FPM_PARAM_ASYNC_DESCENT: return h->async_descent;
+    case FPM_PARAM_JPEG_DEVICE_HUFFMAN: return h->jpeg_device_huffman;
+    case FPM_PARAM_JPEG_PASSES: return h->jpeg_passes;
     case FPM_PARAM_TOLERANCE_RANGE: return h->tol_range;
     case FPM_PARAM_TOLERANCE1: case FPM_PARAM_TOLERANCE2: case FPM_PARAM_TOLERANCE3: case FPM_PARAM_TOLERANCE4:
         return h->tol_r[param - FPM_PARAM_TOLERANCE1];
@@ -1775,16 +1782,167 @@ int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width
     return FPM_OK;
 }
 
-// JPEG file image -> grayscale frame like cv::imread(path, IMREAD_GRAYSCALE): Huffman decoding on the host (fpm_jpeg.h), the
-// quantised luma coefficients go to the device, dequantisation + IDCT + range limit run there
+// ---- JPEG ingest ------------------------------------------------------------------------------------------------------
+// entropy-coded segment without the 0xFF00 stuffing; stops at the first marker (EOI).  out needs n - begin + 16 bytes; the
+// 16 bytes after the data are zero (the device reader looks a few bytes ahead).  Returns the number of data bytes.
+size_t jpeg_unstuff(const uint8_t* d, size_t n, size_t begin, uint8_t* out)
+{
+    size_t i = begin, o = 0;
+    while (i < n) {
+        const uint8_t* ff = static_cast<const uint8_t*>(memchr(d + i, 0xFF, n - i));
+        const size_t run = ff ? (size_t)(ff - (d + i)) : n - i;
+        memcpy(out + o, d + i, run);
+        o += run; i += run;
+        if (!ff || i + 1 >= n) break;
+        if (d[i + 1] == 0x00) { out[o++] = 0xFF; i += 2; }
+        else if (d[i + 1] == 0xFF) { i++; }                              // fill byte
+        else break;                                                     // a marker: end of the scan
+    }
+    memset(out + o, 0, 16);
+    return o;
+}
+
+// device tables and scan geometry of a parsed frame (fpm_jpeg_par.cuh)
+void jpeg_device_tables(const fpm_jpeg::Frame& fr, JpTable* tabs /* 8 */, JpScan* sc, size_t scan_bytes)
+{
+    for (int t = 0; t < 8; t++) {
+        JpTable& T = tabs[t];
+        memset(&T, 0, sizeof(T));
+        const uint8_t* counts = t < 4 ? fr.dc_counts[t] : fr.ac_counts[t - 4];
+        const uint8_t* syms = t < 4 ? fr.dc_syms[t] : fr.ac_syms[t - 4];
+        if (!(t < 4 ? fr.dc[t].defined : fr.ac[t - 4].defined)) continue;
+        uint32_t code = 0;
+        int k = 0;
+        for (int l = 1; l <= 16; l++) {
+            T.valoff[l] = k - (int)code;
+            for (int i = 0; i < counts[l - 1] && k < 256; i++, k++, code++) {
+                T.sym[k] = syms[k];
+                if (l <= 9 && code < (1u << l))
+                    for (uint32_t j = 0; j < (1u << (9 - l)); j++) T.fast[(code << (9 - l)) + j] = (uint16_t)((l << 8) | syms[k]);
+            }
+            T.limit[l] = std::min<uint32_t>(code, 1u << l) << (16 - l);
+            code <<= 1;
+        }
+    }
+    memset(sc, 0, sizeof(*sc));
+    int slot = 0;
+    for (size_t c = 0; c < fr.comp.size(); c++)
+        for (int b = 0; b < fr.comp[c].h * fr.comp[c].v; b++, slot++) {
+            sc->dc_tab[slot] = fr.comp[c].td;
+            sc->ac_tab[slot] = 4 + fr.comp[c].ta;
+        }
+    sc->nslots = slot;
+    sc->luma_h = fr.comp[0].h; sc->luma_v = fr.comp[0].v; sc->luma_slots = sc->luma_h * sc->luma_v;
+    sc->mcux = fr.mcux; sc->mcuy = fr.mcuy; sc->bw = fr.mcux * fr.comp[0].h;
+    sc->total_blocks = (unsigned)fr.mcux * fr.mcuy * slot;
+    sc->nbits = (unsigned)(scan_bytes * 8);
+    sc->nsub = (int)((sc->nbits + JP_SUB_BITS - 1) / JP_SUB_BITS);
+}
+
+// can the scan be decoded by the parallel decoder?  (no restart intervals, sizes inside its 32-bit bit positions)
+bool jpeg_device_ok(const fpm_jpeg::Frame& fr, size_t file_bytes)
+{
+    int slots = 0;
+    for (auto& c : fr.comp) slots += c.h * c.v;
+    return fr.restart_interval == 0 && slots <= JP_MAX_SLOTS && file_bytes < (400u << 20);
+}
+
+// Huffman decoding on the device: the unstuffed scan + the tables are the only H2D traffic.  Leaves the AC coefficients in
+// d_ingest_raw ([bh*bw][64] int16) and the DC values in scan order in *dcval_out; fills *sc.
+int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* file, size_t nbytes, JpScan* sc_out, const int** dcval_out)
+{
+    const size_t cap = nbytes - fr.scan_begin + 16;
+    const size_t tab_bytes = 8 * sizeof(JpTable);
+    CK(h->h_stage.ensure(align_up(cap, 256) + tab_bytes));
+    uint8_t* hbits = h->h_stage.as<uint8_t>();
+    const size_t scan_bytes = jpeg_unstuff(file, nbytes, fr.scan_begin, hbits);
+    JpTable* htabs = reinterpret_cast<JpTable*>(hbits + align_up(cap, 256));
+    JpScan sc;
+    jpeg_device_tables(fr, htabs, &sc, scan_bytes);
+    if (sc.nsub <= 0) { h->err = "JPEG without image data"; return FPM_ERR_INVALID; }
+    const size_t nluma = (size_t)sc.mcux * sc.mcuy * sc.luma_slots;
+    // device layout: [bits + tables | 3 state arrays | first-block index | DC values | flag]
+    const size_t o_tabs = align_up(cap, 256), o_st = o_tabs + align_up(tab_bytes, 256), st_bytes = align_up((size_t)sc.nsub * sizeof(JpState), 256);
+    const size_t o_first = o_st + 3 * st_bytes, o_dc = o_first + align_up((size_t)sc.nsub * 4, 256), o_flag = o_dc + align_up(nluma * 4, 256);
+    CK(h->d_jpeg.ensure(o_flag + 256));
+    uint8_t* base = h->d_jpeg.as<uint8_t>();
+    const size_t cbytes = nluma * 64 * sizeof(int16_t);
+    CK(h->d_ingest_raw.ensure(cbytes));
+    CK(cudaMemcpyAsync(base, hbits, o_tabs + tab_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_ingest_raw.p, 0, cbytes, h->stream));
+    const uint8_t* bits = base;
+    const JpTable* tabs = reinterpret_cast<const JpTable*>(base + o_tabs);
+    JpState* st[2] = {reinterpret_cast<JpState*>(base + o_st), reinterpret_cast<JpState*>(base + o_st + st_bytes)};
+    JpState* used = reinterpret_cast<JpState*>(base + o_st + 2 * st_bytes);
+    unsigned* first = reinterpret_cast<unsigned*>(base + o_first);
+    int* dcval = reinterpret_cast<int*>(base + o_dc);
+    int* flag = reinterpret_cast<int*>(base + o_flag);
+    const int nb = (sc.nsub + 127) / 128;
+    fpm_jpeg_cold_kernel<<<nb, 128, 0, h->stream>>>(bits, tabs, sc, st[0], used);
+    CKL();
+    int cur = 0, passes = 0;
+    CK(h->h_counts.ensure(256));
+    int* hflag = h->h_counts.as<int>();
+    for (;;) {
+        if (++passes > sc.nsub + 1) { h->err = "JPEG scan did not synchronise"; return FPM_ERR_INVALID; }
+        CK(cudaMemsetAsync(flag, 0, 4, h->stream));
+        fpm_jpeg_sync_kernel<<<nb, 128, 0, h->stream>>>(bits, tabs, sc, st[cur], st[cur ^ 1], used, flag);
+        CKL();
+        cur ^= 1;
+        CK(cudaMemcpyAsync(hflag, flag, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (!*hflag) break;
+    }
+    h->jpeg_passes = passes;
+    fpm_jpeg_block_prefix_kernel<<<1, 1024, 0, h->stream>>>(st[cur], sc.nsub, first);
+    CKL();
+    fpm_jpeg_write_kernel<<<nb, 128, 0, h->stream>>>(bits, tabs, sc, st[cur], first, h->d_ingest_raw.as<int16_t>(), dcval);
+    CKL();
+    fpm_jpeg_dc_kernel<<<1, 1024, 0, h->stream>>>((int)nluma, dcval);
+    CKL();
+    *sc_out = sc;
+    *dcval_out = dcval;
+    return FPM_OK;
+}
+
+// JPEG file image -> grayscale frame like cv::imread(path, IMREAD_GRAYSCALE): luma only, libjpeg's ISLOW IDCT.  Scans without
+// restart intervals are Huffman-decoded on the device (fpm_jpeg_par.cuh: the compressed scan is the only H2D traffic); the
+// others on the host (fpm_jpeg.h), their quantised luma coefficients go to the device.  Dequantisation + IDCT + range limit
+// run on the device in both cases.
 int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height)
 {
     if (!h) return FPM_ERR_INVALID;
     if (!file) { h->err = "null JPEG buffer"; return FPM_ERR_INVALID; }
+    fpm_jpeg::Frame fr;
+    {
+        const std::string why = fpm_jpeg::parse(file, nbytes, &fr);
+        if (!why.empty()) { h->err = why; return FPM_ERR_INVALID; }
+    }
+    if (fr.height > 65535 || fr.width > 65535) { h->err = "JPEG too large"; return FPM_ERR_LIMIT; }
+    if (h->jpeg_device_huffman && jpeg_device_ok(fr, nbytes)) {
+        CK(cudaSetDevice(h->device));
+        JpScan sc;
+        const int* dcval = nullptr;
+        int rc = jpeg_decode_device(h, fr, file, nbytes, &sc, &dcval);
+        if (rc) return rc;
+        const int pitch = (int)align_up(fr.width, 128);
+        CK(h->d_ingest.ensure((size_t)pitch * fr.height));
+        FpmJpegQuant qt;
+        memcpy(qt.q, fr.qt[fr.comp[0].tq], sizeof(qt.q));
+        const int bw = sc.bw, bh = sc.mcuy * sc.luma_v, nblk = bw * bh;
+        fpm_ingest_jpeg_idct_kernel<<<(nblk + 127) / 128, 128, 0, h->stream>>>(h->d_ingest_raw.as<int16_t>(), qt, bw, bh, fr.width, fr.height,
+                                                                               h->d_ingest.as<uint8_t>(), pitch, dcval, sc);
+        CKL();
+        CK(cudaStreamSynchronize(h->stream));
+        h->ingest_w = fr.width; h->ingest_h = fr.height; h->ingest_pitch = pitch;
+        if (width) *width = fr.width;
+        if (height) *height = fr.height;
+        return FPM_OK;
+    }
+    h->jpeg_passes = 0;
     fpm_jpeg::Luma im;
-    const std::string why = fpm_jpeg::decode_luma(file, nbytes, &im);
+    const std::string why = fpm_jpeg::decode_scan_host(fr, file, nbytes, &im);
     if (!why.empty()) { h->err = why; return FPM_ERR_INVALID; }
-    if (im.height > 65535 || im.width > 65535) { h->err = "JPEG too large"; return FPM_ERR_LIMIT; }
     CK(cudaSetDevice(h->device));
     const size_t cbytes = im.coef.size() * sizeof(int16_t);
     CK(h->d_ingest_raw.ensure(cbytes));
@@ -1795,7 +1953,7 @@ int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* widt
     memcpy(qt.q, im.quant, sizeof(qt.q));
     const int nblk = im.bw * im.bh;
     fpm_ingest_jpeg_idct_kernel<<<(nblk + 127) / 128, 128, 0, h->stream>>>(h->d_ingest_raw.as<int16_t>(), qt, im.bw, im.bh, im.width,
-                                                                           im.height, h->d_ingest.as<uint8_t>(), pitch);
+                                                                           im.height, h->d_ingest.as<uint8_t>(), pitch, nullptr, JpScan{});
     CKL();
     CK(cudaStreamSynchronize(h->stream));                             // the coefficient vector dies with this call
     h->ingest_w = im.width; h->ingest_h = im.height; h->ingest_pitch = pitch;
@@ -1835,6 +1993,50 @@ int fpm_dbg_jpeg_luma(const uint8_t* file, size_t nbytes, int* width, int* heigh
         if (coef_capacity < im.coef.size()) return FPM_ERR_LIMIT;
         memcpy(coef, im.coef.data(), im.coef.size() * sizeof(int16_t));
     }
+    return FPM_OK;
+}
+
+// the PARALLEL decoder (fpm_jpeg_par.cuh) run thread by thread on the CPU, no device: same outputs as fpm_dbg_jpeg_luma;
+// *passes = synchronisation passes it took
+int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef, size_t coef_capacity, int* passes, char* err, int err_capacity)
+{
+    auto fail = [&](const std::string& why) {
+        if (err && err_capacity > 0) { strncpy(err, why.c_str(), err_capacity - 1); err[err_capacity - 1] = 0; }
+        return FPM_ERR_INVALID;
+    };
+    fpm_jpeg::Frame fr;
+    const std::string why = fpm_jpeg::parse(file, nbytes, &fr);
+    if (!why.empty()) return fail(why);
+    if (!jpeg_device_ok(fr, nbytes)) return fail("scan not eligible for the parallel decoder (restart intervals)");
+    std::vector<uint8_t> bits(nbytes - fr.scan_begin + 16);
+    const size_t scan_bytes = jpeg_unstuff(file, nbytes, fr.scan_begin, bits.data());
+    std::vector<JpTable> tabs(8);
+    JpScan sc;
+    jpeg_device_tables(fr, tabs.data(), &sc, scan_bytes);
+    const size_t nluma = (size_t)sc.mcux * sc.mcuy * sc.luma_slots;
+    if (coef_capacity < nluma * 64) return FPM_ERR_LIMIT;
+    memset(coef, 0, nluma * 64 * sizeof(int16_t));
+    std::vector<JpState> st[2] = {std::vector<JpState>(sc.nsub), std::vector<JpState>(sc.nsub)}, used(sc.nsub);
+    for (int i = 0; i < sc.nsub; i++) jp_pass_cold(i, bits.data(), tabs.data(), sc, st[0].data(), used.data());
+    int cur = 0, np = 0;
+    for (;;) {
+        if (++np > sc.nsub + 1) return fail("JPEG scan did not synchronise");
+        int changed = 0;
+        for (int i = 0; i < sc.nsub; i++) jp_pass_sync(i, bits.data(), tabs.data(), sc, st[cur].data(), st[cur ^ 1].data(), used.data(), &changed);
+        cur ^= 1;
+        if (!changed) break;
+    }
+    std::vector<unsigned> first(sc.nsub);
+    unsigned run = 0;
+    for (int i = 0; i < sc.nsub; i++) { first[i] = run; run += st[cur][i].nblk; }
+    std::vector<int> dcval(nluma, 0);
+    for (int i = 0; i < sc.nsub; i++) jp_pass_write(i, bits.data(), tabs.data(), sc, st[cur].data(), first.data(), coef, dcval.data());
+    int acc = 0;
+    const int bh = sc.mcuy * sc.luma_v;
+    for (size_t L = 0; L < nluma; L++) { acc += dcval[L]; dcval[L] = acc; }
+    for (int r = 0; r < bh; r++)
+        for (int c = 0; c < sc.bw; c++) coef[((size_t)r * sc.bw + c) * 64] = (int16_t)dcval[jp_luma_scan_index(sc, r, c)];
+    if (passes) *passes = np;
     return FPM_OK;
 }
 

@@ -132,14 +132,28 @@ struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0; };
 
 inline uint32_t be16(const uint8_t* p) { return ((uint32_t)p[0] << 8) | p[1]; }
 
+// everything the headers say, up to the first byte of the entropy-coded segment
+struct Frame {
+    int width = 0, height = 0;
+    std::vector<Component> comp;       // frame order; comp[0] = luma
+    int hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
+    int restart_interval = 0;
+    uint16_t qt[4][64];                // natural order
+    bool qt_def[4] = {false, false, false, false};
+    uint8_t dc_counts[4][16], ac_counts[4][16], dc_syms[4][256], ac_syms[4][256];   // the DHT specifications as they came
+    HuffTable dc[4], ac[4];            // lookup tables of the sequential host decoder
+    size_t scan_begin = 0;             // offset of the entropy-coded data
+};
+
 // returns "" on success, else what is wrong / unsupported
-inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
+inline std::string parse(const uint8_t* d, size_t n, Frame* f)
 {
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return "not a JPEG file (no SOI)";
-    uint16_t qt[4][64];
-    bool qt_def[4] = {false, false, false, false};
-    HuffTable dc[4], ac[4];
-    std::vector<Component> comp;
+    uint16_t (&qt)[4][64] = f->qt;
+    bool (&qt_def)[4] = f->qt_def;
+    HuffTable (&dc)[4] = f->dc;
+    HuffTable (&ac)[4] = f->ac;
+    std::vector<Component>& comp = f->comp;
     int restart_interval = 0, width = 0, height = 0;
     bool saw_jfif = false, saw_adobe = false, sof = false;
     int adobe_transform = 0;
@@ -177,6 +191,8 @@ inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
                 if (total > 256 || k + 16 + total > sl) return "bad DHT segment";
                 (tc ? ac[th] : dc[th]).build(s + k, s + k + 16);
                 if (tc) ac[th].build_fast();
+                memcpy(tc ? f->ac_counts[th] : f->dc_counts[th], s + k, 16);
+                memcpy(tc ? f->ac_syms[th] : f->dc_syms[th], s + k + 16, total);
                 k += 16 + total;
             }
         } else if (m == 0xC0 || m == 0xC1) {                             // SOF0 / SOF1
@@ -235,9 +251,23 @@ inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
     if (comp[0].h != hmax || comp[0].v != vmax) return "unsupported JPEG: subsampled luma";
     if (!qt_def[comp[0].tq]) return "JPEG frame uses an undefined quantisation table";
     const int mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
-    out->width = width; out->height = height;
+    f->width = width; f->height = height; f->hmax = hmax; f->vmax = vmax; f->mcux = mcux; f->mcuy = mcuy;
+    f->restart_interval = restart_interval;
+    f->scan_begin = i;
+    return "";
+}
+
+// the sequential decoder: Huffman decoding of the whole scan on one host thread
+inline std::string decode_scan_host(const Frame& fr, const uint8_t* d, size_t n, Luma* out)
+{
+    const std::vector<Component>& comp = fr.comp;
+    const HuffTable (&dc)[4] = fr.dc;
+    const HuffTable (&ac)[4] = fr.ac;
+    const int nf = (int)comp.size(), mcux = fr.mcux, mcuy = fr.mcuy, restart_interval = fr.restart_interval;
+    const size_t i = fr.scan_begin;
+    out->width = fr.width; out->height = fr.height;
     out->bw = mcux * comp[0].h; out->bh = mcuy * comp[0].v;
-    memcpy(out->quant, qt[comp[0].tq], sizeof(out->quant));
+    memcpy(out->quant, fr.qt[comp[0].tq], sizeof(out->quant));
     out->coef.assign((size_t)out->bw * out->bh * 64, 0);
 
     BitReader br(d + i, d + n);
@@ -298,6 +328,14 @@ inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
         }
     }
     return "";
+}
+
+inline std::string decode_luma(const uint8_t* d, size_t n, Luma* out)
+{
+    Frame fr;
+    const std::string why = parse(d, n, &fr);
+    if (!why.empty()) return why;
+    return decode_scan_host(fr, d, n, out);
 }
 
 }  // namespace fpm_jpeg

@@ -1,0 +1,272 @@
+// fpm_jpeg_par.cuh -- Huffman decoding of a baseline JPEG scan ON THE DEVICE (the entropy-coded segment is the only H2D
+// traffic of a JPEG ingest: 1.5 MB for the reference's 12 MP Src6.jpg instead of 24 MB of coefficients or 12 MB of pixels).
+//
+// A Huffman stream has no index, but it is self-synchronising: a decoder that starts at a wrong bit falls into step with
+// the true symbol sequence after a few symbols.  The scan (0xFF00 stuffing removed on the host) is cut into sub-sequences
+// of SUB bits, one thread each:
+//   pass 0     every thread decodes its sub-sequence from its first bit as if a block started there and records its EXIT
+//              state: the bit where its last symbol ended (inside the next sub-sequence), the block slot inside the MCU
+//              and the coefficient index it was at, and how many blocks it completed;
+//   pass 1..n  thread i restarts from the exit state of thread i-1 and decodes again; thread 0 is exact from the start, so
+//              the exit states are a fixed point exactly when every thread started from the true state (induction over i).
+//              Self-synchronisation makes that a handful of passes instead of one per sub-sequence; a thread whose entry
+//              state did not change keeps its result;
+//   then       an exclusive scan of the block counts gives every thread the index of its first block; a last pass decodes
+//              once more and writes the coefficients of the luma blocks (DC as differences); a scan over the luma blocks in
+//              scan order turns the DC differences into values.
+// Every phase function is __host__ __device__: fpm_dbg_jpeg_luma_parallel runs the same code thread by thread on the CPU and
+// tests/test_ingest.py checks it against the sequential decoder (fpm_jpeg.h) in the GPU-less container.
+// Not handled here (the caller falls back to the sequential host decoder): restart intervals.
+#pragma once
+#include "fpm_common.cuh"
+
+#define JP_MAX_SLOTS 10            // blocks per MCU (JPEG limit)
+#define JP_SUB_BITS 1024           // sub-sequence length
+
+struct JpTable {                   // one Huffman table: 9-bit direct lookup + canonical search for longer codes
+    uint16_t fast[512];            // (length << 8) | symbol for codes of <= 9 bits, 0 otherwise
+    uint32_t limit[18];            // limit[l]: first 16-bit window that is NOT a code of <= l bits (left-aligned), l = 1..16
+    int32_t valoff[17];            // symbol index = valoff[l] + (window >> (16 - l))
+    uint8_t sym[256];
+};
+
+struct JpScan {
+    int nslots;                                // blocks per MCU
+    int dc_tab[JP_MAX_SLOTS], ac_tab[JP_MAX_SLOTS];   // table index of each slot (into JpTable[8]: 0..3 DC, 4..7 AC)
+    int luma_slots, luma_h, luma_v;            // the first luma_h * luma_v slots are luma blocks
+    int mcux, mcuy, bw;                        // MCUs per row / column, luma blocks per row
+    unsigned total_blocks;                     // blocks of the whole scan
+    unsigned nbits;                            // length of the unstuffed scan in bits
+    int nsub;                                  // sub-sequences
+};
+
+struct JpState {                   // where a decoder stands: next bit, slot in the MCU, next coefficient index; blocks completed
+    unsigned p;
+    unsigned slot_k;               // slot << 8 | k
+    unsigned nblk;
+    unsigned pad;
+};
+
+FPM_HD unsigned jp_peek32(const uint8_t* __restrict__ bits, unsigned p)
+{
+    const uint8_t* b = bits + (p >> 3);
+    const unsigned hi = ((unsigned)b[0] << 24) | ((unsigned)b[1] << 16) | ((unsigned)b[2] << 8) | b[3];
+    const unsigned lo = b[4];
+    const unsigned s = p & 7;
+    return s ? (hi << s) | (lo >> (8 - s)) : hi;
+}
+
+// one symbol of table t at window w (32 bits, left-aligned): code length and symbol; an invalid code (only met while a
+// thread is still out of step) consumes one bit
+FPM_HD void jp_symbol(const JpTable& t, unsigned w, int* len, int* sym)
+{
+    const unsigned f = t.fast[w >> 23];
+    if (f) { *len = (int)(f >> 8); *sym = (int)(f & 255); return; }
+    const unsigned w16 = w >> 16;
+    for (int l = 10; l <= 16; l++)
+        if (w16 < t.limit[l]) {
+            const int idx = t.valoff[l] + (int)(w16 >> (16 - l));
+            *len = l; *sym = t.sym[idx & 255];
+            return;
+        }
+    *len = 1; *sym = 0;
+}
+
+__device__ __constant__ uint8_t jp_zigzag_dev[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+static const uint8_t jp_zigzag_host[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+FPM_HD int jp_zigzag(int k)
+{
+#ifdef __CUDA_ARCH__
+    return jp_zigzag_dev[k];
+#else
+    return jp_zigzag_host[k];
+#endif
+}
+
+// coefficient block of luma block number `slot` of MCU m
+FPM_HD size_t jp_luma_block(const JpScan& sc, unsigned m, int slot)
+{
+    const unsigned my = m / sc.mcux, mx = m - my * sc.mcux;
+    const int sy = slot / sc.luma_h, sx = slot - sy * sc.luma_h;
+    return (size_t)(my * sc.luma_v + sy) * sc.bw + (mx * sc.luma_h + sx);
+}
+
+// Decode from state `in` up to bit p_end (symbols that START before p_end).  WRITE: blk0 = index of the block the run starts
+// in; the AC coefficients of luma blocks go to coef, their DC DIFFERENCES to dcval[scan-order index of the luma block].
+template <bool WRITE>
+FPM_HD JpState jp_run(const uint8_t* __restrict__ bits, const JpTable* __restrict__ tabs, const JpScan& sc, JpState in, unsigned p_end,
+                      unsigned blk0, int16_t* __restrict__ coef, int* __restrict__ dcval)
+{
+    unsigned p = in.p, nblk = 0;
+    int slot = (int)(in.slot_k >> 8), k = (int)(in.slot_k & 255);
+    unsigned blk = blk0;
+    while (p < p_end && (!WRITE || blk < sc.total_blocks)) {
+        const unsigned w = jp_peek32(bits, p);
+        int len, sym;
+        bool done = false;
+        if (k == 0) {
+            jp_symbol(tabs[sc.dc_tab[slot]], w, &len, &sym);
+            const int s = sym & 15;
+            if (WRITE && slot < sc.luma_slots) {
+                int v = 0;
+                if (s) {
+                    v = (int)((w << len) >> (32 - s));
+                    if (v < (1 << (s - 1))) v = v - (1 << s) + 1;
+                }
+                dcval[(size_t)(blk / sc.nslots) * sc.luma_slots + slot] = v;      // scan-order index of the luma block
+            }
+            p += len + s;
+            k = 1;
+        } else {
+            jp_symbol(tabs[sc.ac_tab[slot]], w, &len, &sym);
+            const int r = sym >> 4, s = sym & 15;
+            p += len + s;
+            if (s == 0) {
+                if (r == 15) { k += 16; done = k >= 64; }
+                else done = true;                                            // EOB
+            } else {
+                k += r;
+                if (k < 64) {
+                    if (WRITE && slot < sc.luma_slots) {
+                        int v = (int)((w << len) >> (32 - s));
+                        if (v < (1 << (s - 1))) v = v - (1 << s) + 1;
+                        coef[jp_luma_block(sc, blk / sc.nslots, slot) * 64 + jp_zigzag(k)] = (int16_t)v;
+                    }
+                    k++;
+                }
+                done = k >= 64;
+            }
+        }
+        if (done) {
+            k = 0;
+            slot = slot + 1 == sc.nslots ? 0 : slot + 1;
+            nblk++;
+            blk++;
+        }
+    }
+    JpState out;
+    out.p = p; out.slot_k = ((unsigned)slot << 8) | (unsigned)k; out.nblk = nblk; out.pad = 0;
+    return out;
+}
+
+// ---- the passes, one call per thread ---------------------------------------------------------------------------------
+// pass 0: cold start at the first bit of the sub-sequence
+FPM_HD void jp_pass_cold(int i, const uint8_t* bits, const JpTable* tabs, const JpScan& sc, JpState* exit_state, JpState* entry_used)
+{
+    if (i >= sc.nsub) return;
+    JpState in;
+    in.p = (unsigned)i * JP_SUB_BITS; in.slot_k = 0; in.nblk = 0; in.pad = 0;
+    const unsigned p_end = min((unsigned)(i + 1) * JP_SUB_BITS, sc.nbits);
+    exit_state[i] = jp_run<false>(bits, tabs, sc, in, p_end, 0, nullptr, nullptr);
+    entry_used[i] = in;
+}
+
+// synchronisation pass: start from the previous pass's exit state of the thread before; *changed is raised when an exit
+// state moved.  prev and next are different arrays.
+FPM_HD void jp_pass_sync(int i, const uint8_t* bits, const JpTable* tabs, const JpScan& sc, const JpState* prev, JpState* next,
+                         JpState* entry_used, int* changed)
+{
+    if (i >= sc.nsub) return;
+    if (i == 0) { next[0] = prev[0]; return; }
+    const JpState in = prev[i - 1];
+    const JpState used = entry_used[i];
+    if (in.p == used.p && in.slot_k == used.slot_k) { next[i] = prev[i]; return; }      // same entry, same result
+    const unsigned p_end = min((unsigned)(i + 1) * JP_SUB_BITS, sc.nbits);
+    JpState out;
+    if (in.p >= p_end) { out = in; out.nblk = 0; }                                        // nothing starts in this sub-sequence
+    else out = jp_run<false>(bits, tabs, sc, in, p_end, 0, nullptr, nullptr);
+    entry_used[i] = in;
+    next[i] = out;
+    const JpState old = prev[i];
+    if (out.p != old.p || out.slot_k != old.slot_k || out.nblk != old.nblk) {
+#ifdef __CUDA_ARCH__
+        atomicOr(changed, 1);
+#else
+        *changed = 1;
+#endif
+    }
+}
+
+// final pass: blk_first[i] = blocks completed before sub-sequence i (exclusive scan of the block counts)
+FPM_HD void jp_pass_write(int i, const uint8_t* bits, const JpTable* tabs, const JpScan& sc, const JpState* state, const unsigned* blk_first,
+                          int16_t* coef, int* dcval)
+{
+    if (i >= sc.nsub) return;
+    JpState in;
+    if (i == 0) { in.p = 0; in.slot_k = 0; in.nblk = 0; in.pad = 0; }
+    else in = state[i - 1];
+    const unsigned p_end = min((unsigned)(i + 1) * JP_SUB_BITS, sc.nbits);
+    if (in.p >= p_end) return;
+    jp_run<true>(bits, tabs, sc, in, p_end, blk_first[i], coef, dcval);
+}
+
+// scan-order index (MCU order, slots inside the MCU) of the luma block at block row / column (row, col)
+FPM_HD unsigned jp_luma_scan_index(const JpScan& sc, int row, int col)
+{
+    const int my = row / sc.luma_v, sy = row - my * sc.luma_v, mx = col / sc.luma_h, sx = col - mx * sc.luma_h;
+    return (unsigned)(my * sc.mcux + mx) * sc.luma_slots + (unsigned)(sy * sc.luma_h + sx);
+}
+
+#ifdef __CUDACC__
+__global__ void fpm_jpeg_cold_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, JpState* exit_state, JpState* entry_used)
+{
+    jp_pass_cold(blockIdx.x * blockDim.x + threadIdx.x, bits, tabs, sc, exit_state, entry_used);
+}
+
+__global__ void fpm_jpeg_sync_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, const JpState* prev, JpState* next,
+                                     JpState* entry_used, int* changed)
+{
+    jp_pass_sync(blockIdx.x * blockDim.x + threadIdx.x, bits, tabs, sc, prev, next, entry_used, changed);
+}
+
+__global__ void fpm_jpeg_write_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, const JpState* state, const unsigned* blk_first,
+                                      int16_t* coef, int* dcval)
+{
+    jp_pass_write(blockIdx.x * blockDim.x + threadIdx.x, bits, tabs, sc, state, blk_first, coef, dcval);
+}
+
+// exclusive scan of the block counts by ONE CTA (a few thousand to a few hundred thousand entries): every thread sums a
+// contiguous chunk, the chunk sums are scanned in shared memory, every thread writes its chunk's prefixes
+__global__ void __launch_bounds__(1024)
+fpm_jpeg_block_prefix_kernel(const JpState* __restrict__ state, int n, unsigned* __restrict__ blk_first)
+{
+    __shared__ unsigned s_sum[1024];
+    const int t = threadIdx.x, per = (n + 1023) / 1024, a = min(n, t * per), b = min(n, a + per);
+    unsigned sum = 0;
+    for (int i = a; i < b; i++) sum += state[i].nblk;
+    s_sum[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned v = t >= o ? s_sum[t - o] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    unsigned run = s_sum[t] - sum;
+    for (int i = a; i < b; i++) { blk_first[i] = run; run += state[i].nblk; }
+}
+
+// DC differences -> DC values: inclusive scan of dcval (luma blocks in scan order) in place, one CTA, same scheme
+__global__ void __launch_bounds__(1024)
+fpm_jpeg_dc_kernel(int n, int* __restrict__ dcval)
+{
+    __shared__ int s_sum[1024];
+    const int t = threadIdx.x, per = (n + 1023) / 1024, a = min(n, t * per), b = min(n, a + per);
+    int sum = 0;
+    for (int L = a; L < b; L++) sum += dcval[L];
+    s_sum[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? s_sum[t - o] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    int run = s_sum[t] - sum;
+    for (int L = a; L < b; L++) { run += dcval[L]; dcval[L] = run; }
+}
+#endif

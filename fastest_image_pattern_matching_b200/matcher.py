@@ -365,6 +365,8 @@ class TemplateMatcher:
     # ---- angle-sharded latency mode: one handle per GPU, two NCCL allgathers on device buffers (fpm_match_sharded) ----
     def setShardUpload(self, v: bool): self._set(L.PARAM_SHARD_UPLOAD, 1 if v else 0)
     def setAsyncDescent(self, v: int): self._set(L.PARAM_ASYNC_DESCENT, int(v))
+    def setJpegDeviceHuffman(self, on: bool): self._set(L.PARAM_JPEG_DEVICE_HUFFMAN, 1 if on else 0)
+    def getJpegPasses(self) -> int: return int(self._lib.fpm_get_param(self._h, L.PARAM_JPEG_PASSES))
     def collectiveCount(self) -> int: return int(self._lib.fpm_collective_count(self._h))
 
     def commInit(self, nranks: int, rank: int, unique_id: bytes):

@@ -66,6 +66,9 @@ enum fpm_param {
                                       PCIe link and the slices are allgathered over NVLink; 0 = every rank uploads the whole frame */
     FPM_PARAM_ASYNC_DESCENT = 22,  /* pyramid descent without a host round trip per layer (grids sized to the top-layer candidate count, live
                                       counts read on the device): -1 = automatic (batches of fewer than 8 frames), 0 = never, 1 = always */
+    FPM_PARAM_JPEG_DEVICE_HUFFMAN = 23, /* fpm_ingest_jpeg: 1 (default) = scans without restart intervals are Huffman-decoded on the device (the
+                                           compressed scan is the only H2D traffic), 0 = always on the host */
+    FPM_PARAM_JPEG_PASSES = 24,    /* read-only: synchronisation passes of the last device-decoded JPEG scan (0 = it was decoded on the host) */
     FPM_PARAM_COUNT_
 };
 
@@ -216,6 +219,9 @@ int fpm_dbg_pyrdown(fpm_handle* h, const uint8_t* src, int w, int hgt, int strid
    quantisation table; coef may be NULL to query the sizes */
 int fpm_dbg_jpeg_luma(const uint8_t* file, size_t nbytes, int* width, int* height, int* bw, int* bh, uint16_t* quant /* 64 */,
                       int16_t* coef, size_t coef_capacity, char* err, int err_capacity);
+/* the parallel (device) Huffman decoder of fpm_ingest_jpeg run thread by thread on the CPU: same coefficients as fpm_dbg_jpeg_luma */
+int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef, size_t coef_capacity, int* passes, char* err,
+                               int err_capacity);
 /* one launch of the two-level pyramid kernel: dst1 = pyrDown(src), dst2 = pyrDown(dst1) (dst2 may be NULL: one level).
    misalign: byte offset of the device copy of src past a 128-byte boundary, also added to its pitch (0 / 8 / 4 / odd select
    the 16- / 8- / 4-byte cp.async and the byte staging paths). */

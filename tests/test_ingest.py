@@ -123,6 +123,36 @@ def test_jpeg_host_decoder_on_the_references_own_jpeg_files(name):
     assert np.array_equal(px, get_image(name))               # the decoded fixture every matching test uses
 
 
+def _parallel_luma(data, shape):
+    import ctypes as C
+    from fastest_image_pattern_matching_b200 import _lib as L
+    lib = L.load()
+    buf = np.frombuffer(data, np.uint8)
+    out = np.zeros(shape, np.int16)
+    passes, err = C.c_int(), C.create_string_buffer(256)
+    rc = lib.fpm_dbg_jpeg_luma_parallel(buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(passes), err, 256)
+    if rc != 0:
+        raise ValueError(err.value.decode())
+    return out, passes.value
+
+
+@pytest.mark.parametrize("name", sorted(_jpeg_cases()) + ["Src6", "Dst10"])
+def test_parallel_huffman_decoder_equals_the_sequential_one(name):
+    """the device Huffman decoder (self-synchronising sub-sequences, fpm_jpeg_par.cuh) run thread by thread on the CPU:
+    the same quantised coefficients as the sequential host decoder, which is pinned against cv2 above"""
+    import os
+    data = _jpeg_cases()[name] if name in _jpeg_cases() else \
+        open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg", name + ".jpg"), "rb").read()
+    w, h, bw, bh, quant, coef = _host_luma(data)
+    if "restart" in name:
+        with pytest.raises(ValueError):                       # restart intervals stay with the host decoder
+            _parallel_luma(data, coef.shape)
+        return
+    got, passes = _parallel_luma(data, coef.shape)
+    assert np.array_equal(got, coef)
+    assert 1 <= passes <= 64, passes
+
+
 def test_jpeg_host_decoder_rejects_what_it_cannot_decode():
     rng = np.random.default_rng(5)
     img = cv2.GaussianBlur(rng.integers(0, 256, (48, 64), dtype=np.uint8), (0, 0), 2)
@@ -142,6 +172,22 @@ def test_gpu_jpeg_ingest_bit_exact(matcher, name):
     w, h = matcher.ingestJpeg(data)
     assert (h, w) == want.shape
     assert np.array_equal(matcher.ingestedPixels(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["gray_q95", "gray_noise_q100", "color_420", "color_411", "gray_restart_7"])
+def test_gpu_jpeg_huffman_on_the_device_and_on_the_host_agree(matcher, name):
+    data = _jpeg_cases()[name]
+    want = O.ingest_image(data)
+    matcher.setJpegDeviceHuffman(True)
+    matcher.ingestJpeg(data)
+    assert np.array_equal(matcher.ingestedPixels(), want)
+    assert (matcher.getJpegPasses() > 0) == ("restart" not in name)       # restart intervals fall back to the host decoder
+    matcher.setJpegDeviceHuffman(False)
+    matcher.ingestJpeg(data)
+    assert np.array_equal(matcher.ingestedPixels(), want)
+    assert matcher.getJpegPasses() == 0
+    matcher.setJpegDeviceHuffman(True)
 
 
 @pytest.mark.gpu
