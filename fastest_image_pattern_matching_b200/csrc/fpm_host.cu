@@ -1848,8 +1848,10 @@ bool jpeg_device_ok(const fpm_jpeg::Frame& fr, size_t file_bytes)
 }
 
 // Huffman decoding on the device: the unstuffed scan + the tables are the only H2D traffic.  Leaves the AC coefficients in
-// d_ingest_raw ([bh*bw][64] int16) and the DC values in scan order in *dcval_out; fills *sc.
-int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* file, size_t nbytes, JpScan* sc_out, const int** dcval_out)
+// d_ingest_raw ([bh*bw][64] int16), the DC values in scan order in *dcval_out (each short of its 4096-value tile's offset
+// (*tile_off_out)[L / 4096]); fills *sc.
+int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* file, size_t nbytes, JpScan* sc_out, const int** dcval_out,
+                       const int** tile_off_out)
 {
     const size_t cap = nbytes - fr.scan_begin + 16;
     const size_t tab_bytes = 8 * sizeof(JpTable);
@@ -1863,7 +1865,10 @@ int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* 
     const size_t nluma = (size_t)sc.mcux * sc.mcuy * sc.luma_slots;
     // device layout: [bits + tables | 3 state arrays | first-block index | DC values | flag]
     const size_t o_tabs = align_up(cap, 256), o_st = o_tabs + align_up(tab_bytes, 256), st_bytes = align_up((size_t)sc.nsub * sizeof(JpState), 256);
-    const size_t o_first = o_st + 3 * st_bytes, o_dc = o_first + align_up((size_t)sc.nsub * 4, 256), o_flag = o_dc + align_up(nluma * 4, 256);
+    const int ntiles = (int)((nluma + JP_DC_TILE - 1) / JP_DC_TILE);
+    const size_t o_first = o_st + 3 * st_bytes, o_dc = o_first + align_up((size_t)sc.nsub * 4, 256), o_tile = o_dc + align_up(nluma * 4, 256);
+    const int nbtiles = (sc.nsub + 4095) / 4096;
+    const size_t o_btile = o_tile + align_up((size_t)ntiles * 4, 256), o_flag = o_btile + align_up((size_t)nbtiles * 4, 256);
     CK(h->d_jpeg.ensure(o_flag + 256));
     uint8_t* base = h->d_jpeg.as<uint8_t>();
     const size_t cbytes = nluma * 64 * sizeof(int16_t);
@@ -1877,31 +1882,43 @@ int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* 
     unsigned* first = reinterpret_cast<unsigned*>(base + o_first);
     int* dcval = reinterpret_cast<int*>(base + o_dc);
     int* flag = reinterpret_cast<int*>(base + o_flag);
-    const int nb = (sc.nsub + 127) / 128;
-    fpm_jpeg_cold_kernel<<<nb, 128, 0, h->stream>>>(bits, tabs, sc, st[0], used);
+    int* tile_off = reinterpret_cast<int*>(base + o_tile);
+    const int nb = (sc.nsub + JP_THREADS - 1) / JP_THREADS;
+    fpm_jpeg_cold_kernel<<<nb, JP_THREADS, 0, h->stream>>>(bits, tabs, sc, st[0], used);
     CKL();
+    // synchronisation passes, two per flag read-back (a pass in which no entry state moved costs a few microseconds: its CTAs
+    // leave before they stage anything)
     int cur = 0, passes = 0;
     CK(h->h_counts.ensure(256));
     int* hflag = h->h_counts.as<int>();
     for (;;) {
-        if (++passes > sc.nsub + 1) { h->err = "JPEG scan did not synchronise"; return FPM_ERR_INVALID; }
-        CK(cudaMemsetAsync(flag, 0, 4, h->stream));
-        fpm_jpeg_sync_kernel<<<nb, 128, 0, h->stream>>>(bits, tabs, sc, st[cur], st[cur ^ 1], used, flag);
-        CKL();
-        cur ^= 1;
-        CK(cudaMemcpyAsync(hflag, flag, 4, cudaMemcpyDeviceToHost, h->stream));
+        if (passes > sc.nsub + 2) { h->err = "JPEG scan did not synchronise"; return FPM_ERR_INVALID; }
+        CK(cudaMemsetAsync(flag, 0, 8, h->stream));
+        for (int k = 0; k < 2; k++) {
+            fpm_jpeg_sync_kernel<<<nb, JP_THREADS, 0, h->stream>>>(bits, tabs, sc, st[cur], st[cur ^ 1], used, flag + k);
+            CKL();
+            cur ^= 1;
+        }
+        CK(cudaMemcpyAsync(hflag, flag, 8, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        if (!*hflag) break;
+        passes += hflag[0] ? 2 : 1;                                   // passes that did work (+ the one that found the fixed point)
+        if (!hflag[1]) break;
     }
     h->jpeg_passes = passes;
-    fpm_jpeg_block_prefix_kernel<<<1, 1024, 0, h->stream>>>(st[cur], sc.nsub, first);
+    int* btile_off = reinterpret_cast<int*>(base + o_btile);
+    fpm_jpeg_block_tile_kernel<<<nbtiles, 256, 0, h->stream>>>(st[cur], sc.nsub, first, btile_off);
     CKL();
-    fpm_jpeg_write_kernel<<<nb, 128, 0, h->stream>>>(bits, tabs, sc, st[cur], first, h->d_ingest_raw.as<int16_t>(), dcval);
+    fpm_jpeg_dc_offsets_kernel<<<1, 1024, 0, h->stream>>>(nbtiles, btile_off);
     CKL();
-    fpm_jpeg_dc_kernel<<<1, 1024, 0, h->stream>>>((int)nluma, dcval);
+    fpm_jpeg_write_kernel<<<nb, JP_THREADS, 0, h->stream>>>(bits, tabs, sc, st[cur], first, btile_off, h->d_ingest_raw.as<int16_t>(), dcval);
+    CKL();
+    fpm_jpeg_dc_tile_kernel<<<ntiles, 256, 0, h->stream>>>((int)nluma, dcval, tile_off);
+    CKL();
+    fpm_jpeg_dc_offsets_kernel<<<1, 1024, 0, h->stream>>>(ntiles, tile_off);
     CKL();
     *sc_out = sc;
     *dcval_out = dcval;
+    *tile_off_out = tile_off;
     return FPM_OK;
 }
 
@@ -1922,8 +1939,8 @@ int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* widt
     if (h->jpeg_device_huffman && jpeg_device_ok(fr, nbytes)) {
         CK(cudaSetDevice(h->device));
         JpScan sc;
-        const int* dcval = nullptr;
-        int rc = jpeg_decode_device(h, fr, file, nbytes, &sc, &dcval);
+        const int *dcval = nullptr, *tile_off = nullptr;
+        int rc = jpeg_decode_device(h, fr, file, nbytes, &sc, &dcval, &tile_off);
         if (rc) return rc;
         const int pitch = (int)align_up(fr.width, 128);
         CK(h->d_ingest.ensure((size_t)pitch * fr.height));
@@ -1931,7 +1948,7 @@ int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* widt
         memcpy(qt.q, fr.qt[fr.comp[0].tq], sizeof(qt.q));
         const int bw = sc.bw, bh = sc.mcuy * sc.luma_v, nblk = bw * bh;
         fpm_ingest_jpeg_idct_kernel<<<(nblk + 127) / 128, 128, 0, h->stream>>>(h->d_ingest_raw.as<int16_t>(), qt, bw, bh, fr.width, fr.height,
-                                                                               h->d_ingest.as<uint8_t>(), pitch, dcval, sc);
+                                                                               h->d_ingest.as<uint8_t>(), pitch, dcval, tile_off, sc);
         CKL();
         CK(cudaStreamSynchronize(h->stream));
         h->ingest_w = fr.width; h->ingest_h = fr.height; h->ingest_pitch = pitch;
@@ -1953,7 +1970,7 @@ int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* widt
     memcpy(qt.q, im.quant, sizeof(qt.q));
     const int nblk = im.bw * im.bh;
     fpm_ingest_jpeg_idct_kernel<<<(nblk + 127) / 128, 128, 0, h->stream>>>(h->d_ingest_raw.as<int16_t>(), qt, im.bw, im.bh, im.width,
-                                                                           im.height, h->d_ingest.as<uint8_t>(), pitch, nullptr, JpScan{});
+                                                                           im.height, h->d_ingest.as<uint8_t>(), pitch, nullptr, nullptr, JpScan{});
     CKL();
     CK(cudaStreamSynchronize(h->stream));                             // the coefficient vector dies with this call
     h->ingest_w = im.width; h->ingest_h = im.height; h->ingest_pitch = pitch;
@@ -2017,12 +2034,13 @@ int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef
     if (coef_capacity < nluma * 64) return FPM_ERR_LIMIT;
     memset(coef, 0, nluma * 64 * sizeof(int16_t));
     std::vector<JpState> st[2] = {std::vector<JpState>(sc.nsub), std::vector<JpState>(sc.nsub)}, used(sc.nsub);
-    for (int i = 0; i < sc.nsub; i++) jp_pass_cold(i, bits.data(), tabs.data(), sc, st[0].data(), used.data());
+    const JpBytes src{bits.data()};
+    for (int i = 0; i < sc.nsub; i++) jp_pass_cold(i, src, tabs.data(), sc, st[0].data(), used.data());
     int cur = 0, np = 0;
     for (;;) {
         if (++np > sc.nsub + 1) return fail("JPEG scan did not synchronise");
         int changed = 0;
-        for (int i = 0; i < sc.nsub; i++) jp_pass_sync(i, bits.data(), tabs.data(), sc, st[cur].data(), st[cur ^ 1].data(), used.data(), &changed);
+        for (int i = 0; i < sc.nsub; i++) jp_pass_sync(i, src, tabs.data(), sc, st[cur].data(), st[cur ^ 1].data(), used.data(), &changed);
         cur ^= 1;
         if (!changed) break;
     }
@@ -2030,7 +2048,7 @@ int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef
     unsigned run = 0;
     for (int i = 0; i < sc.nsub; i++) { first[i] = run; run += st[cur][i].nblk; }
     std::vector<int> dcval(nluma, 0);
-    for (int i = 0; i < sc.nsub; i++) jp_pass_write(i, bits.data(), tabs.data(), sc, st[cur].data(), first.data(), coef, dcval.data());
+    for (int i = 0; i < sc.nsub; i++) jp_pass_write(i, src, tabs.data(), sc, st[cur].data(), first.data(), nullptr, coef, dcval.data());
     int acc = 0;
     const int bh = sc.mcuy * sc.luma_v;
     for (size_t L = 0; L < nluma; L++) { acc += dcval[L]; dcval[L] = acc; }

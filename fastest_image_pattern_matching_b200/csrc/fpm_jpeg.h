@@ -189,8 +189,7 @@ inline std::string parse(const uint8_t* d, size_t n, Frame* f)
                 int total = 0;
                 for (int z = 0; z < 16; z++) total += s[k + z];
                 if (total > 256 || k + 16 + total > sl) return "bad DHT segment";
-                (tc ? ac[th] : dc[th]).build(s + k, s + k + 16);
-                if (tc) ac[th].build_fast();
+                (tc ? ac[th] : dc[th]).defined = true;                     // the 64 K-entry lookup tables are built by the host decoder only
                 memcpy(tc ? f->ac_counts[th] : f->dc_counts[th], s + k, 16);
                 memcpy(tc ? f->ac_syms[th] : f->dc_syms[th], s + k + 16, total);
                 k += 16 + total;
@@ -261,8 +260,11 @@ inline std::string parse(const uint8_t* d, size_t n, Frame* f)
 inline std::string decode_scan_host(const Frame& fr, const uint8_t* d, size_t n, Luma* out)
 {
     const std::vector<Component>& comp = fr.comp;
-    const HuffTable (&dc)[4] = fr.dc;
-    const HuffTable (&ac)[4] = fr.ac;
+    HuffTable dc[4], ac[4];
+    for (const Component& c : comp) {
+        if (dc[c.td].look.empty()) dc[c.td].build(fr.dc_counts[c.td], fr.dc_syms[c.td]);
+        if (ac[c.ta].look.empty()) { ac[c.ta].build(fr.ac_counts[c.ta], fr.ac_syms[c.ta]); ac[c.ta].build_fast(); }
+    }
     const int nf = (int)comp.size(), mcux = fr.mcux, mcuy = fr.mcuy, restart_interval = fr.restart_interval;
     const size_t i = fr.scan_begin;
     out->width = fr.width; out->height = fr.height;

@@ -21,7 +21,9 @@
 #include "fpm_common.cuh"
 
 #define JP_MAX_SLOTS 10            // blocks per MCU (JPEG limit)
-#define JP_SUB_BITS 1024           // sub-sequence length
+#define JP_SUB_BITS 512            // sub-sequence length: a thread is a chain of dependent steps, so short sub-sequences (more
+                                   // threads, a few more synchronisation passes) are faster: 83 us per pass at 1024 bits on a 1.5 MB scan
+#define JP_SUB_WORDS (JP_SUB_BITS / 32)
 
 struct JpTable {                   // one Huffman table: 9-bit direct lookup + canonical search for longer codes
     uint16_t fast[512];            // (length << 8) | symbol for codes of <= 9 bits, 0 otherwise
@@ -47,14 +49,32 @@ struct JpState {                   // where a decoder stands: next bit, slot in 
     unsigned pad;
 };
 
-FPM_HD unsigned jp_peek32(const uint8_t* __restrict__ bits, unsigned p)
-{
-    const uint8_t* b = bits + (p >> 3);
-    const unsigned hi = ((unsigned)b[0] << 24) | ((unsigned)b[1] << 16) | ((unsigned)b[2] << 8) | b[3];
-    const unsigned lo = b[4];
-    const unsigned s = p & 7;
-    return s ? (hi << s) | (lo >> (8 - s)) : hi;
-}
+// where the bits come from: a plain byte array (host emulation, global memory) ...
+struct JpBytes {
+    const uint8_t* bits;
+    FPM_HD unsigned peek32(unsigned p) const
+    {
+        const uint8_t* b = bits + (p >> 3);
+        const unsigned hi = ((unsigned)b[0] << 24) | ((unsigned)b[1] << 16) | ((unsigned)b[2] << 8) | b[3];
+        const unsigned lo = b[4];
+        const unsigned s = p & 7;
+        return s ? (hi << s) | (lo >> (8 - s)) : hi;
+    }
+};
+
+// ... or the CTA's chunk in shared memory as big-endian 32-bit words, one pad word after the words of every sub-sequence:
+// the 32 lanes of a warp sit at roughly the same offset of consecutive sub-sequences -- with a power-of-two distance the
+// loads of a warp pile up on a few banks (1024-bit sub-sequences: ONE bank, 3x slower)
+struct JpWords {
+    const uint32_t* words;         // words[k + k / JP_SUB_WORDS] = big-endian word k of the CTA's chunk
+    unsigned bit0;                 // absolute bit position of word 0
+    FPM_HD unsigned peek32(unsigned p) const
+    {
+        const unsigned q = p - bit0, k = q >> 5, s = q & 31;
+        const unsigned w0 = words[k + k / JP_SUB_WORDS], w1 = words[k + 1 + (k + 1) / JP_SUB_WORDS];
+        return s ? (w0 << s) | (w1 >> (32 - s)) : w0;
+    }
+};
 
 // one symbol of table t at window w (32 bits, left-aligned): code length and symbol; an invalid code (only met while a
 // thread is still out of step) consumes one bit
@@ -97,15 +117,22 @@ FPM_HD size_t jp_luma_block(const JpScan& sc, unsigned m, int slot)
 
 // Decode from state `in` up to bit p_end (symbols that START before p_end).  WRITE: blk0 = index of the block the run starts
 // in; the AC coefficients of luma blocks go to coef, their DC DIFFERENCES to dcval[scan-order index of the luma block].
-template <bool WRITE>
-FPM_HD JpState jp_run(const uint8_t* __restrict__ bits, const JpTable* __restrict__ tabs, const JpScan& sc, JpState in, unsigned p_end,
+template <bool WRITE, class Src>
+FPM_HD JpState jp_run(const Src& bits, const JpTable* __restrict__ tabs, const JpScan& sc, JpState in, unsigned p_end,
                       unsigned blk0, int16_t* __restrict__ coef, int* __restrict__ dcval)
 {
     unsigned p = in.p, nblk = 0;
     int slot = (int)(in.slot_k >> 8), k = (int)(in.slot_k & 255);
     unsigned blk = blk0;
+    // where the current block's coefficients go (recomputed when a block ends, not per coefficient: the index arithmetic
+    // divides)
+    size_t cbase = 0, dcidx = 0;
+    if (WRITE && slot < sc.luma_slots && blk < sc.total_blocks) {
+        cbase = jp_luma_block(sc, blk / sc.nslots, slot) * 64;
+        dcidx = (size_t)(blk / sc.nslots) * sc.luma_slots + slot;
+    }
     while (p < p_end && (!WRITE || blk < sc.total_blocks)) {
-        const unsigned w = jp_peek32(bits, p);
+        const unsigned w = bits.peek32(p);
         int len, sym;
         bool done = false;
         if (k == 0) {
@@ -117,7 +144,7 @@ FPM_HD JpState jp_run(const uint8_t* __restrict__ bits, const JpTable* __restric
                     v = (int)((w << len) >> (32 - s));
                     if (v < (1 << (s - 1))) v = v - (1 << s) + 1;
                 }
-                dcval[(size_t)(blk / sc.nslots) * sc.luma_slots + slot] = v;      // scan-order index of the luma block
+                dcval[dcidx] = v;
             }
             p += len + s;
             k = 1;
@@ -134,7 +161,7 @@ FPM_HD JpState jp_run(const uint8_t* __restrict__ bits, const JpTable* __restric
                     if (WRITE && slot < sc.luma_slots) {
                         int v = (int)((w << len) >> (32 - s));
                         if (v < (1 << (s - 1))) v = v - (1 << s) + 1;
-                        coef[jp_luma_block(sc, blk / sc.nslots, slot) * 64 + jp_zigzag(k)] = (int16_t)v;
+                        coef[cbase + jp_zigzag(k)] = (int16_t)v;
                     }
                     k++;
                 }
@@ -146,6 +173,10 @@ FPM_HD JpState jp_run(const uint8_t* __restrict__ bits, const JpTable* __restric
             slot = slot + 1 == sc.nslots ? 0 : slot + 1;
             nblk++;
             blk++;
+            if (WRITE && slot < sc.luma_slots && blk < sc.total_blocks) {
+                cbase = jp_luma_block(sc, blk / sc.nslots, slot) * 64;
+                dcidx = (size_t)(blk / sc.nslots) * sc.luma_slots + slot;
+            }
         }
     }
     JpState out;
@@ -155,7 +186,8 @@ FPM_HD JpState jp_run(const uint8_t* __restrict__ bits, const JpTable* __restric
 
 // ---- the passes, one call per thread ---------------------------------------------------------------------------------
 // pass 0: cold start at the first bit of the sub-sequence
-FPM_HD void jp_pass_cold(int i, const uint8_t* bits, const JpTable* tabs, const JpScan& sc, JpState* exit_state, JpState* entry_used)
+template <class Src>
+FPM_HD void jp_pass_cold(int i, const Src& bits, const JpTable* tabs, const JpScan& sc, JpState* exit_state, JpState* entry_used)
 {
     if (i >= sc.nsub) return;
     JpState in;
@@ -167,7 +199,8 @@ FPM_HD void jp_pass_cold(int i, const uint8_t* bits, const JpTable* tabs, const 
 
 // synchronisation pass: start from the previous pass's exit state of the thread before; *changed is raised when an exit
 // state moved.  prev and next are different arrays.
-FPM_HD void jp_pass_sync(int i, const uint8_t* bits, const JpTable* tabs, const JpScan& sc, const JpState* prev, JpState* next,
+template <class Src>
+FPM_HD void jp_pass_sync(int i, const Src& bits, const JpTable* tabs, const JpScan& sc, const JpState* prev, JpState* next,
                          JpState* entry_used, int* changed)
 {
     if (i >= sc.nsub) return;
@@ -191,9 +224,10 @@ FPM_HD void jp_pass_sync(int i, const uint8_t* bits, const JpTable* tabs, const 
     }
 }
 
-// final pass: blk_first[i] = blocks completed before sub-sequence i (exclusive scan of the block counts)
-FPM_HD void jp_pass_write(int i, const uint8_t* bits, const JpTable* tabs, const JpScan& sc, const JpState* state, const unsigned* blk_first,
-                          int16_t* coef, int* dcval)
+// final pass: blk_first[i] (+ blk_tile_off[i / 4096] when given) = blocks completed before sub-sequence i
+template <class Src>
+FPM_HD void jp_pass_write(int i, const Src& bits, const JpTable* tabs, const JpScan& sc, const JpState* state, const unsigned* blk_first,
+                          const int* blk_tile_off, int16_t* coef, int* dcval)
 {
     if (i >= sc.nsub) return;
     JpState in;
@@ -201,7 +235,7 @@ FPM_HD void jp_pass_write(int i, const uint8_t* bits, const JpTable* tabs, const
     else in = state[i - 1];
     const unsigned p_end = min((unsigned)(i + 1) * JP_SUB_BITS, sc.nbits);
     if (in.p >= p_end) return;
-    jp_run<true>(bits, tabs, sc, in, p_end, blk_first[i], coef, dcval);
+    jp_run<true>(bits, tabs, sc, in, p_end, blk_first[i] + (blk_tile_off ? (unsigned)blk_tile_off[i / 4096] : 0u), coef, dcval);
 }
 
 // scan-order index (MCU order, slots inside the MCU) of the luma block at block row / column (row, col)
@@ -212,52 +246,141 @@ FPM_HD unsigned jp_luma_scan_index(const JpScan& sc, int row, int col)
 }
 
 #ifdef __CUDACC__
-__global__ void fpm_jpeg_cold_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, JpState* exit_state, JpState* entry_used)
-{
-    jp_pass_cold(blockIdx.x * blockDim.x + threadIdx.x, bits, tabs, sc, exit_state, entry_used);
-}
+// A decoder thread is one long chain of dependent loads (window -> table -> next window): out of global memory that is
+// ~1.4 us per symbol with one warp per SM sub-partition.  The CTA therefore stages its 128 sub-sequences (16 KB + the few
+// bytes the last symbol may reach into the next one) and the eight tables (11 KB) in shared memory first.
+#define JP_THREADS 128
+#define JP_CHUNK_BYTES (JP_THREADS * JP_SUB_BITS / 8)
 
-__global__ void fpm_jpeg_sync_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, const JpState* prev, JpState* next,
-                                     JpState* entry_used, int* changed)
-{
-    jp_pass_sync(blockIdx.x * blockDim.x + threadIdx.x, bits, tabs, sc, prev, next, entry_used, changed);
-}
+#define JP_CHUNK_WORDS (JP_CHUNK_BYTES / 4)
+struct JpShared {
+    JpTable tabs[8];
+    JpScan sc;                                                  // indexed by the slot: not from the parameter bank
+    uint32_t words[JP_CHUNK_WORDS + JP_CHUNK_WORDS / JP_SUB_WORDS + 8];
+};
 
-__global__ void fpm_jpeg_write_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, const JpState* state, const unsigned* blk_first,
-                                      int16_t* coef, int* dcval)
+__device__ __forceinline__ JpWords jp_stage(JpShared& sh, const uint8_t* __restrict__ bits, const JpTable* __restrict__ tabs,
+                                            const JpScan& sc)
 {
-    jp_pass_write(blockIdx.x * blockDim.x + threadIdx.x, bits, tabs, sc, state, blk_first, coef, dcval);
-}
-
-// exclusive scan of the block counts by ONE CTA (a few thousand to a few hundred thousand entries): every thread sums a
-// contiguous chunk, the chunk sums are scanned in shared memory, every thread writes its chunk's prefixes
-__global__ void __launch_bounds__(1024)
-fpm_jpeg_block_prefix_kernel(const JpState* __restrict__ state, int n, unsigned* __restrict__ blk_first)
-{
-    __shared__ unsigned s_sum[1024];
-    const int t = threadIdx.x, per = (n + 1023) / 1024, a = min(n, t * per), b = min(n, a + per);
-    unsigned sum = 0;
-    for (int i = a; i < b; i++) sum += state[i].nblk;
-    s_sum[t] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const unsigned v = t >= o ? s_sum[t - o] : 0;
-        __syncthreads();
-        s_sum[t] += v;
-        __syncthreads();
+    const size_t byte0 = (size_t)blockIdx.x * JP_CHUNK_BYTES;
+    const size_t total = (((size_t)sc.nbits + 7) / 8 + 16 + 3) & ~(size_t)3;     // data + the zero padding the host appended
+    const uint32_t* gt = reinterpret_cast<const uint32_t*>(tabs);
+    uint32_t* st = reinterpret_cast<uint32_t*>(sh.tabs);
+    for (int i = threadIdx.x; i < (int)(sizeof(sh.tabs) / 4); i += JP_THREADS) st[i] = gt[i];
+    if (threadIdx.x == 0) sh.sc = sc;
+    const uint32_t* gb = reinterpret_cast<const uint32_t*>(bits + byte0);       // byte0 is a multiple of the chunk size
+    for (int k = threadIdx.x; k < JP_CHUNK_WORDS + 4; k += JP_THREADS) {
+        const uint32_t v = byte0 + 4 * (size_t)k + 4 <= total ? gb[k] : 0u;
+        sh.words[k + k / JP_SUB_WORDS] = __byte_perm(v, 0, 0x0123);
     }
-    unsigned run = s_sum[t] - sum;
-    for (int i = a; i < b; i++) { blk_first[i] = run; run += state[i].nblk; }
+    __syncthreads();
+    JpWords src;
+    src.words = sh.words;
+    src.bit0 = (unsigned)(byte0 * 8);
+    return src;
 }
 
-// DC differences -> DC values: inclusive scan of dcval (luma blocks in scan order) in place, one CTA, same scheme
+__global__ void __launch_bounds__(JP_THREADS)
+fpm_jpeg_cold_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, JpState* exit_state, JpState* entry_used)
+{
+    __shared__ JpShared sh;
+    const JpWords b = jp_stage(sh, bits, tabs, sc);
+    jp_pass_cold(blockIdx.x * JP_THREADS + threadIdx.x, b, sh.tabs, sh.sc, exit_state, entry_used);
+}
+
+__global__ void __launch_bounds__(JP_THREADS)
+fpm_jpeg_sync_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, const JpState* prev, JpState* next,
+                     JpState* entry_used, int* changed)
+{
+    __shared__ JpShared sh;
+    // a CTA whose entry states did not move has nothing to decode: skip the staging too
+    const int i = blockIdx.x * JP_THREADS + threadIdx.x;
+    bool work = false;
+    if (i > 0 && i < sc.nsub) {
+        const JpState in = prev[i - 1], used = entry_used[i];
+        work = in.p != used.p || in.slot_k != used.slot_k;
+    }
+    if (!__syncthreads_or(work)) {
+        if (i < sc.nsub) next[i] = prev[i];
+        return;
+    }
+    const JpWords b = jp_stage(sh, bits, tabs, sc);
+    jp_pass_sync(i, b, sh.tabs, sh.sc, prev, next, entry_used, changed);
+}
+
+__global__ void __launch_bounds__(JP_THREADS)
+fpm_jpeg_write_kernel(const uint8_t* bits, const JpTable* tabs, JpScan sc, const JpState* state, const unsigned* blk_first,
+                      const int* blk_tile_off, int16_t* coef, int* dcval)
+{
+    __shared__ JpShared sh;
+    const JpWords b = jp_stage(sh, bits, tabs, sc);
+    jp_pass_write(blockIdx.x * JP_THREADS + threadIdx.x, b, sh.tabs, sh.sc, state, blk_first, blk_tile_off, coef, dcval);
+}
+
+// Exclusive scan of the block counts: tiles of 4096 sub-sequences by one CTA each (blk_first[i] = blocks before i inside its
+// tile, tile_sum = the tile's total), fpm_jpeg_dc_offsets_kernel scans the totals, the write pass adds its tile's offset.
+__global__ void __launch_bounds__(256)
+fpm_jpeg_block_tile_kernel(const JpState* __restrict__ state, int n, unsigned* __restrict__ blk_first, int* __restrict__ tile_sum)
+{
+    __shared__ int s_warp[8];
+    const int t = threadIdx.x, base = blockIdx.x * 4096 + t * 16;
+    int v[16], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { v[k] = sum; sum += base + k < n ? (int)state[base + k].nblk : 0; }     // exclusive inside the thread
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((t & 31) >= o) inc += u;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < (t >> 5); w++) woff += s_warp[w];
+    const int excl = woff + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        if (base + k < n) blk_first[base + k] = (unsigned)(v[k] + excl);
+    if (t == 255) tile_sum[blockIdx.x] = woff + inc;
+}
+
+// DC differences -> DC values: an inclusive scan over the luma blocks in scan order.  Tiles of 4096 values are scanned in
+// place by one CTA each (fpm_jpeg_dc_tile_kernel), the tile totals by one CTA (fpm_jpeg_dc_offsets_kernel); the IDCT kernel
+// adds the offset of a value's tile when it reads it.
+#define JP_DC_TILE 4096
+__global__ void __launch_bounds__(256)
+fpm_jpeg_dc_tile_kernel(int n, int* __restrict__ dcval, int* __restrict__ tile_sum)
+{
+    __shared__ int s_warp[8];
+    const int t = threadIdx.x, base = blockIdx.x * JP_DC_TILE + t * 16;
+    int v[16], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { v[k] = base + k < n ? dcval[base + k] : 0; sum += v[k]; v[k] = sum; }
+    int inc = sum;                                                       // inclusive scan of the thread totals over the CTA
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((t & 31) >= o) inc += u;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < (t >> 5); w++) woff += s_warp[w];
+    const int excl = woff + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        if (base + k < n) dcval[base + k] = v[k] + excl;
+    if (t == 255) tile_sum[blockIdx.x] = woff + inc;
+}
+
+// exclusive scan of the tile totals in place, one CTA (a 12 MP image has 47 tiles)
 __global__ void __launch_bounds__(1024)
-fpm_jpeg_dc_kernel(int n, int* __restrict__ dcval)
+fpm_jpeg_dc_offsets_kernel(int ntiles, int* __restrict__ tile_sum)
 {
     __shared__ int s_sum[1024];
-    const int t = threadIdx.x, per = (n + 1023) / 1024, a = min(n, t * per), b = min(n, a + per);
+    const int t = threadIdx.x, per = (ntiles + 1023) / 1024, a = min(ntiles, t * per), b = min(ntiles, a + per);
     int sum = 0;
-    for (int L = a; L < b; L++) sum += dcval[L];
+    for (int i = a; i < b; i++) sum += tile_sum[i];
     s_sum[t] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -267,6 +390,6 @@ fpm_jpeg_dc_kernel(int n, int* __restrict__ dcval)
         __syncthreads();
     }
     int run = s_sum[t] - sum;
-    for (int L = a; L < b; L++) { run += dcval[L]; dcval[L] = run; }
+    for (int i = a; i < b; i++) { const int v = tile_sum[i]; tile_sum[i] = run; run += v; }
 }
 #endif

@@ -1522,10 +1522,12 @@ __device__ __forceinline__ void fpm_idct_islow_1d(const int (&in)[8], int (&out)
     out[3] = (tmp13 + tmp0 + r) >> shift; out[4] = (tmp13 - tmp0 + r) >> shift;
 }
 
-// dcval (optional): DC values of the luma blocks in scan order (device Huffman path: fpm_jpeg_par.cuh); else coef[b][0]
+// dcval (optional): DC values of the luma blocks in scan order, each still short of its tile's offset dc_tile_off[L / 4096]
+// (device Huffman path: fpm_jpeg_par.cuh); else coef[b][0]
 __global__ void __launch_bounds__(128)
 fpm_ingest_jpeg_idct_kernel(const int16_t* __restrict__ coef, FpmJpegQuant qt, int bw, int bh, int w, int h,
-                            uint8_t* __restrict__ dst, int dpitch, const int* __restrict__ dcval, JpScan sc)
+                            uint8_t* __restrict__ dst, int dpitch, const int* __restrict__ dcval, const int* __restrict__ dc_tile_off,
+                            JpScan sc)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= bw * bh) return;
@@ -1542,7 +1544,10 @@ fpm_ingest_jpeg_idct_kernel(const int16_t* __restrict__ coef, FpmJpegQuant qt, i
             ws[r][2 * k + 1] = (int)(int16_t)(u[k] >> 16) * (int)qt.q[8 * r + 2 * k + 1];
         }
     }
-    if (dcval) ws[0][0] = dcval[jp_luma_scan_index(sc, by, bx)] * (int)qt.q[0];
+    if (dcval) {
+        const unsigned L = jp_luma_scan_index(sc, by, bx);
+        ws[0][0] = (int)(int16_t)(dcval[L] + dc_tile_off[L / JP_DC_TILE]) * (int)qt.q[0];
+    }
 #pragma unroll
     for (int c = 0; c < 8; c++) {                                       // pass 1: columns, results scaled up by 4
         int in[8], out[8];

@@ -150,7 +150,7 @@ def test_parallel_huffman_decoder_equals_the_sequential_one(name):
         return
     got, passes = _parallel_luma(data, coef.shape)
     assert np.array_equal(got, coef)
-    assert 1 <= passes <= 64, passes
+    assert 1 <= passes <= 128, passes                    # worst fixture: incompressible noise at quality 100
 
 
 def test_jpeg_host_decoder_rejects_what_it_cannot_decode():
