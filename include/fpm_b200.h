@@ -132,7 +132,8 @@ int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int
 int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
 /* fpm_ingest_jpeg: a baseline / extended-sequential Huffman JPEG file image (8-bit, one scan, grayscale or YCbCr with any chroma
  * subsampling, restart intervals) -> the frame cv::imread(path, IMREAD_GRAYSCALE) returns, bit for bit (luma only, libjpeg's
- * ISLOW integer IDCT): the entropy decoding runs on the host, dequantisation + IDCT + range limit on the device.  Progressive,
+ * ISLOW integer IDCT): Huffman decoding (scans without restart intervals; else on the host), dequantisation, IDCT and range
+ * limit run on the device, the compressed scan is the only host-to-device traffic.  Progressive,
  * arithmetic, 12-bit, CMYK / RGB-coded and multi-scan files are rejected with FPM_ERR_INVALID and a message.
  * fpm_ingest_image: BMP or JPEG by the file's signature, like cv::imread. */
 int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
