@@ -15,7 +15,8 @@ order = []
 for r in rows:
     lid = int(r[0])
     if lid not in launches:
-        launches[lid] = {"name": re.sub(r"\(.*", "", r[4]), "grid": r[8]}
+        # "void fpm_pyrdown_kernel<(bool)1>(Pd2Args, ...)" -> "fpm_pyrdown_kernel"
+        launches[lid] = {"name": re.sub(r"[<(].*", "", re.sub(r"^void\s+", "", r[4])), "grid": r[8]}
         order.append(lid)
     launches[lid][r[12]] = float(r[14]) * ({"us": 1.0, "ms": 1000.0, "ns": 0.001, "s": 1e6}.get(r[13], 1.0) if "time" in r[12]
                                               else {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[13], 1.0))
