@@ -1783,11 +1783,14 @@ int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width
 }
 
 // ---- JPEG ingest ------------------------------------------------------------------------------------------------------
-// entropy-coded segment without the 0xFF00 stuffing; stops at the first marker (EOI).  out needs n - begin + 16 bytes; the
-// 16 bytes after the data are zero (the device reader looks a few bytes ahead).  Returns the number of data bytes.
-size_t jpeg_unstuff(const uint8_t* d, size_t n, size_t begin, uint8_t* out)
+enum { FPM_ERR_UNSUPPORTED_LOCAL = -1000 };                             // internal: "take the host decoder instead"
+// entropy-coded segment without the 0xFF00 stuffing and without the RSTn markers (their positions go to rst_bits: first bit of
+// every restart interval + a final sentinel); stops at the first other marker (EOI).  out needs n - begin + 16 bytes; the 16
+// bytes after the data are zero (the device reader looks a few bytes ahead).  Returns the number of data bytes.
+size_t jpeg_unstuff(const uint8_t* d, size_t n, size_t begin, uint8_t* out, std::vector<unsigned>* rst_bits)
 {
     size_t i = begin, o = 0;
+    if (rst_bits) { rst_bits->clear(); rst_bits->push_back(0); }
     while (i < n) {
         const uint8_t* ff = static_cast<const uint8_t*>(memchr(d + i, 0xFF, n - i));
         const size_t run = ff ? (size_t)(ff - (d + i)) : n - i;
@@ -1796,9 +1799,11 @@ size_t jpeg_unstuff(const uint8_t* d, size_t n, size_t begin, uint8_t* out)
         if (!ff || i + 1 >= n) break;
         if (d[i + 1] == 0x00) { out[o++] = 0xFF; i += 2; }
         else if (d[i + 1] == 0xFF) { i++; }                              // fill byte
+        else if (rst_bits && d[i + 1] >= 0xD0 && d[i + 1] <= 0xD7) { rst_bits->push_back((unsigned)(o * 8)); i += 2; }   // RSTn: next interval
         else break;                                                     // a marker: end of the scan
     }
     memset(out + o, 0, 16);
+    if (rst_bits) rst_bits->push_back((unsigned)(o * 8));               // sentinel: rst[nint] = nbits
     return o;
 }
 
@@ -1837,14 +1842,25 @@ void jpeg_device_tables(const fpm_jpeg::Frame& fr, JpTable* tabs /* 8 */, JpScan
     sc->total_blocks = (unsigned)fr.mcux * fr.mcuy * slot;
     sc->nbits = (unsigned)(scan_bytes * 8);
     sc->nsub = (int)((sc->nbits + JP_SUB_BITS - 1) / JP_SUB_BITS);
+    sc->restart_blocks = (unsigned)fr.restart_interval * slot;
+    sc->nint = 1;
+    sc->rst = nullptr;
 }
 
-// can the scan be decoded by the parallel decoder?  (no restart intervals, sizes inside its 32-bit bit positions)
+// number of restart intervals the frame header promises
+int jpeg_expected_intervals(const fpm_jpeg::Frame& fr)
+{
+    if (!fr.restart_interval) return 1;
+    const long long mcus = (long long)fr.mcux * fr.mcuy;
+    return (int)((mcus + fr.restart_interval - 1) / fr.restart_interval);
+}
+
+// can the scan be decoded by the parallel decoder?  (sizes inside its 32-bit bit positions)
 bool jpeg_device_ok(const fpm_jpeg::Frame& fr, size_t file_bytes)
 {
     int slots = 0;
     for (auto& c : fr.comp) slots += c.h * c.v;
-    return fr.restart_interval == 0 && slots <= JP_MAX_SLOTS && file_bytes < (400u << 20);
+    return slots <= JP_MAX_SLOTS && file_bytes < (400u << 20);
 }
 
 // Huffman decoding on the device: the unstuffed scan + the tables are the only H2D traffic.  Leaves the AC coefficients in
@@ -1857,11 +1873,16 @@ int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* 
     const size_t tab_bytes = 8 * sizeof(JpTable);
     CK(h->h_stage.ensure(align_up(cap, 256) + tab_bytes));
     uint8_t* hbits = h->h_stage.as<uint8_t>();
-    const size_t scan_bytes = jpeg_unstuff(file, nbytes, fr.scan_begin, hbits);
+    std::vector<unsigned> rst;
+    const size_t scan_bytes = jpeg_unstuff(file, nbytes, fr.scan_begin, hbits, fr.restart_interval ? &rst : nullptr);
     JpTable* htabs = reinterpret_cast<JpTable*>(hbits + align_up(cap, 256));
     JpScan sc;
     jpeg_device_tables(fr, htabs, &sc, scan_bytes);
     if (sc.nsub <= 0) { h->err = "JPEG without image data"; return FPM_ERR_INVALID; }
+    if (fr.restart_interval) {
+        sc.nint = (int)rst.size() - 1;
+        if (sc.nint != jpeg_expected_intervals(fr)) return FPM_ERR_UNSUPPORTED_LOCAL;     // damaged: the host decoder says what is wrong
+    }
     const size_t nluma = (size_t)sc.mcux * sc.mcuy * sc.luma_slots;
     // device layout: [bits + tables | 3 state arrays | first-block index | DC values | flag]
     const size_t o_tabs = align_up(cap, 256), o_st = o_tabs + align_up(tab_bytes, 256), st_bytes = align_up((size_t)sc.nsub * sizeof(JpState), 256);
@@ -1869,8 +1890,13 @@ int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* 
     const size_t o_first = o_st + 3 * st_bytes, o_dc = o_first + align_up((size_t)sc.nsub * 4, 256), o_tile = o_dc + align_up(nluma * 4, 256);
     const int nbtiles = (sc.nsub + 4095) / 4096;
     const size_t o_btile = o_tile + align_up((size_t)ntiles * 4, 256), o_flag = o_btile + align_up((size_t)nbtiles * 4, 256);
-    CK(h->d_jpeg.ensure(o_flag + 256));
+    const size_t o_rst = o_flag + 256;
+    CK(h->d_jpeg.ensure(o_rst + align_up(rst.size() * 4 + 4, 256)));
     uint8_t* base = h->d_jpeg.as<uint8_t>();
+    if (fr.restart_interval) {
+        CK(cudaMemcpyAsync(base + o_rst, rst.data(), rst.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        sc.rst = reinterpret_cast<const unsigned*>(base + o_rst);
+    }
     const size_t cbytes = nluma * 64 * sizeof(int16_t);
     CK(h->d_ingest_raw.ensure(cbytes));
     CK(cudaMemcpyAsync(base, hbits, o_tabs + tab_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -1936,12 +1962,16 @@ int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* widt
         if (!why.empty()) { h->err = why; return FPM_ERR_INVALID; }
     }
     if (fr.height > 65535 || fr.width > 65535) { h->err = "JPEG too large"; return FPM_ERR_LIMIT; }
-    if (h->jpeg_device_huffman && jpeg_device_ok(fr, nbytes)) {
+    bool on_device = h->jpeg_device_huffman && jpeg_device_ok(fr, nbytes);
+    JpScan sc;
+    const int *dcval = nullptr, *tile_off = nullptr;
+    if (on_device) {
         CK(cudaSetDevice(h->device));
-        JpScan sc;
-        const int *dcval = nullptr, *tile_off = nullptr;
         int rc = jpeg_decode_device(h, fr, file, nbytes, &sc, &dcval, &tile_off);
-        if (rc) return rc;
+        if (rc == FPM_ERR_UNSUPPORTED_LOCAL) on_device = false;          // e.g. a restart marker is missing: host decoder
+        else if (rc) return rc;
+    }
+    if (on_device) {
         const int pitch = (int)align_up(fr.width, 128);
         CK(h->d_ingest.ensure((size_t)pitch * fr.height));
         FpmJpegQuant qt;
@@ -2024,12 +2054,18 @@ int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef
     fpm_jpeg::Frame fr;
     const std::string why = fpm_jpeg::parse(file, nbytes, &fr);
     if (!why.empty()) return fail(why);
-    if (!jpeg_device_ok(fr, nbytes)) return fail("scan not eligible for the parallel decoder (restart intervals)");
+    if (!jpeg_device_ok(fr, nbytes)) return fail("scan not eligible for the parallel decoder");
     std::vector<uint8_t> bits(nbytes - fr.scan_begin + 16);
-    const size_t scan_bytes = jpeg_unstuff(file, nbytes, fr.scan_begin, bits.data());
+    std::vector<unsigned> rst;
+    const size_t scan_bytes = jpeg_unstuff(file, nbytes, fr.scan_begin, bits.data(), fr.restart_interval ? &rst : nullptr);
     std::vector<JpTable> tabs(8);
     JpScan sc;
     jpeg_device_tables(fr, tabs.data(), &sc, scan_bytes);
+    if (fr.restart_interval) {
+        sc.nint = (int)rst.size() - 1;
+        sc.rst = rst.data();
+        if (sc.nint != jpeg_expected_intervals(fr)) return fail("restart markers do not match the frame header");
+    }
     const size_t nluma = (size_t)sc.mcux * sc.mcuy * sc.luma_slots;
     if (coef_capacity < nluma * 64) return FPM_ERR_LIMIT;
     memset(coef, 0, nluma * 64 * sizeof(int16_t));
@@ -2051,7 +2087,12 @@ int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef
     for (int i = 0; i < sc.nsub; i++) jp_pass_write(i, src, tabs.data(), sc, st[cur].data(), first.data(), nullptr, coef, dcval.data());
     int acc = 0;
     const int bh = sc.mcuy * sc.luma_v;
-    for (size_t L = 0; L < nluma; L++) { acc += dcval[L]; dcval[L] = acc; }
+    const size_t seg = sc.restart_blocks ? (size_t)sc.restart_blocks / sc.nslots * sc.luma_slots : 0;
+    for (size_t L = 0; L < nluma; L++) {
+        if (seg && L % seg == 0) acc = 0;                               // the DC prediction restarts with every interval
+        acc += dcval[L];
+        dcval[L] = acc;
+    }
     for (int r = 0; r < bh; r++)
         for (int c = 0; c < sc.bw; c++) coef[((size_t)r * sc.bw + c) * 64] = (int16_t)dcval[jp_luma_scan_index(sc, r, c)];
     if (passes) *passes = np;

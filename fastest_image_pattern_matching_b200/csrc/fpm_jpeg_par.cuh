@@ -16,7 +16,9 @@
 //              scan order turns the DC differences into values.
 // Every phase function is __host__ __device__: fpm_dbg_jpeg_luma_parallel runs the same code thread by thread on the CPU and
 // tests/test_ingest.py checks it against the sequential decoder (fpm_jpeg.h) in the GPU-less container.
-// Not handled here (the caller falls back to the sequential host decoder): restart intervals.
+// Restart intervals are exact entry points: a decoder that reaches the (all-ones, < 8 bits) padding at the end of an interval,
+// or runs over its end while it is out of step, restarts at the first bit of the next interval; the DC differences are then
+// summed per interval.
 #pragma once
 #include "fpm_common.cuh"
 
@@ -40,6 +42,11 @@ struct JpScan {
     unsigned total_blocks;                     // blocks of the whole scan
     unsigned nbits;                            // length of the unstuffed scan in bits
     int nsub;                                  // sub-sequences
+    // restart intervals (DRI): the RSTn markers are removed with the stuffing; rst[r] = first bit of interval r (byte aligned),
+    // rst[nint] = nbits.  restart_blocks = blocks per interval (0: none, then rst is not read)
+    unsigned restart_blocks;
+    int nint;
+    const unsigned* rst;
 };
 
 struct JpState {                   // where a decoder stands: next bit, slot in the MCU, next coefficient index; blocks completed
@@ -124,6 +131,18 @@ FPM_HD JpState jp_run(const Src& bits, const JpTable* __restrict__ tabs, const J
     unsigned p = in.p, nblk = 0;
     int slot = (int)(in.slot_k >> 8), k = (int)(in.slot_k & 255);
     unsigned blk = blk0;
+    // restart interval of p and where the next one starts
+    int ri = 0;
+    unsigned nxt = 0xffffffffu;
+    if (sc.restart_blocks) {
+        int lo = 0, hi = sc.nint;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sc.rst[mid] <= p) lo = mid; else hi = mid;
+        }
+        ri = lo;
+        if (ri + 1 < sc.nint) nxt = sc.rst[ri + 1];
+    }
     // where the current block's coefficients go (recomputed when a block ends, not per coefficient: the index arithmetic
     // divides)
     size_t cbase = 0, dcidx = 0;
@@ -168,15 +187,30 @@ FPM_HD JpState jp_run(const Src& bits, const JpTable* __restrict__ tabs, const J
                 done = k >= 64;
             }
         }
+        bool jump = false;
+        if (nxt != 0xffffffffu) {
+            if (p >= nxt) {
+                jump = true;                                                 // over the end: only a thread out of step gets here
+            } else if (done) {
+                const unsigned rem = nxt - p;                                // the padding of an interval: < 8 bits, all ones
+                jump = rem < 8 && (bits.peek32(p) >> (32 - rem)) == (1u << rem) - 1u;
+            }
+        }
         if (done) {
             k = 0;
             slot = slot + 1 == sc.nslots ? 0 : slot + 1;
             nblk++;
             blk++;
-            if (WRITE && slot < sc.luma_slots && blk < sc.total_blocks) {
-                cbase = jp_luma_block(sc, blk / sc.nslots, slot) * 64;
-                dcidx = (size_t)(blk / sc.nslots) * sc.luma_slots + slot;
-            }
+        }
+        if (jump) {
+            p = nxt; slot = 0; k = 0;
+            ri++;
+            nxt = ri + 1 < sc.nint ? sc.rst[ri + 1] : 0xffffffffu;
+            if (WRITE) blk = (unsigned)ri * sc.restart_blocks;
+        }
+        if ((done || jump) && WRITE && slot < sc.luma_slots && blk < sc.total_blocks) {
+            cbase = jp_luma_block(sc, blk / sc.nslots, slot) * 64;
+            dcidx = (size_t)(blk / sc.nslots) * sc.luma_slots + slot;
         }
     }
     JpState out;

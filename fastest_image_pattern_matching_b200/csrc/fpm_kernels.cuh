@@ -1546,7 +1546,12 @@ fpm_ingest_jpeg_idct_kernel(const int16_t* __restrict__ coef, FpmJpegQuant qt, i
     }
     if (dcval) {
         const unsigned L = jp_luma_scan_index(sc, by, bx);
-        ws[0][0] = (int)(int16_t)(dcval[L] + dc_tile_off[L / JP_DC_TILE]) * (int)qt.q[0];
+        int dc = dcval[L] + dc_tile_off[L / JP_DC_TILE];
+        if (sc.restart_blocks) {                                        // the DC prediction restarts with every interval
+            const unsigned seg = sc.restart_blocks / sc.nslots * sc.luma_slots, s0 = L / seg * seg;
+            if (s0) dc -= dcval[s0 - 1] + dc_tile_off[(s0 - 1) / JP_DC_TILE];
+        }
+        ws[0][0] = (int)(int16_t)dc * (int)qt.q[0];
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) {                                       // pass 1: columns, results scaled up by 4

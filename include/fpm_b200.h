@@ -66,8 +66,8 @@ enum fpm_param {
                                       PCIe link and the slices are allgathered over NVLink; 0 = every rank uploads the whole frame */
     FPM_PARAM_ASYNC_DESCENT = 22,  /* pyramid descent without a host round trip per layer (grids sized to the top-layer candidate count, live
                                       counts read on the device): -1 = automatic (batches of fewer than 8 frames), 0 = never, 1 = always */
-    FPM_PARAM_JPEG_DEVICE_HUFFMAN = 23, /* fpm_ingest_jpeg: 1 (default) = scans without restart intervals are Huffman-decoded on the device (the
-                                           compressed scan is the only H2D traffic), 0 = always on the host */
+    FPM_PARAM_JPEG_DEVICE_HUFFMAN = 23, /* fpm_ingest_jpeg: 1 (default) = the scan is Huffman-decoded on the device (the compressed scan is the
+                                           only H2D traffic), 0 = on the host (sequential; its coefficients are uploaded) */
     FPM_PARAM_JPEG_PASSES = 24,    /* read-only: synchronisation passes of the last device-decoded JPEG scan (0 = it was decoded on the host) */
     FPM_PARAM_COUNT_
 };
@@ -132,8 +132,8 @@ int fpm_ocr_assemble(const double* cx, const double* cy, const char* labels, int
 int fpm_ingest_bmp(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
 /* fpm_ingest_jpeg: a baseline / extended-sequential Huffman JPEG file image (8-bit, one scan, grayscale or YCbCr with any chroma
  * subsampling, restart intervals) -> the frame cv::imread(path, IMREAD_GRAYSCALE) returns, bit for bit (luma only, libjpeg's
- * ISLOW integer IDCT): Huffman decoding (scans without restart intervals; else on the host), dequantisation, IDCT and range
- * limit run on the device, the compressed scan is the only host-to-device traffic.  Progressive,
+ * ISLOW integer IDCT): Huffman decoding, dequantisation, IDCT and range limit run on the device, the compressed scan is the
+ * only host-to-device traffic.  Progressive,
  * arithmetic, 12-bit, CMYK / RGB-coded and multi-scan files are rejected with FPM_ERR_INVALID and a message.
  * fpm_ingest_image: BMP or JPEG by the file's signature, like cv::imread. */
 int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);

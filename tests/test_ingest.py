@@ -78,6 +78,9 @@ def _jpeg_cases():
         "color_422_restart": enc(col[:130, :151], Q, 75, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, RST, 3),
         "color_411": enc(col, Q, 60, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411),
         "tiny_1x1": enc(np.full((1, 1), 77, np.uint8), Q, 90),
+        "gray_restart_1": enc(smooth[:64, :200], Q, 70, RST, 1),          # a restart marker after every MCU
+        "color_420_restart_2": enc(col, Q, 88, SS, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, RST, 2),
+        "gray_flat_restart_3": enc(np.full((40, 120), 128, np.uint8), Q, 90, RST, 3),   # 4-bit blocks: intervals shorter than a byte of padding
     }
 
 
@@ -144,10 +147,6 @@ def test_parallel_huffman_decoder_equals_the_sequential_one(name):
     data = _jpeg_cases()[name] if name in _jpeg_cases() else \
         open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg", name + ".jpg"), "rb").read()
     w, h, bw, bh, quant, coef = _host_luma(data)
-    if "restart" in name:
-        with pytest.raises(ValueError):                       # restart intervals stay with the host decoder
-            _parallel_luma(data, coef.shape)
-        return
     got, passes = _parallel_luma(data, coef.shape)
     assert np.array_equal(got, coef)
     assert 1 <= passes <= 128, passes                    # worst fixture: incompressible noise at quality 100
@@ -175,19 +174,47 @@ def test_gpu_jpeg_ingest_bit_exact(matcher, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["gray_q95", "gray_noise_q100", "color_420", "color_411", "gray_restart_7"])
+@pytest.mark.parametrize("name", ["gray_q95", "gray_noise_q100", "color_420", "color_411", "gray_restart_7", "gray_restart_1",
+                                  "color_420_restart_2", "gray_flat_restart_3"])
 def test_gpu_jpeg_huffman_on_the_device_and_on_the_host_agree(matcher, name):
     data = _jpeg_cases()[name]
     want = O.ingest_image(data)
     matcher.setJpegDeviceHuffman(True)
     matcher.ingestJpeg(data)
     assert np.array_equal(matcher.ingestedPixels(), want)
-    assert (matcher.getJpegPasses() > 0) == ("restart" not in name)       # restart intervals fall back to the host decoder
+    assert matcher.getJpegPasses() > 0                                     # decoded on the device, restart intervals too
     matcher.setJpegDeviceHuffman(False)
     matcher.ingestJpeg(data)
     assert np.array_equal(matcher.ingestedPixels(), want)
     assert matcher.getJpegPasses() == 0
     matcher.setJpegDeviceHuffman(True)
+
+
+@pytest.mark.gpu
+def test_gpu_jpeg_ingest_survives_damaged_scans(matcher):
+    """bytes of the entropy-coded segment overwritten or cut off: the device decoder must neither hang nor fault (an out-of-step
+    thread only ever produces garbage coefficients inside its bounds); the call returns a frame of the right size or an error,
+    and the next good file decodes bit-exactly"""
+    from fastest_image_pattern_matching_b200 import FpmError
+    rng = np.random.default_rng(17)
+    for name in ("gray_q95", "color_420", "gray_restart_7"):
+        good = _jpeg_cases()[name]
+        want = O.ingest_image(good)
+        for trial in range(6):
+            bad = bytearray(good)
+            lo = len(bad) // 2
+            if trial < 4:
+                for pos in rng.integers(lo, len(bad) - 2, 12):
+                    bad[pos] = int(rng.integers(0, 255))                 # never 0xFF: no accidental markers
+            else:
+                bad = bad[:lo + int(rng.integers(0, len(bad) - lo - 2))]     # truncated, no EOI
+            try:
+                w, h = matcher.ingestJpeg(bytes(bad))
+                assert (h, w) == want.shape and matcher.ingestedPixels().shape == want.shape
+            except FpmError:
+                pass
+        matcher.ingestJpeg(good)
+        assert np.array_equal(matcher.ingestedPixels(), want)
 
 
 @pytest.mark.gpu
