@@ -16,6 +16,8 @@
 #define FPM_ROI_PAD 6                               // getRotatedROI: size + 6 (TemplateMatcher.cpp:1079)
 #define FPM_NSHIFT 7                                // 7x7 score patch per refinement eval
 #define FPM_NCELL 49
+#define FPM_WSTRIDE 8                               // ints per (eval, ROI row) record of the window row sums rowS / rowQ: the 7 shifts + 1 pad
+                                                    // = one aligned 32-byte sector, written and read with two 128-bit accesses
 
 #define FPM_HD __host__ __device__ __forceinline__
 

@@ -421,8 +421,8 @@ fpm_corr_warp_kernel(const FpmWarpJob* __restrict__ jobs, int n_cands, FpmLevel 
             for (int r = 0; r < FW_R; r++) {
                 if (r >= nrows) break;
                 int sc = (int)s0[r], qc = (int)q0[r];
-                int32_t* ps = rowS + ((size_t)e * rh + (y0 + r)) * FPM_NSHIFT;
-                int32_t* pq = rowQ + ((size_t)e * rh + (y0 + r)) * FPM_NSHIFT;
+                int32_t* ps = rowS + ((size_t)e * rh + (y0 + r)) * FPM_WSTRIDE;
+                int32_t* pq = rowQ + ((size_t)e * rh + (y0 + r)) * FPM_WSTRIDE;
 #pragma unroll
                 for (int c = 0; c < FPM_NSHIFT; c++) {
                     if (c > 0) {

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <map>
@@ -505,7 +506,8 @@ int launch_corr_fused(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_
 
 // raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
 int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
-                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr, int n_ang = 1)
+                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr, int n_ang = 1,
+                    size_t row_stride = 0)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (ne + MM_M - 1) / MM_M;
@@ -513,7 +515,9 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     *e_pad_out = e_pad;
     CK(h->d_raw.ensure((size_t)rh * e_pad * MM_N * sizeof(int32_t)));
     CUtensorMap map_a, map_b;
-    int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)rpitch, (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
+    // roi_stride = bytes between evals, row_stride = bytes between the rows of a patch (0: rpitch)
+    int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)(row_stride ? row_stride : (size_t)rpitch),
+                         (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
     if (rc) return rc;
     rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
     if (rc) return rc;
@@ -801,7 +805,7 @@ int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt
         KL(K_WARP_TOP, 2.0 * nc * (double)p.maxW * p.maxH,
            fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(jobs + c0, 1, h->levels[top],
                                                                 h->d_rot.as<uint8_t>() + (size_t)c0 * rot_stride, rpitch, rot_stride,
-                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr, FpmRefineGeom{}));
+                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr, FpmRefineGeom{}, 0));
         dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, nc);
         dim3 block(TS_THREADS);
         KL(K_TOP_SCORE, (double)nc * maxRW * maxRH * t.w * t.h,      // MACs
@@ -856,7 +860,7 @@ RefineLayer refine_layer(const fpm_handle* h, int layer, int n_ang)
     // correlation path this level can take (dp4a [h][49], row-split tensor-core raw[h+6][64], or the fused kernel's
     // 64 numerators + 14 window totals)
     r.warp_fused = corr_warp_usable(h, t.w, n_ang, L);
-    r.per_eval = (r.warp_fused ? 0 : r.roi_stride) + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4 + sizeof(FpmWarpJob);
+    r.per_eval = (r.warp_fused ? 0 : r.roi_stride) + 2 * (size_t)(t.h + FPM_ROI_PAD) * FPM_WSTRIDE * 4 + sizeof(FpmWarpJob);
     if (mma_usable(h, t.w) || mma_narrow_fused(h, t.w))
         r.per_eval += std::max((size_t)(t.h + FPM_ROI_PAD) * MM_N * 4, (size_t)MM_N * 4 + 2 * FPM_NSHIFT * 8);
     if (!mma_usable(h, t.w)) r.per_eval += (size_t)t.h * FPM_NCELL * 4;
@@ -918,8 +922,8 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
         CK(h->d_jobs_ref.ensure((size_t)wave_evals * sizeof(FpmWarpJob)));
         if (!warp_fused) CK(h->d_roi.ensure(roi_stride * wave_evals));
         if (!mma_usable(h, t.w)) CK(h->d_rowsum.ensure((size_t)wave_evals * t.h * FPM_NCELL * 4));
-        CK(h->d_rowS.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
-        CK(h->d_rowQ.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_NSHIFT * 4));
+        CK(h->d_rowS.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_WSTRIDE * 4));
+        CK(h->d_rowQ.ensure((size_t)wave_evals * (t.h + FPM_ROI_PAD) * FPM_WSTRIDE * 4));
         if (h->trace) {
             CK(h->d_trace.ensure((size_t)n * n_ang * sizeof(FpmEvalTrace)));
             CK(cudaMemsetAsync(h->d_trace.p, 0, (size_t)n * n_ang * sizeof(FpmEvalTrace), h->stream));
@@ -955,21 +959,29 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                 const int wtiles_x = (rpitch + WA_TW - 1) / WA_TW;
                 dim3 wgrid(wtiles_x * ((t.h + FPM_ROI_PAD + WA_TH - 1) / WA_TH), nc);      // one CTA = one tile of the n_ang ROIs of a candidate
                 // algorithmic bytes: 1 B gathered + 1 B written per ROI pixel
+                // which correlation kernel will read the patches (the one-CTA-per-128-evals kernel only pays for many LIVE evals:
+                // never with an upper-bound count)
+                const bool go_fused = (mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) &&
+                                      (!async || h->use_tc == 4) &&
+                                      fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc, h->num_sms);
+                // row-split tensor-core kernel: patches row-interleaved, [row][eval][rpitch]
+                static const bool roi_interleave = getenv("FPM_ROI_INTERLEAVE") && atoi(getenv("FPM_ROI_INTERLEAVE")) != 0;
+                const bool inter = roi_interleave && !go_fused && mma_usable(h, t.w);
+                const size_t job_stride = inter ? (size_t)rpitch : roi_stride, row_stride = inter ? (size_t)ne * rpitch : 0;
+                { static bool said = false; if (inter && !said) { said = true; fprintf(stderr, "[fpm] ROI patches row-interleaved (ne %d, rpitch %d)\n", ne, rpitch); } }
                 KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
                    fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(nullptr, n_ang, L,
-                                                                        h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
+                                                                        h->d_roi.as<uint8_t>(), rpitch, job_stride, 0, wtiles_x,
                                                                         level_vec_ok(L), n_dev,
-                                                                        FpmRefineGeom{cands + c0, n_ang, step, L.w, L.h, t.w, t.h}));
-                // (the one-CTA-per-128-evals kernel only pays for many LIVE evals: never with an upper-bound count)
-                if ((mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) && (!async || h->use_tc == 4) &&
-                    fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc, h->num_sms)) {
+                                                                        FpmRefineGeom{cands + c0, n_ang, step, L.w, L.h, t.w, t.h}, row_stride));
+                if (go_fused) {
                     int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
                                                 t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
                     if (rcm) return rcm;
                     fused = true;
                 } else if (mma_usable(h, t.w)) {
-                    int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
-                                              t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
+                    int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, job_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                              t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang, row_stride);
                     if (rcm) return rcm;
                 } else {
                     dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
@@ -2534,7 +2546,7 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     const int tiles_x = (dp + WA_TW - 1) / WA_TW;
     dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
     fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), 1, s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
-                                                        tiles_x, level_vec_ok(s), nullptr, FpmRefineGeom{});
+                                                        tiles_x, level_vec_ok(s), nullptr, FpmRefineGeom{}, 0);
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -2551,7 +2563,7 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int
     CK(h->d_dbg[0].ensure(roi_bytes));
     CK(h->d_dbg[1].ensure(t_bytes));
     CK(h->d_dbg[2].ensure((size_t)th * FPM_NCELL * 4));
-    CK(h->d_dbg[3].ensure(2 * (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4));
+    CK(h->d_dbg[3].ensure(2 * (size_t)(th + FPM_ROI_PAD) * FPM_WSTRIDE * 4));
     CK(cudaMemsetAsync(h->d_dbg[0].p, 0, roi_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_dbg[1].p, 0, t_bytes, h->stream));
     CK(cudaMemcpy2DAsync(h->d_dbg[0].p, rpitch, roi, tw + FPM_ROI_PAD, tw + FPM_ROI_PAD, th + FPM_ROI_PAD, cudaMemcpyHostToDevice,
@@ -2565,14 +2577,15 @@ int fpm_dbg_corr_rows(fpm_handle* h, const uint8_t* roi, const uint8_t* tpl, int
     if (cc.smem > 48 * 1024)
         CK(ensure_dyn_smem((const void*)fpm_corr_rows_kernel, h->device, cc.smem));
     int32_t* dS = h->d_dbg[3].as<int32_t>();
-    int32_t* dQ = dS + (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT;
+    int32_t* dQ = dS + (size_t)(th + FPM_ROI_PAD) * FPM_WSTRIDE;
     dim3 grid(cc.blocks_y_rows, 1);
     fpm_corr_rows_kernel<<<grid, cc.threads, cc.smem, h->stream>>>(h->d_dbg[0].as<uint8_t>(), rpitch, roi_bytes, td, 1, cc.rb,
                                                                     cc.evals_per_cta, h->d_dbg[2].as<int32_t>(), dS, dQ, nullptr, 1);
     CKL();
     CK(cudaMemcpyAsync(rowsum, h->d_dbg[2].p, (size_t)th * FPM_NCELL * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(rowS, dS, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(rowQ, dQ, (size_t)(th + FPM_ROI_PAD) * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
+    // the device records are 8 ints per (eval, row); the caller gets the 7 window sums of each
+    CK(cudaMemcpy2DAsync(rowS, FPM_NSHIFT * 4, dS, FPM_WSTRIDE * 4, FPM_NSHIFT * 4, (size_t)(th + FPM_ROI_PAD), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(rowQ, FPM_NSHIFT * 4, dQ, FPM_WSTRIDE * 4, FPM_NSHIFT * 4, (size_t)(th + FPM_ROI_PAD), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return FPM_OK;
 }
@@ -2589,7 +2602,7 @@ int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois, int ne, const uint
     const size_t roi_stride = (size_t)rpitch * rh;
     CK(h->d_dbg[0].ensure(roi_stride * ne));
     CK(h->d_dbg[1].ensure((size_t)tp * th + (size_t)8 * th * bpitch + 256));
-    CK(h->d_dbg[3].ensure(2 * (size_t)ne * rh * FPM_NSHIFT * 4));
+    CK(h->d_dbg[3].ensure(2 * (size_t)ne * rh * FPM_WSTRIDE * 4));
     CK(cudaMemsetAsync(h->d_dbg[0].p, 0, roi_stride * ne, h->stream));
     CK(cudaMemsetAsync(h->d_dbg[1].p, 0, (size_t)tp * th, h->stream));
     for (int e = 0; e < ne; e++)
@@ -2601,14 +2614,14 @@ int fpm_dbg_corr_rows_mma(fpm_handle* h, const uint8_t* rois, int ne, const uint
     fpm_shift_template_kernel<<<g, 128, 0, h->stream>>>(h->d_dbg[1].as<uint8_t>(), tw, th, tp, tsh, bpitch);
     CKL();
     int32_t* dS = h->d_dbg[3].as<int32_t>();
-    int32_t* dQ = dS + (size_t)ne * rh * FPM_NSHIFT;
+    int32_t* dQ = dS + (size_t)ne * rh * FPM_WSTRIDE;
     int e_pad = 0;
     int rc = launch_corr_mma(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, &e_pad, dS, dQ);
     if (rc) return rc;
     std::vector<int32_t> raw((size_t)rh * e_pad * MM_N);
     CK(cudaMemcpyAsync(raw.data(), h->d_raw.p, raw.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(rowS, dS, (size_t)ne * rh * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(rowQ, dQ, (size_t)ne * rh * FPM_NSHIFT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(rowS, FPM_NSHIFT * 4, dS, FPM_WSTRIDE * 4, FPM_NSHIFT * 4, (size_t)ne * rh, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(rowQ, FPM_NSHIFT * 4, dQ, FPM_WSTRIDE * 4, FPM_NSHIFT * 4, (size_t)ne * rh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int e = 0; e < ne; e++)
         for (int tr = 0; tr < th; tr++)
@@ -2630,10 +2643,10 @@ int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t
     const size_t roi_stride = (size_t)rpitch * rh;
     CK(h->d_dbg[0].ensure(roi_stride * ne));
     CK(h->d_dbg[1].ensure((size_t)tp * th + (size_t)8 * th * bpitch + 256));
-    CK(h->d_dbg[3].ensure(2 * (size_t)ne * rh * FPM_NSHIFT * 4));
+    CK(h->d_dbg[3].ensure(2 * (size_t)ne * rh * FPM_WSTRIDE * 4));
     CK(cudaMemsetAsync(h->d_dbg[0].p, 0, roi_stride * ne, h->stream));
     CK(cudaMemsetAsync(h->d_dbg[1].p, 0, (size_t)tp * th, h->stream));
-    CK(cudaMemsetAsync(h->d_dbg[3].p, 0xff, 2 * (size_t)ne * rh * FPM_NSHIFT * 4, h->stream));   // rows the kernel must not need stay poisoned
+    CK(cudaMemsetAsync(h->d_dbg[3].p, 0xff, 2 * (size_t)ne * rh * FPM_WSTRIDE * 4, h->stream));   // rows the kernel must not need stay poisoned
     for (int e = 0; e < ne; e++)
         CK(cudaMemcpy2DAsync(h->d_dbg[0].as<uint8_t>() + e * roi_stride, rpitch, rois + (size_t)e * rh * rw, rw, rw, rh,
                              cudaMemcpyHostToDevice, h->stream));
@@ -2643,7 +2656,7 @@ int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t
     fpm_shift_template_kernel<<<g, 128, 0, h->stream>>>(h->d_dbg[1].as<uint8_t>(), tw, th, tp, tsh, bpitch);
     CKL();
     int32_t* dS = h->d_dbg[3].as<int32_t>();
-    int32_t* dQ = dS + (size_t)ne * rh * FPM_NSHIFT;
+    int32_t* dQ = dS + (size_t)ne * rh * FPM_WSTRIDE;
     int rc = launch_corr_fused(h, h->d_dbg[0].as<uint8_t>(), rpitch, roi_stride, tsh, bpitch, tw, th, ne, dS, dQ);
     if (rc) return rc;
     std::vector<float> hn((size_t)ne * MM_N);
@@ -2652,8 +2665,8 @@ int fpm_dbg_corr_fused(fpm_handle* h, const uint8_t* rois, int ne, const uint8_t
     CK(cudaMemcpyAsync(hn.data(), h->d_numer.p, hn.size() * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(tS.data(), h->d_totS.p, tS.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(tQ.data(), h->d_totQ.p, tQ.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(rS.data(), dS, rS.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(rQ.data(), dQ, rQ.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(rS.data(), FPM_NSHIFT * 4, dS, FPM_WSTRIDE * 4, FPM_NSHIFT * 4, (size_t)ne * rh, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(rQ.data(), FPM_NSHIFT * 4, dQ, FPM_WSTRIDE * 4, FPM_NSHIFT * 4, (size_t)ne * rh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (edge_rowS) memcpy(edge_rowS, rS.data(), rS.size() * 4);
     // same window arithmetic as fpm_refine_finalize_kernel's fused branch

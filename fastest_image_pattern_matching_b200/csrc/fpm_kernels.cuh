@@ -1113,7 +1113,7 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
         uint32_t hb[6];
         hb[0] = head0 & 255; hb[1] = (head0 >> 8) & 255; hb[2] = (head0 >> 16) & 255; hb[3] = head0 >> 24;
         hb[4] = head1 & 255; hb[5] = (head1 >> 8) & 255;
-        size_t base = ((size_t)e * rh + y) * FPM_NSHIFT;
+        size_t base = ((size_t)e * rh + y) * FPM_WSTRIDE;
         uint32_t cs = sS, cq = sQ;
         rowS[base] = (int32_t)cs; rowQ[base] = (int32_t)cq;
 #pragma unroll
@@ -1281,16 +1281,20 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
         if (j < n_ang) {
             const int e = ci * n_ang + j;
             const int rh = th + FPM_ROI_PAD;
-            const int32_t* ps = rowS + (size_t)e * rh * FPM_NSHIFT;
-            const int32_t* pq = rowQ + (size_t)e * rh * FPM_NSHIFT;
+            const int32_t* ps = rowS + (size_t)e * rh * FPM_WSTRIDE;
+            const int32_t* pq = rowQ + (size_t)e * rh * FPM_WSTRIDE;
             long long ts[FPM_NSHIFT], tq[FPM_NSHIFT];
 #pragma unroll
             for (int c = 0; c < FPM_NSHIFT; c++) { ts[c] = 0; tq[c] = 0; }
 #pragma unroll 2
             for (int y = cell; y < rh; y += 64) {
-                int a[FPM_NSHIFT], b[FPM_NSHIFT];
-#pragma unroll
-                for (int c = 0; c < FPM_NSHIFT; c++) { a[c] = ps[(size_t)y * FPM_NSHIFT + c]; b[c] = pq[(size_t)y * FPM_NSHIFT + c]; }
+                int a[FPM_WSTRIDE], b[FPM_WSTRIDE];
+                {                                                        // one 32-byte record per row: two 128-bit loads each
+                    const int4 a0 = __ldg(reinterpret_cast<const int4*>(ps + (size_t)y * FPM_WSTRIDE)), a1 = __ldg(reinterpret_cast<const int4*>(ps + (size_t)y * FPM_WSTRIDE) + 1);
+                    const int4 b0 = __ldg(reinterpret_cast<const int4*>(pq + (size_t)y * FPM_WSTRIDE)), b1 = __ldg(reinterpret_cast<const int4*>(pq + (size_t)y * FPM_WSTRIDE) + 1);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+                }
 #pragma unroll
                 for (int c = 0; c < FPM_NSHIFT; c++) { ts[c] += a[c]; tq[c] += b[c]; }
                 if (y < FPM_ROI_PAD) {
@@ -1329,10 +1333,10 @@ fpm_refine_finalize_kernel(const FpmCand* __restrict__ cands, int n_ang, double 
             const float numf = numer[(size_t)e * 64 + c * 8 + (7 - r)];
             const int rh = th + FPM_ROI_PAD;
             long long ws = totS[(size_t)e * FPM_NSHIFT + c], wq = totQ[(size_t)e * FPM_NSHIFT + c];
-            const int32_t* ps = rowS + (size_t)e * rh * FPM_NSHIFT + c;
-            const int32_t* pq = rowQ + (size_t)e * rh * FPM_NSHIFT + c;
-            for (int y = 0; y < r; y++) { ws -= ps[(size_t)y * FPM_NSHIFT]; wq -= pq[(size_t)y * FPM_NSHIFT]; }
-            for (int y = r + th; y < rh; y++) { ws -= ps[(size_t)y * FPM_NSHIFT]; wq -= pq[(size_t)y * FPM_NSHIFT]; }
+            const int32_t* ps = rowS + (size_t)e * rh * FPM_WSTRIDE + c;
+            const int32_t* pq = rowQ + (size_t)e * rh * FPM_WSTRIDE + c;
+            for (int y = 0; y < r; y++) { ws -= ps[(size_t)y * FPM_WSTRIDE]; wq -= pq[(size_t)y * FPM_WSTRIDE]; }
+            for (int y = r + th; y < rh; y++) { ws -= ps[(size_t)y * FPM_WSTRIDE]; wq -= pq[(size_t)y * FPM_WSTRIDE]; }
             sc = fpm_ccoeff_epilogue(numf, (double)ws, (double)wq, tpl.mean, tpl.norm, tpl.inv_area);
         } else {
             // row sums either as [e][tr][49] (dp4a kernel) or as raw[y][e_pad][64] with y = tr + r and

@@ -232,13 +232,21 @@ __device__ __forceinline__ void fpm_mm_stats(uint32_t base_u32, uint32_t bar0, i
         }
         int sc = (int)s0, qc = (int)q0;
         const bool store = live && (kAllRows || y < FPM_ROI_PAD || y >= th);
-        int32_t* ps = rowS + ((size_t)e * rh + y) * FPM_NSHIFT;
-        int32_t* pq = rowQ + ((size_t)e * rh + y) * FPM_NSHIFT;
+        int vs[FPM_WSTRIDE], vq[FPM_WSTRIDE];
+        vs[FPM_NSHIFT] = 0; vq[FPM_NSHIFT] = 0;
 #pragma unroll
         for (int c = 0; c < FPM_NSHIFT; c++) {
             if (c > 0) { sc += tl[c - 1] - hd[c - 1]; qc += tl[c - 1] * tl[c - 1] - hd[c - 1] * hd[c - 1]; }
             if (!kAllRows) { ts[c] += sc; tq[c] += qc; }
-            if (store) { ps[c] = sc; pq[c] = qc; }
+            vs[c] = sc; vq[c] = qc;
+        }
+        if (store) {
+            // one aligned 32-byte record per (eval, row): two 128-bit stores each (14 scattered 4-byte stores per row and
+            // thread had the statistics warps waiting on the store queue: a third of the kernel's stall samples)
+            int4* ps = reinterpret_cast<int4*>(rowS + ((size_t)e * rh + y) * FPM_WSTRIDE);
+            int4* pq = reinterpret_cast<int4*>(rowQ + ((size_t)e * rh + y) * FPM_WSTRIDE);
+            ps[0] = make_int4(vs[0], vs[1], vs[2], vs[3]); ps[1] = make_int4(vs[4], vs[5], vs[6], vs[7]);
+            pq[0] = make_int4(vq[0], vq[1], vq[2], vq[3]); pq[1] = make_int4(vq[4], vq[5], vq[6], vq[7]);
         }
     }
 }
