@@ -506,8 +506,7 @@ int launch_corr_fused(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_
 
 // raw[y][e_pad][64] s32 + rowS/rowQ for `ne` ROI patches of one template level
 int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_stride, const uint8_t* tsh, int bpitch, int tw, int th,
-                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr, int n_ang = 1,
-                    size_t row_stride = 0)
+                    int ne, int* e_pad_out, int32_t* rowS, int32_t* rowQ, const int* n_cands_dev = nullptr, int n_ang = 1)
 {
     const int rh = th + FPM_ROI_PAD;
     const int m_tiles = (ne + MM_M - 1) / MM_M;
@@ -515,9 +514,7 @@ int launch_corr_mma(fpm_handle* h, const uint8_t* roi, int rpitch, size_t roi_st
     *e_pad_out = e_pad;
     CK(h->d_raw.ensure((size_t)rh * e_pad * MM_N * sizeof(int32_t)));
     CUtensorMap map_a, map_b;
-    // roi_stride = bytes between evals, row_stride = bytes between the rows of a patch (0: rpitch)
-    int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)(row_stride ? row_stride : (size_t)rpitch),
-                         (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
+    int rc = make_map_3d(h, &map_a, roi, (uint64_t)rpitch, (uint64_t)rh, (uint64_t)ne, (uint64_t)rpitch, (uint64_t)roi_stride, MM_KCHUNK, 1, MM_M);
     if (rc) return rc;
     rc = make_map_3d(h, &map_b, tsh, (uint64_t)bpitch, (uint64_t)th, 8, (uint64_t)bpitch, (uint64_t)bpitch * th, MM_KCHUNK, 8, 8);
     if (rc) return rc;
@@ -805,7 +802,7 @@ int run_top(fpm_handle* h, int top, int j0, int nj, FpmPick* picks_out, int* cnt
         KL(K_WARP_TOP, 2.0 * nc * (double)p.maxW * p.maxH,
            fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(jobs + c0, 1, h->levels[top],
                                                                 h->d_rot.as<uint8_t>() + (size_t)c0 * rot_stride, rpitch, rot_stride,
-                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr, FpmRefineGeom{}, 0));
+                                                                h->border, tiles_x, level_vec_ok(h->levels[top]), nullptr, FpmRefineGeom{}));
         dim3 grid((maxRW + TS_TW - 1) / TS_TW, (maxRH + TS_TH - 1) / TS_TH, nc);
         dim3 block(TS_THREADS);
         KL(K_TOP_SCORE, (double)nc * maxRW * maxRH * t.w * t.h,      // MACs
@@ -964,24 +961,19 @@ int run_refine(fpm_handle* h, int top, int n_cands, int* n_refined_out)
                 const bool go_fused = (mma_narrow_fused(h, t.w) || (mma_usable(h, t.w) && h->use_simd && h->use_tc != 3)) &&
                                       (!async || h->use_tc == 4) &&
                                       fused_pays(ne, t.h + FPM_ROI_PAD, rpitch, t.w + FPM_ROI_PAD, h->use_tc, h->num_sms);
-                // row-split tensor-core kernel: patches row-interleaved, [row][eval][rpitch]
-                static const bool roi_interleave = getenv("FPM_ROI_INTERLEAVE") && atoi(getenv("FPM_ROI_INTERLEAVE")) != 0;
-                const bool inter = roi_interleave && !go_fused && mma_usable(h, t.w);
-                const size_t job_stride = inter ? (size_t)rpitch : roi_stride, row_stride = inter ? (size_t)ne * rpitch : 0;
-                { static bool said = false; if (inter && !said) { said = true; fprintf(stderr, "[fpm] ROI patches row-interleaved (ne %d, rpitch %d)\n", ne, rpitch); } }
                 KL(K_WARP_ROI, 2.0 * ne * (double)(t.w + FPM_ROI_PAD) * (t.h + FPM_ROI_PAD),
                    fpm_warp_kernel<<<wgrid, WA_THREADS, 0, h->stream>>>(nullptr, n_ang, L,
-                                                                        h->d_roi.as<uint8_t>(), rpitch, job_stride, 0, wtiles_x,
+                                                                        h->d_roi.as<uint8_t>(), rpitch, roi_stride, 0, wtiles_x,
                                                                         level_vec_ok(L), n_dev,
-                                                                        FpmRefineGeom{cands + c0, n_ang, step, L.w, L.h, t.w, t.h}, row_stride));
+                                                                        FpmRefineGeom{cands + c0, n_ang, step, L.w, L.h, t.w, t.h}));
                 if (go_fused) {
                     int rcm = launch_corr_fused(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
                                                 t.w, t.h, ne, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
                     if (rcm) return rcm;
                     fused = true;
                 } else if (mma_usable(h, t.w)) {
-                    int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, job_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
-                                              t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang, row_stride);
+                    int rcm = launch_corr_mma(h, h->d_roi.as<uint8_t>(), rpitch, roi_stride, h->d_tsh.as<uint8_t>() + t.tsh_off, t.bpitch,
+                                              t.w, t.h, ne, &raw_epad, h->d_rowS.as<int32_t>(), h->d_rowQ.as<int32_t>(), n_dev, n_ang);
                     if (rcm) return rcm;
                 } else {
                     dim3 cgrid(cc.blocks_y_rows, (ne + cc.evals_per_cta - 1) / cc.evals_per_cta);
@@ -2546,7 +2538,7 @@ int fpm_dbg_warp_affine(fpm_handle* h, const uint8_t* src, int w, int hgt, int s
     const int tiles_x = (dp + WA_TW - 1) / WA_TW;
     dim3 grid(tiles_x * ((dh + WA_TH - 1) / WA_TH), 1);
     fpm_warp_kernel<<<grid, WA_THREADS, 0, h->stream>>>(h->d_dbg[2].as<FpmWarpJob>(), 1, s, h->d_dbg[1].as<uint8_t>(), dp, 0, border,
-                                                        tiles_x, level_vec_ok(s), nullptr, FpmRefineGeom{}, 0);
+                                                        tiles_x, level_vec_ok(s), nullptr, FpmRefineGeom{});
     CKL();
     CK(cudaMemcpy2DAsync(dst, dw, h->d_dbg[1].p, dp, dw, dh, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
