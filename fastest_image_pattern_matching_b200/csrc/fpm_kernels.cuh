@@ -1115,13 +1115,18 @@ fpm_corr_rows_kernel(const uint8_t* __restrict__ roi, int rpitch, size_t roi_str
         hb[4] = head1 & 255; hb[5] = (head1 >> 8) & 255;
         size_t base = ((size_t)e * rh + y) * FPM_WSTRIDE;
         uint32_t cs = sS, cq = sQ;
-        rowS[base] = (int32_t)cs; rowQ[base] = (int32_t)cq;
+        int vs[FPM_WSTRIDE], vq[FPM_WSTRIDE];
+        vs[0] = (int)cs; vq[0] = (int)cq; vs[FPM_NSHIFT] = 0; vq[FPM_NSHIFT] = 0;
 #pragma unroll
         for (int c = 1; c < FPM_NSHIFT; c++) {
             cs = cs - hb[c - 1] + tailb[c - 1];
             cq = cq - hb[c - 1] * hb[c - 1] + tailb[c - 1] * tailb[c - 1];
-            rowS[base + c] = (int32_t)cs; rowQ[base + c] = (int32_t)cq;
+            vs[c] = (int)cs; vq[c] = (int)cq;
         }
+        int4* ps = reinterpret_cast<int4*>(rowS + base);                // one aligned 32-byte record per (eval, row)
+        int4* pq = reinterpret_cast<int4*>(rowQ + base);
+        ps[0] = make_int4(vs[0], vs[1], vs[2], vs[3]); ps[1] = make_int4(vs[4], vs[5], vs[6], vs[7]);
+        pq[0] = make_int4(vq[0], vq[1], vq[2], vq[3]); pq[1] = make_int4(vq[4], vq[5], vq[6], vq[7]);
     }
     // ---- transpose through shared memory: out[el][tr_local][cell], then coalesced global stores
     uint32_t* s_o = smem_w;                                // [evals_per_cta][n_trow][49]
