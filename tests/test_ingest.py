@@ -152,6 +152,34 @@ def test_parallel_huffman_decoder_equals_the_sequential_one(name):
     assert 1 <= passes <= 128, passes                    # worst fixture: incompressible noise at quality 100
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_jpeg_decoders_on_random_encodings(seed):
+    """random size / content / quality / chroma subsampling / restart interval / optimised Huffman tables: the sequential host
+    decoder + the IDCT model equal cv2.imdecode, and the parallel decoder equals the sequential one"""
+    rng = np.random.default_rng(1000 + seed)
+    h, w = int(rng.integers(1, 200)), int(rng.integers(1, 260))
+    color = bool(rng.integers(0, 2))
+    img = rng.integers(0, 256, (h, w, 3) if color else (h, w), dtype=np.uint8)
+    if rng.integers(0, 2):
+        img = cv2.GaussianBlur(img, (0, 0), float(rng.uniform(0.6, 4.0)))
+    params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(5, 101))]
+    if color:
+        params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, int(rng.choice([cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+                                                                     cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440,
+                                                                     cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]))]
+    if rng.integers(0, 2):
+        params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 9))]
+    if rng.integers(0, 2):
+        params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+    data = bytes(cv2.imencode(".jpg", img, params)[1])
+    want = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+    gw, gh, bw, bh, quant, coef = _host_luma(data)
+    px = O.jpeg_idct_islow(coef, quant).reshape(bh, bw, 8, 8).transpose(0, 2, 1, 3).reshape(bh * 8, bw * 8)[:gh, :gw]
+    assert np.array_equal(px, want), params
+    got, passes = _parallel_luma(data, coef.shape)
+    assert np.array_equal(got, coef), params
+
+
 def test_jpeg_host_decoder_rejects_what_it_cannot_decode():
     rng = np.random.default_rng(5)
     img = cv2.GaussianBlur(rng.integers(0, 256, (48, 64), dtype=np.uint8), (0, 0), 2)
