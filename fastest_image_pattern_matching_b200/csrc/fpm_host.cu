@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1956,16 +1957,27 @@ int jpeg_decode_device(fpm_handle* h, const fpm_jpeg::Frame& fr, const uint8_t* 
 // restart intervals are Huffman-decoded on the device (fpm_jpeg_par.cuh: the compressed scan is the only H2D traffic); the
 // others on the host (fpm_jpeg.h), their quantised luma coefficients go to the device.  Dequantisation + IDCT + range limit
 // run on the device in both cases.
+static int ingest_jpeg_impl(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height);
 int fpm_ingest_jpeg(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height)
 {
     if (!h) return FPM_ERR_INVALID;
     if (!file) { h->err = "null JPEG buffer"; return FPM_ERR_INVALID; }
+    try {                                                             // nothing may be thrown across the C ABI
+        return ingest_jpeg_impl(h, file, nbytes, width, height);
+    } catch (const std::bad_alloc&) {
+        h->err = "out of host memory while decoding the JPEG";
+        return FPM_ERR_LIMIT;
+    }
+}
+
+static int ingest_jpeg_impl(fpm_handle* h, const uint8_t* file, size_t nbytes, int* width, int* height)
+{
     fpm_jpeg::Frame fr;
     {
         const std::string why = fpm_jpeg::parse(file, nbytes, &fr);
         if (!why.empty()) { h->err = why; return FPM_ERR_INVALID; }
     }
-    if (fr.height > 65535 || fr.width > 65535) { h->err = "JPEG too large"; return FPM_ERR_LIMIT; }
+    if ((size_t)fr.height * fr.width > ((size_t)1 << 30)) { h->err = "JPEG too large (more than 2^30 pixels, OpenCV's own limit)"; return FPM_ERR_LIMIT; }
     bool on_device = h->jpeg_device_huffman && jpeg_device_ok(fr, nbytes);
     JpScan sc;
     const int *dcval = nullptr, *tile_off = nullptr;
@@ -2028,7 +2040,7 @@ int fpm_ingest_image(fpm_handle* h, const uint8_t* file, size_t nbytes, int* wid
 // the CPU-side pin of the Huffman decoder against cv2 (tests/test_ingest.py).  coef may be NULL to query the sizes.
 int fpm_dbg_jpeg_luma(const uint8_t* file, size_t nbytes, int* width, int* height, int* bw, int* bh, uint16_t* quant /* 64 */,
                       int16_t* coef, size_t coef_capacity, char* err, int err_capacity)
-{
+try {
     fpm_jpeg::Luma im;
     const std::string why = fpm_jpeg::decode_luma(file, nbytes, &im);
     if (!why.empty()) {
@@ -2045,12 +2057,14 @@ int fpm_dbg_jpeg_luma(const uint8_t* file, size_t nbytes, int* width, int* heigh
         memcpy(coef, im.coef.data(), im.coef.size() * sizeof(int16_t));
     }
     return FPM_OK;
+} catch (const std::bad_alloc&) {
+    return FPM_ERR_LIMIT;
 }
 
 // the PARALLEL decoder (fpm_jpeg_par.cuh) run thread by thread on the CPU, no device: same outputs as fpm_dbg_jpeg_luma;
 // *passes = synchronisation passes it took
 int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef, size_t coef_capacity, int* passes, char* err, int err_capacity)
-{
+try {
     auto fail = [&](const std::string& why) {
         if (err && err_capacity > 0) { strncpy(err, why.c_str(), err_capacity - 1); err[err_capacity - 1] = 0; }
         return FPM_ERR_INVALID;
@@ -2101,6 +2115,8 @@ int fpm_dbg_jpeg_luma_parallel(const uint8_t* file, size_t nbytes, int16_t* coef
         for (int c = 0; c < sc.bw; c++) coef[((size_t)r * sc.bw + c) * 64] = (int16_t)dcval[jp_luma_scan_index(sc, r, c)];
     if (passes) *passes = np;
     return FPM_OK;
+} catch (const std::bad_alloc&) {
+    return FPM_ERR_LIMIT;
 }
 
 int fpm_ingest_rgb32(fpm_handle* h, const uint32_t* pixels, int width, int height, int stride_bytes)

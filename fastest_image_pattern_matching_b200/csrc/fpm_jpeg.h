@@ -13,6 +13,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -220,6 +221,7 @@ inline std::string parse(const uint8_t* d, size_t n, Frame* f)
             if (sl >= 12 && memcmp(s, "Adobe", 5) == 0) { saw_adobe = true; adobe_transform = s[11]; }
         } else if (m == 0xDA) {                                          // SOS
             if (!sof) return "JPEG scan before the frame header";
+            if (sl < 1) return "bad SOS segment";
             const int ns = s[0];
             if (ns != (int)comp.size()) return "unsupported JPEG: more than one scan";
             if (sl < (size_t)(1 + 2 * ns + 3)) return "bad SOS segment";
@@ -270,7 +272,11 @@ inline std::string decode_scan_host(const Frame& fr, const uint8_t* d, size_t n,
     out->width = fr.width; out->height = fr.height;
     out->bw = mcux * comp[0].h; out->bh = mcuy * comp[0].v;
     memcpy(out->quant, fr.qt[comp[0].tq], sizeof(out->quant));
-    out->coef.assign((size_t)out->bw * out->bh * 64, 0);
+    try {
+        out->coef.assign((size_t)out->bw * out->bh * 64, 0);
+    } catch (const std::bad_alloc&) {
+        return "JPEG too large for host memory";
+    }
 
     BitReader br(d + i, d + n);
     int pred[3] = {0, 0, 0};
