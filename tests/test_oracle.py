@@ -53,7 +53,14 @@ def test_restated_simd_matches_reference_build():
     """oracle/_ref/libimconv_ref.so is the reference's own IM_Conv_SIMD compiled from its source."""
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libimconv_ref.so")
     if not os.path.exists(ref_path):
-        pytest.skip("oracle/_ref not built (reference absent)")
+        # policy: where the reference is mounted the pin must run -- build it, and fail (not skip) if that does not work;
+        # only a box without /root/reference (the GPU box) may skip, and then only if the prebuilt .so did not travel
+        if os.path.isdir("/root/reference"):
+            import subprocess
+            subprocess.run(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")], check=False, capture_output=True)
+            assert os.path.exists(ref_path), "oracle/_ref could not be built from /root/reference (oracle/build_ref.sh)"
+        else:
+            pytest.skip("oracle/_ref not present and /root/reference not mounted")
     ref = ctypes.CDLL(ref_path)
     ref.ref_IM_Conv_SIMD.restype = ctypes.c_int
     ref.ref_cell.restype = ctypes.c_float
