@@ -1577,10 +1577,13 @@ int fpm_match_batch(fpm_handle* h, const uint8_t* src, int batch, int width, int
     const int pitch = linear ? width : (int)align_up(width, 128);
     const size_t img = linear ? frame_stride : align_up((size_t)pitch * height, 256);
     int chunk = std::max(1, std::min(batch, (int)std::max<size_t>(1, (size_t)(512ull << 20) / img)));
-    // measured on B200 (cfg1): H2D of c frames takes 0.22c ms, matching c frames 0.63 + 0.073c ms, so the
-    // pipeline is copy-bound from c = 8 on while the fill/drain cost stays small
-    if (batch >= 16) chunk = std::min(chunk, 8);
-    else if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
+    // Chunk size by BYTES: about 96 MB = 1.7 ms of copy at the 55 GB/s of a PCIe 5 x16 link.  Measured on B200: matching c
+    // cfg1 frames takes 0.63 + 0.073c ms, so from ~96 MB on the pipeline is copy-bound while the fill (the first chunk's
+    // copy) and the drain (the last chunk's match) stay short -- 8 frames of 12 MB (cfg1..cfg4), ONE frame of 67 MB
+    // (cfg5: +10 % against chunks of 4)
+    const int by_bytes = (int)std::max<size_t>(1, ((size_t)(96ull << 20) + img / 2) / img);
+    chunk = std::min(chunk, by_bytes);
+    if (batch > 1) chunk = std::min(chunk, (batch + 1) / 2);
     if (h->h2d_chunk > 0) chunk = std::min(batch, h->h2d_chunk);
     const size_t buf_bytes = align_up(img * chunk, 256);
     CK(h->d_src.ensure(buf_bytes * 2));
