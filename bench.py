@@ -535,6 +535,11 @@ def main():
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": traffic.get(dom), "traffic_source": traffic_src if traffic else None,
                         "peak_source": hbm_src}
+            if dom.startswith("fpm_warp_kernel"):
+                # SURVEY 8d counts this stage in bytes, so the contract's fraction is against HBM -- but HBM is not what limits it
+                roofline["limiter"] = ("bilinear gather kernel bound by instruction issue (80 % of peak) and the shared-memory pipe "
+                                       "(77 %), not by HBM: its DRAM traffic is 0.6x the algorithmic bytes (ncu: "
+                                       "profiles/r02_ncu_final_l0_warp_mma_finalize_summary.txt); 34 thread-instructions per ROI pixel")
     # the HBM-bound stages the north_star names (pyramid, rotation): always reported beside the dominant kernel
     hbm_kernels = {}
     for name in ("fpm_pyrdown_kernel", "fpm_warp_kernel(roi)"):
