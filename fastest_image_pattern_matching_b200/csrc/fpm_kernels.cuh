@@ -11,7 +11,9 @@
 //   fpm_refine_finalize_kernel float row chain + CCOEFF_Denominator + argmax + pose update (:304-367)
 //   fpm_final_kernel          filterWithScore / RotatedRect / NMS / output    (:373-432)
 //   fpm_ingest_*_kernel       cv::imread(IMREAD_GRAYSCALE) of a BMP / JPEG (dequantisation + ISLOW IDCT), camera RGB32 -> gray (MatchToolDialog.cpp:314, :1557)
-// and, in fpm_mma.cuh, the tcgen05 versions of the row dot products (fpm_corr_mma_kernel, fpm_corr_fused_kernel).
+//   fpm_jpeg_*_kernel         Huffman decoding of a JPEG scan (self-synchronising sub-sequences)   [fpm_jpeg_par.cuh]
+// and, in fpm_mma.cuh / fpm_fused.cuh, the tcgen05 versions of the row dot products (fpm_corr_mma_kernel,
+// fpm_corr_fused_kernel, fpm_corr_warp_kernel).
 //
 // All integer work is exact; all double/float epilogues are written op-by-op (the library is
 // compiled with -fmad=false) so they round like the reference's x86-64 (no FMA) build.
